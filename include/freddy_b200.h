@@ -1,0 +1,133 @@
+/* freddy_b200.h — C-ABI of the B200-native IVFADC / PQ k-NN engine.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, caller-
+ * allocated outputs, int status codes, no exceptions, no torch / C++ types.
+ * Each entry point names the interface of the reference PostgreSQL extension
+ * (guenthermi/postgres-word2vec, paths relative to freddy_extension/) that it
+ * replaces.  The Postgres-side shim that would call it is shown in
+ * INTEGRATION.md; tests/ and bench.py call it through ctypes.
+ *
+ * Model: one engine per process (= one Postgres backend; a CUDA context cannot
+ * cross fork()).  The index tables are uploaded ONCE per session
+ * (fb_load_*), transformed into the device layout and pinned in HBM; every
+ * search call then runs entirely on the GPU.  The reference instead re-reads
+ * codebook, coarse quantizer and inverted lists through SPI on every call
+ * (freddy.c:239-241, :324-343).
+ *
+ * Result contract (identical to the reference's SRF output):
+ *   - exactly k (id, distance) pairs per query, ascending distance; among
+ *     equal distances the later table row comes first; admission is strict
+ *     (`d < kth`), so which of several boundary ties survive follows the
+ *     reference's insertion order (index_utils.c:19-33) exactly;
+ *   - unfilled slots are id = -1 with the SRF's sentinel distance;
+ *   - distances are the reference's fp32 values bit for bit (sequential,
+ *     unfused sub/mul/add); the "%f" text rounding of the SRF is applied by
+ *     the shim / fb_round_through_text, not here.
+ */
+#ifndef FREDDY_B200_H
+#define FREDDY_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_engine fb_engine;
+
+enum {
+  FB_OK = 0,
+  FB_ERR_INVALID = -1,      /* bad argument / index not loaded            */
+  FB_ERR_CUDA = -2,         /* CUDA runtime error (see fb_last_error)     */
+  FB_ERR_UNSUPPORTED = -3,  /* shape outside what the kernels support     */
+  FB_ERR_REFERENCE_UB = -4  /* the reference would run into undefined
+                               behaviour here (e.g. fewer than w unprobed
+                               lists left, freddy.c:262-302 with id = -1) */
+};
+
+/* which codebook / code table a call refers to (index_utils.h:87-99 tableType) */
+enum {
+  FB_CB_RESIDUAL = 0,  /* residual_codebook  + fine_quantization  (IVFADC)   */
+  FB_CB_PQ = 1,        /* pq_codebook        + pq_quantization    (flat PQ)  */
+  FB_CB_KINDS = 2
+};
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int fb_create(int device, fb_engine** out);
+void fb_destroy(fb_engine* e);
+/* message of the last failing call on this engine (or of fb_create if e==NULL) */
+const char* fb_last_error(const fb_engine* e);
+
+/* ---- index upload: "pin once per session" -------------------------------- */
+/* coarse_quantization table, row = coarse id (replaces getCoarseQuantizer,
+ * index_utils.c:531-575).  coarse: host [C][d] fp32. */
+int fb_load_coarse(fb_engine* e, const float* coarse, int C, int d);
+/* (residual_)codebook table as a dense [m][K][sub] fp32 array indexed by
+ * (pos, code) (replaces getCodebook, index_utils.c:577-630). */
+int fb_load_codebook(fb_engine* e, int kind, const float* codebook, int m, int K, int sub);
+/* fine_quantization rows in table order: id, coarse_id, int2[m] codes
+ * (replaces the per-call `SELECT id, vector, coarse_id FROM fine WHERE
+ * coarse_id IN (...)`, freddy.c:324-343).  Table order is the arrival order
+ * of the reference's top-k loop. */
+int fb_load_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids,
+                 const int16_t* codes, int64_t N, int m);
+/* pq_quantization rows in table order (freddy.c:99-103, :544-562, :1099-1113) */
+int fb_load_pq(fb_engine* e, const int32_t* ids, const int16_t* codes, int64_t N, int m);
+
+/* ---- search -------------------------------------------------------------- */
+/* ivfadc_search(bytea query, int k) with parameter w = get_w()
+ * (freddy.c:174-410), batched over nq independent queries.
+ * queries: [nq][d] fp32; out_ids/out_dists: [nq][k].  Host buffers. */
+int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w,
+                     int32_t* out_ids, float* out_dists);
+/* Same, all pointers are DEVICE pointers on the engine's device; the call is
+ * enqueued on the engine stream and is complete on return only after
+ * fb_synchronize().  No host<->device copies. */
+int fb_ivfadc_search_dev(fb_engine* e, const float* d_queries, int nq, int k, int w,
+                         int32_t* d_out_ids, float* d_out_dists);
+
+/* pq_search(bytea, int) (freddy.c:28-170): exhaustive ADC over pq_quantization,
+ * sentinel distance 100.0. */
+int fb_pq_search(fb_engine* e, const float* queries, int nq, int k,
+                 int32_t* out_ids, float* out_dists);
+/* pq_search_in(bytea, int, int[]) / pq_search_in_batch(bytea[], int[], int,
+ * int[], bool) (freddy.c:1028-1174, :414-675): ADC over the rows whose id is
+ * in targets; sentinel 1000.0.  use_target_lists only changes the reference's
+ * loop nest, not its results; accepted for signature parity. */
+int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k,
+                          const int32_t* targets, int n_targets, int use_target_lists,
+                          int32_t* out_ids, float* out_dists);
+
+int fb_synchronize(fb_engine* e);
+
+/* ---- knobs / introspection ---------------------------------------------- */
+enum {
+  FB_OPT_FORCE_EXACT_PATH = 1, /* 1: send every query through the general
+                                  (tie/re-probe exact) kernel; testing aid    */
+  FB_OPT_PROFILE = 2,          /* 1: bracket every kernel with CUDA events on
+                                  the engine stream and accumulate fb_counters */
+  FB_OPT_QUERY_CHUNK = 3       /* queries per pipeline chunk (LUT scratch =
+                                  chunk * w * m * K * 4 bytes)                */
+};
+int fb_set_option(fb_engine* e, int option, int64_t value);
+
+typedef struct {
+  int64_t queries;          /* queries answered since the last reset            */
+  int64_t rows_scanned;     /* fine/pq rows whose ADC distance was computed     */
+  int64_t scan_bytes;       /* algorithmic bytes of those rows: m*2 + 4 each    */
+  int64_t exact_path_queries; /* queries re-done by the general kernel          */
+  int64_t kernel_launches;  /* kernels launched by this library                 */
+  double ms_coarse, ms_lut, ms_scan, ms_finalize, ms_exact; /* FB_OPT_PROFILE   */
+  int64_t n_scan_launches;
+} fb_counters;
+int fb_get_counters(fb_engine* e, fb_counters* out);  /* synchronizes the stream */
+int fb_reset_counters(fb_engine* e);
+
+/* snprintf("%f") -> float4in, as every SRF returns distances (freddy.c:401-408) */
+float fb_round_through_text(float distance);
+
+const char* fb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

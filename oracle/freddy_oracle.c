@@ -1,0 +1,342 @@
+/* freddy_oracle.c — CPU ORACLE. TEST INFRASTRUCTURE ONLY (see freddy_oracle.h).
+ *
+ * Restates, function by function, the search arithmetic of the reference
+ * PostgreSQL extension over in-memory arrays.  "ref:" comments give the
+ * reference file:line (relative to /root/reference/freddy_extension/) that
+ * the code below follows.  Written from scratch; no reference source is
+ * copied.  Build: gcc -O2 -ffp-contract=off (no -march, hence no FMA), which
+ * is what PGXS gives the reference.
+ */
+#include "freddy_oracle.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* kernel-level restatements                                                  */
+/* ------------------------------------------------------------------------- */
+
+/* ref: index_utils.c:500-508 squareDistance — sequential fp32 sum of
+ * (a-b)*(a-b), accumulator starts at 0. */
+float fo_square_distance(const float* v1, const float* v2, int n) {
+  float acc = 0;
+  for (int i = 0; i < n; i++) {
+    float diff = v1[i] - v2[i];
+    float sq = diff * diff;
+    acc = acc + sq;
+  }
+  return acc;
+}
+
+/* ref: index_utils.c:19-33 updateTopK.  Scan from the tail for the last slot
+ * whose distance is strictly smaller, insert just behind it, shift the rest
+ * one slot right (the old last entry falls off).  Callers gate on
+ * `distance < tk[k-1].distance`.  NOTE (kept from the reference): when the
+ * gate is violated the write lands on tk[k] — callers here never do that. */
+void fo_update_topk(FoTopKEntry* tk, float distance, int id, int k) {
+  int slot = k;
+  while (slot > 0 && !(tk[slot - 1].distance < distance)) slot--;
+  if (slot >= k) return; /* gate violated: the reference would write tk[k] (out of bounds) */
+  for (int j = k - 1; j > slot; j--) tk[j] = tk[j - 1];
+  tk[slot].distance = distance;
+  tk[slot].id = id;
+}
+
+/* ref: index_utils.c:66-72 initTopK */
+void fo_init_topk(FoTopKEntry* tk, int k, float max_dist) {
+  for (int i = 0; i < k; i++) {
+    tk[i].distance = max_dist;
+    tk[i].id = -1;
+  }
+}
+
+/* ref: index_utils.c:445-455 getPrecomputedDistances.  The reference walks a
+ * list of (pos, code, vector) codebook rows and writes preDists[pos*K+code];
+ * with a dense [m][K][sub] codebook that is the double loop below (the result
+ * does not depend on row order). */
+void fo_precomputed_distances(float* pre_dists, int positions, int codes, int sub,
+                              const float* query, const float* codebook) {
+  for (int pos = 0; pos < positions; pos++) {
+    for (int code = 0; code < codes; code++) {
+      const float* cw = codebook + ((size_t)pos * codes + code) * sub;
+      pre_dists[pos * codes + code] = fo_square_distance(query + pos * sub, cw, sub);
+    }
+  }
+}
+
+/* ref: index_utils.c:1126-1133 computePQDistanceInt16 (and the inline copies
+ * at freddy.c:364-368, :958-965, :1135-1138): left-to-right fp32 sum from 0. */
+float fo_pq_distance_int16(const float* pre_dists, const int16_t* codes, int positions, int ncodes) {
+  float dist = 0;
+  for (int l = 0; l < positions; l++) dist = dist + pre_dists[ncodes * l + codes[l]];
+  return dist;
+}
+
+/* ref: freddy.c:401-408 / output_utils.c:8-28 — distances leave every SRF as
+ * snprintf(buf,16,"%f") text and re-enter SQL through float4in. */
+float fo_round_through_text(float distance) {
+  char buf[16];
+  snprintf(buf, sizeof buf, "%f", distance);
+  return strtof(buf, NULL);
+}
+
+/* ------------------------------------------------------------------------- */
+/* index image helpers (not in the reference: stand in for the SPI fetch)     */
+/* ------------------------------------------------------------------------- */
+
+int fo_index_prepare(FoIndex* ix) {
+  ix->list_offsets = NULL;
+  ix->list_rows = NULL;
+  if (ix->C <= 0 || ix->coarse_ids == NULL) return 0;
+  ix->list_offsets = calloc((size_t)ix->C + 1, sizeof(int32_t));
+  ix->list_rows = malloc(sizeof(int32_t) * (size_t)(ix->N > 0 ? ix->N : 1));
+  if (!ix->list_offsets || !ix->list_rows) return -1;
+  for (int r = 0; r < ix->N; r++) {
+    int c = ix->coarse_ids[r];
+    if (c < 0 || c >= ix->C) return -2;
+    ix->list_offsets[c + 1]++;
+  }
+  for (int c = 0; c < ix->C; c++) ix->list_offsets[c + 1] += ix->list_offsets[c];
+  int32_t* cursor = malloc(sizeof(int32_t) * (size_t)ix->C);
+  memcpy(cursor, ix->list_offsets, sizeof(int32_t) * (size_t)ix->C);
+  for (int r = 0; r < ix->N; r++) ix->list_rows[cursor[ix->coarse_ids[r]]++] = r; /* stays id-ascending */
+  free(cursor);
+  return 0;
+}
+
+void fo_index_release(FoIndex* ix) {
+  free(ix->list_offsets);
+  free(ix->list_rows);
+  ix->list_offsets = NULL;
+  ix->list_rows = NULL;
+}
+
+/* ------------------------------------------------------------------------- */
+/* ivfadc_search                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* ref: freddy.c:247-378 (first-call body of ivfadc_search), parameter w from
+ * get_w() (freddy.c:229).  The SQL `SELECT id, vector, coarse_id FROM fine
+ * WHERE coarse_id IN (...)` (freddy.c:324-338) returns heap order = ascending
+ * id; here that is a w-way merge of the probed lists by row number. */
+int fo_ivfadc_search(const FoIndex* ix, const float* query, int k, int w,
+                     FoTopKEntry* topk, int64_t* stats) {
+  const float MAX_DIST = 1000;                       /* ref: freddy.c:184 */
+  const int d = ix->d, m = ix->m, K = ix->K, C = ix->C, sub = d / m;
+  int rc = 0;
+  int found = 0;                                     /* ref: :255 foundInstances */
+  int64_t rows_scanned = 0, rounds = 0;
+  unsigned char* blacklisted = calloc((size_t)C, 1); /* ref: :256, index_utils.c:157-176 */
+  FoTopKEntry* sel = malloc(sizeof(FoTopKEntry) * (size_t)w);
+  float* residual = malloc(sizeof(float) * (size_t)d);
+  float* luts = malloc(sizeof(float) * (size_t)w * m * K);
+  int* cursor = malloc(sizeof(int) * (size_t)w);
+  int n_blacklisted = 0;
+
+  fo_init_topk(topk, k, MAX_DIST);                   /* ref: :258-259 */
+  float max_dist = MAX_DIST;                         /* ref: :260 */
+
+  while (found < k) {                                /* ref: :262 */
+    rounds++;
+    if (C - n_blacklisted < w) { rc = -1; break; }   /* reference would index cq[-1] */
+    float min_dist = 1000.0f;                        /* ref: :266 */
+    for (int i = 0; i < w; i++) { sel[i].distance = 100.0f; sel[i].id = -1; } /* ref: :268-271 */
+    for (int i = 0; i < C; i++) {                    /* ref: :272-283 */
+      if (blacklisted[i]) continue;
+      float dist = fo_square_distance(query, ix->coarse + (size_t)i * d, d);
+      if (dist < min_dist) {
+        if (!(dist < 100.0f)) { rc = -2; break; }    /* reference would write sel[w] */
+        fo_update_topk(sel, dist, i, w);
+        min_dist = sel[w - 1].distance;
+      }
+    }
+    if (rc) break;
+    for (int j = 0; j < w; j++) { blacklisted[sel[j].id] = 1; n_blacklisted++; } /* ref: :289-293 */
+
+    for (int j = 0; j < w; j++) {                    /* ref: :296-314 */
+      const float* cvec = ix->coarse + (size_t)sel[j].id * d;
+      for (int t = 0; t < d; t++) residual[t] = query[t] - cvec[t];
+      fo_precomputed_distances(luts + (size_t)j * m * K, m, K, sub, residual, ix->codebook);
+    }
+
+    /* ref: :324-377 — rows with coarse_id in sel, ascending id */
+    int n_rows = 0;
+    for (int j = 0; j < w; j++) {
+      cursor[j] = ix->list_offsets[sel[j].id];
+      n_rows += ix->list_offsets[sel[j].id + 1] - ix->list_offsets[sel[j].id];
+    }
+    for (int r = 0; r < n_rows; r++) {
+      int best = -1, best_row = 0;
+      for (int j = 0; j < w; j++) {
+        if (cursor[j] < ix->list_offsets[sel[j].id + 1]) {
+          int row = ix->list_rows[cursor[j]];
+          if (best < 0 || row < best_row) { best = j; best_row = row; }
+        }
+      }
+      cursor[best]++;
+      const int16_t* codes = ix->codes + (size_t)best_row * m;
+      const float* lut = luts + (size_t)best * m * K;
+      float dist = 0;                                /* ref: :364-368 */
+      for (int l = 0; l < m; l++) dist = dist + lut[l * K + codes[l]];
+      if (dist < max_dist) {                         /* ref: :369-372 */
+        fo_update_topk(topk, dist, ix->ids[best_row], k);
+        max_dist = topk[k - 1].distance;
+      }
+    }
+    rows_scanned += n_rows;
+    found += n_rows;                                 /* ref: :377 */
+  }
+  if (stats) { stats[0] = rows_scanned; stats[1] = rounds; }
+  free(blacklisted); free(sel); free(residual); free(luts); free(cursor);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------- */
+/* flat PQ                                                                    */
+/* ------------------------------------------------------------------------- */
+
+/* ref: freddy.c:74-134 pq_search: LUT on the raw query, every row of
+ * pq_quantization in table order, sentinel 100.0 (freddy.c:90-92). */
+int fo_pq_search(const FoIndex* ix, const float* query, int k, FoTopKEntry* topk) {
+  const int m = ix->m, K = ix->K, sub = ix->d / m;
+  float* lut = malloc(sizeof(float) * (size_t)m * K);
+  fo_precomputed_distances(lut, m, K, sub, query, ix->codebook);
+  fo_init_topk(topk, k, 100.0f);
+  float max_dist = 100.0f;
+  for (int r = 0; r < ix->N; r++) {
+    float dist = fo_pq_distance_int16(lut, ix->codes + (size_t)r * m, m, K);
+    if (dist < max_dist) {
+      fo_update_topk(topk, dist, ix->ids[r], k);
+      max_dist = topk[k - 1].distance;
+    }
+  }
+  free(lut);
+  return 0;
+}
+
+static int cmp_i32(const void* a, const void* b) {
+  int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+  return (x > y) - (x < y);
+}
+
+/* Rows selected by `WHERE id IN (targets)` in table order: ids are ascending,
+ * duplicates and unknown ids in the IN-list select nothing extra. */
+static int select_target_rows(const FoIndex* ix, const int32_t* targets, int n_targets, int32_t** rows_out) {
+  int32_t* sorted = malloc(sizeof(int32_t) * (size_t)(n_targets > 0 ? n_targets : 1));
+  int32_t* rows = malloc(sizeof(int32_t) * (size_t)(n_targets > 0 ? n_targets : 1));
+  memcpy(sorted, targets, sizeof(int32_t) * (size_t)n_targets);
+  qsort(sorted, (size_t)n_targets, sizeof(int32_t), cmp_i32);
+  int n = 0;
+  for (int i = 0; i < n_targets; i++) {
+    if (i > 0 && sorted[i] == sorted[i - 1]) continue;
+    int lo = 0, hi = ix->N - 1;
+    while (lo <= hi) {
+      int mid = lo + (hi - lo) / 2;
+      if (ix->ids[mid] < sorted[i]) lo = mid + 1;
+      else if (ix->ids[mid] > sorted[i]) hi = mid - 1;
+      else { rows[n++] = mid; break; }
+    }
+  }
+  free(sorted);
+  *rows_out = rows;
+  return n;
+}
+
+/* ref: freddy.c:1070-1143 pq_search_in: sentinel 1000.0 (freddy.c:1094-1098) */
+int fo_pq_search_in(const FoIndex* ix, const float* query, int k,
+                    const int32_t* targets, int n_targets, FoTopKEntry* topk) {
+  return fo_pq_search_in_batch(ix, query, 1, k, targets, n_targets, 0, topk);
+}
+
+/* ref: freddy.c:514-631 pq_search_in_batch.  use_target_lists only changes
+ * the loop nest (row-major :600-608 vs query-major :613-631); each query sees
+ * the rows in the same order either way.  Both nests are kept so the oracle
+ * exercises what the reference executes. */
+int fo_pq_search_in_batch(const FoIndex* ix, const float* queries, int nq, int k,
+                          const int32_t* targets, int n_targets, int use_target_lists,
+                          FoTopKEntry* topks) {
+  const float MAX_DIST = 1000.0f;                    /* ref: freddy.c:415 */
+  const int d = ix->d, m = ix->m, K = ix->K, sub = d / m;
+  float* luts = malloc(sizeof(float) * (size_t)nq * m * K);
+  float* max_dists = malloc(sizeof(float) * (size_t)(nq > 0 ? nq : 1));
+  for (int i = 0; i < nq; i++) {                     /* ref: :517-525 */
+    fo_init_topk(topks + (size_t)i * k, k, MAX_DIST);
+    max_dists[i] = MAX_DIST;
+    fo_precomputed_distances(luts + (size_t)i * m * K, m, K, sub, queries + (size_t)i * d, ix->codebook);
+  }
+  int32_t* rows;
+  int n_rows = select_target_rows(ix, targets, n_targets, &rows); /* ref: :544-562 */
+  if (!use_target_lists) {
+    for (int r = 0; r < n_rows; r++) {               /* ref: :600-608 */
+      const int16_t* codes = ix->codes + (size_t)rows[r] * m;
+      for (int j = 0; j < nq; j++) {
+        float dist = fo_pq_distance_int16(luts + (size_t)j * m * K, codes, m, K);
+        if (dist < max_dists[j]) {
+          fo_update_topk(topks + (size_t)j * k, dist, ix->ids[rows[r]], k);
+          max_dists[j] = topks[(size_t)j * k + k - 1].distance;
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < nq; i++) {                   /* ref: :613-631 */
+      for (int r = 0; r < n_rows; r++) {
+        const int16_t* codes = ix->codes + (size_t)rows[r] * m;
+        float dist = 0;
+        for (int l = 0; l < m; l++) dist = dist + luts[(size_t)i * m * K + K * l + codes[l]];
+        if (dist < max_dists[i]) {
+          fo_update_topk(topks + (size_t)i * k, dist, ix->ids[rows[r]], k);
+          max_dists[i] = topks[(size_t)i * k + k - 1].distance;
+        }
+      }
+    }
+  }
+  free(rows); free(luts); free(max_dists);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* multi-threaded runner for the CPU baseline (one shard per thread)          */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  const FoIndex* ix; const float* queries; int begin, end, k, w;
+  FoTopKEntry* out; int64_t rows; int rc;
+} ManyArgs;
+
+static void* many_worker(void* p) {
+  ManyArgs* a = p;
+  a->rows = 0; a->rc = 0;
+  for (int q = a->begin; q < a->end; q++) {
+    int64_t st[2];
+    int rc = fo_ivfadc_search(a->ix, a->queries + (size_t)q * a->ix->d, a->k, a->w,
+                              a->out + (size_t)q * a->k, st);
+    if (rc) a->rc = rc;
+    a->rows += st[0];
+  }
+  return NULL;
+}
+
+int fo_ivfadc_search_many(const FoIndex* ix, const float* queries, int nq, int k, int w,
+                          int n_threads, FoTopKEntry* out_topk, int64_t* rows_scanned) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
+  pthread_t* th = malloc(sizeof(pthread_t) * (size_t)n_threads);
+  ManyArgs* args = malloc(sizeof(ManyArgs) * (size_t)n_threads);
+  int rc = 0;
+  int64_t rows = 0;
+  for (int t = 0; t < n_threads; t++) {
+    args[t] = (ManyArgs){ix, queries, (int)((int64_t)nq * t / n_threads),
+                         (int)((int64_t)nq * (t + 1) / n_threads), k, w, out_topk, 0, 0};
+    pthread_create(&th[t], NULL, many_worker, &args[t]);
+  }
+  for (int t = 0; t < n_threads; t++) {
+    pthread_join(th[t], NULL);
+    if (args[t].rc) rc = args[t].rc;
+    rows += args[t].rows;
+  }
+  if (rows_scanned) *rows_scanned = rows;
+  free(th); free(args);
+  return rc;
+}

@@ -1,0 +1,87 @@
+/* freddy_oracle.h — CPU ORACLE. TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of the search arithmetic of guenthermi/postgres-word2vec
+ * (freddy_extension C files), over in-memory arrays instead of SPI rows.  It exists
+ * to check the CUDA engine; it is never linked into, imported by or called from
+ * the product library (postgres-word2vec_b200/).  Only tests/, bench.py's
+ * cpu_baseline / --impl reference leg and __graft_entry__.smoke() may use it.
+ *
+ * Parity pin: every kernel-level function below is checked bit-for-bit against
+ * the reference's own index_utils.c / cosine_similarity.c compiled unmodified
+ * into oracle/_ref/libfreddy_ref.so (tests/test_oracle_vs_ref.py) and against
+ * golden vectors generated from that library (tests/golden/).  The SRF driver
+ * bodies (which interleave arithmetic with SPI row iteration and cannot run
+ * without a Postgres server) are restated line by line; each cites the
+ * reference file:line it follows.
+ *
+ * All arithmetic: IEEE fp32, each + - * individually rounded (compile with
+ * -O2 -ffp-contract=off and no -march: the PGXS default), loops left to right.
+ */
+#ifndef FREDDY_ORACLE_H
+#define FREDDY_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int id; float distance; } FoTopKEntry; /* index_utils.h:17-20 */
+
+/* In-memory image of the index tables.  Rows are in table
+ * (= ascending id) order, exactly what a heap scan of the bulk-loaded tables
+ * returns. */
+typedef struct {
+  int d;   /* vector dimensionality                                        */
+  int m;   /* sub-quantizer positions (codebook "pos" 0..m-1)              */
+  int K;   /* codes per position ("code" 0..K-1)                           */
+  int C;   /* coarse centroids (0 for a flat PQ index)                     */
+  int N;   /* rows of the fine / pq quantization table                     */
+  const float* coarse;        /* [C][d]   coarse_quantization.vector, row = id      */
+  const float* codebook;      /* [m][K][d/m]  (residual_)codebook rows by (pos,code) */
+  const int32_t* ids;         /* [N] ascending                                       */
+  const int32_t* coarse_ids;  /* [N] fine_quantization.coarse_id (NULL for flat PQ)  */
+  const int16_t* codes;       /* [N][m] int2[] payload                               */
+  /* derived by fo_index_prepare(): CSR over coarse_id (rows stay id-ascending) */
+  int32_t* list_offsets;      /* [C+1] */
+  int32_t* list_rows;         /* [N] row numbers grouped by coarse id */
+} FoIndex;
+
+int fo_index_prepare(FoIndex* ix);   /* builds the CSR; returns 0 on success */
+void fo_index_release(FoIndex* ix);
+
+/* ---- kernel-level restatements (checked against oracle/_ref) ---- */
+float fo_square_distance(const float* v1, const float* v2, int n);
+void fo_update_topk(FoTopKEntry* tk, float distance, int id, int k);
+void fo_init_topk(FoTopKEntry* tk, int k, float max_dist);
+void fo_precomputed_distances(float* pre_dists, int positions, int codes, int sub,
+                              const float* query, const float* codebook);
+float fo_pq_distance_int16(const float* pre_dists, const int16_t* codes, int positions, int ncodes);
+/* "%f" through text, as every SRF emits distances (freddy.c:401-408) */
+float fo_round_through_text(float distance);
+
+/* ---- SRF driver restatements ---- */
+/* ivfadc_search (freddy.c:174-393).  Returns 0, or <0 where the reference
+ * would hit undefined behaviour (fewer than w unprobed lists left; coarse
+ * distance >= 100).  stats (optional, may be NULL): [0]=rows scanned,
+ * [1]=rounds of the re-probe loop. */
+int fo_ivfadc_search(const FoIndex* ix, const float* query, int k, int w,
+                     FoTopKEntry* out_topk, int64_t* stats);
+/* pq_search (freddy.c:28-134): exhaustive ADC over all rows, sentinel 100.0 */
+int fo_pq_search(const FoIndex* ix, const float* query, int k, FoTopKEntry* out_topk);
+/* pq_search_in (freddy.c:1028-1143): ADC over the rows whose id is in targets */
+int fo_pq_search_in(const FoIndex* ix, const float* query, int k,
+                    const int32_t* targets, int n_targets, FoTopKEntry* out_topk);
+/* pq_search_in_batch (freddy.c:414-631): out_topk is [nq][k] */
+int fo_pq_search_in_batch(const FoIndex* ix, const float* queries, int nq, int k,
+                          const int32_t* targets, int n_targets, int use_target_lists,
+                          FoTopKEntry* out_topk);
+
+/* Run fo_ivfadc_search over nq queries on n_threads host threads (disjoint
+ * query shards = n_threads concurrent backends).  out_topk is [nq][k]. */
+int fo_ivfadc_search_many(const FoIndex* ix, const float* queries, int nq, int k, int w,
+                          int n_threads, FoTopKEntry* out_topk, int64_t* rows_scanned);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,151 @@
+"""ctypes access to the CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+  libfreddy_oracle.so      our plain-C restatement (oracle/freddy_oracle.c)
+  _ref/libfreddy_ref.so    the reference's own index_utils.c / cosine_similarity.c,
+                           compiled unmodified (oracle/Makefile `ref`)
+
+Nothing under postgres-word2vec_b200/ imports this module; only tests/,
+bench.py's CPU-baseline legs and __graft_entry__.smoke() do.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libfreddy_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libfreddy_ref.so")
+
+
+def build(quiet=True):
+    subprocess.run(["make", "-C", _HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None, stderr=subprocess.STDOUT if quiet else None)
+
+
+class TopKEntry(C.Structure):
+    _fields_ = [("id", C.c_int), ("distance", C.c_float)]
+
+
+class FoIndex(C.Structure):
+    _fields_ = [("d", C.c_int), ("m", C.c_int), ("K", C.c_int), ("C", C.c_int), ("N", C.c_int),
+                ("coarse", C.c_void_p), ("codebook", C.c_void_p), ("ids", C.c_void_p),
+                ("coarse_ids", C.c_void_p), ("codes", C.c_void_p),
+                ("list_offsets", C.c_void_p), ("list_rows", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        L = C.CDLL(ORACLE_SO)
+        L.fo_square_distance.restype = C.c_float
+        L.fo_square_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.fo_update_topk.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+        L.fo_init_topk.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.fo_precomputed_distances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fo_pq_distance_int16.restype = C.c_float
+        L.fo_pq_distance_int16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.fo_round_through_text.restype = C.c_float
+        L.fo_round_through_text.argtypes = [C.c_float]
+        L.fo_index_prepare.argtypes = [C.POINTER(FoIndex)]
+        L.fo_index_release.argtypes = [C.POINTER(FoIndex)]
+        L.fo_ivfadc_search.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fo_pq_search.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_pq_search_in.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_pq_search_in_batch.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_void_p]
+        L.fo_ivfadc_search_many.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own compiled kernels, or None when not built/shipped."""
+    if not os.path.exists(REF_SO):
+        return None
+    R = C.CDLL(REF_SO)
+    R.squareDistance.restype = C.c_float
+    R.squareDistance.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.updateTopK.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int]
+    R.computePQDistanceInt16.restype = C.c_float
+    R.computePQDistanceInt16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    R.getPrecomputedDistances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return R
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleIndex:
+    """In-memory image of the index tables for the oracle (keeps arrays alive)."""
+
+    def __init__(self, index, flat_pq=False):
+        L = lib()
+        self.k = None
+        self.arr = {}
+        ix = FoIndex()
+        ix.d, ix.m, ix.K, ix.N = int(index["d"]), int(index["m"]), int(index["K"]), int(index["N"])
+        if flat_pq:
+            ix.C = 0
+            self.arr["cb"] = np.ascontiguousarray(index["pq_codebook"], np.float32)
+            self.arr["codes"] = np.ascontiguousarray(index["pq_codes"], np.int16)
+            ix.coarse, ix.coarse_ids = None, None
+        else:
+            ix.C = int(index["C"])
+            self.arr["coarse"] = np.ascontiguousarray(index["coarse"], np.float32)
+            self.arr["cb"] = np.ascontiguousarray(index["residual_codebook"], np.float32)
+            self.arr["codes"] = np.ascontiguousarray(index["codes"], np.int16)
+            self.arr["coarse_ids"] = np.ascontiguousarray(index["coarse_ids"], np.int32)
+            ix.coarse = _p(self.arr["coarse"])
+            ix.coarse_ids = _p(self.arr["coarse_ids"])
+        self.arr["ids"] = np.ascontiguousarray(index["ids"], np.int32)
+        ix.codebook, ix.ids, ix.codes = _p(self.arr["cb"]), _p(self.arr["ids"]), _p(self.arr["codes"])
+        self.ix = ix
+        rc = L.fo_index_prepare(C.byref(ix))
+        if rc:
+            raise RuntimeError(f"fo_index_prepare failed: {rc}")
+
+    def __del__(self):
+        try:
+            lib().fo_index_release(C.byref(self.ix))
+        except Exception:
+            pass
+
+    @staticmethod
+    def _unpack(tk, nq, k):
+        a = np.frombuffer(tk, dtype=[("id", np.int32), ("distance", np.float32)]).reshape(nq, k)
+        return a["id"].copy(), a["distance"].copy()
+
+    def ivfadc_search(self, queries, k, w, threads=1):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.ix.d)
+        nq = q.shape[0]
+        tk = (TopKEntry * (nq * k))()
+        rows = C.c_int64(0)
+        rc = lib().fo_ivfadc_search_many(C.byref(self.ix), _p(q), nq, k, w, threads, tk, C.byref(rows))
+        ids, d = self._unpack(tk, nq, k)
+        return ids, d, rc, rows.value
+
+    def pq_search(self, queries, k):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.ix.d)
+        nq = q.shape[0]
+        ids, ds = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
+        for i in range(nq):
+            tk = (TopKEntry * k)()
+            lib().fo_pq_search(C.byref(self.ix), _p(q[i]), k, tk)
+            ids[i], ds[i] = self._unpack(tk, 1, k)
+        return ids, ds
+
+    def pq_search_in_batch(self, queries, k, targets, use_target_lists=False):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.ix.d)
+        nq = q.shape[0]
+        t = np.ascontiguousarray(targets, np.int32)
+        tk = (TopKEntry * (nq * k))()
+        lib().fo_pq_search_in_batch(C.byref(self.ix), _p(q), nq, k, _p(t), t.shape[0], 1 if use_target_lists else 0, tk)
+        return self._unpack(tk, nq, k)

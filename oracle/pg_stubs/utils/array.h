@@ -1,0 +1,10 @@
+/* stub (see ../postgres.h): only what getArray() in the reference touches */
+#ifndef FB_STUB_ARRAY_H
+#define FB_STUB_ARRAY_H
+#include "postgres.h"
+typedef struct ArrayType { int32 vl_len_; int ndim; int32 dataoffset; Oid elemtype; } ArrayType;
+#define ARR_ELEMTYPE(a) ((a)->elemtype)
+void get_typlenbyvalalign(Oid typid, int16* typlen, bool* typbyval, char* typalign);
+void deconstruct_array(ArrayType* array, Oid elmtype, int elmlen, bool elmbyval, char elmalign,
+                       Datum** elemsp, bool** nullsp, int* nelemsp);
+#endif

@@ -1,0 +1,778 @@
+// engine.cu — host side of libfreddy_b200.so: the C-ABI (include/freddy_b200.h),
+// index upload ("pin once per session"), scratch management and the kernel
+// pipeline.  No Postgres, no torch: plain CUDA runtime.  Every entry point
+// returns a status code; C++ exceptions never cross the boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/freddy_b200.h"
+#include "exact_kernels.cuh"
+#include "ivfadc_kernels.cuh"
+
+using namespace fb;
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) count = 1;
+    cudaError_t err = cudaMalloc(&p, count * sizeof(T));
+    if (err == cudaSuccess) n = count;
+    return err;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct CodeTable {
+  DevBuf<uint2> units;
+  DevBuf<int32_t> rowno, list_blk, list_len, ids;
+  int m = 0, U = 0, n_lists = 0;
+  int64_t N = 0, n_blocks = 0;
+  bool loaded = false;
+  std::vector<int32_t> h_list_len;
+  CodeTableDev dev() const {
+    CodeTableDev t;
+    t.units = units.p; t.rowno = rowno.p; t.list_blk = list_blk.p; t.list_len = list_len.p;
+    t.ids = ids.p; t.m = m; t.U = U; t.n_lists = n_lists;
+    return t;
+  }
+  void release() { units.release(); rowno.release(); list_blk.release(); list_len.release(); ids.release(); loaded = false; }
+};
+
+struct Codebook {
+  DevBuf<float> cbT;  // [m][sub][K]
+  int m = 0, K = 0, sub = 0;
+  bool loaded = false;
+};
+
+enum Stage { ST_COARSE = 0, ST_LUT, ST_SCAN, ST_FINALIZE, ST_EXACT, ST_COUNT };
+
+}  // namespace
+
+struct fb_engine {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // index
+  DevBuf<float> coarse, coarseT;
+  int C = 0, Cs = 0, d = 0;
+  bool coarse_loaded = false;
+  Codebook cb[FB_CB_KINDS];
+  CodeTable fine, pq, tmp;  // tmp: per-call target subset of pq
+  std::vector<int32_t> pq_ids_host;
+  bool pq_ids_sorted = true;
+  std::unordered_map<int32_t, int32_t> pq_id_to_row;
+  DevBuf<int32_t> iota_lists;
+
+  // scratch
+  DevBuf<float> lut, exact_lut, q_stage, dist_stage;
+  DevBuf<int32_t> probes, exact_list, id_stage, sel_rows;
+  DevBuf<uint32_t> qflags;
+  DevBuf<u64> partial, kth;
+  DevBuf<int32_t> small;   // [0]=exact_count [1]=work_counter [2]=error_flag
+  DevBuf<u64> counters64;  // [0]=rows scanned [1]=exact queries
+
+  // options
+  bool force_exact = false;
+  bool profile = false;
+  int64_t query_chunk = 2048;
+
+  // profiling
+  struct Ev { cudaEvent_t a, b; int stage; };
+  std::vector<Ev> events;
+  size_t events_used = 0;
+  double ms[ST_COUNT] = {0, 0, 0, 0, 0};
+  int64_t n_scan_launches = 0;
+  int64_t launches = 0;
+  int64_t queries_done = 0;
+  int bytes_per_row = 0;
+  int64_t host_rows = 0;
+};
+
+namespace {
+
+int fail(fb_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define FB_CUDA(e, call)                                                                       \
+  do {                                                                                         \
+    cudaError_t err__ = (call);                                                                \
+    if (err__ != cudaSuccess)                                                                  \
+      return fail((e), FB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+struct StageTimer {
+  fb_engine* e;
+  int idx = -1;
+  StageTimer(fb_engine* eng, int stage) : e(eng) {
+    if (!e->profile) return;
+    if (e->events_used == e->events.size()) {
+      fb_engine::Ev ev;
+      cudaEventCreate(&ev.a);
+      cudaEventCreate(&ev.b);
+      e->events.push_back(ev);
+    }
+    idx = (int)e->events_used++;
+    e->events[idx].stage = stage;
+    cudaEventRecord(e->events[idx].a, e->stream);
+  }
+  ~StageTimer() {
+    if (idx >= 0) cudaEventRecord(e->events[idx].b, e->stream);
+  }
+};
+
+void drain_events(fb_engine* e) {
+  for (size_t i = 0; i < e->events_used; i++) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, e->events[i].a, e->events[i].b) == cudaSuccess) e->ms[e->events[i].stage] += t;
+  }
+  e->events_used = 0;
+}
+
+// ---- host-side layout transform of a code table ---------------------------
+int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
+                int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K) {
+  if (N < 0 || m <= 0) return fail(e, FB_ERR_INVALID, "bad table shape N=%lld m=%d", (long long)N, m);
+  if (N >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
+  const int U = (m + 3) / 4;
+  if (list_of_row == nullptr) n_lists = (int)std::max<int64_t>(1, (N + rows_per_pseudo_list - 1) / rows_per_pseudo_list);
+  std::vector<int32_t> len(n_lists, 0), blk(n_lists, 0);
+  for (int64_t r = 0; r < N; r++) {
+    int c = list_of_row ? list_of_row[r] : (int)(r / rows_per_pseudo_list);
+    if (c < 0 || c >= n_lists) return fail(e, FB_ERR_INVALID, "row %lld: coarse_id %d out of range [0,%d)", (long long)r, c, n_lists);
+    len[c]++;
+  }
+  int64_t n_blocks = 0;
+  for (int c = 0; c < n_lists; c++) { blk[c] = (int32_t)n_blocks; n_blocks += (len[c] + 31) / 32; }
+  std::vector<uint2> units((size_t)std::max<int64_t>(1, n_blocks) * U * 32, make_uint2(0, 0));
+  std::vector<int32_t> rowno((size_t)std::max<int64_t>(1, n_blocks) * 32, -1);
+  std::vector<int32_t> cursor(n_lists, 0);
+  for (int64_t r = 0; r < N; r++) {
+    int c = list_of_row ? list_of_row[r] : (int)(r / rows_per_pseudo_list);
+    int slot = cursor[c]++;
+    int64_t b = blk[c] + slot / 32;
+    int L = slot % 32;
+    const int16_t* cr = codes + (size_t)r * m;
+    for (int u = 0; u < U; u++) {
+      uint32_t f[4] = {0, 0, 0, 0};
+      for (int t = 0; t < 4; t++) {
+        int p = 4 * u + t;
+        if (p < m) {
+          int code = cr[p];
+          if (code < 0 || code >= K) return fail(e, FB_ERR_INVALID, "row %lld pos %d: code %d out of range [0,%d)", (long long)r, p, code, K);
+          f[t] = (uint32_t)code * 4u;  // pre-scaled: byte offset into a K-float LUT row
+        }
+      }
+      units[((size_t)b * U + u) * 32 + L] = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
+    }
+    rowno[(size_t)b * 32 + L] = (int32_t)r;
+  }
+  FB_CUDA(e, tab.units.ensure(units.size()));
+  FB_CUDA(e, tab.rowno.ensure(rowno.size()));
+  FB_CUDA(e, tab.list_blk.ensure(n_lists));
+  FB_CUDA(e, tab.list_len.ensure(n_lists));
+  FB_CUDA(e, tab.ids.ensure((size_t)std::max<int64_t>(1, N)));
+  FB_CUDA(e, cudaMemcpy(tab.units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(tab.rowno.p, rowno.data(), rowno.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(tab.list_blk.p, blk.data(), n_lists * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(tab.list_len.p, len.data(), n_lists * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (N > 0) FB_CUDA(e, cudaMemcpy(tab.ids.p, ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  tab.m = m; tab.U = U; tab.n_lists = n_lists; tab.N = N; tab.n_blocks = n_blocks;
+  tab.h_list_len = len;
+  tab.loaded = true;
+  return FB_OK;
+}
+
+__global__ void iota_kernel(int32_t* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+__global__ void count_rows_kernel(const int32_t* __restrict__ probes, int n, const int32_t* __restrict__ list_len,
+                                  u64* __restrict__ counter) {
+  u64 local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) local += (u64)list_len[probes[i]];
+  for (int s = 16; s >= 1; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
+}
+
+// gather selected rows of the flat pq table (blocked in table order) into a
+// temporary blocked table (freddy.c:544-562 `WHERE id IN (...)`)
+__global__ void gather_rows_kernel(const uint2* __restrict__ src_units, int U, const int32_t* __restrict__ rows, int n,
+                                   uint2* __restrict__ dst_units, int32_t* __restrict__ dst_rowno, int n_dst_slots) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_dst_slots) return;
+  int db = s >> 5, dl = s & 31;
+  if (s < n) {
+    int r = rows[s];
+    int sb = r >> 5, sl = r & 31;
+    for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = src_units[((size_t)sb * U + u) * 32 + sl];
+    dst_rowno[s] = r;
+  } else {
+    for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = make_uint2(0, 0);
+    dst_rowno[s] = -1;
+  }
+}
+
+// ---- kernel launch helpers -------------------------------------------------
+template <int QT>
+int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k) {
+  size_t smem = ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float);
+  auto kern = coarse_select_kernel_t<QT>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(nq + QT - 1) / QT, kCoarseThreads, smem, e->stream>>>(
+      d_q, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k, e->probes.p, e->qflags.p,
+      e->force_exact ? 1 : 0);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+int launch_coarse(fb_engine* e, const float* d_q, int nq, int w, int k) {
+  StageTimer t(e, ST_COARSE);
+  auto need = [&](int QT) { return ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float); };
+  const size_t two_per_sm = 100 * 1024;
+  if (need(16) <= two_per_sm) return launch_coarse_t<16>(e, d_q, nq, w, k);
+  if (need(8) <= two_per_sm) return launch_coarse_t<8>(e, d_q, nq, w, k);
+  if (need(4) <= e->smem_optin) return launch_coarse_t<4>(e, d_q, nq, w, k);
+  if (need(1) <= e->smem_optin) return launch_coarse_t<1>(e, d_q, nq, w, k);
+  return fail(e, FB_ERR_UNSUPPORTED, "coarse table too large for shared memory (C=%d d=%d)", e->C, e->d);
+}
+
+template <int W>
+int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
+                 int jobs_per_query, int njobs, float* d_lut) {
+  const int K = cb.K, sub = cb.sub, m = cb.m;
+  int TK = std::min(1024, (K + 31) / 32 * 32);
+  const size_t budget = std::min<size_t>(e->smem_optin, 200 * 1024) - 4096;
+  while ((size_t)sub * TK * sizeof(float) > budget && TK > 32) TK -= 32;
+  if ((size_t)sub * TK * sizeof(float) > budget) return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
+  const int tiles = (K + TK - 1) / TK;
+  constexpr int WS = (W + 3) & ~3;
+  size_t smem = ((size_t)sub * TK + (size_t)sub * WS) * sizeof(float);
+  auto kern = lut_build_kernel<W>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int groups = std::max(1, e->num_sms / std::max(1, m * tiles));
+  groups = std::min(groups, (njobs + W - 1) / W);
+  dim3 grid(m * tiles, groups);
+  kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+int launch_lut(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
+               int jobs_per_query, int njobs, float* d_lut) {
+  StageTimer t(e, ST_LUT);
+  int W;
+  if (jobs_per_query >= kLutMaxJobs) W = kLutMaxJobs;
+  else W = jobs_per_query * (kLutMaxJobs / jobs_per_query);
+  if (njobs < W) W = njobs;
+  switch (W) {
+#define FB_LUT_CASE(n) case n: return launch_lut_w<n>(e, cb, d_q, d_coarse, d_probes, jobs_per_query, njobs, d_lut);
+    FB_LUT_CASE(1) FB_LUT_CASE(2) FB_LUT_CASE(3) FB_LUT_CASE(4) FB_LUT_CASE(5) FB_LUT_CASE(6) FB_LUT_CASE(7)
+    FB_LUT_CASE(8) FB_LUT_CASE(9) FB_LUT_CASE(10) FB_LUT_CASE(11) FB_LUT_CASE(12) FB_LUT_CASE(13)
+    FB_LUT_CASE(14) FB_LUT_CASE(15) FB_LUT_CASE(16)
+#undef FB_LUT_CASE
+  }
+  return fail(e, FB_ERR_INVALID, "bad LUT job width %d", W);
+}
+
+template <int M>
+int launch_scan_m(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
+                  int list_mod, const float* d_lut, int K, int KK, u64* d_partial) {
+  size_t smem = (size_t)tab.m * K * sizeof(float);
+  if (smem > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT (%zu bytes) exceeds shared memory", smem);
+  auto kern = adc_scan_kernel<M>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ntasks, kScanThreads, smem, e->stream>>>(tab.dev(), d_task_list, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+  e->launches++;
+  e->n_scan_launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+int launch_scan(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
+                int list_mod, const float* d_lut, int K, int KK, u64* d_partial) {
+  StageTimer t(e, ST_SCAN);
+  switch (tab.m) {
+    case 8: return launch_scan_m<8>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+    case 12: return launch_scan_m<12>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+    case 16: return launch_scan_m<16>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+    default: return launch_scan_m<0>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+  }
+}
+
+int launch_finalize(fb_engine* e, const CodeTable& tab, int lists_per_query, int KK, int k, int nq, float sentinel,
+                    const uint32_t* d_flags, int32_t* d_out_ids, float* d_out_dists) {
+  StageTimer t(e, ST_FINALIZE);
+  const int warps = 8;
+  finalize_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, e->stream>>>(
+      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, d_flags, d_out_ids, d_out_dists,
+      e->exact_list.p, e->small.p + 0, e->counters64.p + 1, e->kth.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+int check_common(fb_engine* e, int nq, int k) {
+  if (!e) return FB_ERR_INVALID;
+  if (nq < 0) return fail(e, FB_ERR_INVALID, "nq < 0");
+  if (k < 1 || k > kExactMaxK) return fail(e, FB_ERR_UNSUPPORTED, "k=%d outside [1,%d]", k, kExactMaxK);
+  return FB_OK;
+}
+
+size_t exact_smem_bytes(const fb_engine* e, int w) {
+  return kExactFixedSmem + sizeof(float) * e->Cs + sizeof(float) * ((e->d + 3) & ~3) +
+         (sizeof(float) + sizeof(int)) * ((w + 3) & ~3) + (size_t)e->C + 16;
+}
+
+// ---- the IVFADC pipeline on device pointers --------------------------------
+int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists) {
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded || !e->fine.loaded)
+    return fail(e, FB_ERR_INVALID, "IVFADC index not loaded (coarse / residual codebook / fine table)");
+  const Codebook& cb = e->cb[FB_CB_RESIDUAL];
+  if (cb.m != e->fine.m) return fail(e, FB_ERR_INVALID, "codebook m=%d but fine table m=%d", cb.m, e->fine.m);
+  if (cb.m * cb.sub != e->d) return fail(e, FB_ERR_INVALID, "m*sub=%d != d=%d", cb.m * cb.sub, e->d);
+  if (w < 1) return fail(e, FB_ERR_INVALID, "w=%d", w);
+  if (w > e->C) return fail(e, FB_ERR_REFERENCE_UB, "w=%d > %d coarse centroids: the reference indexes cq[-1] (freddy.c:296-302)", w, e->C);
+  if (nq == 0) return FB_OK;
+  const int m = cb.m, K = cb.K;
+  const bool fast = (k <= 31 && w <= 31);
+  const int KK = k + 1;
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
+  const size_t lut_per_query = (size_t)w * m * K;
+
+  FB_CUDA(e, e->probes.ensure((size_t)chunk * w));
+  FB_CUDA(e, e->qflags.ensure((size_t)chunk));
+  FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
+  FB_CUDA(e, e->kth.ensure((size_t)chunk));
+  if (fast) {
+    FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
+    FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+  }
+  // general-kernel scratch: one LUT set per resident CTA
+  int exact_ctas = 2 * e->num_sms;
+  const size_t exact_budget = (size_t)1 << 30;
+  while (exact_ctas > 1 && (size_t)exact_ctas * lut_per_query * sizeof(float) > exact_budget) exact_ctas /= 2;
+  if (!fast || true) FB_CUDA(e, e->exact_lut.ensure((size_t)exact_ctas * lut_per_query));
+  const size_t ex_smem = exact_smem_bytes(e, w);
+  if (ex_smem > e->smem_optin) return fail(e, FB_ERR_UNSUPPORTED, "general kernel needs %zu bytes of shared memory", ex_smem);
+  FB_CUDA(e, cudaFuncSetAttribute(ivfadc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+
+  for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+    const int n = (int)std::min<int64_t>(chunk, nq - q0);
+    const float* dq = d_q + (size_t)q0 * e->d;
+    int32_t* oi = d_out_ids + (size_t)q0 * k;
+    float* od = d_out_dists + (size_t)q0 * k;
+    FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
+    if (fast) {
+      if ((rc = launch_coarse(e, dq, n, w, k))) return rc;
+      count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, n * w, e->fine.list_len.p, e->counters64.p + 0);
+      e->launches++;
+      if ((rc = launch_lut(e, cb, dq, e->coarse.p, e->probes.p, w, n * w, e->lut.p))) return rc;
+      if ((rc = launch_scan(e, e->fine, e->probes.p, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
+      if ((rc = launch_finalize(e, e->fine, w * kScanWarps, KK, k, n, 1000.0f, e->qflags.p, oi, od))) return rc;
+    } else {
+      iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
+      int32_t cnt = n;
+      FB_CUDA(e, cudaMemcpyAsync(e->small.p, &cnt, sizeof cnt, cudaMemcpyHostToDevice, e->stream));
+      e->launches++;
+    }
+    {
+      StageTimer t(e, ST_EXACT);
+      ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
+          dq, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
+          e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p, oi, od, e->small.p + 2);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
+  }
+  e->queries_done += nq;
+  e->bytes_per_row = 2 * m + 4;
+  return FB_OK;
+}
+
+int check_error_flag(fb_engine* e) {
+  int32_t flag = 0;
+  FB_CUDA(e, cudaMemcpy(&flag, e->small.p + 2, sizeof flag, cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(e->small.p + 2, 0, sizeof(int32_t));
+    return fail(e, FB_ERR_REFERENCE_UB,
+                "a query hit a state where the reference is undefined (fewer than w unprobed lists left, or a coarse distance >= 100)");
+  }
+  return FB_OK;
+}
+
+// ---- flat PQ pipeline over `tab` (the pq table or a per-call subset) --------
+int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, float sentinel,
+           int32_t* d_out_ids, float* d_out_dists) {
+  const Codebook& cb = e->cb[FB_CB_PQ];
+  const int m = cb.m, K = cb.K;
+  const bool fast = (k <= 31);
+  const int KK = k + 1;
+  const int nl = tab.n_lists;
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
+  // bound the per-warp partial lists (chunk * nl * 8 * KK keys)
+  while (chunk > 1 && (size_t)chunk * nl * kScanWarps * KK * sizeof(u64) > ((size_t)1 << 30)) chunk /= 2;
+  FB_CUDA(e, e->lut.ensure((size_t)chunk * m * K));
+  FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
+  FB_CUDA(e, e->kth.ensure((size_t)chunk));
+  FB_CUDA(e, e->iota_lists.ensure((size_t)nl));
+  if (fast) FB_CUDA(e, e->partial.ensure((size_t)chunk * nl * kScanWarps * KK));
+  iota_kernel<<<(nl + 255) / 256, 256, 0, e->stream>>>(e->iota_lists.p, nl);
+  e->launches++;
+  const size_t ex_smem = kExactFixedSmem;
+  FB_CUDA(e, cudaFuncSetAttribute(pq_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+  int rc;
+  for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+    const int n = (int)std::min<int64_t>(chunk, nq - q0);
+    const float* dq = d_q + (size_t)q0 * e->d;
+    int32_t* oi = d_out_ids + (size_t)q0 * k;
+    float* od = d_out_dists + (size_t)q0 * k;
+    FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
+    if ((rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, n, e->lut.p))) return rc;   // freddy.c:519-525
+    if (fast && !e->force_exact) {
+      if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, e->lut.p, K, KK, e->partial.p))) return rc;
+      if ((rc = launch_finalize(e, tab, nl * kScanWarps, KK, k, n, sentinel, nullptr, oi, od))) return rc;
+    } else {
+      iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
+      int32_t cnt = n;
+      FB_CUDA(e, cudaMemcpyAsync(e->small.p, &cnt, sizeof cnt, cudaMemcpyHostToDevice, e->stream));
+      e->launches++;
+    }
+    {
+      StageTimer t(e, ST_EXACT);
+      pq_exact_kernel<<<2 * e->num_sms, kExactThreads, ex_smem, e->stream>>>(
+          tab.dev(), e->iota_lists.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1, oi, od);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
+    e->host_rows += (int64_t)n * tab.N;  // every query sees every row of the table
+  }
+  e->queries_done += nq;
+  e->bytes_per_row = 2 * m + 4;
+  return FB_OK;
+}
+
+int check_pq_ready(fb_engine* e) {
+  if (!e->cb[FB_CB_PQ].loaded || !e->pq.loaded) return fail(e, FB_ERR_INVALID, "flat PQ index not loaded (pq codebook / pq table)");
+  const Codebook& cb = e->cb[FB_CB_PQ];
+  if (cb.m != e->pq.m) return fail(e, FB_ERR_INVALID, "pq codebook m=%d but pq table m=%d", cb.m, e->pq.m);
+  e->d = cb.m * cb.sub;
+  return FB_OK;
+}
+
+}  // namespace
+
+// ============================ C-ABI =========================================
+extern "C" {
+
+const char* fb_version(void) { return "freddy_b200 0.1 (sm_100a)"; }
+
+const char* fb_last_error(const fb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int fb_create(int device, fb_engine** out) {
+  if (!out) return FB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return fail(nullptr, FB_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(err));
+  if (device < 0 || device >= count) return fail(nullptr, FB_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  fb_engine* e = new (std::nothrow) fb_engine();
+  if (!e) return fail(nullptr, FB_ERR_INVALID, "out of host memory");
+  e->device = device;
+  cudaDeviceProp prop;
+  if ((err = cudaSetDevice(device)) != cudaSuccess || (err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, FB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(err));
+  }
+  if (prop.major < 10) {
+    delete e;
+    return fail(nullptr, FB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  }
+  e->num_sms = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (err = e->small.ensure(4)) != cudaSuccess || (err = e->counters64.ensure(2)) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, FB_ERR_CUDA, "engine setup: %s", cudaGetErrorString(err));
+  }
+  cudaMemset(e->small.p, 0, 4 * sizeof(int32_t));
+  cudaMemset(e->counters64.p, 0, 2 * sizeof(u64));
+  *out = e;
+  return FB_OK;
+}
+
+void fb_destroy(fb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (auto& ev : e->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  e->coarse.release(); e->coarseT.release();
+  for (auto& c : e->cb) c.cbT.release();
+  e->fine.release(); e->pq.release(); e->tmp.release();
+  e->iota_lists.release();
+  e->lut.release(); e->exact_lut.release(); e->q_stage.release(); e->dist_stage.release();
+  e->probes.release(); e->exact_list.release(); e->id_stage.release(); e->sel_rows.release();
+  e->qflags.release(); e->partial.release(); e->kth.release(); e->small.release(); e->counters64.release();
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int fb_load_coarse(fb_engine* e, const float* coarse, int C, int d) {
+  if (!e || !coarse || C < 1 || d < 1) return fail(e, FB_ERR_INVALID, "fb_load_coarse: bad arguments");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int Cs = (C + 31) / 32 * 32;
+  std::vector<float> t((size_t)d * Cs, 0.0f);
+  for (int c = 0; c < C; c++)
+    for (int i = 0; i < d; i++) t[(size_t)i * Cs + c] = coarse[(size_t)c * d + i];
+  FB_CUDA(e, e->coarse.ensure((size_t)C * d));
+  FB_CUDA(e, e->coarseT.ensure(t.size()));
+  FB_CUDA(e, cudaMemcpy(e->coarse.p, coarse, (size_t)C * d * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(e->coarseT.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  e->C = C; e->Cs = Cs; e->d = d; e->coarse_loaded = true;
+  return FB_OK;
+}
+
+int fb_load_codebook(fb_engine* e, int kind, const float* codebook, int m, int K, int sub) {
+  if (!e || !codebook || kind < 0 || kind >= FB_CB_KINDS || m < 1 || K < 1 || sub < 1)
+    return fail(e, FB_ERR_INVALID, "fb_load_codebook: bad arguments");
+  if (K % 4 != 0 || K > 16384) return fail(e, FB_ERR_UNSUPPORTED, "K=%d: need K %% 4 == 0 and K <= 16384", K);
+  FB_CUDA(e, cudaSetDevice(e->device));
+  std::vector<float> t((size_t)m * sub * K);
+  for (int p = 0; p < m; p++)
+    for (int c = 0; c < K; c++)
+      for (int i = 0; i < sub; i++) t[((size_t)p * sub + i) * K + c] = codebook[((size_t)p * K + c) * sub + i];
+  Codebook& cb = e->cb[kind];
+  FB_CUDA(e, cb.cbT.ensure(t.size()));
+  FB_CUDA(e, cudaMemcpy(cb.cbT.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  cb.m = m; cb.K = K; cb.sub = sub; cb.loaded = true;
+  return FB_OK;
+}
+
+int fb_load_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids, const int16_t* codes, int64_t N, int m) {
+  if (!e || (N > 0 && (!ids || !coarse_ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_load_fine: bad arguments");
+  if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded)
+    return fail(e, FB_ERR_INVALID, "fb_load_fine: load the coarse table and the residual codebook first");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  return build_table(e, e->fine, ids, coarse_ids, e->C, 0, codes, N, m, e->cb[FB_CB_RESIDUAL].K);
+}
+
+int fb_load_pq(fb_engine* e, const int32_t* ids, const int16_t* codes, int64_t N, int m) {
+  if (!e || (N > 0 && (!ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_load_pq: bad arguments");
+  if (!e->cb[FB_CB_PQ].loaded) return fail(e, FB_ERR_INVALID, "fb_load_pq: load the pq codebook first");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  int rc = build_table(e, e->pq, ids, nullptr, 0, 8192, codes, N, m, e->cb[FB_CB_PQ].K);
+  if (rc) return rc;
+  e->pq_ids_host.assign(ids, ids + N);
+  e->pq_ids_sorted = std::is_sorted(e->pq_ids_host.begin(), e->pq_ids_host.end());
+  e->pq_id_to_row.clear();
+  if (!e->pq_ids_sorted)
+    for (int64_t r = 0; r < N; r++) e->pq_id_to_row.emplace(ids[r], (int32_t)r);  // first row wins
+  return FB_OK;
+}
+
+int fb_ivfadc_search_dev(fb_engine* e, const float* d_queries, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists) {
+  if (!e) return FB_ERR_INVALID;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  return ivfadc_dev(e, d_queries, nq, k, w, d_out_ids, d_out_dists);
+}
+
+int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w, int32_t* out_ids, float* out_dists) {
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if ((rc = ivfadc_dev(e, e->q_stage.p, nq, k, w, e->id_stage.p, e->dist_stage.p))) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return check_error_flag(e);
+}
+
+int fb_pq_search(fb_engine* e, const float* queries, int nq, int k, int32_t* out_ids, float* out_dists) {
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if ((rc = check_pq_ready(e))) return rc;
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if ((rc = pq_dev(e, e->pq, e->q_stage.p, nq, k, 100.0f, e->id_stage.p, e->dist_stage.p))) return rc;  // freddy.c:90-92
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
+int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                          int use_target_lists, int32_t* out_ids, float* out_dists) {
+  (void)use_target_lists;  // loop-nest choice of the reference (freddy.c:600-631); results are identical
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if ((rc = check_pq_ready(e))) return rc;
+  if (n_targets < 0 || (n_targets > 0 && !targets)) return fail(e, FB_ERR_INVALID, "bad target array");
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  // rows selected by `WHERE id IN (targets)` in table order (freddy.c:544-562)
+  std::vector<int32_t> rows;
+  rows.reserve(n_targets);
+  for (int i = 0; i < n_targets; i++) {
+    if (e->pq_ids_sorted) {
+      auto it = std::lower_bound(e->pq_ids_host.begin(), e->pq_ids_host.end(), targets[i]);
+      if (it != e->pq_ids_host.end() && *it == targets[i]) rows.push_back((int32_t)(it - e->pq_ids_host.begin()));
+    } else {
+      auto it = e->pq_id_to_row.find(targets[i]);
+      if (it != e->pq_id_to_row.end()) rows.push_back(it->second);
+    }
+  }
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+  const int n = (int)rows.size();
+  // temporary blocked table over the selected rows
+  CodeTable& tmp = e->tmp;
+  const int per_list = 4096;
+  const int nl = std::max(1, (n + per_list - 1) / per_list);
+  std::vector<int32_t> len(nl, 0), blk(nl, 0);
+  int64_t n_blocks = 0;
+  for (int c = 0; c < nl; c++) {
+    len[c] = std::max(0, std::min(per_list, n - c * per_list));
+    blk[c] = (int32_t)n_blocks;
+    n_blocks += (len[c] + 31) / 32;
+  }
+  const int U = e->pq.U;
+  const int n_slots = (int)std::max<int64_t>(1, n_blocks) * 32;
+  FB_CUDA(e, tmp.units.ensure((size_t)n_slots * U));
+  FB_CUDA(e, tmp.rowno.ensure((size_t)n_slots));
+  FB_CUDA(e, tmp.list_blk.ensure(nl));
+  FB_CUDA(e, tmp.list_len.ensure(nl));
+  FB_CUDA(e, e->sel_rows.ensure((size_t)std::max(1, n)));
+  FB_CUDA(e, cudaMemcpyAsync(tmp.list_blk.p, blk.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(tmp.list_len.p, len.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  if (n > 0) FB_CUDA(e, cudaMemcpyAsync(e->sel_rows.p, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  gather_rows_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->pq.units.p, U, e->sel_rows.p, n, tmp.units.p, tmp.rowno.p, n_slots);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));  // host vectors go out of scope below
+  CodeTable view;  // borrow buffers; ids come from the full pq table (rowno = pq row)
+  view.units = tmp.units; view.rowno = tmp.rowno; view.list_blk = tmp.list_blk; view.list_len = tmp.list_len;
+  view.ids = e->pq.ids; view.m = e->pq.m; view.U = U; view.n_lists = nl; view.N = n; view.n_blocks = n_blocks;
+
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  rc = pq_dev(e, view, e->q_stage.p, nq, k, 1000.0f, e->id_stage.p, e->dist_stage.p);  // freddy.c:415
+  if (rc) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
+int fb_synchronize(fb_engine* e) {
+  if (!e) return FB_ERR_INVALID;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return check_error_flag(e);
+}
+
+int fb_set_option(fb_engine* e, int option, int64_t value) {
+  if (!e) return FB_ERR_INVALID;
+  switch (option) {
+    case FB_OPT_FORCE_EXACT_PATH: e->force_exact = value != 0; return FB_OK;
+    case FB_OPT_PROFILE: e->profile = value != 0; return FB_OK;
+    case FB_OPT_QUERY_CHUNK:
+      if (value < 1) return fail(e, FB_ERR_INVALID, "query chunk must be >= 1");
+      e->query_chunk = value;
+      return FB_OK;
+  }
+  return fail(e, FB_ERR_INVALID, "unknown option %d", option);
+}
+
+int fb_get_counters(fb_engine* e, fb_counters* out) {
+  if (!e || !out) return FB_ERR_INVALID;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  drain_events(e);
+  u64 c64[2] = {0, 0};
+  FB_CUDA(e, cudaMemcpy(c64, e->counters64.p, sizeof c64, cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof *out);
+  out->queries = e->queries_done;
+  out->rows_scanned = (int64_t)c64[0] + e->host_rows;
+  out->scan_bytes = out->rows_scanned * e->bytes_per_row;
+  out->exact_path_queries = (int64_t)c64[1];
+  out->kernel_launches = e->launches;
+  out->ms_coarse = e->ms[ST_COARSE]; out->ms_lut = e->ms[ST_LUT]; out->ms_scan = e->ms[ST_SCAN];
+  out->ms_finalize = e->ms[ST_FINALIZE]; out->ms_exact = e->ms[ST_EXACT];
+  out->n_scan_launches = e->n_scan_launches;
+  return FB_OK;
+}
+
+int fb_reset_counters(fb_engine* e) {
+  if (!e) return FB_ERR_INVALID;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  drain_events(e);
+  FB_CUDA(e, cudaMemset(e->counters64.p, 0, 2 * sizeof(u64)));
+  for (double& v : e->ms) v = 0;
+  e->launches = 0; e->queries_done = 0; e->n_scan_launches = 0; e->host_rows = 0;
+  return FB_OK;
+}
+
+float fb_round_through_text(float distance) {
+  char buf[16];
+  snprintf(buf, sizeof buf, "%f", distance);
+  return strtof(buf, nullptr);
+}
+
+}  // extern "C"

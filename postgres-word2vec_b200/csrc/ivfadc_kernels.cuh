@@ -1,0 +1,369 @@
+// ivfadc_kernels.cuh — the IVFADC / PQ hot path as sm_100a kernels.
+//
+// Pipeline for a chunk of queries (reference: freddy.c:247-378, ivfadc_search):
+//   coarse_select_kernel   HOT(1) coarse L2 distances + top-w lists   freddy.c:264-283
+//   lut_build_kernel       HOT(2) residuals + per-(query,probe) LUTs  freddy.c:295-314, index_utils.c:445-455
+//   adc_scan_kernel        HOT(3)+(4) ADC over the probed lists' codes + per-warp top-(k+1)   freddy.c:347-372
+//   finalize_kernel        merge per-warp lists, reference tie order, flag rare cases
+//   (exact_kernels.cuh)    general path for flagged queries (boundary ties, re-probe loop)
+//
+// Exactness: every distance is the reference's own fp32 chain (common.cuh).
+// Selection uses keys (distance bits, arrival order); the reference's
+// order-dependent insertion (index_utils.c:19-33) is reproduced exactly when no
+// tie straddles the k-th place, which finalize_kernel checks; the rest goes to
+// the general kernel.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+// ---------------------------------------------------------------------------
+// Device image of one code table (fine_quantization or pq_quantization).
+// Rows are grouped by inverted list, each list padded to a multiple of 32 rows
+// and stored in blocks of 32 rows x U units; a unit is 4 codes = 8 bytes, codes
+// are pre-scaled by 4 (byte offset into one K-float LUT row):
+//   unit u of lane L of block b  ->  units[(b*U + u)*32 + L]
+// so a warp reads one block with U fully coalesced 256-byte loads.
+// rowno[b*32 + L] is the row's position in the uploaded table (arrival order of
+// the reference's loop), -1 for padding.  Algorithmic bytes per row: 2*m + 4.
+// ---------------------------------------------------------------------------
+struct CodeTableDev {
+  const uint2* units;       // [n_blocks][U][32]
+  const int32_t* rowno;     // [n_blocks][32]
+  const int32_t* list_blk;  // [n_lists] first block of each list
+  const int32_t* list_len;  // [n_lists] rows in each list
+  const int32_t* ids;       // [N] id by table row number
+  int m, U, n_lists;
+};
+
+constexpr uint32_t kFlagExact = 1u;     // needs the general kernel
+constexpr int kCoarseThreads = 256;
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / kWarp;
+constexpr int kLutMaxJobs = 16;
+
+// ---------------------------------------------------------------------------
+// HOT(1) coarse quantizer: squared L2 of each query against all C centroids
+// (sequential 3-op chain per dimension, index_utils.c:500-508), then the w
+// nearest lists per query (freddy.c:264-283).  One CTA = QT (<=16) queries x all
+// centroids; one thread = one centroid x QT independent chains, centroid
+// table transposed ([d][Cs]) so the per-dimension load is coalesced and shared
+// by the QT queries.  Selection: one warp per query keeps an ascending key list.
+// ---------------------------------------------------------------------------
+template <int QT>
+__global__ void __launch_bounds__(kCoarseThreads, 2)
+coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
+                     const float* __restrict__ coarseT, int C, int Cs,
+                     const int32_t* __restrict__ list_len, int w, int k,
+                     int32_t* __restrict__ probes,      // [nq][w]
+                     uint32_t* __restrict__ qflags,      // [nq]
+                     int force_exact) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qs = reinterpret_cast<float*>(smem_raw);     // [d][QT]
+  float* dist = qs + (size_t)d * QT;           // [QT][Cs]
+  const int q0 = blockIdx.x * QT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int idx = tid; idx < d * QT; idx += kCoarseThreads) {
+    int i = idx / QT, qq = idx % QT;
+    int q = q0 + qq;
+    qs[idx] = (q < nq) ? queries[(size_t)q * d + i] : 0.0f;
+  }
+  __syncthreads();
+
+  for (int c = tid; c < Cs; c += kCoarseThreads) {
+    float acc[QT];
+#pragma unroll
+    for (int qq = 0; qq < QT; qq++) acc[qq] = 0.0f;
+    const float* col = coarseT + c;
+#pragma unroll 2
+    for (int i = 0; i < d; i++) {
+      float cv = __ldg(col + (size_t)i * Cs);
+      if (QT % 4 == 0) {
+        const float4* qrow = reinterpret_cast<const float4*>(qs + i * QT);
+#pragma unroll
+        for (int v = 0; v < QT / 4; v++) {
+          float4 qv = qrow[v];
+          float t0 = xsub(qv.x, cv), t1 = xsub(qv.y, cv), t2 = xsub(qv.z, cv), t3 = xsub(qv.w, cv);
+          acc[4 * v + 0] = xadd(acc[4 * v + 0], xmul(t0, t0));
+          acc[4 * v + 1] = xadd(acc[4 * v + 1], xmul(t1, t1));
+          acc[4 * v + 2] = xadd(acc[4 * v + 2], xmul(t2, t2));
+          acc[4 * v + 3] = xadd(acc[4 * v + 3], xmul(t3, t3));
+        }
+      } else {
+#pragma unroll
+        for (int qq = 0; qq < QT; qq++) {
+          float t = xsub(qs[i * QT + qq], cv);
+          acc[qq] = xadd(acc[qq], xmul(t, t));
+        }
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < QT; qq++) dist[qq * Cs + c] = acc[qq];
+  }
+  __syncthreads();
+
+  // selection: top-(w+1) by (distance, centroid id); w + 1 <= 32 (host-checked)
+  for (int qq = warp; qq < QT; qq += kCoarseThreads / kWarp) {
+    const int q = q0 + qq;
+    if (q >= nq) continue;
+    u64 mine = kKeyInf;
+    u64 thr = kKeyInf;
+    for (int c0 = 0; c0 < Cs; c0 += 32) {
+      int c = c0 + lane;
+      u64 key = (c < C) ? make_key(dist[qq * Cs + c], (uint32_t)c) : kKeyInf;
+      unsigned mask = __ballot_sync(0xffffffffu, key < thr);
+      while (mask) {
+        int src = __ffs(mask) - 1;
+        u64 nk = shfl_u64(key, src);
+        warp_list_insert(mine, nk, lane);
+        thr = shfl_u64(mine, w);
+        mask &= mask - 1;
+        mask &= __ballot_sync(0xffffffffu, key < thr);
+      }
+    }
+    // lanes 0..w-1: the w nearest lists; lane w: the runner-up
+    uint32_t flags = force_exact ? kFlagExact : 0u;
+    u64 kw = shfl_u64(mine, w), kw1 = shfl_u64(mine, w - 1);
+    // a tie across the w-th place makes the kept set order dependent
+    if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact;
+    // sentinel quirk of the reference: a selected distance >= 100 is undefined
+    if (key_dist(kw1) >= 100.0f) flags |= kFlagExact;
+    int len = 0;
+    if (lane < w) {
+      int cid = (int)key_t(mine);
+      probes[(size_t)q * w + lane] = cid;
+      len = list_len[cid];
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) len += __shfl_xor_sync(0xffffffffu, len, s);
+    if (len < k) flags |= kFlagExact;  // re-probe loop (freddy.c:262) needed
+    if (lane == 0) qflags[q] = flags;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// HOT(2) LUT build.  job = (query, probed centroid | none).  LUT[job][pos][code]
+// = squareDistance(residual + pos*sub, codeword(pos,code), sub) with residual =
+// query - centroid (freddy.c:296-314, index_utils.c:445-455); for flat PQ the
+// raw query is used (freddy.c:519-525).
+// One CTA owns one (pos, tile of <=1024 codes): its codebook slice [sub][TK] is
+// staged ONCE into shared memory by the TMA engine (1-D bulk copies) and reused
+// for every job the CTA processes; one thread = one code, W jobs at a time = W
+// independent accumulation chains fed by broadcast reads of the residuals.
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(1024, 1)
+lut_build_kernel(const float* __restrict__ queries, int d,
+                 const float* __restrict__ coarse,        // [C][d] row-major or nullptr
+                 const int32_t* __restrict__ probes,      // [njobs] centroid per job or nullptr
+                 int jobs_per_query, int njobs,
+                 const float* __restrict__ cbT,           // [m][sub][K]
+                 int m, int K, int sub, int TK,
+                 float* __restrict__ lut) {               // [njobs][m][K]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  float* cbs = reinterpret_cast<float*>(smem_raw);        // [sub][TK]
+  constexpr int WS = (W + 3) & ~3;                        // residual row stride (16-byte rows)
+  float* rs = cbs + (size_t)sub * TK;                     // [sub][WS]
+  const int tiles = (K + TK - 1) / TK;
+  const int pos = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+  const int code0 = tile * TK;
+  const int ncodes = min(TK, K - code0);
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(sub * ncodes * sizeof(float)));
+    for (int i = 0; i < sub; i++)
+      bulk_g2s(cbs + (size_t)i * TK, cbT + ((size_t)pos * sub + i) * K + code0,
+               (uint32_t)(ncodes * sizeof(float)), &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  for (int job0 = blockIdx.y * W; job0 < njobs; job0 += gridDim.y * W) {
+    __syncthreads();  // previous group's readers of rs are done
+    for (int idx = tid; idx < sub * W; idx += blockDim.x) {
+      const int i = idx / W, jj = idx % W;
+      int job = min(job0 + jj, njobs - 1);
+      int q = job / jobs_per_query;
+      float qv = queries[(size_t)q * d + pos * sub + i];
+      float r = qv;
+      if (probes != nullptr) r = xsub(qv, coarse[(size_t)probes[job] * d + pos * sub + i]);
+      rs[i * WS + jj] = r;
+    }
+    __syncthreads();
+    if (tid < ncodes) {
+      float acc[W];
+#pragma unroll
+      for (int jj = 0; jj < W; jj++) acc[jj] = 0.0f;
+#pragma unroll 5
+      for (int i = 0; i < sub; i++) {
+        float cv = cbs[(size_t)i * TK + tid];
+        const float* rrow = rs + i * WS;
+#pragma unroll
+        for (int jj = 0; jj < W; jj++) {
+          float t = xsub(rrow[jj], cv);
+          acc[jj] = xadd(acc[jj], xmul(t, t));
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < W; jj++) {
+        int job = job0 + jj;
+        if (job < njobs) lut[((size_t)job * m + pos) * K + code0 + tid] = acc[jj];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// HOT(3)+(4) ADC scan + top-(k+1).  One CTA = one task = (LUT, list).  The
+// task's LUT (m*K fp32, 48 KB at m=12,K=1024) is pulled into shared memory with
+// one bulk async copy; each lane then owns one row per 32-row block: U coalesced
+// 8-byte loads of pre-scaled codes, m shared-memory gathers, m sequential adds
+// (freddy.c:364-368 / index_utils.c:1126-1133).  Each warp keeps the KK = k+1
+// smallest (distance, arrival) keys it has seen in registers (lane i = i-th);
+// a row is looked at again only if it beats the warp's current KK-th key.
+// Output: per-warp ascending key lists, merged by finalize_kernel.
+// ---------------------------------------------------------------------------
+template <int M>  // M > 0: compile-time m (unrolled); M == 0: runtime m
+__global__ void __launch_bounds__(kScanThreads, 4)
+adc_scan_kernel(CodeTableDev tab,
+                const int32_t* __restrict__ task_list,   // [ntasks] list per task, or nullptr (list = task % n_lists... see host)
+                int tasks_per_lut,                       // LUT index = task / tasks_per_lut
+                int lists_per_task_mod,                  // if task_list == nullptr: list = task % lists_per_task_mod
+                const float* __restrict__ lut, int K, int KK,
+                u64* __restrict__ partial) {             // [ntasks][kScanWarps][KK]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  float* slut = reinterpret_cast<float*>(smem_raw);
+  const int m = (M > 0) ? M : tab.m;
+  const int U = (M > 0) ? (M + 3) / 4 : tab.U;
+  const int task = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lut_bytes = (uint32_t)((size_t)m * K * sizeof(float));
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, lut_bytes);
+    bulk_g2s(slut, lut + (size_t)(task / tasks_per_lut) * m * K, lut_bytes, &bar);
+  }
+  const int list = (task_list != nullptr) ? task_list[task] : (task % lists_per_task_mod);
+  const int blk0 = tab.list_blk[list];
+  const int len = tab.list_len[list];
+  const int nblk = (len + 31) >> 5;
+  mbar_wait(&bar, 0);
+
+  u64 mine = kKeyInf;
+  uint32_t thr_bits = 0xFFFFFFFFu;
+  const char* lut_bytes_base = reinterpret_cast<const char*>(slut);
+  const uint32_t row_stride = (uint32_t)K * 4u;
+
+  for (int b = warp; b < nblk; b += kScanWarps) {
+    const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
+    float acc = 0.0f;
+    if (M > 0) {
+      uint2 v[(M > 0) ? (M + 3) / 4 : 1];
+#pragma unroll
+      for (int u = 0; u < (M + 3) / 4; u++) v[u] = __ldg(up + u * 32);
+#pragma unroll
+      for (int u = 0; u < (M + 3) / 4; u++) {
+        uint32_t wlo = v[u].x, whi = v[u].y;
+        const char* base = lut_bytes_base + (size_t)(4 * u) * row_stride;
+        if (4 * u + 0 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
+        if (4 * u + 1 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + row_stride + (wlo >> 16)));
+        if (4 * u + 2 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * row_stride + (whi & 0xFFFFu)));
+        if (4 * u + 3 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * row_stride + (whi >> 16)));
+      }
+    } else {
+      for (int u = 0; u < U; u++) {
+        uint2 vv = __ldg(up + u * 32);
+        uint32_t wlo = vv.x, whi = vv.y;
+        const char* base = lut_bytes_base + (size_t)(4 * u) * row_stride;
+        int p = 4 * u;
+        if (p + 0 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
+        if (p + 1 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + row_stride + (wlo >> 16)));
+        if (p + 2 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * row_stride + (whi & 0xFFFFu)));
+        if (p + 3 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * row_stride + (whi >> 16)));
+      }
+    }
+    const bool valid = (b * 32 + lane) < len;
+    const uint32_t dbits = __float_as_uint(acc);
+    bool cand = valid && (dbits <= thr_bits);
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    if (mask) {
+      u64 key = kKeyInf;
+      if (cand) key = make_key(acc, (uint32_t)tab.rowno[(size_t)(blk0 + b) * 32 + lane]);
+      while (mask) {
+        int src = __ffs(mask) - 1;
+        u64 nk = shfl_u64(key, src);
+        warp_list_insert(mine, nk, lane);
+        mask &= mask - 1;
+      }
+      thr_bits = key_dbits(shfl_u64(mine, KK - 1));
+    }
+  }
+  if (lane < KK) partial[((size_t)task * kScanWarps + warp) * KK + lane] = mine;
+}
+
+// ---------------------------------------------------------------------------
+// finalize: one warp per query merges its n_lists per-warp key lists, checks the
+// tie condition, and writes the k results in the reference's order: ascending
+// distance, later arrival first among equal distances (index_utils.c:19-33).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, int k,
+                int nq, const int32_t* __restrict__ ids, float sentinel,
+                const uint32_t* __restrict__ qflags_in,   // may be nullptr
+                int32_t* __restrict__ out_ids, float* __restrict__ out_dists,   // [nq][k]
+                int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
+                u64* __restrict__ exact_total,            // cumulative statistic
+                u64* __restrict__ kth_key) {              // [nq] k-th smallest key (bound for the general kernel)
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  u64 mine = kKeyInf;
+  const u64* base = partial + (size_t)q * lists_per_query * KK;
+  for (int l = 0; l < lists_per_query; l++) {
+    u64 other = (lane < KK) ? base[(size_t)l * KK + lane] : kKeyInf;
+    if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
+    warp_list_merge(mine, other, lane);
+  }
+  uint32_t flags = qflags_in ? qflags_in[q] : 0u;
+  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
+  if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) flags |= kFlagExact;  // tie across the k-th place
+  if (lane == 0) kth_key[q] = kk1;
+  if (flags & kFlagExact) {
+    if (lane == 0) {
+      exact_list[atomicAdd(exact_count, 1)] = q;
+      atomicAdd(exact_total, 1ull);
+    }
+    return;
+  }
+  // reference order inside runs of equal distance: later arrival first
+  const uint32_t dbits = key_dbits(mine);
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, dbits, 1);
+  const bool in_range = lane < k;
+  const bool start = in_range && (lane == 0 || dbits != prev);
+  const unsigned starts = __ballot_sync(0xffffffffu, start);
+  if (in_range) {
+    unsigned below = starts & (0xffffffffu >> (31 - lane));  // start bits at or below this lane
+    int s = 31 - __clz(below);
+    unsigned above = starts & ~(0xffffffffu >> (31 - lane));
+    int e = above ? (__ffs(above) - 2) : (k - 1);
+    int outpos = s + (e - lane);
+    bool filled = mine != kKeyInf;
+    out_ids[(size_t)q * k + outpos] = filled ? ids[key_t(mine)] : -1;
+    out_dists[(size_t)q * k + outpos] = filled ? key_dist(mine) : sentinel;
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,67 @@
+"""ctypes binding of libfreddy_b200.so (C-ABI: include/freddy_b200.h).
+
+The library is the product; there is no Python or CPU fallback.  If the shared
+object is missing or no CUDA device is present every entry point fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfreddy_b200.so")
+
+FB_OK = 0
+FB_ERR_INVALID, FB_ERR_CUDA, FB_ERR_UNSUPPORTED, FB_ERR_REFERENCE_UB = -1, -2, -3, -4
+FB_CB_RESIDUAL, FB_CB_PQ = 0, 1
+FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK = 1, 2, 3
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("queries", C.c_int64), ("rows_scanned", C.c_int64), ("scan_bytes", C.c_int64),
+        ("exact_path_queries", C.c_int64), ("kernel_launches", C.c_int64),
+        ("ms_coarse", C.c_double), ("ms_lut", C.c_double), ("ms_scan", C.c_double),
+        ("ms_finalize", C.c_double), ("ms_exact", C.c_double), ("n_scan_launches", C.c_int64),
+    ]
+
+
+# every symbol include/freddy_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "fb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "fb_destroy": (None, [_P]),
+    "fb_last_error": (C.c_char_p, [_P]),
+    "fb_load_coarse": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "fb_load_codebook": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int]),
+    "fb_load_fine": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int]),
+    "fb_load_pq": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
+    "fb_ivfadc_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "fb_ivfadc_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "fb_pq_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "fb_pq_search_in_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "fb_synchronize": (C.c_int, [_P]),
+    "fb_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "fb_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
+    "fb_reset_counters": (C.c_int, [_P]),
+    "fb_round_through_text": (C.c_float, [C.c_float]),
+    "fb_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the product library and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` or "
+            "`make -C postgres-word2vec_b200/csrc` (there is no fallback implementation)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,145 @@
+"""Host-side handle over the C-ABI engine: one per process / GPU, index pinned once.
+
+Mirrors what a Postgres backend would hold per session: the
+coarse table, codebooks and code tables are uploaded once; searches then run on
+the GPU only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class FreddyError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"freddy_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.fb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FreddyError(rc, (self._lib.fb_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.d = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FreddyError(rc, (self._lib.fb_last_error(self._h) or b"").decode())
+
+    # ---- index upload -------------------------------------------------
+    def load_coarse(self, coarse):
+        coarse = _f32(coarse)
+        self.d = coarse.shape[1]
+        self._check(self._lib.fb_load_coarse(self._h, _ptr(coarse), coarse.shape[0], coarse.shape[1]))
+
+    def load_codebook(self, kind, codebook):
+        cb = _f32(codebook)
+        m, K, sub = cb.shape
+        if self.d is None:
+            self.d = m * sub
+        self._check(self._lib.fb_load_codebook(self._h, kind, _ptr(cb), m, K, sub))
+
+    def load_fine(self, ids, coarse_ids, codes):
+        ids, coarse_ids = _i32(ids), _i32(coarse_ids)
+        codes = np.ascontiguousarray(codes, dtype=np.int16)
+        self._check(self._lib.fb_load_fine(self._h, _ptr(ids), _ptr(coarse_ids), _ptr(codes), codes.shape[0], codes.shape[1]))
+
+    def load_pq(self, ids, codes):
+        ids = _i32(ids)
+        codes = np.ascontiguousarray(codes, dtype=np.int16)
+        self._check(self._lib.fb_load_pq(self._h, _ptr(ids), _ptr(codes), codes.shape[0], codes.shape[1]))
+
+    def load_ivfadc_index(self, index):
+        """index: dict with coarse, residual_codebook, ids, coarse_ids, codes."""
+        self.load_coarse(index["coarse"])
+        self.load_codebook(_lib.FB_CB_RESIDUAL, index["residual_codebook"])
+        self.load_fine(index["ids"], index["coarse_ids"], index["codes"])
+
+    def load_pq_index(self, index):
+        self.load_codebook(_lib.FB_CB_PQ, index["pq_codebook"])
+        self.load_pq(index["ids"], index["pq_codes"])
+
+    # ---- searches (host buffers) --------------------------------------
+    def ivfadc_search(self, queries, k, w, out_ids=None, out_dists=None):
+        q = _f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), np.int32)
+        dists = out_dists if out_dists is not None else np.empty((nq, k), np.float32)
+        self._check(self._lib.fb_ivfadc_search(self._h, _ptr(q), nq, k, w, _ptr(ids), _ptr(dists)))
+        return ids, dists
+
+    def ivfadc_search_ptr(self, q_ptr, nq, k, w, ids_ptr, dists_ptr):
+        """host pointers given as integers (e.g. pinned torch tensors' data_ptr())"""
+        self._check(self._lib.fb_ivfadc_search(self._h, C.c_void_p(q_ptr), nq, k, w, C.c_void_p(ids_ptr), C.c_void_p(dists_ptr)))
+
+    def ivfadc_search_dev(self, d_queries_ptr, nq, k, w, d_ids_ptr, d_dists_ptr):
+        """device pointers; enqueued on the engine stream, see synchronize()"""
+        self._check(self._lib.fb_ivfadc_search_dev(self._h, C.c_void_p(d_queries_ptr), nq, k, w,
+                                                   C.c_void_p(d_ids_ptr), C.c_void_p(d_dists_ptr)))
+
+    def pq_search(self, queries, k):
+        q = _f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
+        self._check(self._lib.fb_pq_search(self._h, _ptr(q), nq, k, _ptr(ids), _ptr(dists)))
+        return ids, dists
+
+    def pq_search_in_batch(self, queries, k, targets, use_target_lists=False):
+        q = _f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        t = _i32(targets)
+        ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
+        self._check(self._lib.fb_pq_search_in_batch(self._h, _ptr(q), nq, k, _ptr(t), t.shape[0],
+                                                    1 if use_target_lists else 0, _ptr(ids), _ptr(dists)))
+        return ids, dists
+
+    def synchronize(self):
+        self._check(self._lib.fb_synchronize(self._h))
+
+    # ---- knobs --------------------------------------------------------
+    def set_option(self, option, value):
+        self._check(self._lib.fb_set_option(self._h, option, int(value)))
+
+    def counters(self):
+        c = _lib.Counters()
+        self._check(self._lib.fb_get_counters(self._h, C.byref(c)))
+        return {name: getattr(c, name) for name, _ in c._fields_}
+
+    def reset_counters(self):
+        self._check(self._lib.fb_reset_counters(self._h))
+
+
+def round_through_text(dists):
+    """snprintf('%f') -> float4in, as the SRFs return distances (freddy.c:401-408)"""
+    lib = _lib.load()
+    flat = np.asarray(dists, dtype=np.float32).ravel()
+    return np.array([lib.fb_round_through_text(float(x)) for x in flat], np.float32).reshape(np.shape(dists))

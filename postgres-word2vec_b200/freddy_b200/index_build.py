@@ -1,0 +1,119 @@
+"""Seeded synthetic index builder — stands in for the reference's
+offline index_creation/*.py (scipy k-means + faiss flat search + SQL inserts),
+which needs faiss/psycopg2/Postgres and is outside the search-parity boundary
+("for a fixed index").  It follows the reference's *format and encode rule*:
+
+  vectors   L2-normalised fp32 [N][d]            index_creation/index_utils.py:29-31
+  coarse    C centroids, Lloyd k-means           quantizer_creation.py:31-33
+  residual  m x K codewords on residuals         quantizer_creation.py:35-52
+  codes     nearest codeword per sub-vector      ivfadc.py:60-90      (int16, ivfadc.py:112)
+  ids       1-based, table order = id order      vec2database.py:84-87
+  flat PQ   m x K codewords on raw sub-vectors   quantizer_creation.py:13-29, pq_index.py:106
+
+torch is used as the array engine (GPU when available) — this is index
+construction, not the search path.
+"""
+import numpy as np
+import torch
+
+
+def _kmeans(x, k, iters, gen):
+    """Lloyd k-means on rows of x (float32 tensor); empty clusters keep their centroid."""
+    n = x.shape[0]
+    perm = torch.randperm(n, generator=gen, device=x.device)[:k]
+    cent = x[perm].clone()
+    if k > n:  # tiny inputs: pad with jittered copies
+        extra = x[torch.randint(0, n, (k - n,), generator=gen, device=x.device)]
+        cent = torch.cat([cent, extra + 1e-3 * torch.randn(extra.shape, generator=gen, device=x.device)])
+    for _ in range(iters):
+        assign = _nearest(x, cent)
+        sums = torch.zeros_like(cent).index_add_(0, assign, x)
+        cnt = torch.zeros(k, device=x.device).index_add_(0, assign, torch.ones(n, device=x.device))
+        nz = cnt > 0
+        cent[nz] = sums[nz] / cnt[nz].unsqueeze(1)
+    return cent
+
+
+def _nearest(x, cent, chunk=65536):
+    """argmin_j ||x_i - cent_j||^2, chunked (the reference uses faiss IndexFlatL2)."""
+    out = torch.empty(x.shape[0], dtype=torch.long, device=x.device)
+    cn = (cent * cent).sum(1)
+    for s in range(0, x.shape[0], chunk):
+        xs = x[s:s + chunk]
+        d = cn.unsqueeze(0) - 2.0 * (xs @ cent.t())
+        out[s:s + chunk] = d.argmin(1)
+    return out
+
+
+def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clusters=1000,
+                         sigma=0.3, kmeans_iters=10, seed=1234, device=None, with_pq=False,
+                         keep_vectors=False):
+    """Returns a dict of numpy arrays (plus 'vectors_t': the torch tensor, if keep_vectors)."""
+    assert d % m == 0, "d must be divisible by m"
+    sub = d // m
+    dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+
+    # --- vectors: mixture of Gaussian clusters with Zipf-ish sizes, then normalised
+    centres = torch.randn(n_clusters, d, generator=gen, device=dev)
+    pc = 1.0 / torch.arange(10, 10 + n_clusters, device=dev, dtype=torch.float32) ** 0.7
+    pc = pc / pc.sum()
+    vecs = torch.empty(N, d, device=dev, dtype=torch.float32)
+    step = 262144
+    for s in range(0, N, step):
+        n = min(step, N - s)
+        cl = torch.multinomial(pc, n, replacement=True, generator=gen)
+        v = centres[cl] + sigma * torch.randn(n, d, generator=gen, device=dev)
+        vecs[s:s + n] = v / v.norm(dim=1, keepdim=True)
+    ntr = min(n_train, N)
+    train = vecs[:ntr]
+
+    # --- coarse quantizer
+    coarse = _kmeans(train, C, kmeans_iters, gen)
+    coarse_ids = _nearest(vecs, coarse)
+
+    # --- residual PQ codebook (trained on the residuals of the training prefix)
+    res_train = train - coarse[coarse_ids[:ntr]]
+    res_cb = torch.empty(m, K, sub, device=dev)
+    for p in range(m):
+        res_cb[p] = _kmeans(res_train[:, p * sub:(p + 1) * sub].contiguous(), K, kmeans_iters, gen)
+    codes = torch.empty(N, m, dtype=torch.int16, device=dev)
+    for s in range(0, N, step):
+        r = vecs[s:s + step] - coarse[coarse_ids[s:s + step]]
+        for p in range(m):
+            codes[s:s + step, p] = _nearest(r[:, p * sub:(p + 1) * sub].contiguous(), res_cb[p]).to(torch.int16)
+
+    out = {
+        "d": d, "m": m, "K": K, "C": C, "N": N,
+        "coarse": coarse.cpu().numpy(),
+        "residual_codebook": res_cb.cpu().numpy(),
+        "ids": np.arange(1, N + 1, dtype=np.int32),
+        "coarse_ids": coarse_ids.to(torch.int32).cpu().numpy(),
+        "codes": codes.cpu().numpy(),
+    }
+    if with_pq:
+        pq_cb = torch.empty(m, K, sub, device=dev)
+        for p in range(m):
+            pq_cb[p] = _kmeans(train[:, p * sub:(p + 1) * sub].contiguous(), K, kmeans_iters, gen)
+        pq_codes = torch.empty(N, m, dtype=torch.int16, device=dev)
+        for s in range(0, N, step):
+            v = vecs[s:s + step]
+            for p in range(m):
+                pq_codes[s:s + step, p] = _nearest(v[:, p * sub:(p + 1) * sub].contiguous(), pq_cb[p]).to(torch.int16)
+        out["pq_codebook"] = pq_cb.cpu().numpy()
+        out["pq_codes"] = pq_codes.cpu().numpy()
+    if keep_vectors:
+        out["vectors_t"] = vecs
+    else:
+        del vecs
+    return out
+
+
+def sample_queries(index, vectors_t, n, seed=4321):
+    """Queries are stored vectors, as the reference's harness samples stored words
+    (evaluation/evaluation_utils.py:103-116)."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    sel = torch.randperm(vectors_t.shape[0], generator=g)[:n]
+    return vectors_t[sel.to(vectors_t.device)].cpu().numpy(), (sel + 1).numpy().astype(np.int32)

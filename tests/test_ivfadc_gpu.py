@@ -1,0 +1,137 @@
+"""GPU parity: the CUDA engine (through the C-ABI) against the CPU oracle on the
+same seeded indexes.  Bar: ids/ranks AND distances bit-exact (same fp32 chain)."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_topk, queries_from, small_index
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from freddy_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _run_both(eng, oracle_mod, ix, q, k, w, force_exact=False):
+    from freddy_b200 import _lib
+    eng.load_ivfadc_index(ix)
+    eng.set_option(_lib.FB_OPT_FORCE_EXACT_PATH, 1 if force_exact else 0)
+    eng.reset_counters()
+    ids, d = eng.ivfadc_search(q, k, w)
+    eng.set_option(_lib.FB_OPT_FORCE_EXACT_PATH, 0)
+    oi = oracle_mod.OracleIndex(ix)
+    eids, ed, rc, rows = oi.ivfadc_search(q, k, w, threads=4)
+    assert rc == 0
+    return ids, d, eids, ed, rows
+
+
+@pytest.mark.parametrize("k,w", [(5, 4), (1, 1), (10, 3), (31, 8)])
+def test_parity_small(eng, oracle_mod, k, w):
+    ix = small_index()
+    q = queries_from(ix, 300)
+    ids, d, eids, ed, rows = _run_both(eng, oracle_mod, ix, q, k, w)
+    assert_same_topk(ids, d, eids, ed, f"k={k} w={w}")
+    c = eng.counters()
+    assert c["rows_scanned"] == rows
+    assert c["queries"] == 300
+
+
+def test_parity_general_kernel(eng, oracle_mod):
+    ix = small_index()
+    q = queries_from(ix, 120, seed=5)
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 4, force_exact=True)
+    assert_same_topk(ids, d, eids, ed, "forced general kernel")
+    assert eng.counters()["exact_path_queries"] == 120
+
+
+def test_parity_noisy_queries_and_chunks(eng, oracle_mod):
+    from freddy_b200 import _lib
+    ix = small_index()
+    q = queries_from(ix, 257, seed=3, noise=0.05)
+    eng.set_option(_lib.FB_OPT_QUERY_CHUNK, 100)   # 3 chunks, last one ragged
+    try:
+        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 7, 5)
+    finally:
+        eng.set_option(_lib.FB_OPT_QUERY_CHUNK, 2048)
+    assert_same_topk(ids, d, eids, ed, "chunked")
+
+
+def test_ties_everywhere(eng, oracle_mod):
+    """K=4 codes over 2-d sub-vectors: thousands of rows share identical code
+    vectors, so distance ties straddle the k-th place all the time."""
+    ix = small_index(N=6000, d=24, m=12, K=4, C=8, seed=3, n_clusters=5)
+    q = queries_from(ix, 200, seed=9)
+    for k, w in ((5, 2), (3, 8), (20, 3)):
+        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, k, w)
+        assert_same_topk(ids, d, eids, ed, f"ties k={k} w={w}")
+        assert eng.counters()["exact_path_queries"] > 0
+
+
+def test_reprobe_loop(eng, oracle_mod):
+    """lists much shorter than k: the reference re-probes with a blacklist (freddy.c:262)"""
+    ix = small_index(N=150, d=24, m=12, K=8, C=64, seed=5, n_clusters=20)
+    q = queries_from(ix, 60, seed=2)
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 12, 2)
+    assert_same_topk(ids, d, eids, ed, "re-probe")
+    assert eng.counters()["exact_path_queries"] > 0
+
+
+def test_large_k_and_w(eng, oracle_mod):
+    ix = small_index()
+    q = queries_from(ix, 40, seed=8)
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 100, 6)   # k > 31: general kernel
+    assert_same_topk(ids, d, eids, ed, "k=100")
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 36)    # w > 31: general kernel
+    assert_same_topk(ids, d, eids, ed, "w=36")
+
+
+def test_generic_m(eng, oracle_mod):
+    ix = small_index(N=8000, d=40, m=10, K=32, C=16, seed=11)         # m=10: runtime-m scan kernel
+    q = queries_from(ix, 100, seed=4)
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 3)
+    assert_same_topk(ids, d, eids, ed, "m=10")
+
+
+def test_readme_shape(eng, oracle_mod):
+    """d=300, m=12, K=1024 (README.md:125-128) on a 60k-row table"""
+    ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)
+    q = queries_from(ix, 150, seed=6)
+    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 10)
+    assert_same_topk(ids, d, eids, ed, "d=300 K=1024")
+
+
+def test_edge_cases(eng, oracle_mod):
+    from freddy_b200 import FreddyError, _lib
+    ix = small_index()
+    eng.load_ivfadc_index(ix)
+    ids, d = eng.ivfadc_search(np.zeros((0, ix["d"]), np.float32), 5, 3)
+    assert ids.shape == (0, 5)
+    with pytest.raises(FreddyError) as ei:
+        eng.ivfadc_search(queries_from(ix, 2), 5, ix["C"] + 1)
+    assert ei.value.code == _lib.FB_ERR_REFERENCE_UB
+    with pytest.raises(FreddyError):
+        eng.ivfadc_search(queries_from(ix, 2), 0, 3)
+
+
+def test_flat_pq(eng, oracle_mod):
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    eng.load_pq_index(ix)
+    oi = oracle_mod.OracleIndex(ix, flat_pq=True)
+    q = queries_from(ix, 40, seed=13)
+    ids, d = eng.pq_search(q, 5)
+    eids, ed = oi.pq_search(q, 5)
+    assert_same_topk(ids, d, eids, ed, "pq_search")
+    rng = np.random.default_rng(0)
+    targets = rng.choice(np.arange(1, ix["N"] + 500), size=3000, replace=True).astype(np.int32)  # dups + unknown ids
+    for tl in (False, True):
+        ids, d = eng.pq_search_in_batch(q, 6, targets, use_target_lists=tl)
+        eids, ed = oi.pq_search_in_batch(q, 6, targets, use_target_lists=tl)
+        assert_same_topk(ids, d, eids, ed, "pq_search_in_batch")
+    few = targets[:3]
+    ids, d = eng.pq_search_in_batch(q, 6, few)
+    eids, ed = oi.pq_search_in_batch(q, 6, few)
+    assert_same_topk(ids, d, eids, ed, "fewer targets than k")

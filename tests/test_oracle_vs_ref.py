@@ -1,0 +1,126 @@
+"""Pins the oracle: kernel-level restatements vs the reference's own compiled
+index_utils.c (oracle/_ref/libfreddy_ref.so), bit for bit, and vs the golden
+vectors generated from it (tests/golden/make_golden.py)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def libs(oracle_mod):
+    R = oracle_mod.ref_lib()
+    if R is None:
+        pytest.skip("oracle/_ref not built (reference sources absent and no prebuilt .so)")
+    return oracle_mod.lib(), R
+
+
+def test_square_distance_bitexact(libs):
+    L, R = libs
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 25, 150, 300, 301):
+        for _ in range(50):
+            a = rng.standard_normal(n).astype(np.float32)
+            b = rng.standard_normal(n).astype(np.float32)
+            x, y = L.fo_square_distance(_p(a), _p(b), n), R.squareDistance(_p(a), _p(b), n)
+            assert np.float32(x).view(np.uint32) == np.float32(y).view(np.uint32)
+
+
+def test_update_topk_matches_reference_including_ties(libs, oracle_mod):
+    L, R = libs
+    rng = np.random.default_rng(1)
+    for trial in range(300):
+        k = int(rng.integers(1, 9))
+        n = int(rng.integers(1, 40))
+        # few distinct distances => many ties
+        d = rng.integers(0, 6, size=n).astype(np.float32) / 4
+        a = (oracle_mod.TopKEntry * k)()
+        b = (oracle_mod.TopKEntry * k)()
+        L.fo_init_topk(a, k, 1000.0)
+        L.fo_init_topk(b, k, 1000.0)
+        for i in range(n):
+            if d[i] < a[k - 1].distance:
+                L.fo_update_topk(a, float(d[i]), i, k)
+            if d[i] < b[k - 1].distance:
+                R.updateTopK(b, float(d[i]), i, k, 0)
+        assert [(e.id, e.distance) for e in a] == [(e.id, e.distance) for e in b]
+
+
+def test_survey_tie_example(libs, oracle_mod):
+    # (0,3)(1,1)(2,3)(3,2)(4,1)(5,.5)(6,3), k=5
+    L, _ = libs
+    k = 5
+    tk = (oracle_mod.TopKEntry * k)()
+    L.fo_init_topk(tk, k, 1000.0)
+    for i, dist in enumerate([3, 1, 3, 2, 1, .5, 3]):
+        if dist < tk[k - 1].distance:
+            L.fo_update_topk(tk, dist, i, k)
+    assert [(e.id, e.distance) for e in tk] == [(5, .5), (4, 1.0), (1, 1.0), (3, 2.0), (2, 3.0)]
+
+
+class CodebookEntry(C.Structure):  # index_utils.h:51-55
+    _fields_ = [("pos", C.c_int), ("code", C.c_int), ("vector", C.c_void_p)]
+
+
+def test_precomputed_distances_and_adc_bitexact(libs):
+    L, R = libs
+    rng = np.random.default_rng(2)
+    for (m, K, sub) in ((12, 64, 25), (4, 16, 3), (30, 32, 10)):
+        cb = rng.standard_normal((m, K, sub)).astype(np.float32)
+        q = rng.standard_normal(m * sub).astype(np.float32)
+        mine = np.empty(m * K, np.float32)
+        L.fo_precomputed_distances(_p(mine), m, K, sub, _p(q), _p(cb))
+        # reference walks (pos, code, vector*) rows, here in shuffled row order
+        order = rng.permutation(m * K)
+        ents = (CodebookEntry * (m * K))()
+        for slot, idx in enumerate(order):
+            p, c = divmod(int(idx), K)
+            ents[slot].pos, ents[slot].code = p, c
+            ents[slot].vector = cb[p, c].ctypes.data
+        ref = np.empty(m * K, np.float32)
+        R.getPrecomputedDistances(_p(ref), m, K, sub, _p(q), ents)
+        np.testing.assert_array_equal(mine.view(np.uint32), ref.view(np.uint32))
+        for _ in range(100):
+            codes = rng.integers(0, K, size=m).astype(np.int16)
+            x = L.fo_pq_distance_int16(_p(mine), _p(codes), m, K)
+            y = R.computePQDistanceInt16(_p(ref), _p(codes), m, K)
+            assert np.float32(x).view(np.uint32) == np.float32(y).view(np.uint32)
+
+
+def test_golden_vectors(oracle_mod):
+    """fixtures produced by tests/golden/make_golden.py from oracle/_ref (the real reference code)"""
+    path = os.path.join(HERE, "golden", "kernels_golden.json")
+    g = json.load(open(path))
+    L = oracle_mod.lib()
+    for case in g["square_distance"]:
+        a = np.array(case["a_bits"], np.uint32).view(np.float32)
+        b = np.array(case["b_bits"], np.uint32).view(np.float32)
+        got = np.float32(L.fo_square_distance(_p(a), _p(b), len(a))).view(np.uint32)
+        assert int(got) == case["out_bits"]
+    for case in g["topk"]:
+        k = case["k"]
+        tk = (oracle_mod.TopKEntry * k)()
+        L.fo_init_topk(tk, k, 1000.0)
+        for i, dist in enumerate(case["stream"]):
+            if dist < tk[k - 1].distance:
+                L.fo_update_topk(tk, dist, i, k)
+        assert [[e.id, e.distance] for e in tk] == case["out"]
+    for case in g["lut_adc"]:
+        m, K, sub = case["m"], case["K"], case["sub"]
+        cb = np.array(case["cb_bits"], np.uint32).view(np.float32)
+        q = np.array(case["q_bits"], np.uint32).view(np.float32)
+        lut = np.empty(m * K, np.float32)
+        L.fo_precomputed_distances(_p(lut), m, K, sub, _p(q), _p(cb))
+        assert lut.view(np.uint32).tolist() == case["lut_bits"]
+        for codes, out in zip(case["codes"], case["adc_bits"]):
+            c = np.array(codes, np.int16)
+            got = np.float32(L.fo_pq_distance_int16(_p(lut), _p(c), m, K)).view(np.uint32)
+            assert int(got) == out
