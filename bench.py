@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — IVFADC queries/s at k=5, nprobe(w)=10 on a synthetic 3M x 300, m=12,
+K=1024, C=1000 index (BASELINE.json metric; config[1] in its throughput form).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA engine, C-ABI)
+  python bench.py --impl reference ...                      CPU arm (the oracle on host threads)
+
+A "step" = one pass of the hot path over one batch of --batch queries per GPU:
+coarse quantizer -> residual LUTs -> ADC scan of the w probed lists -> top-k.
+  value : whole-job queries/s, query batch already resident in HBM
+  e2e   : same through fb_ivfadc_search with pinned HOST buffers (H2D queries +
+          D2H results inside the timed region)
+  roofline : ADC-scan kernel, algorithmic bytes (rows * (2m+4)) / CUDA-event time
+          of the scan launches (events recorded by the engine on the launch stream)
+Multi-GPU: index replicated, queries sharded (weak scaling: --batch per GPU),
+one NCCL all-gather of the per-rank top-k per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "postgres-word2vec_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "ivfadc_queries_per_sec_k5_w10"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=3_000_000)
+    ap.add_argument("--d", type=int, default=300)
+    ap.add_argument("--m", type=int, default=12)
+    ap.add_argument("--K", type=int, default=1024)
+    ap.add_argument("--C", type=int, default=1000)
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--w", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=10000, help="queries per GPU per step")
+    ap.add_argument("--sigma", type=float, default=1.0,
+                    help="within-cluster noise of the synthetic vectors (per dimension, centres ~ N(0,I)); "
+                         "1.0 keeps PQ codes diverse like real word embeddings, 0.3 collapses clusters onto "
+                         "identical codes (25%% duplicate rows) and sends a quarter of the queries down the tie path")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"k_nearest_neighbour_ivfadc throughput form: {a.batch} queries/GPU/step, k={a.k}, w={a.w}, "
+            f"synthetic N={a.n} d={a.d} m={a.m} K={a.K} C={a.C} (1000 Zipf-sized Gaussian clusters, sigma={a.sigma}, L2-normalised)")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_index(a, device):
+    from freddy_b200.index_build import make_synthetic_index
+    t0 = time.time()
+    ix = make_synthetic_index(a.n, d=a.d, m=a.m, K=a.K, C=a.C, n_train=min(100_000, a.n), n_clusters=1000,
+                              sigma=a.sigma, kmeans_iters=10, seed=1234, device=device, keep_vectors=True)
+    return ix, time.time() - t0
+
+
+def cpu_arm(a, ix, queries, seconds):
+    """times the oracle (plain-C restatement of freddy.c:247-378) on all host threads"""
+    from oracle import oracle
+    oi = oracle.OracleIndex(ix)
+    threads = os.cpu_count() or 1
+    # calibrate on a small sample, then size one run to ~`seconds`
+    n0 = min(len(queries), 4 * threads)
+    t = time.time()
+    oi.ivfadc_search(queries[:n0], a.k, a.w, threads=threads)
+    per_q = max((time.time() - t) / n0, 1e-6)
+    n = int(max(n0, min(len(queries), seconds / per_q)))
+    t = time.time()
+    _, _, rc, rows = oi.ivfadc_search(queries[:n], a.k, a.w, threads=threads)
+    dt = time.time() - t
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} of the step's queries, one pass, {threads} host threads (oracle/freddy_oracle.c, SPI-free upper bound)",
+            "seconds": dt, "rows_per_query": rows / max(n, 1), "rc": rc}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+
+    # ------------------------------------------------------------------ CPU arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        ix, _ = build_index(a, dev)
+        vec = ix.pop("vectors_t")
+        g = torch.Generator(); g.manual_seed(4321)
+        sel = torch.randperm(a.n, generator=g)[:a.batch]
+        queries = vec[sel.to(vec.device)].cpu().numpy()
+        del vec
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r = cpu_arm(a, ix, queries, max(1.0, a.cpu_seconds / max(1, a.steps)))
+            if i >= a.warmup:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        n_s = int(np.mean([r["value"] * r["seconds"] for r in vals]))
+        out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_name(a), "note": "each step = a bounded sample of the step's query batch"},
+               "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[0]["cores"], "kind": "port",
+                                "sample": f"~{n_s} queries per step on {vals[0]['cores']} host threads"},
+               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from freddy_b200 import Engine, _lib
+
+    # index: built once on rank 0, replicated to every rank (broadcast over NCCL)
+    names = ["coarse", "residual_codebook", "coarse_ids", "codes"]
+    if rank == 0:
+        ix, t_build = build_index(a, dev)
+        vec = ix.pop("vectors_t")
+        g = torch.Generator(); g.manual_seed(4321)
+        sel = torch.randperm(a.n, generator=g)[:a.batch * world]
+        all_q = vec[sel.to(dev)].contiguous()
+        del vec
+    else:
+        ix, t_build, all_q = {"d": a.d, "m": a.m, "K": a.K, "C": a.C, "N": a.n}, 0.0, None
+    if world > 1:
+        shapes = {"coarse": ((a.C, a.d), torch.float32), "residual_codebook": ((a.m, a.K, a.d // a.m), torch.float32),
+                  "coarse_ids": ((a.n,), torch.int32), "codes": ((a.n, a.m), torch.int16)}
+        for nm in names:
+            shp, dt = shapes[nm]
+            t = torch.from_numpy(ix[nm]).to(dev) if rank == 0 else torch.empty(shp, dtype=dt, device=dev)
+            dist.broadcast(t, 0)
+            ix[nm] = t.cpu().numpy()
+        if rank != 0:
+            all_q = torch.empty(a.batch * world, a.d, device=dev)
+            ix["ids"] = np.arange(1, a.n + 1, dtype=np.int32)
+        dist.broadcast(all_q, 0)
+    torch.cuda.empty_cache()
+    my_q = all_q[rank * a.batch:(rank + 1) * a.batch].contiguous()
+
+    eng = Engine(local_rank)
+    eng.load_ivfadc_index(ix)
+    stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    eng.set_stream(stream.cuda_stream)
+    eng.set_option(_lib.FB_OPT_PROFILE, 1)
+
+    nq, k, w = a.batch, a.k, a.w
+    d_ids = torch.empty(nq, k, dtype=torch.int32, device=dev)
+    d_dist = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    g_ids = torch.empty(world * nq, k, dtype=torch.int32, device=dev) if world > 1 else None
+    g_dist = torch.empty(world * nq, k, dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_dev():
+        eng.ivfadc_search_dev(my_q.data_ptr(), nq, k, w, d_ids.data_ptr(), d_dist.data_ptr())
+        if world > 1:   # the path's one exchange: all-gather of per-rank top-k
+            dist.all_gather_into_tensor(g_ids, d_ids)
+            dist.all_gather_into_tensor(g_dist, d_dist)
+
+    h_q = my_q.cpu().pin_memory()
+    h_ids = torch.empty(nq, k, dtype=torch.int32).pin_memory()
+    h_dist = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        eng.ivfadc_search_ptr(h_q.data_ptr(), nq, k, w, h_ids.data_ptr(), h_dist.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, use_events):
+        """K steps, L2 flushed between steps; device time by CUDA events on the launch stream"""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall = []
+        barrier()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            if use_events:
+                evs[i][0].record(stream)
+                step_fn()
+                evs[i][1].record(stream)
+            else:
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                step_fn()
+                wall.append((time.perf_counter() - t) * 1e3)
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs) if use_events else sum(wall)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, a.warmup)):
+        step_dev()
+    eng.synchronize()
+    eng.reset_counters()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_total = timed(step_dev, a.steps, True)
+    clk = clocks.stop()
+    c = eng.counters()
+    value = world * nq * a.steps / (ms_total / 1e3)
+
+    # roofline of the dominant kernel (ADC scan): algorithmic bytes / event time of its launches
+    peak, peak_src = peaks()
+    scan_gbs = (c["scan_bytes"] / 1e9) / (c["ms_scan"] / 1e3) if c["ms_scan"] > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "adc_scan_kernel<12>", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
+                "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, c["n_scan_launches"]),
+                "ms_per_launch": c["ms_scan"] / max(1, c["n_scan_launches"]),
+                "stage_ms_per_step": {s: c["ms_" + s] / a.steps for s in ("coarse", "lut", "scan", "finalize", "exact")}}
+    launches = c["kernel_launches"]
+    exact_q = c["exact_path_queries"]
+
+    # end to end through the host-buffer C-ABI call
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps, False)
+    e2e_value = world * nq * a.steps / (ms_e2e / 1e3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_arm(a, ix, h_q.numpy(), a.cpu_seconds)
+        cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+               "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_name(a), "parallelism": f"replicated index, queries sharded x{world}",
+                          "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1),
+                          "exact_path_queries_per_step": exact_q / a.steps,
+                          "exact_path_reasons_per_step": {r: c["exact_" + r] / a.steps for r in
+                                                          ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")}},
+               "clocks": clk, "gpu_launches": launches,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * a.d * 4 * world,
+                       "d2h_bytes_per_step": nq * k * 8 * world, "ms_per_step": ms_e2e / a.steps},
+               "roofline": roofline}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,10 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k,
                           int32_t* out_ids, float* out_dists);
 
 int fb_synchronize(fb_engine* e);
+/* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the engine's own stream).  Lets a host runtime order the
+ * engine's kernels with its own copies/events without extra synchronisation. */
+int fb_set_stream(fb_engine* e, void* cuda_stream);
 
 /* ---- knobs / introspection ---------------------------------------------- */
 enum {
@@ -105,8 +109,11 @@ enum {
                                   (tie/re-probe exact) kernel; testing aid    */
   FB_OPT_PROFILE = 2,          /* 1: bracket every kernel with CUDA events on
                                   the engine stream and accumulate fb_counters */
-  FB_OPT_QUERY_CHUNK = 3       /* queries per pipeline chunk (LUT scratch =
+  FB_OPT_QUERY_CHUNK = 3,      /* queries per pipeline chunk (LUT scratch =
                                   chunk * w * m * K * 4 bytes)                */
+  FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
+                                  one-CTA-per-query scan (default 64); smaller
+                                  ones use one CTA per (query, list)          */
 };
 int fb_set_option(fb_engine* e, int option, int64_t value);
 
@@ -118,6 +125,8 @@ typedef struct {
   int64_t kernel_launches;  /* kernels launched by this library                 */
   double ms_coarse, ms_lut, ms_scan, ms_finalize, ms_exact; /* FB_OPT_PROFILE   */
   int64_t n_scan_launches;
+  /* why queries took the general kernel (a query can have several reasons) */
+  int64_t exact_coarse_tie, exact_coarse_far, exact_few_rows, exact_scan_tie, exact_forced;
 } fb_counters;
 int fb_get_counters(fb_engine* e, fb_counters* out);  /* synchronizes the stream */
 int fb_reset_counters(fb_engine* e);

@@ -121,19 +121,36 @@ void fo_index_release(FoIndex* ix) {
  * get_w() (freddy.c:229).  The SQL `SELECT id, vector, coarse_id FROM fine
  * WHERE coarse_id IN (...)` (freddy.c:324-338) returns heap order = ascending
  * id; here that is a w-way merge of the probed lists by row number. */
-int fo_ivfadc_search(const FoIndex* ix, const float* query, int k, int w,
-                     FoTopKEntry* topk, int64_t* stats) {
+/* scratch the reference pallocs per call (freddy.c:296-311); the multi-threaded
+ * runner keeps one per thread so that 100+ threads do not serialise on mmap */
+typedef struct { unsigned char* blacklisted; FoTopKEntry* sel; float* residual; float* luts; int* cursor; } FoScratch;
+
+static int scratch_alloc(FoScratch* s, const FoIndex* ix, int w) {
+  s->blacklisted = malloc((size_t)(ix->C > 0 ? ix->C : 1));
+  s->sel = malloc(sizeof(FoTopKEntry) * (size_t)w);
+  s->residual = malloc(sizeof(float) * (size_t)ix->d);
+  s->luts = malloc(sizeof(float) * (size_t)w * ix->m * ix->K);
+  s->cursor = malloc(sizeof(int) * (size_t)w);
+  return (s->blacklisted && s->sel && s->residual && s->luts && s->cursor) ? 0 : -1;
+}
+static void scratch_free(FoScratch* s) {
+  free(s->blacklisted); free(s->sel); free(s->residual); free(s->luts); free(s->cursor);
+}
+
+static int ivfadc_search_ws(const FoIndex* ix, const float* query, int k, int w,
+                            FoTopKEntry* topk, int64_t* stats, FoScratch* ws) {
   const float MAX_DIST = 1000;                       /* ref: freddy.c:184 */
   const int d = ix->d, m = ix->m, K = ix->K, C = ix->C, sub = d / m;
   int rc = 0;
   int found = 0;                                     /* ref: :255 foundInstances */
   int64_t rows_scanned = 0, rounds = 0;
-  unsigned char* blacklisted = calloc((size_t)C, 1); /* ref: :256, index_utils.c:157-176 */
-  FoTopKEntry* sel = malloc(sizeof(FoTopKEntry) * (size_t)w);
-  float* residual = malloc(sizeof(float) * (size_t)d);
-  float* luts = malloc(sizeof(float) * (size_t)w * m * K);
-  int* cursor = malloc(sizeof(int) * (size_t)w);
+  unsigned char* blacklisted = ws->blacklisted;      /* ref: :256, index_utils.c:157-176 */
+  FoTopKEntry* sel = ws->sel;
+  float* residual = ws->residual;
+  float* luts = ws->luts;
+  int* cursor = ws->cursor;
   int n_blacklisted = 0;
+  memset(blacklisted, 0, (size_t)C);
 
   fo_init_topk(topk, k, MAX_DIST);                   /* ref: :258-259 */
   float max_dist = MAX_DIST;                         /* ref: :260 */
@@ -189,7 +206,15 @@ int fo_ivfadc_search(const FoIndex* ix, const float* query, int k, int w,
     found += n_rows;                                 /* ref: :377 */
   }
   if (stats) { stats[0] = rows_scanned; stats[1] = rounds; }
-  free(blacklisted); free(sel); free(residual); free(luts); free(cursor);
+  return rc;
+}
+
+int fo_ivfadc_search(const FoIndex* ix, const float* query, int k, int w,
+                     FoTopKEntry* topk, int64_t* stats) {
+  FoScratch ws;
+  if (scratch_alloc(&ws, ix, w)) return -3;
+  int rc = ivfadc_search_ws(ix, query, k, w, topk, stats, &ws);
+  scratch_free(&ws);
   return rc;
 }
 
@@ -308,13 +333,16 @@ typedef struct {
 static void* many_worker(void* p) {
   ManyArgs* a = p;
   a->rows = 0; a->rc = 0;
+  FoScratch ws;
+  if (scratch_alloc(&ws, a->ix, a->w)) { a->rc = -3; return NULL; }
   for (int q = a->begin; q < a->end; q++) {
     int64_t st[2];
-    int rc = fo_ivfadc_search(a->ix, a->queries + (size_t)q * a->ix->d, a->k, a->w,
-                              a->out + (size_t)q * a->k, st);
+    int rc = ivfadc_search_ws(a->ix, a->queries + (size_t)q * a->ix->d, a->k, a->w,
+                              a->out + (size_t)q * a->k, st, &ws);
     if (rc) a->rc = rc;
     a->rows += st[0];
   }
+  scratch_free(&ws);
   return NULL;
 }
 

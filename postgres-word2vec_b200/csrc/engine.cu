@@ -76,6 +76,7 @@ struct fb_engine {
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   std::string err;
 
   // index
@@ -101,6 +102,7 @@ struct fb_engine {
   bool force_exact = false;
   bool profile = false;
   int64_t query_chunk = 2048;
+  int qscan_min_queries = 64;
 
   // profiling
   struct Ev { cudaEvent_t a, b; int stage; };
@@ -336,12 +338,46 @@ int launch_scan(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, 
   }
 }
 
+template <int M, int KC>
+int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int nq, int w, const float* d_lut, int K, int KK, int k,
+                    float sentinel, int32_t* d_out_ids, float* d_out_dists) {
+  size_t smem = std::max<size_t>(2 * (size_t)tab.m * K * sizeof(float), kQScanWarps * 32 * sizeof(u64));
+  if (smem > e->smem_optin - 1024) return FB_ERR_UNSUPPORTED;  // caller falls back to one list per CTA
+  auto kern = adc_scan_query_kernel<M, KC>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab.dev(), e->probes.p, w, d_lut, K, KK, k, sentinel, e->qflags.p,
+                                               d_out_ids, d_out_dists, e->exact_list.p, e->small.p + 0,
+                                               e->counters64.p + 1, e->kth.p);
+  e->launches++;
+  e->n_scan_launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+// throughput form: one CTA per query, finalize fused
+int launch_qscan(fb_engine* e, const CodeTable& tab, int nq, int w, const float* d_lut, int K, int KK, int k,
+                 float sentinel, int32_t* oi, float* od) {
+  StageTimer t(e, ST_SCAN);
+#define FB_QS(M_, K_) return launch_qscan_mk<M_, K_>(e, tab, nq, w, d_lut, K, KK, k, sentinel, oi, od)
+  if (K == 1024) {
+    if (tab.m == 12) FB_QS(12, 1024);
+    if (tab.m == 8) FB_QS(8, 1024);
+    if (tab.m == 16) FB_QS(16, 1024);
+  } else if (K == 256) {
+    if (tab.m == 12) FB_QS(12, 256);
+    if (tab.m == 8) FB_QS(8, 256);
+    if (tab.m == 16) FB_QS(16, 256);
+  }
+  FB_QS(0, 0);
+#undef FB_QS
+}
+
 int launch_finalize(fb_engine* e, const CodeTable& tab, int lists_per_query, int KK, int k, int nq, float sentinel,
-                    const uint32_t* d_flags, int32_t* d_out_ids, float* d_out_dists) {
+                    bool has_input_flags, int32_t* d_out_ids, float* d_out_dists) {
   StageTimer t(e, ST_FINALIZE);
   const int warps = 8;
   finalize_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, e->stream>>>(
-      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, d_flags, d_out_ids, d_out_dists,
+      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, e->qflags.p, has_input_flags ? 1 : 0, d_out_ids, d_out_dists,
       e->exact_list.p, e->small.p + 0, e->counters64.p + 1, e->kth.p);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -406,8 +442,15 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, n * w, e->fine.list_len.p, e->counters64.p + 0);
       e->launches++;
       if ((rc = launch_lut(e, cb, dq, e->coarse.p, e->probes.p, w, n * w, e->lut.p))) return rc;
-      if ((rc = launch_scan(e, e->fine, e->probes.p, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
-      if ((rc = launch_finalize(e, e->fine, w * kScanWarps, KK, k, n, 1000.0f, e->qflags.p, oi, od))) return rc;
+      // throughput form (one CTA per query) when the chunk fills the GPU; else one CTA per (query, list)
+      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, n, w, e->lut.p, K, KK, k, 1000.0f, oi, od)
+                                       : FB_ERR_UNSUPPORTED;
+      if (rc == FB_ERR_UNSUPPORTED) {
+        if ((rc = launch_scan(e, e->fine, e->probes.p, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
+        if ((rc = launch_finalize(e, e->fine, w * kScanWarps, KK, k, n, 1000.0f, true, oi, od))) return rc;
+      } else if (rc) {
+        return rc;
+      }
     } else {
       iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
       int32_t cnt = n;
@@ -418,7 +461,8 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       StageTimer t(e, ST_EXACT);
       ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
           dq, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
-          e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p, oi, od, e->small.p + 2);
+          e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
+          fast ? e->qflags.p : nullptr, e->probes.p, e->lut.p, e->kth.p, oi, od, e->small.p + 2);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }
@@ -451,6 +495,7 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
   // bound the per-warp partial lists (chunk * nl * 8 * KK keys)
   while (chunk > 1 && (size_t)chunk * nl * kScanWarps * KK * sizeof(u64) > ((size_t)1 << 30)) chunk /= 2;
   FB_CUDA(e, e->lut.ensure((size_t)chunk * m * K));
+  FB_CUDA(e, e->qflags.ensure((size_t)chunk));
   FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
   FB_CUDA(e, e->kth.ensure((size_t)chunk));
   FB_CUDA(e, e->iota_lists.ensure((size_t)nl));
@@ -469,7 +514,7 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
     if ((rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, n, e->lut.p))) return rc;   // freddy.c:519-525
     if (fast && !e->force_exact) {
       if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, e->lut.p, K, KK, e->partial.p))) return rc;
-      if ((rc = launch_finalize(e, tab, nl * kScanWarps, KK, k, n, sentinel, nullptr, oi, od))) return rc;
+      if ((rc = launch_finalize(e, tab, nl * kScanWarps, KK, k, n, sentinel, false, oi, od))) return rc;
     } else {
       iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
       int32_t cnt = n;
@@ -479,7 +524,8 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
     {
       StageTimer t(e, ST_EXACT);
       pq_exact_kernel<<<2 * e->num_sms, kExactThreads, ex_smem, e->stream>>>(
-          tab.dev(), e->iota_lists.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1, oi, od);
+          tab.dev(), e->iota_lists.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1,
+          (fast && !e->force_exact) ? e->kth.p : nullptr, oi, od);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }
@@ -529,13 +575,14 @@ int fb_create(int device, fb_engine** out) {
   }
   e->num_sms = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
-  if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (err = e->small.ensure(4)) != cudaSuccess || (err = e->counters64.ensure(2)) != cudaSuccess) {
+  if ((err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (err = e->small.ensure(4)) != cudaSuccess || (err = e->counters64.ensure(8)) != cudaSuccess) {
     delete e;
     return fail(nullptr, FB_ERR_CUDA, "engine setup: %s", cudaGetErrorString(err));
   }
+  e->stream = e->own_stream;
   cudaMemset(e->small.p, 0, 4 * sizeof(int32_t));
-  cudaMemset(e->counters64.p, 0, 2 * sizeof(u64));
+  cudaMemset(e->counters64.p, 0, 8 * sizeof(u64));
   *out = e;
   return FB_OK;
 }
@@ -552,7 +599,7 @@ void fb_destroy(fb_engine* e) {
   e->lut.release(); e->exact_lut.release(); e->q_stage.release(); e->dist_stage.release();
   e->probes.release(); e->exact_list.release(); e->id_stage.release(); e->sel_rows.release();
   e->qflags.release(); e->partial.release(); e->kth.release(); e->small.release(); e->counters64.release();
-  cudaStreamDestroy(e->stream);
+  cudaStreamDestroy(e->own_stream);
   delete e;
 }
 
@@ -726,11 +773,23 @@ int fb_synchronize(fb_engine* e) {
   return check_error_flag(e);
 }
 
+int fb_set_stream(fb_engine* e, void* cuda_stream) {
+  if (!e) return FB_ERR_INVALID;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  drain_events(e);
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return FB_OK;
+}
+
 int fb_set_option(fb_engine* e, int option, int64_t value) {
   if (!e) return FB_ERR_INVALID;
   switch (option) {
     case FB_OPT_FORCE_EXACT_PATH: e->force_exact = value != 0; return FB_OK;
     case FB_OPT_PROFILE: e->profile = value != 0; return FB_OK;
+    case FB_OPT_QSCAN_MIN_QUERIES:
+      e->qscan_min_queries = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
+      return FB_OK;
     case FB_OPT_QUERY_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "query chunk must be >= 1");
       e->query_chunk = value;
@@ -744,13 +803,15 @@ int fb_get_counters(fb_engine* e, fb_counters* out) {
   FB_CUDA(e, cudaSetDevice(e->device));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
   drain_events(e);
-  u64 c64[2] = {0, 0};
+  u64 c64[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   FB_CUDA(e, cudaMemcpy(c64, e->counters64.p, sizeof c64, cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof *out);
   out->queries = e->queries_done;
   out->rows_scanned = (int64_t)c64[0] + e->host_rows;
   out->scan_bytes = out->rows_scanned * e->bytes_per_row;
   out->exact_path_queries = (int64_t)c64[1];
+  out->exact_coarse_tie = (int64_t)c64[2]; out->exact_coarse_far = (int64_t)c64[3];
+  out->exact_few_rows = (int64_t)c64[4]; out->exact_scan_tie = (int64_t)c64[5]; out->exact_forced = (int64_t)c64[6];
   out->kernel_launches = e->launches;
   out->ms_coarse = e->ms[ST_COARSE]; out->ms_lut = e->ms[ST_LUT]; out->ms_scan = e->ms[ST_SCAN];
   out->ms_finalize = e->ms[ST_FINALIZE]; out->ms_exact = e->ms[ST_EXACT];
@@ -763,7 +824,7 @@ int fb_reset_counters(fb_engine* e) {
   FB_CUDA(e, cudaSetDevice(e->device));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
   drain_events(e);
-  FB_CUDA(e, cudaMemset(e->counters64.p, 0, 2 * sizeof(u64)));
+  FB_CUDA(e, cudaMemset(e->counters64.p, 0, 8 * sizeof(u64)));
   for (double& v : e->ms) v = 0;
   e->launches = 0; e->queries_done = 0; e->n_scan_launches = 0; e->host_rows = 0;
   return FB_OK;

@@ -88,9 +88,11 @@ __device__ __forceinline__ void radix_pick(ExactShared& sh, uint32_t& prefix, in
 
 // One pass of the reference's row loop (freddy.c:347-373 and its siblings) over
 // n_pairs (list, LUT) pairs, continuing from the top-k state in sh.tk_*.
+// If the k-th smallest distance v is already known (the streaming pass computed it:
+// finalize_kernel's kth_key), pass have_v = true and skip the radix select.
 __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pairs,
                             const float* __restrict__ luts, size_t lut_stride, int K, int k,
-                            ExactShared& sh) {
+                            ExactShared& sh, bool have_v = false, uint32_t v_known = 0) {
   const int tid = threadIdx.x;
   long long n_rows = 0;
   for (int j = 0; j < n_pairs; j++) n_rows += tab.list_len[lists[j]];
@@ -100,7 +102,9 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
 
   // ---- v = k-th smallest distance bits among carried entries and rows ----
   uint32_t vbits = 0xFFFFFFFFu;
-  if (total >= k) {
+  if (have_v) {
+    vbits = v_known;
+  } else if (total >= k) {
     uint32_t prefix = 0;
     int remaining = k;
     for (int pass = 0; pass < 4; pass++) {
@@ -253,6 +257,10 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     const int32_t* __restrict__ exact_list, const int32_t* __restrict__ exact_count,
                     int32_t* __restrict__ work_counter,
                     float* __restrict__ lut_scratch,     // [gridDim.x][w][m*K]
+                    // products of the streaming pass, reusable when the only reason is a scan tie:
+                    const uint32_t* __restrict__ qflags, const int32_t* __restrict__ probes,   // [nq][w]
+                    const float* __restrict__ chunk_luts,                                      // [nq][w][m*K]
+                    const u64* __restrict__ kth_key,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                     int32_t* __restrict__ error_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,6 +289,18 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
     for (int i = tid; i < C; i += kExactThreads) black[i] = 0;
     for (int i = tid; i < k; i += kExactThreads) { sh.tk_d[i] = MAX_DIST; sh.tk_t[i] = kNoRow; }  // freddy.c:258-260
     __syncthreads();
+    const uint32_t why = qflags ? qflags[q] : kWhyForced;
+    if ((why & ~(kFlagExact | kWhyScanTie)) == 0) {
+      // Only a distance tie across the k-th place: the coarse selection, the LUTs and the
+      // k-th distance of the streaming pass stand (one round, freddy.c:262 exits after it);
+      // replay the tied neighbourhood literally.
+      for (int j = tid; j < w; j += kExactThreads) sel[j] = probes[(size_t)q * w + j];
+      __syncthreads();
+      exact_round(tab, sel, w, chunk_luts + (size_t)q * w * lut_stride, lut_stride, K, k, sh, true,
+                  key_dbits(kth_key[q]));
+      exact_write_result(sh, k, tab.ids, out_ids + (size_t)q * k, out_dists + (size_t)q * k);
+      continue;
+    }
     long long found = 0;
     int n_black = 0;
     bool failed = false;
@@ -354,6 +374,7 @@ pq_exact_kernel(CodeTableDev tab, const int32_t* __restrict__ all_lists,  // [n_
                 const float* __restrict__ lut, int K, int k, float sentinel,
                 const int32_t* __restrict__ exact_list, const int32_t* __restrict__ exact_count,
                 int32_t* __restrict__ work_counter,
+                const u64* __restrict__ kth_key,          // from the streaming pass, or nullptr
                 int32_t* __restrict__ out_ids, float* __restrict__ out_dists) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ExactShared sh = exact_carve(smem_raw, k);
@@ -370,7 +391,8 @@ pq_exact_kernel(CodeTableDev tab, const int32_t* __restrict__ all_lists,  // [n_
     for (int i = tid; i < k; i += kExactThreads) { sh.tk_d[i] = sentinel; sh.tk_t[i] = kNoRow; }
     __syncthreads();
     // every pair uses the same LUT: stride 0
-    exact_round(tab, all_lists, tab.n_lists, lut + (size_t)q * lut_stride, 0, K, k, sh);
+    exact_round(tab, all_lists, tab.n_lists, lut + (size_t)q * lut_stride, 0, K, k, sh, kth_key != nullptr,
+                kth_key ? key_dbits(kth_key[q]) : 0u);
     exact_write_result(sh, k, tab.ids, out_ids + (size_t)q * k, out_dists + (size_t)q * k);
   }
 }

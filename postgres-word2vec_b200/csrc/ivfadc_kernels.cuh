@@ -37,6 +37,8 @@ struct CodeTableDev {
 };
 
 constexpr uint32_t kFlagExact = 1u;     // needs the general kernel
+// why (statistics only)
+constexpr uint32_t kWhyCoarseTie = 2u, kWhyCoarseFar = 4u, kWhyFewRows = 8u, kWhyScanTie = 16u, kWhyForced = 32u;
 constexpr int kCoarseThreads = 256;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / kWarp;
@@ -76,25 +78,33 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
 #pragma unroll
     for (int qq = 0; qq < QT; qq++) acc[qq] = 0.0f;
     const float* col = coarseT + c;
-#pragma unroll 2
-    for (int i = 0; i < d; i++) {
-      float cv = __ldg(col + (size_t)i * Cs);
-      if (QT % 4 == 0) {
-        const float4* qrow = reinterpret_cast<const float4*>(qs + i * QT);
+    constexpr int PF = 4;  // centroid values in flight per thread
+    for (int i0 = 0; i0 < d; i0 += PF) {
+      float cvs[PF];
 #pragma unroll
-        for (int v = 0; v < QT / 4; v++) {
-          float4 qv = qrow[v];
-          float t0 = xsub(qv.x, cv), t1 = xsub(qv.y, cv), t2 = xsub(qv.z, cv), t3 = xsub(qv.w, cv);
-          acc[4 * v + 0] = xadd(acc[4 * v + 0], xmul(t0, t0));
-          acc[4 * v + 1] = xadd(acc[4 * v + 1], xmul(t1, t1));
-          acc[4 * v + 2] = xadd(acc[4 * v + 2], xmul(t2, t2));
-          acc[4 * v + 3] = xadd(acc[4 * v + 3], xmul(t3, t3));
-        }
-      } else {
+      for (int u = 0; u < PF; u++) cvs[u] = (i0 + u < d) ? __ldg(col + (size_t)(i0 + u) * Cs) : 0.0f;
 #pragma unroll
-        for (int qq = 0; qq < QT; qq++) {
-          float t = xsub(qs[i * QT + qq], cv);
-          acc[qq] = xadd(acc[qq], xmul(t, t));
+      for (int u = 0; u < PF; u++) {
+        const int i = i0 + u;
+        if (i >= d) break;
+        const float cv = cvs[u];
+        if (QT % 4 == 0) {
+          const float4* qrow = reinterpret_cast<const float4*>(qs + i * QT);
+#pragma unroll
+          for (int v = 0; v < QT / 4; v++) {
+            float4 qv = qrow[v];
+            float t0 = xsub(qv.x, cv), t1 = xsub(qv.y, cv), t2 = xsub(qv.z, cv), t3 = xsub(qv.w, cv);
+            acc[4 * v + 0] = xadd(acc[4 * v + 0], xmul(t0, t0));
+            acc[4 * v + 1] = xadd(acc[4 * v + 1], xmul(t1, t1));
+            acc[4 * v + 2] = xadd(acc[4 * v + 2], xmul(t2, t2));
+            acc[4 * v + 3] = xadd(acc[4 * v + 3], xmul(t3, t3));
+          }
+        } else {
+#pragma unroll
+          for (int qq = 0; qq < QT; qq++) {
+            float t = xsub(qs[i * QT + qq], cv);
+            acc[qq] = xadd(acc[qq], xmul(t, t));
+          }
         }
       }
     }
@@ -123,12 +133,12 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
       }
     }
     // lanes 0..w-1: the w nearest lists; lane w: the runner-up
-    uint32_t flags = force_exact ? kFlagExact : 0u;
+    uint32_t flags = force_exact ? (kFlagExact | kWhyForced) : 0u;
     u64 kw = shfl_u64(mine, w), kw1 = shfl_u64(mine, w - 1);
     // a tie across the w-th place makes the kept set order dependent
-    if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact;
+    if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact | kWhyCoarseTie;
     // sentinel quirk of the reference: a selected distance >= 100 is undefined
-    if (key_dist(kw1) >= 100.0f) flags |= kFlagExact;
+    if (key_dist(kw1) >= 100.0f) flags |= kFlagExact | kWhyCoarseFar;
     int len = 0;
     if (lane < w) {
       int cid = (int)key_t(mine);
@@ -137,7 +147,7 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) len += __shfl_xor_sync(0xffffffffu, len, s);
-    if (len < k) flags |= kFlagExact;  // re-probe loop (freddy.c:262) needed
+    if (len < k) flags |= kFlagExact | kWhyFewRows;  // re-probe loop (freddy.c:262) needed
     if (lane == 0) qflags[q] = flags;
   }
 }
@@ -203,11 +213,18 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       for (int jj = 0; jj < W; jj++) acc[jj] = 0.0f;
 #pragma unroll 5
       for (int i = 0; i < sub; i++) {
-        float cv = cbs[(size_t)i * TK + tid];
-        const float* rrow = rs + i * WS;
+        const float cv = cbs[(size_t)i * TK + tid];
+        // the W residuals of this dimension: broadcast 16-byte shared-memory reads
+        const float4* rrow4 = reinterpret_cast<const float4*>(rs + i * WS);
+        float rv[WS];
+#pragma unroll
+        for (int v = 0; v < WS / 4; v++) {
+          float4 t4 = rrow4[v];
+          rv[4 * v + 0] = t4.x; rv[4 * v + 1] = t4.y; rv[4 * v + 2] = t4.z; rv[4 * v + 3] = t4.w;
+        }
 #pragma unroll
         for (int jj = 0; jj < W; jj++) {
-          float t = xsub(rrow[jj], cv);
+          float t = xsub(rv[jj], cv);
           acc[jj] = xadd(acc[jj], xmul(t, t));
         }
       }
@@ -218,6 +235,44 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// ADC distance of the row owned by this lane in one 32-row block, LUT in shared
+// memory.  M > 0 / KC > 0: compile-time m / K (unrolled, immediate LUT offsets).
+// ---------------------------------------------------------------------------
+template <int M, int KC>
+__device__ __forceinline__ float adc_block_row(const uint2* __restrict__ up, const char* lut_base,
+                                               int m_rt, int U_rt, uint32_t row_stride_rt) {
+  float acc = 0.0f;
+  if (M > 0) {
+    constexpr int UU = (M + 3) / 4;
+    const uint32_t rs = (KC > 0) ? (uint32_t)KC * 4u : row_stride_rt;
+    uint2 v[UU > 0 ? UU : 1];
+#pragma unroll
+    for (int u = 0; u < UU; u++) v[u] = __ldg(up + u * 32);
+#pragma unroll
+    for (int u = 0; u < UU; u++) {
+      const uint32_t wlo = v[u].x, whi = v[u].y;
+      const char* base = lut_base + (size_t)(4 * u) * rs;
+      if (4 * u + 0 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
+      if (4 * u + 1 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + rs + (wlo >> 16)));
+      if (4 * u + 2 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * rs + (whi & 0xFFFFu)));
+      if (4 * u + 3 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * rs + (whi >> 16)));
+    }
+  } else {
+    for (int u = 0; u < U_rt; u++) {
+      const uint2 vv = __ldg(up + u * 32);
+      const uint32_t wlo = vv.x, whi = vv.y;
+      const char* base = lut_base + (size_t)(4 * u) * row_stride_rt;
+      const int p = 4 * u;
+      if (p + 0 < m_rt) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
+      if (p + 1 < m_rt) acc = xadd(acc, *reinterpret_cast<const float*>(base + row_stride_rt + (wlo >> 16)));
+      if (p + 2 < m_rt) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * row_stride_rt + (whi & 0xFFFFu)));
+      if (p + 3 < m_rt) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * row_stride_rt + (whi >> 16)));
+    }
+  }
+  return acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -269,32 +324,7 @@ adc_scan_kernel(CodeTableDev tab,
 
   for (int b = warp; b < nblk; b += kScanWarps) {
     const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
-    float acc = 0.0f;
-    if (M > 0) {
-      uint2 v[(M > 0) ? (M + 3) / 4 : 1];
-#pragma unroll
-      for (int u = 0; u < (M + 3) / 4; u++) v[u] = __ldg(up + u * 32);
-#pragma unroll
-      for (int u = 0; u < (M + 3) / 4; u++) {
-        uint32_t wlo = v[u].x, whi = v[u].y;
-        const char* base = lut_bytes_base + (size_t)(4 * u) * row_stride;
-        if (4 * u + 0 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
-        if (4 * u + 1 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + row_stride + (wlo >> 16)));
-        if (4 * u + 2 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * row_stride + (whi & 0xFFFFu)));
-        if (4 * u + 3 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * row_stride + (whi >> 16)));
-      }
-    } else {
-      for (int u = 0; u < U; u++) {
-        uint2 vv = __ldg(up + u * 32);
-        uint32_t wlo = vv.x, whi = vv.y;
-        const char* base = lut_bytes_base + (size_t)(4 * u) * row_stride;
-        int p = 4 * u;
-        if (p + 0 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
-        if (p + 1 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + row_stride + (wlo >> 16)));
-        if (p + 2 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * row_stride + (whi & 0xFFFFu)));
-        if (p + 3 < m) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * row_stride + (whi >> 16)));
-      }
-    }
+    const float acc = adc_block_row<M, 0>(up, lut_bytes_base, m, U, row_stride);
     const bool valid = (b * 32 + lane) < len;
     const uint32_t dbits = __float_as_uint(acc);
     bool cand = valid && (dbits <= thr_bits);
@@ -314,6 +344,143 @@ adc_scan_kernel(CodeTableDev tab,
   if (lane < KK) partial[((size_t)task * kScanWarps + warp) * KK + lane] = mine;
 }
 
+// Write the k results of one query in the reference's order (ascending distance,
+// later arrival first among equal distances, index_utils.c:19-33) from an ascending
+// key list held one key per lane, or flag the query for the general kernel when a
+// distance tie straddles the k-th place.  Called by one full warp.
+__device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int k, uint32_t flags,
+                                               const int32_t* __restrict__ ids, float sentinel,
+                                               uint32_t* __restrict__ qflags,
+                                               int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
+                                               int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
+                                               u64* __restrict__ exact_total, u64* __restrict__ kth_key) {
+  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
+  if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) flags |= kFlagExact | kWhyScanTie;
+  if (lane == 0) { kth_key[q] = kk1; qflags[q] = flags; }
+  if (flags & kFlagExact) {
+    if (lane == 0) {
+      exact_list[atomicAdd(exact_count, 1)] = q;
+      atomicAdd(exact_total, 1ull);
+      for (int b = 1; b <= 5; b++)
+        if (flags & (1u << b)) atomicAdd(exact_total + b, 1ull);
+    }
+    return;
+  }
+  const uint32_t dbits = key_dbits(mine);
+  const uint32_t prev = __shfl_up_sync(0xffffffffu, dbits, 1);
+  const bool in_range = lane < k;
+  const bool start = in_range && (lane == 0 || dbits != prev);
+  const unsigned starts = __ballot_sync(0xffffffffu, start);
+  if (in_range) {
+    const unsigned below = starts & (0xffffffffu >> (31 - lane));
+    const int s = 31 - __clz(below);
+    const unsigned above = starts & ~(0xffffffffu >> (31 - lane));
+    const int e = above ? (__ffs(above) - 2) : (k - 1);
+    const int outpos = s + (e - lane);
+    const bool filled = mine != kKeyInf;
+    out_ids[(size_t)q * k + outpos] = filled ? ids[key_t(mine)] : -1;
+    out_dists[(size_t)q * k + outpos] = filled ? key_dist(mine) : sentinel;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// HOT(3)+(4), throughput form: one CTA = one query.  The CTA walks the query's w
+// probed lists; LUT j+1 streams into the second shared-memory buffer (bulk async
+// copy + mbarrier) while list j is scanned, so a warp's top-(k+1) key list and the
+// CTA-wide admission threshold persist across all w lists (far fewer insertions
+// than one list at a time), and the merge + reference ordering of finalize_kernel
+// is fused at the end.
+// ---------------------------------------------------------------------------
+constexpr int kQScanThreads = 512;
+constexpr int kQScanWarps = kQScanThreads / kWarp;
+
+template <int M, int KC>
+__global__ void __launch_bounds__(kQScanThreads, 2)
+adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int w,
+                      const float* __restrict__ lut, int K, int KK, int k, float sentinel,
+                      uint32_t* __restrict__ qflags,
+                      int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
+                      int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
+                      u64* __restrict__ exact_total, u64* __restrict__ kth_key) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t s_thr;
+  const int m = (M > 0) ? M : tab.m;
+  const int U = (M > 0) ? (M + 3) / 4 : tab.U;
+  const int Kc = (KC > 0) ? KC : K;
+  const size_t lut_floats = (size_t)m * Kc;
+  const uint32_t lut_bytes = (uint32_t)(lut_floats * sizeof(float));
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* qlut = lut + (size_t)q * w * lut_floats;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+    s_thr = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], lut_bytes);
+    bulk_g2s(smem_raw, qlut, lut_bytes, &bar[0]);
+    if (w > 1) {
+      mbar_expect_tx(&bar[1], lut_bytes);
+      bulk_g2s(smem_raw + lut_bytes, qlut + lut_floats, lut_bytes, &bar[1]);
+    }
+  }
+
+  u64 mine = kKeyInf;
+  uint32_t my_thr = 0xFFFFFFFFu;
+  const uint32_t row_stride = (uint32_t)Kc * 4u;
+
+  for (int j = 0; j < w; j++) {
+    const int list = probes[(size_t)q * w + j];
+    const int blk0 = tab.list_blk[list];
+    const int len = tab.list_len[list];
+    const int nblk = (len + 31) >> 5;
+    mbar_wait(&bar[j & 1], (uint32_t)((j >> 1) & 1));
+    const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)(j & 1) * lut_bytes;
+    for (int b = warp; b < nblk; b += kQScanWarps) {
+      const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
+      const float acc = adc_block_row<M, KC>(up, lut_base, m, U, row_stride);
+      const uint32_t thr = min(my_thr, *reinterpret_cast<volatile uint32_t*>(&s_thr));
+      const uint32_t dbits = __float_as_uint(acc);
+      const bool cand = ((b * 32 + lane) < len) && (dbits <= thr);
+      unsigned mask = __ballot_sync(0xffffffffu, cand);
+      if (mask) {
+        u64 key = kKeyInf;
+        if (cand) key = make_key(acc, (uint32_t)tab.rowno[(size_t)(blk0 + b) * 32 + lane]);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          warp_list_insert(mine, shfl_u64(key, src), lane);
+          mask &= mask - 1;
+        }
+        my_thr = key_dbits(shfl_u64(mine, KK - 1));
+        if (lane == 0 && my_thr < thr) atomicMin(&s_thr, my_thr);
+      }
+    }
+    __syncthreads();  // every warp is done with buf[j & 1]
+    if (tid == 0 && j + 2 < w) {
+      mbar_expect_tx(&bar[j & 1], lut_bytes);
+      bulk_g2s(smem_raw + (size_t)(j & 1) * lut_bytes, qlut + (size_t)(j + 2) * lut_floats, lut_bytes, &bar[j & 1]);
+    }
+  }
+  // merge the warps' lists (all LUT loads have landed and been consumed: reuse buffer 0)
+  u64* stage = reinterpret_cast<u64*>(smem_raw);
+  stage[warp * 32 + lane] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    for (int l = 1; l < kQScanWarps; l++) {
+      const u64 other = stage[l * 32 + lane];
+      if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
+      warp_list_merge(mine, other, lane);
+    }
+    warp_emit_topk(mine, lane, q, k, qflags[q], tab.ids, sentinel, qflags, out_ids, out_dists,
+                   exact_list, exact_count, exact_total, kth_key);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // finalize: one warp per query merges its n_lists per-warp key lists, checks the
 // tie condition, and writes the k results in the reference's order: ascending
@@ -322,7 +489,7 @@ adc_scan_kernel(CodeTableDev tab,
 __global__ void __launch_bounds__(256)
 finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, int k,
                 int nq, const int32_t* __restrict__ ids, float sentinel,
-                const uint32_t* __restrict__ qflags_in,   // may be nullptr
+                uint32_t* __restrict__ qflags, int has_input_flags,   // in (from the coarse kernel) / out
                 int32_t* __restrict__ out_ids, float* __restrict__ out_dists,   // [nq][k]
                 int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
                 u64* __restrict__ exact_total,            // cumulative statistic
@@ -337,33 +504,9 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
     if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
     warp_list_merge(mine, other, lane);
   }
-  uint32_t flags = qflags_in ? qflags_in[q] : 0u;
-  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
-  if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) flags |= kFlagExact;  // tie across the k-th place
-  if (lane == 0) kth_key[q] = kk1;
-  if (flags & kFlagExact) {
-    if (lane == 0) {
-      exact_list[atomicAdd(exact_count, 1)] = q;
-      atomicAdd(exact_total, 1ull);
-    }
-    return;
-  }
-  // reference order inside runs of equal distance: later arrival first
-  const uint32_t dbits = key_dbits(mine);
-  const uint32_t prev = __shfl_up_sync(0xffffffffu, dbits, 1);
-  const bool in_range = lane < k;
-  const bool start = in_range && (lane == 0 || dbits != prev);
-  const unsigned starts = __ballot_sync(0xffffffffu, start);
-  if (in_range) {
-    unsigned below = starts & (0xffffffffu >> (31 - lane));  // start bits at or below this lane
-    int s = 31 - __clz(below);
-    unsigned above = starts & ~(0xffffffffu >> (31 - lane));
-    int e = above ? (__ffs(above) - 2) : (k - 1);
-    int outpos = s + (e - lane);
-    bool filled = mine != kKeyInf;
-    out_ids[(size_t)q * k + outpos] = filled ? ids[key_t(mine)] : -1;
-    out_dists[(size_t)q * k + outpos] = filled ? key_dist(mine) : sentinel;
-  }
+  const uint32_t flags = has_input_flags ? qflags[q] : 0u;
+  warp_emit_topk(mine, lane, q, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
+                 exact_total, kth_key);
 }
 
 }  // namespace fb

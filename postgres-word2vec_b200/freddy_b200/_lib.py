@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfreddy_b200.so")
 FB_OK = 0
 FB_ERR_INVALID, FB_ERR_CUDA, FB_ERR_UNSUPPORTED, FB_ERR_REFERENCE_UB = -1, -2, -3, -4
 FB_CB_RESIDUAL, FB_CB_PQ = 0, 1
-FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK = 1, 2, 3
+FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK, FB_OPT_QSCAN_MIN_QUERIES = 1, 2, 3, 4
 
 
 class Counters(C.Structure):
@@ -21,6 +21,8 @@ class Counters(C.Structure):
         ("exact_path_queries", C.c_int64), ("kernel_launches", C.c_int64),
         ("ms_coarse", C.c_double), ("ms_lut", C.c_double), ("ms_scan", C.c_double),
         ("ms_finalize", C.c_double), ("ms_exact", C.c_double), ("n_scan_launches", C.c_int64),
+        ("exact_coarse_tie", C.c_int64), ("exact_coarse_far", C.c_int64), ("exact_few_rows", C.c_int64),
+        ("exact_scan_tie", C.c_int64), ("exact_forced", C.c_int64),
     ]
 
 
@@ -39,6 +41,7 @@ SIGNATURES = {
     "fb_pq_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search_in_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "fb_synchronize": (C.c_int, [_P]),
+    "fb_set_stream": (C.c_int, [_P, _P]),
     "fb_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "fb_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "fb_reset_counters": (C.c_int, [_P]),

@@ -122,6 +122,10 @@ class Engine:
                                                     1 if use_target_lists else 0, _ptr(ids), _ptr(dists)))
         return ids, dists
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream) or 0/None"""
+        self._check(self._lib.fb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
     def synchronize(self):
         self._check(self._lib.fb_synchronize(self._h))
 

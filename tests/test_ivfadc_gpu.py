@@ -16,24 +16,28 @@ def eng():
     e.close()
 
 
-def _run_both(eng, oracle_mod, ix, q, k, w, force_exact=False):
+def _run_both(eng, oracle_mod, ix, q, k, w, force_exact=False, qscan_min=64):
+    """qscan_min: 0 = always the one-CTA-per-query scan, 1<<30 = always one CTA per (query, list)"""
     from freddy_b200 import _lib
     eng.load_ivfadc_index(ix)
     eng.set_option(_lib.FB_OPT_FORCE_EXACT_PATH, 1 if force_exact else 0)
+    eng.set_option(_lib.FB_OPT_QSCAN_MIN_QUERIES, qscan_min)
     eng.reset_counters()
     ids, d = eng.ivfadc_search(q, k, w)
     eng.set_option(_lib.FB_OPT_FORCE_EXACT_PATH, 0)
+    eng.set_option(_lib.FB_OPT_QSCAN_MIN_QUERIES, 64)
     oi = oracle_mod.OracleIndex(ix)
     eids, ed, rc, rows = oi.ivfadc_search(q, k, w, threads=4)
     assert rc == 0
     return ids, d, eids, ed, rows
 
 
+@pytest.mark.parametrize("qscan_min", [0, 1 << 30])
 @pytest.mark.parametrize("k,w", [(5, 4), (1, 1), (10, 3), (31, 8)])
-def test_parity_small(eng, oracle_mod, k, w):
+def test_parity_small(eng, oracle_mod, k, w, qscan_min):
     ix = small_index()
     q = queries_from(ix, 300)
-    ids, d, eids, ed, rows = _run_both(eng, oracle_mod, ix, q, k, w)
+    ids, d, eids, ed, rows = _run_both(eng, oracle_mod, ix, q, k, w, qscan_min=qscan_min)
     assert_same_topk(ids, d, eids, ed, f"k={k} w={w}")
     c = eng.counters()
     assert c["rows_scanned"] == rows
@@ -61,14 +65,15 @@ def test_parity_noisy_queries_and_chunks(eng, oracle_mod):
 
 
 def test_ties_everywhere(eng, oracle_mod):
-    """K=4 codes over 2-d sub-vectors: thousands of rows share identical code
-    vectors, so distance ties straddle the k-th place all the time."""
-    ix = small_index(N=6000, d=24, m=12, K=4, C=8, seed=3, n_clusters=5)
-    q = queries_from(ix, 200, seed=9)
-    for k, w in ((5, 2), (3, 8), (20, 3)):
-        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, k, w)
-        assert_same_topk(ids, d, eids, ed, f"ties k={k} w={w}")
-        assert eng.counters()["exact_path_queries"] > 0
+    """m=2 (or 4) positions x K=4 codes: every list holds only 16 (256) distinct
+    code vectors, so distance ties straddle the k-th place all the time."""
+    for (d, m) in ((8, 2), (16, 4)):
+        ix = small_index(N=6000, d=d, m=m, K=4, C=8, seed=3, n_clusters=5)
+        q = queries_from(ix, 200, seed=9)
+        for k, w in ((5, 2), (3, 8), (20, 3)):
+            ids, d_, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, k, w, qscan_min=(1 << 30) if k == 3 else 0)
+            assert_same_topk(ids, d_, eids, ed, f"ties m={m} k={k} w={w}")
+            assert eng.counters()["exact_path_queries"] > 0
 
 
 def test_reprobe_loop(eng, oracle_mod):
@@ -100,8 +105,9 @@ def test_readme_shape(eng, oracle_mod):
     """d=300, m=12, K=1024 (README.md:125-128) on a 60k-row table"""
     ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)
     q = queries_from(ix, 150, seed=6)
-    ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 10)
-    assert_same_topk(ids, d, eids, ed, "d=300 K=1024")
+    for qmin in (0, 1 << 30):
+        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 10, qscan_min=qmin)
+        assert_same_topk(ids, d, eids, ed, f"d=300 K=1024 qscan_min={qmin}")
 
 
 def test_edge_cases(eng, oracle_mod):
