@@ -52,6 +52,8 @@ def parse():
                     help="within-cluster noise of the synthetic vectors (per dimension, centres ~ N(0,I)); "
                          "1.0 keeps PQ codes diverse like real word embeddings, 0.3 collapses clusters onto "
                          "identical codes (25%% duplicate rows) and sends a quarter of the queries down the tie path")
+    ap.add_argument("--zipf", type=float, default=0.35,
+                    help="cluster-size skew of the synthetic vectors: size ~ 1/(10+rank)^zipf")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -59,7 +61,7 @@ def parse():
 
 def workload_name(a):
     return (f"k_nearest_neighbour_ivfadc throughput form: {a.batch} queries/GPU/step, k={a.k}, w={a.w}, "
-            f"synthetic N={a.n} d={a.d} m={a.m} K={a.K} C={a.C} (1000 Zipf-sized Gaussian clusters, sigma={a.sigma}, L2-normalised)")
+            f"synthetic N={a.n} d={a.d} m={a.m} K={a.K} C={a.C} (1000 Zipf-sized Gaussian clusters, sigma={a.sigma}, zipf={a.zipf}, L2-normalised)")
 
 
 def peaks():
@@ -118,7 +120,7 @@ def build_index(a, device):
     from freddy_b200.index_build import make_synthetic_index
     t0 = time.time()
     ix = make_synthetic_index(a.n, d=a.d, m=a.m, K=a.K, C=a.C, n_train=min(100_000, a.n), n_clusters=1000,
-                              sigma=a.sigma, kmeans_iters=10, seed=1234, device=device, keep_vectors=True)
+                              sigma=a.sigma, zipf=a.zipf, kmeans_iters=10, seed=1234, device=device, keep_vectors=True)
     return ix, time.time() - t0
 
 
@@ -314,6 +316,7 @@ def main():
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": workload_name(a), "parallelism": f"replicated index, queries sharded x{world}",
                           "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1),
+                          "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]),
                           "exact_path_queries_per_step": exact_q / a.steps,
                           "exact_path_reasons_per_step": {r: c["exact_" + r] / a.steps for r in
                                                           ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")}},

@@ -284,7 +284,7 @@ int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float
   if ((size_t)sub * TK * sizeof(float) > budget) return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
   const int tiles = (K + TK - 1) / TK;
   constexpr int WS = (W + 3) & ~3;
-  size_t smem = ((size_t)sub * TK + (size_t)sub * WS) * sizeof(float);
+  size_t smem = ((size_t)sub * TK + 2 * (size_t)sub * WS) * sizeof(float);
   auto kern = lut_build_kernel<W>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int groups = std::max(1, e->num_sms / std::max(1, m * tiles));
@@ -427,8 +427,10 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   const size_t exact_budget = (size_t)1 << 30;
   while (exact_ctas > 1 && (size_t)exact_ctas * lut_per_query * sizeof(float) > exact_budget) exact_ctas /= 2;
   if (!fast || true) FB_CUDA(e, e->exact_lut.ensure((size_t)exact_ctas * lut_per_query));
-  const size_t ex_smem = exact_smem_bytes(e, w);
+  size_t ex_smem = exact_smem_bytes(e, w);
   if (ex_smem > e->smem_optin) return fail(e, FB_ERR_UNSUPPORTED, "general kernel needs %zu bytes of shared memory", ex_smem);
+  int ex_stage = 0;  // LUT staging buffer when it fits next to the rest
+  if (ex_smem + (size_t)m * K * sizeof(float) <= e->smem_optin) { ex_stage = m * K; ex_smem += (size_t)m * K * sizeof(float); }
   FB_CUDA(e, cudaFuncSetAttribute(ivfadc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
 
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -462,7 +464,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
           dq, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
           e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
-          fast ? e->qflags.p : nullptr, e->probes.p, e->lut.p, e->kth.p, oi, od, e->small.p + 2);
+          fast ? e->qflags.p : nullptr, e->probes.p, e->lut.p, e->kth.p, oi, od, e->small.p + 2, ex_stage);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }
@@ -502,7 +504,9 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
   if (fast) FB_CUDA(e, e->partial.ensure((size_t)chunk * nl * kScanWarps * KK));
   iota_kernel<<<(nl + 255) / 256, 256, 0, e->stream>>>(e->iota_lists.p, nl);
   e->launches++;
-  const size_t ex_smem = kExactFixedSmem;
+  size_t ex_smem = kExactFixedSmem;
+  int ex_stage = 0;
+  if (ex_smem + (size_t)m * K * sizeof(float) <= e->smem_optin) { ex_stage = m * K; ex_smem += (size_t)m * K * sizeof(float); }
   FB_CUDA(e, cudaFuncSetAttribute(pq_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
   int rc;
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -525,7 +529,7 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
       StageTimer t(e, ST_EXACT);
       pq_exact_kernel<<<2 * e->num_sms, kExactThreads, ex_smem, e->stream>>>(
           tab.dev(), e->iota_lists.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1,
-          (fast && !e->force_exact) ? e->kth.p : nullptr, oi, od);
+          (fast && !e->force_exact) ? e->kth.p : nullptr, oi, od, ex_stage);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }

@@ -38,6 +38,7 @@ struct ExactShared {
   u64* sbuf;        // [kExactSortN] merged, sorted by arrival
   unsigned* hist;   // [256]
   int* misc;        // [8]
+  float* slut;      // [m*K] staging for the LUT of the list being scanned, or nullptr (then global reads)
 };
 
 // ADC distance of one row (codes pre-scaled by 4) against a LUT in global memory:
@@ -86,6 +87,17 @@ __device__ __forceinline__ void radix_pick(ExactShared& sh, uint32_t& prefix, in
   __syncthreads();
 }
 
+// copy the LUT of pair j into shared memory (all threads) when a staging buffer exists
+#define FB_EXACT_LUT(j)                                                                         \
+  const float* lut = luts + (size_t)(j) * lut_stride;                                           \
+  if (sh.slut != nullptr) {                                                                     \
+    __syncthreads();                                                                            \
+    for (int x_ = tid; x_ < lut_n4; x_ += kExactThreads)                                        \
+      reinterpret_cast<float4*>(sh.slut)[x_] = reinterpret_cast<const float4*>(lut)[x_];        \
+    __syncthreads();                                                                            \
+    lut = sh.slut;                                                                              \
+  }
+
 // One pass of the reference's row loop (freddy.c:347-373 and its siblings) over
 // n_pairs (list, LUT) pairs, continuing from the top-k state in sh.tk_*.
 // If the k-th smallest distance v is already known (the streaming pass computed it:
@@ -94,6 +106,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
                             const float* __restrict__ luts, size_t lut_stride, int K, int k,
                             ExactShared& sh, bool have_v = false, uint32_t v_known = 0) {
   const int tid = threadIdx.x;
+  const int lut_n4 = tab.m * K / 4;
   long long n_rows = 0;
   for (int j = 0; j < n_pairs; j++) n_rows += tab.list_len[lists[j]];
   int carried = 0;
@@ -120,7 +133,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
       }
       for (int j = 0; j < n_pairs; j++) {
         const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
-        const float* lut = luts + (size_t)j * lut_stride;
+        FB_EXACT_LUT(j)
         for (int r = tid; r < len; r += kExactThreads) {
           uint32_t db = __float_as_uint(adc_row_global(tab, blk0 + (r >> 5), r & 31, lut, K));
           if (pass == 0 || (db >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(db >> shift) & 255u], 1u);
@@ -139,7 +152,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
     __syncthreads();
     for (int j = 0; j < n_pairs; j++) {
       const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
-      const float* lut = luts + (size_t)j * lut_stride;
+      FB_EXACT_LUT(j)
       for (int r = tid; r < len; r += kExactThreads) {
         const int blk = blk0 + (r >> 5), ln = r & 31;
         uint32_t db = __float_as_uint(adc_row_global(tab, blk, ln, lut, K));
@@ -167,7 +180,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
       __syncthreads();
       for (int j = 0; j < n_pairs; j++) {
         const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
-        const float* lut = luts + (size_t)j * lut_stride;
+        FB_EXACT_LUT(j)
         for (int r = tid; r < len; r += kExactThreads) {
           const int blk = blk0 + (r >> 5), ln = r & 31;
           uint32_t db = __float_as_uint(adc_row_global(tab, blk, ln, lut, K));
@@ -217,7 +230,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
   __syncthreads();
 }
 
-__device__ __forceinline__ ExactShared exact_carve(unsigned char* p, int k) {
+__device__ __forceinline__ ExactShared exact_carve(unsigned char* p, int k, int lut_stage_floats) {
   ExactShared sh;
   sh.lbuf = reinterpret_cast<u64*>(p); p += sizeof(u64) * kExactMaxK;
   sh.ebuf = reinterpret_cast<u64*>(p); p += sizeof(u64) * kExactECap;
@@ -226,12 +239,13 @@ __device__ __forceinline__ ExactShared exact_carve(unsigned char* p, int k) {
   sh.tk_t = reinterpret_cast<uint32_t*>(p); p += sizeof(uint32_t) * kExactMaxK;
   sh.hist = reinterpret_cast<unsigned*>(p); p += sizeof(unsigned) * 256;
   sh.misc = reinterpret_cast<int*>(p); p += sizeof(int) * 8;
+  sh.slut = lut_stage_floats > 0 ? reinterpret_cast<float*>(p) : nullptr;
   (void)k;
   return sh;
 }
 constexpr size_t kExactFixedSmem = sizeof(u64) * (kExactMaxK + kExactECap + kExactSortN) +
                                    sizeof(float) * kExactMaxK + sizeof(uint32_t) * kExactMaxK +
-                                   sizeof(unsigned) * 256 + sizeof(int) * 8;
+                                   sizeof(unsigned) * 256 + sizeof(int) * 8;  // multiple of 16; the LUT stage follows
 
 __device__ __forceinline__ void exact_write_result(const ExactShared& sh, int k, const int32_t* ids,
                                                    int32_t* out_ids, float* out_dists) {
@@ -262,10 +276,10 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     const float* __restrict__ chunk_luts,                                      // [nq][w][m*K]
                     const u64* __restrict__ kth_key,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
-                    int32_t* __restrict__ error_flag) {
+                    int32_t* __restrict__ error_flag, int lut_stage_floats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ExactShared sh = exact_carve(smem_raw, k);
-  unsigned char* p = smem_raw + kExactFixedSmem;
+  ExactShared sh = exact_carve(smem_raw, k, lut_stage_floats);
+  unsigned char* p = smem_raw + kExactFixedSmem + sizeof(float) * (size_t)lut_stage_floats;
   float* cdist = reinterpret_cast<float*>(p); p += sizeof(float) * Cs;
   float* qv = reinterpret_cast<float*>(p); p += sizeof(float) * ((d + 3) & ~3);
   float* sel_d = reinterpret_cast<float*>(p); p += sizeof(float) * ((w + 3) & ~3);
@@ -375,9 +389,9 @@ pq_exact_kernel(CodeTableDev tab, const int32_t* __restrict__ all_lists,  // [n_
                 const int32_t* __restrict__ exact_list, const int32_t* __restrict__ exact_count,
                 int32_t* __restrict__ work_counter,
                 const u64* __restrict__ kth_key,          // from the streaming pass, or nullptr
-                int32_t* __restrict__ out_ids, float* __restrict__ out_dists) {
+                int32_t* __restrict__ out_ids, float* __restrict__ out_dists, int lut_stage_floats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ExactShared sh = exact_carve(smem_raw, k);
+  ExactShared sh = exact_carve(smem_raw, k, lut_stage_floats);
   __shared__ int s_item;
   const int tid = threadIdx.x;
   const size_t lut_stride = (size_t)tab.m * K;

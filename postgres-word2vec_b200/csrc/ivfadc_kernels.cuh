@@ -39,7 +39,7 @@ struct CodeTableDev {
 constexpr uint32_t kFlagExact = 1u;     // needs the general kernel
 // why (statistics only)
 constexpr uint32_t kWhyCoarseTie = 2u, kWhyCoarseFar = 4u, kWhyFewRows = 8u, kWhyScanTie = 16u, kWhyForced = 32u;
-constexpr int kCoarseThreads = 256;
+constexpr int kCoarseThreads = 512;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / kWarp;
 constexpr int kLutMaxJobs = 16;
@@ -175,7 +175,7 @@ lut_build_kernel(const float* __restrict__ queries, int d,
   __shared__ __align__(8) uint64_t bar;
   float* cbs = reinterpret_cast<float*>(smem_raw);        // [sub][TK]
   constexpr int WS = (W + 3) & ~3;                        // residual row stride (16-byte rows)
-  float* rs = cbs + (size_t)sub * TK;                     // [sub][WS]
+  float* rs = cbs + (size_t)sub * TK;                     // 2 x [sub][WS]
   const int tiles = (K + TK - 1) / TK;
   const int pos = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int code0 = tile * TK;
@@ -195,18 +195,51 @@ lut_build_kernel(const float* __restrict__ queries, int d,
   }
   mbar_wait(&bar, 0);
 
-  for (int job0 = blockIdx.y * W; job0 < njobs; job0 += gridDim.y * W) {
-    __syncthreads();  // previous group's readers of rs are done
-    for (int idx = tid; idx < sub * W; idx += blockDim.x) {
-      const int i = idx / W, jj = idx % W;
-      int job = min(job0 + jj, njobs - 1);
-      int q = job / jobs_per_query;
-      float qv = queries[(size_t)q * d + pos * sub + i];
-      float r = qv;
-      if (probes != nullptr) r = xsub(qv, coarse[(size_t)probes[job] * d + pos * sub + i]);
-      rs[i * WS + jj] = r;
+  // Residuals of the next job group are fetched (two dependent global loads) while the
+  // current group is being computed; rs is double-buffered so one barrier per group suffices.
+  constexpr int kPre = 4;                                  // residual elements a thread may own
+  const int n_res = sub * W;
+  const bool pipelined = n_res <= kPre * (int)blockDim.x;
+  float pre_q[kPre], pre_c[kPre];
+  auto prefetch = [&](int job0) {
+#pragma unroll
+    for (int e = 0; e < kPre; e++) {
+      const int idx = tid + e * (int)blockDim.x;
+      pre_q[e] = 0.0f;
+      pre_c[e] = 0.0f;
+      if (idx < n_res) {
+        const int i = idx / W, jj = idx % W;
+        const int job = min(job0 + jj, njobs - 1);
+        const int q = job / jobs_per_query;
+        pre_q[e] = queries[(size_t)q * d + pos * sub + i];
+        if (probes != nullptr) pre_c[e] = coarse[(size_t)probes[job] * d + pos * sub + i];
+      }
     }
-    __syncthreads();
+  };
+  int cur = 0;
+  if (pipelined) prefetch(blockIdx.y * W);
+  for (int job0 = blockIdx.y * W; job0 < njobs; job0 += gridDim.y * W) {
+    float* rsc = cur ? rs + (size_t)sub * WS : rs;
+    if (pipelined) {
+#pragma unroll
+      for (int e = 0; e < kPre; e++) {
+        const int idx = tid + e * (int)blockDim.x;
+        if (idx < n_res) rsc[(idx / W) * WS + (idx % W)] = (probes != nullptr) ? xsub(pre_q[e], pre_c[e]) : pre_q[e];
+      }
+      __syncthreads();
+      const int next = job0 + gridDim.y * W;
+      if (next < njobs) prefetch(next);
+    } else {
+      __syncthreads();  // previous group's readers are done
+      for (int idx = tid; idx < n_res; idx += blockDim.x) {
+        const int i = idx / W, jj = idx % W;
+        const int job = min(job0 + jj, njobs - 1);
+        const int q = job / jobs_per_query;
+        const float qv = queries[(size_t)q * d + pos * sub + i];
+        rsc[i * WS + jj] = (probes != nullptr) ? xsub(qv, coarse[(size_t)probes[job] * d + pos * sub + i]) : qv;
+      }
+      __syncthreads();
+    }
     if (tid < ncodes) {
       float acc[W];
 #pragma unroll
@@ -215,7 +248,7 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       for (int i = 0; i < sub; i++) {
         const float cv = cbs[(size_t)i * TK + tid];
         // the W residuals of this dimension: broadcast 16-byte shared-memory reads
-        const float4* rrow4 = reinterpret_cast<const float4*>(rs + i * WS);
+        const float4* rrow4 = reinterpret_cast<const float4*>(rsc + i * WS);
         float rv[WS];
 #pragma unroll
         for (int v = 0; v < WS / 4; v++) {
@@ -234,6 +267,7 @@ lut_build_kernel(const float* __restrict__ queries, int d,
         if (job < njobs) lut[((size_t)job * m + pos) * K + code0 + tid] = acc[jj];
       }
     }
+    if (pipelined) cur ^= 1;
   }
 }
 

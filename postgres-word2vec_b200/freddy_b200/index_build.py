@@ -47,7 +47,7 @@ def _nearest(x, cent, chunk=65536):
 
 def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clusters=1000,
                          sigma=0.3, kmeans_iters=10, seed=1234, device=None, with_pq=False,
-                         keep_vectors=False):
+                         keep_vectors=False, zipf=0.7):
     """Returns a dict of numpy arrays (plus 'vectors_t': the torch tensor, if keep_vectors)."""
     assert d % m == 0, "d must be divisible by m"
     sub = d // m
@@ -57,7 +57,7 @@ def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clus
 
     # --- vectors: mixture of Gaussian clusters with Zipf-ish sizes, then normalised
     centres = torch.randn(n_clusters, d, generator=gen, device=dev)
-    pc = 1.0 / torch.arange(10, 10 + n_clusters, device=dev, dtype=torch.float32) ** 0.7
+    pc = 1.0 / torch.arange(10, 10 + n_clusters, device=dev, dtype=torch.float32) ** zipf
     pc = pc / pc.sum()
     vecs = torch.empty(N, d, device=dev, dtype=torch.float32)
     step = 262144
