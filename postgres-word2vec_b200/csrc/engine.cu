@@ -278,19 +278,31 @@ template <int W>
 int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
                  int jobs_per_query, int njobs, float* d_lut) {
   const int K = cb.K, sub = cb.sub, m = cb.m;
-  int TK = std::min(1024, (K + 31) / 32 * 32);
-  const size_t budget = std::min<size_t>(e->smem_optin, 200 * 1024) - 4096;
-  while ((size_t)sub * TK * sizeof(float) > budget && TK > 32) TK -= 32;
-  if ((size_t)sub * TK * sizeof(float) > budget) return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
-  const int tiles = (K + TK - 1) / TK;
   constexpr int WS = (W + 3) & ~3;
-  size_t smem = ((size_t)sub * TK + 2 * (size_t)sub * WS) * sizeof(float);
-  auto kern = lut_build_kernel<W>;
-  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t budget = std::min<size_t>(e->smem_optin, 200 * 1024) - 4096;
+  const size_t rs_bytes = 2 * (size_t)sub * WS * sizeof(float);
+  int TK = std::min(1024, (K + 31) / 32 * 32);
+  // constant row stride (immediate shared-memory offsets) whenever the padded slice fits
+  const bool const_stride = (size_t)sub * 1024 * sizeof(float) + rs_bytes <= budget;
+  if (!const_stride) {
+    while ((size_t)sub * TK * sizeof(float) + rs_bytes > budget && TK > 32) TK -= 32;
+    if ((size_t)sub * TK * sizeof(float) + rs_bytes > budget)
+      return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
+  }
+  const int tiles = (K + TK - 1) / TK;
+  const size_t smem = (size_t)sub * (const_stride ? 1024 : TK) * sizeof(float) + rs_bytes;
   int groups = std::max(1, e->num_sms / std::max(1, m * tiles));
   groups = std::min(groups, (njobs + W - 1) / W);
   dim3 grid(m * tiles, groups);
-  kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+  if (const_stride) {
+    auto kern = lut_build_kernel<W, 1024>;
+    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+  } else {
+    auto kern = lut_build_kernel<W, 0>;
+    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+  }
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
@@ -339,15 +351,15 @@ int launch_scan(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, 
 }
 
 template <int M, int KC>
-int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int nq, int w, const float* d_lut, int K, int KK, int k,
+int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
                     float sentinel, int32_t* d_out_ids, float* d_out_dists) {
   size_t smem = std::max<size_t>(2 * (size_t)tab.m * K * sizeof(float), kQScanWarps * 32 * sizeof(u64));
   if (smem > e->smem_optin - 1024) return FB_ERR_UNSUPPORTED;  // caller falls back to one list per CTA
   auto kern = adc_scan_query_kernel<M, KC>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab.dev(), e->probes.p, w, d_lut, K, KK, k, sentinel, e->qflags.p,
-                                               d_out_ids, d_out_dists, e->exact_list.p, e->small.p + 0,
-                                               e->counters64.p + 1, e->kth.p);
+  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab.dev(), e->probes.p + (size_t)q0 * w, w, d_lut, K, KK, k, sentinel,
+                                               e->qflags.p + q0, d_out_ids, d_out_dists, e->exact_list.p,
+                                               e->small.p + 0, e->counters64.p + 1, e->kth.p + q0, q0);
   e->launches++;
   e->n_scan_launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -355,10 +367,10 @@ int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int nq, int w, const flo
 }
 
 // throughput form: one CTA per query, finalize fused
-int launch_qscan(fb_engine* e, const CodeTable& tab, int nq, int w, const float* d_lut, int K, int KK, int k,
+int launch_qscan(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
                  float sentinel, int32_t* oi, float* od) {
   StageTimer t(e, ST_SCAN);
-#define FB_QS(M_, K_) return launch_qscan_mk<M_, K_>(e, tab, nq, w, d_lut, K, KK, k, sentinel, oi, od)
+#define FB_QS(M_, K_) return launch_qscan_mk<M_, K_>(e, tab, q0, nq, w, d_lut, K, KK, k, sentinel, oi, od)
   if (K == 1024) {
     if (tab.m == 12) FB_QS(12, 1024);
     if (tab.m == 8) FB_QS(8, 1024);
@@ -372,13 +384,13 @@ int launch_qscan(fb_engine* e, const CodeTable& tab, int nq, int w, const float*
 #undef FB_QS
 }
 
-int launch_finalize(fb_engine* e, const CodeTable& tab, int lists_per_query, int KK, int k, int nq, float sentinel,
+int launch_finalize(fb_engine* e, const CodeTable& tab, int q0, int lists_per_query, int KK, int k, int nq, float sentinel,
                     bool has_input_flags, int32_t* d_out_ids, float* d_out_dists) {
   StageTimer t(e, ST_FINALIZE);
   const int warps = 8;
   finalize_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, e->stream>>>(
-      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, e->qflags.p, has_input_flags ? 1 : 0, d_out_ids, d_out_dists,
-      e->exact_list.p, e->small.p + 0, e->counters64.p + 1, e->kth.p);
+      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, e->qflags.p + q0, has_input_flags ? 1 : 0, d_out_ids,
+      d_out_dists, e->exact_list.p, e->small.p + 0, e->counters64.p + 1, e->kth.p + q0, q0);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
@@ -414,60 +426,65 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
   const size_t lut_per_query = (size_t)w * m * K;
 
-  FB_CUDA(e, e->probes.ensure((size_t)chunk * w));
-  FB_CUDA(e, e->qflags.ensure((size_t)chunk));
-  FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
-  FB_CUDA(e, e->kth.ensure((size_t)chunk));
+  // per-query products of the streaming pass live for the whole call (the general
+  // kernel runs once at the end); only the LUT scratch is per chunk
+  FB_CUDA(e, e->probes.ensure((size_t)nq * w));
+  FB_CUDA(e, e->qflags.ensure((size_t)nq));
+  FB_CUDA(e, e->exact_list.ensure((size_t)nq));
+  FB_CUDA(e, e->kth.ensure((size_t)nq));
   if (fast) {
     FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
-    FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+    if (chunk < e->qscan_min_queries) FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
   }
   // general-kernel scratch: one LUT set per resident CTA
   int exact_ctas = 2 * e->num_sms;
   const size_t exact_budget = (size_t)1 << 30;
   while (exact_ctas > 1 && (size_t)exact_ctas * lut_per_query * sizeof(float) > exact_budget) exact_ctas /= 2;
-  if (!fast || true) FB_CUDA(e, e->exact_lut.ensure((size_t)exact_ctas * lut_per_query));
+  FB_CUDA(e, e->exact_lut.ensure((size_t)exact_ctas * lut_per_query));
   size_t ex_smem = exact_smem_bytes(e, w);
   if (ex_smem > e->smem_optin) return fail(e, FB_ERR_UNSUPPORTED, "general kernel needs %zu bytes of shared memory", ex_smem);
   int ex_stage = 0;  // LUT staging buffer when it fits next to the rest
   if (ex_smem + (size_t)m * K * sizeof(float) <= e->smem_optin) { ex_stage = m * K; ex_smem += (size_t)m * K * sizeof(float); }
   FB_CUDA(e, cudaFuncSetAttribute(ivfadc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
 
-  for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
-    const int n = (int)std::min<int64_t>(chunk, nq - q0);
-    const float* dq = d_q + (size_t)q0 * e->d;
-    int32_t* oi = d_out_ids + (size_t)q0 * k;
-    float* od = d_out_dists + (size_t)q0 * k;
-    FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
-    if (fast) {
-      if ((rc = launch_coarse(e, dq, n, w, k))) return rc;
-      count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, n * w, e->fine.list_len.p, e->counters64.p + 0);
-      e->launches++;
-      if ((rc = launch_lut(e, cb, dq, e->coarse.p, e->probes.p, w, n * w, e->lut.p))) return rc;
-      // throughput form (one CTA per query) when the chunk fills the GPU; else one CTA per (query, list)
-      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, n, w, e->lut.p, K, KK, k, 1000.0f, oi, od)
+  FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
+  if (fast) {
+    if ((rc = launch_coarse(e, d_q, nq, w, k))) return rc;   // HOT(1) for the whole batch
+    count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, nq * w, e->fine.list_len.p, e->counters64.p + 0);
+    e->launches++;
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+      const int n = (int)std::min<int64_t>(chunk, nq - q0);
+      const float* dq = d_q + (size_t)q0 * e->d;
+      const int32_t* pr = e->probes.p + (size_t)q0 * w;
+      int32_t* oi = d_out_ids + (size_t)q0 * k;
+      float* od = d_out_dists + (size_t)q0 * k;
+      if ((rc = launch_lut(e, cb, dq, e->coarse.p, pr, w, n * w, e->lut.p))) return rc;          // HOT(2)
+      // HOT(3)+(4): one CTA per query when the chunk fills the GPU, else one CTA per (query, list)
+      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, e->lut.p, K, KK, k, 1000.0f, oi, od)
                                        : FB_ERR_UNSUPPORTED;
       if (rc == FB_ERR_UNSUPPORTED) {
-        if ((rc = launch_scan(e, e->fine, e->probes.p, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
-        if ((rc = launch_finalize(e, e->fine, w * kScanWarps, KK, k, n, 1000.0f, true, oi, od))) return rc;
+        FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+        if ((rc = launch_scan(e, e->fine, pr, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
+        if ((rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, 1000.0f, true, oi, od))) return rc;
       } else if (rc) {
         return rc;
       }
-    } else {
-      iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
-      int32_t cnt = n;
-      FB_CUDA(e, cudaMemcpyAsync(e->small.p, &cnt, sizeof cnt, cudaMemcpyHostToDevice, e->stream));
-      e->launches++;
     }
-    {
-      StageTimer t(e, ST_EXACT);
-      ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
-          dq, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
-          e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
-          fast ? e->qflags.p : nullptr, e->probes.p, e->lut.p, e->kth.p, oi, od, e->small.p + 2, ex_stage);
-      e->launches++;
-      FB_CUDA(e, cudaGetLastError());
-    }
+  } else {
+    iota_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, nq);
+    int32_t cnt = nq;
+    FB_CUDA(e, cudaMemcpyAsync(e->small.p, &cnt, sizeof cnt, cudaMemcpyHostToDevice, e->stream));
+    e->launches++;
+  }
+  {
+    // flagged queries (boundary ties, re-probe loop, large k/w): the literal kernel, once per call
+    StageTimer t(e, ST_EXACT);
+    ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
+        d_q, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
+        e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
+        fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
   }
   e->queries_done += nq;
   e->bytes_per_row = 2 * m + 4;
@@ -518,7 +535,7 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
     if ((rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, n, e->lut.p))) return rc;   // freddy.c:519-525
     if (fast && !e->force_exact) {
       if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, e->lut.p, K, KK, e->partial.p))) return rc;
-      if ((rc = launch_finalize(e, tab, nl * kScanWarps, KK, k, n, sentinel, false, oi, od))) return rc;
+      if ((rc = launch_finalize(e, tab, 0, nl * kScanWarps, KK, k, n, sentinel, false, oi, od))) return rc;
     } else {
       iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
       int32_t cnt = n;

@@ -24,7 +24,7 @@
 
 namespace fb {
 
-constexpr int kExactThreads = 256;
+constexpr int kExactThreads = 1024;
 constexpr int kExactMaxK = 1024;
 constexpr int kExactECap = 1024;  // capacity for rows with d == v (must be >= kExactMaxK)
 constexpr int kExactSortN = 2048;
@@ -56,6 +56,21 @@ __device__ __forceinline__ float adc_row_global(const CodeTableDev& tab, int blk
     if (p + 3 < tab.m) acc = xadd(acc, lut[(size_t)(p + 3) * K + (v.y >> 18)]);
   }
   return acc;
+}
+
+// visit every row of one list, two rows in flight per thread (the loads of both are
+// issued before either is consumed); f(row_in_list, adc_distance)
+template <typename F>
+__device__ __forceinline__ void for_rows2(const CodeTableDev& tab, int blk0, int len,
+                                          const float* __restrict__ lut, int K, F f) {
+  for (int r = threadIdx.x; r < len; r += 2 * kExactThreads) {
+    const int r1 = r + kExactThreads;
+    const bool v1 = r1 < len;
+    const float a0 = adc_row_global(tab, blk0 + (r >> 5), r & 31, lut, K);
+    const float a1 = v1 ? adc_row_global(tab, blk0 + (r1 >> 5), r1 & 31, lut, K) : 0.0f;
+    f(r, a0);
+    if (v1) f(r1, a1);
+  }
 }
 
 // literal updateTopK (index_utils.c:19-33) on the shared top-k arrays
@@ -134,10 +149,10 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
       for (int j = 0; j < n_pairs; j++) {
         const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
         FB_EXACT_LUT(j)
-        for (int r = tid; r < len; r += kExactThreads) {
-          uint32_t db = __float_as_uint(adc_row_global(tab, blk0 + (r >> 5), r & 31, lut, K));
+        for_rows2(tab, blk0, len, lut, K, [&](int, float a) {
+          const uint32_t db = __float_as_uint(a);
           if (pass == 0 || (db >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(db >> shift) & 255u], 1u);
-        }
+        });
       }
       radix_pick(sh, prefix, remaining);
     }
@@ -153,11 +168,10 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
     for (int j = 0; j < n_pairs; j++) {
       const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
       FB_EXACT_LUT(j)
-      for (int r = tid; r < len; r += kExactThreads) {
-        const int blk = blk0 + (r >> 5), ln = r & 31;
-        uint32_t db = __float_as_uint(adc_row_global(tab, blk, ln, lut, K));
-        if (db > vbits) continue;
-        uint32_t t = (uint32_t)tab.rowno[(size_t)blk * 32 + ln];
+      for_rows2(tab, blk0, len, lut, K, [&](int r, float a) {
+        const uint32_t db = __float_as_uint(a);
+        if (db > vbits) return;
+        const uint32_t t = (uint32_t)tab.rowno[(size_t)(blk0 + (r >> 5)) * 32 + (r & 31)];
         if (db < vbits) {
           int slot = atomicAdd(&sh.misc[2], 1);
           if (slot < kExactMaxK) sh.lbuf[slot] = ((u64)t << 32) | db;
@@ -165,7 +179,7 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
           int slot = atomicAdd(&sh.misc[3], 1);
           if (slot < kExactECap) sh.ebuf[slot] = ((u64)t << 32) | db;
         }
-      }
+      });
     }
     __syncthreads();
     if (sh.misc[3] <= kExactECap) break;
@@ -181,13 +195,11 @@ __device__ void exact_round(const CodeTableDev& tab, const int* lists, int n_pai
       for (int j = 0; j < n_pairs; j++) {
         const int list = lists[j], blk0 = tab.list_blk[list], len = tab.list_len[list];
         FB_EXACT_LUT(j)
-        for (int r = tid; r < len; r += kExactThreads) {
-          const int blk = blk0 + (r >> 5), ln = r & 31;
-          uint32_t db = __float_as_uint(adc_row_global(tab, blk, ln, lut, K));
-          if (db != vbits) continue;
-          uint32_t t = (uint32_t)tab.rowno[(size_t)blk * 32 + ln];
+        for_rows2(tab, blk0, len, lut, K, [&](int r, float a) {
+          if (__float_as_uint(a) != vbits) return;
+          const uint32_t t = (uint32_t)tab.rowno[(size_t)(blk0 + (r >> 5)) * 32 + (r & 31)];
           if (pass == 0 || (t >> (shift + 8)) == prefix) atomicAdd(&sh.hist[(t >> shift) & 255u], 1u);
-        }
+        });
       }
       radix_pick(sh, prefix, remaining);
     }
@@ -271,9 +283,8 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     const int32_t* __restrict__ exact_list, const int32_t* __restrict__ exact_count,
                     int32_t* __restrict__ work_counter,
                     float* __restrict__ lut_scratch,     // [gridDim.x][w][m*K]
-                    // products of the streaming pass, reusable when the only reason is a scan tie:
+                    // products of the streaming pass, reused when the only reason is a scan tie:
                     const uint32_t* __restrict__ qflags, const int32_t* __restrict__ probes,   // [nq][w]
-                    const float* __restrict__ chunk_luts,                                      // [nq][w][m*K]
                     const u64* __restrict__ kth_key,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                     int32_t* __restrict__ error_flag, int lut_stage_floats) {
@@ -303,15 +314,31 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
     for (int i = tid; i < C; i += kExactThreads) black[i] = 0;
     for (int i = tid; i < k; i += kExactThreads) { sh.tk_d[i] = MAX_DIST; sh.tk_t[i] = kNoRow; }  // freddy.c:258-260
     __syncthreads();
+    // LUTs of the lists in sel[] (freddy.c:296-314) into this CTA's scratch
+    auto build_luts = [&]() {
+      for (int idx = tid; idx < w * m * K; idx += kExactThreads) {
+        int j = idx / (m * K), rem = idx % (m * K);
+        int pos = rem / K, code = rem % K;
+        const float* cvec = coarse + (size_t)sel[j] * d + pos * sub;
+        float acc = 0.0f;
+        for (int i = 0; i < sub; i++) {
+          float r = xsub(qv[pos * sub + i], cvec[i]);
+          float t = xsub(r, cbT[((size_t)pos * sub + i) * K + code]);
+          acc = xadd(acc, xmul(t, t));
+        }
+        my_luts[(size_t)j * lut_stride + rem] = acc;
+      }
+      __syncthreads();
+    };
     const uint32_t why = qflags ? qflags[q] : kWhyForced;
     if ((why & ~(kFlagExact | kWhyScanTie)) == 0) {
-      // Only a distance tie across the k-th place: the coarse selection, the LUTs and the
-      // k-th distance of the streaming pass stand (one round, freddy.c:262 exits after it);
-      // replay the tied neighbourhood literally.
+      // Only a distance tie across the k-th place: the coarse selection and the k-th
+      // distance of the streaming pass stand (one round, freddy.c:262 exits after it);
+      // rebuild the LUTs and replay the tied neighbourhood literally.
       for (int j = tid; j < w; j += kExactThreads) sel[j] = probes[(size_t)q * w + j];
       __syncthreads();
-      exact_round(tab, sel, w, chunk_luts + (size_t)q * w * lut_stride, lut_stride, K, k, sh, true,
-                  key_dbits(kth_key[q]));
+      build_luts();
+      exact_round(tab, sel, w, my_luts, lut_stride, K, k, sh, true, key_dbits(kth_key[q]));
       exact_write_result(sh, k, tab.ids, out_ids + (size_t)q * k, out_dists + (size_t)q * k);
       continue;
     }
@@ -352,20 +379,7 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
       __syncthreads();
       if (sh.misc[4]) { failed = true; break; }
       n_black += w;
-      // LUTs of the w probes (freddy.c:296-314)
-      for (int idx = tid; idx < w * m * K; idx += kExactThreads) {
-        int j = idx / (m * K), rem = idx % (m * K);
-        int pos = rem / K, code = rem % K;
-        const float* cvec = coarse + (size_t)sel[j] * d + pos * sub;
-        float acc = 0.0f;
-        for (int i = 0; i < sub; i++) {
-          float r = xsub(qv[pos * sub + i], cvec[i]);
-          float t = xsub(r, cbT[((size_t)pos * sub + i) * K + code]);
-          acc = xadd(acc, xmul(t, t));
-        }
-        my_luts[(size_t)j * lut_stride + rem] = acc;
-      }
-      __syncthreads();
+      build_luts();
       exact_round(tab, sel, w, my_luts, lut_stride, K, k, sh);
       for (int j = 0; j < w; j++) found += tab.list_len[sel[j]];   // freddy.c:377
       __syncthreads();

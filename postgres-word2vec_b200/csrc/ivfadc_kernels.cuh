@@ -78,16 +78,18 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
 #pragma unroll
     for (int qq = 0; qq < QT; qq++) acc[qq] = 0.0f;
     const float* col = coarseT + c;
-    constexpr int PF = 4;  // centroid values in flight per thread
-    for (int i0 = 0; i0 < d; i0 += PF) {
-      float cvs[PF];
+    constexpr int PF = 4;  // dimensions per prefetch group; the next group loads while this one computes
+    float cur[PF], nxt[PF];
 #pragma unroll
-      for (int u = 0; u < PF; u++) cvs[u] = (i0 + u < d) ? __ldg(col + (size_t)(i0 + u) * Cs) : 0.0f;
+    for (int u = 0; u < PF; u++) cur[u] = (u < d) ? __ldg(col + (size_t)u * Cs) : 0.0f;
+    for (int i0 = 0; i0 < d; i0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) nxt[u] = (i0 + PF + u < d) ? __ldg(col + (size_t)(i0 + PF + u) * Cs) : 0.0f;
 #pragma unroll
       for (int u = 0; u < PF; u++) {
         const int i = i0 + u;
         if (i >= d) break;
-        const float cv = cvs[u];
+        const float cv = cur[u];
         if (QT % 4 == 0) {
           const float4* qrow = reinterpret_cast<const float4*>(qs + i * QT);
 #pragma unroll
@@ -107,6 +109,8 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < PF; u++) cur[u] = nxt[u];
     }
 #pragma unroll
     for (int qq = 0; qq < QT; qq++) dist[qq * Cs + c] = acc[qq];
@@ -162,7 +166,9 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
 // for every job the CTA processes; one thread = one code, W jobs at a time = W
 // independent accumulation chains fed by broadcast reads of the residuals.
 // ---------------------------------------------------------------------------
-template <int W>
+// TKS > 0: the shared-memory row stride of the codebook slice is the compile-time
+// constant TKS (immediate LDS offsets in the unrolled loop); TKS == 0: stride = TK.
+template <int W, int TKS>
 __global__ void __launch_bounds__(1024, 1)
 lut_build_kernel(const float* __restrict__ queries, int d,
                  const float* __restrict__ coarse,        // [C][d] row-major or nullptr
@@ -173,9 +179,10 @@ lut_build_kernel(const float* __restrict__ queries, int d,
                  float* __restrict__ lut) {               // [njobs][m][K]
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
-  float* cbs = reinterpret_cast<float*>(smem_raw);        // [sub][TK]
+  float* cbs = reinterpret_cast<float*>(smem_raw);        // [sub][stride]
   constexpr int WS = (W + 3) & ~3;                        // residual row stride (16-byte rows)
-  float* rs = cbs + (size_t)sub * TK;                     // 2 x [sub][WS]
+  const int stride = (TKS > 0) ? TKS : TK;
+  float* rs = cbs + (size_t)sub * stride;                 // 2 x [sub][WS]
   const int tiles = (K + TK - 1) / TK;
   const int pos = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int code0 = tile * TK;
@@ -190,7 +197,7 @@ lut_build_kernel(const float* __restrict__ queries, int d,
   if (tid == 0) {
     mbar_expect_tx(&bar, (uint32_t)(sub * ncodes * sizeof(float)));
     for (int i = 0; i < sub; i++)
-      bulk_g2s(cbs + (size_t)i * TK, cbT + ((size_t)pos * sub + i) * K + code0,
+      bulk_g2s(cbs + (size_t)i * stride, cbT + ((size_t)pos * sub + i) * K + code0,
                (uint32_t)(ncodes * sizeof(float)), &bar);
   }
   mbar_wait(&bar, 0);
@@ -244,11 +251,10 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       float acc[W];
 #pragma unroll
       for (int jj = 0; jj < W; jj++) acc[jj] = 0.0f;
-#pragma unroll 5
-      for (int i = 0; i < sub; i++) {
-        const float cv = cbs[(size_t)i * TK + tid];
-        // the W residuals of this dimension: broadcast 16-byte shared-memory reads
-        const float4* rrow4 = reinterpret_cast<const float4*>(rsc + i * WS);
+      // one dimension of the chain for all W jobs: r - c, squared, accumulated (3 rounded ops)
+      auto step = [&](const float* pc, const float* pr) {
+        const float cv = *pc;
+        const float4* rrow4 = reinterpret_cast<const float4*>(pr);   // broadcast 16-byte reads
         float rv[WS];
 #pragma unroll
         for (int v = 0; v < WS / 4; v++) {
@@ -260,7 +266,15 @@ lut_build_kernel(const float* __restrict__ queries, int d,
           float t = xsub(rv[jj], cv);
           acc[jj] = xadd(acc[jj], xmul(t, t));
         }
+      };
+      const float* pc = cbs + tid;
+      const float* pr = rsc;
+      int i = 0;
+      for (; i + 5 <= sub; i += 5, pc += 5 * stride, pr += 5 * WS) {
+#pragma unroll
+        for (int u = 0; u < 5; u++) step(pc + u * stride, pr + u * WS);
       }
+      for (; i < sub; i++, pc += stride, pr += WS) step(pc, pr);
 #pragma unroll
       for (int jj = 0; jj < W; jj++) {
         int job = job0 + jj;
@@ -382,7 +396,8 @@ adc_scan_kernel(CodeTableDev tab,
 // later arrival first among equal distances, index_utils.c:19-33) from an ascending
 // key list held one key per lane, or flag the query for the general kernel when a
 // distance tie straddles the k-th place.  Called by one full warp.
-__device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int k, uint32_t flags,
+// q indexes the (chunk-offset) per-query arrays; q + q_base is what goes into exact_list.
+__device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_base, int k, uint32_t flags,
                                                const int32_t* __restrict__ ids, float sentinel,
                                                uint32_t* __restrict__ qflags,
                                                int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
@@ -393,7 +408,7 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int k,
   if (lane == 0) { kth_key[q] = kk1; qflags[q] = flags; }
   if (flags & kFlagExact) {
     if (lane == 0) {
-      exact_list[atomicAdd(exact_count, 1)] = q;
+      exact_list[atomicAdd(exact_count, 1)] = q + q_base;
       atomicAdd(exact_total, 1ull);
       for (int b = 1; b <= 5; b++)
         if (flags & (1u << b)) atomicAdd(exact_total + b, 1ull);
@@ -435,7 +450,7 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
                       uint32_t* __restrict__ qflags,
                       int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                       int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
-                      u64* __restrict__ exact_total, u64* __restrict__ kth_key) {
+                      u64* __restrict__ exact_total, u64* __restrict__ kth_key, int q_base) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ uint32_t s_thr;
@@ -510,7 +525,7 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
       if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
       warp_list_merge(mine, other, lane);
     }
-    warp_emit_topk(mine, lane, q, k, qflags[q], tab.ids, sentinel, qflags, out_ids, out_dists,
+    warp_emit_topk(mine, lane, q, q_base, k, qflags[q], tab.ids, sentinel, qflags, out_ids, out_dists,
                    exact_list, exact_count, exact_total, kth_key);
   }
 }
@@ -527,7 +542,8 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
                 int32_t* __restrict__ out_ids, float* __restrict__ out_dists,   // [nq][k]
                 int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
                 u64* __restrict__ exact_total,            // cumulative statistic
-                u64* __restrict__ kth_key) {              // [nq] k-th smallest key (bound for the general kernel)
+                u64* __restrict__ kth_key,                // [nq] k-th smallest key (bound for the general kernel)
+                int q_base) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
@@ -539,7 +555,7 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
     warp_list_merge(mine, other, lane);
   }
   const uint32_t flags = has_input_flags ? qflags[q] : 0u;
-  warp_emit_topk(mine, lane, q, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
+  warp_emit_topk(mine, lane, q, q_base, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
                  exact_total, kth_key);
 }
 
