@@ -111,6 +111,8 @@ enum {
                                   the engine stream and accumulate fb_counters */
   FB_OPT_QUERY_CHUNK = 3,      /* queries per pipeline chunk (LUT scratch =
                                   chunk * w * m * K * 4 bytes)                */
+  FB_OPT_PACKED_FP32 = 5,      /* 1 (default): LUT build uses the packed f32x2
+                                  forms of the same rounded operations; 0: scalar */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

@@ -20,6 +20,37 @@ __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
 
+// Packed fp32x2 forms of the same three individually rounded operations (sm_100a
+// FADD2 / FMUL2 / FFMA2: two IEEE fp32 lanes per instruction, one issue slot).
+// ptxas 12.9 contracts `mul.rn.f32x2` + `add.rn.f32x2` into one FFMA2 (single
+// rounding) even under -fmad=false, so the accumulate step is written as
+// fma(m, ONE, acc) with ONE = (1.0f, 1.0f) supplied at RUN time: m * 1.0 is exact,
+// so the result is round(m + acc) — bit-identical to add.rn — and there is nothing
+// left for ptxas to contract.  tests/ check the bits on the GPU.
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 xsub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 xmul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 xacc2(u64 m, u64 one2, u64 acc) {  // acc + m, rounded once per lane
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(m), "l"(one2), "l"(acc));
+  return r;
+}
+
 // Selection key: distances are sums of squares (>= +0), so their bit patterns
 // order like unsigned integers.  Low word = arrival order t (table row number):
 // ascending key == (distance asc, arrival asc).

@@ -103,6 +103,8 @@ struct fb_engine {
   bool profile = false;
   int64_t query_chunk = 2048;
   int qscan_min_queries = 64;
+  bool packed_fp32 = true;
+  volatile float one = 1.0f;
 
   // profiling
   struct Ev { cudaEvent_t a, b; int stage; };
@@ -294,14 +296,19 @@ int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float
   int groups = std::max(1, e->num_sms / std::max(1, m * tiles));
   groups = std::min(groups, (njobs + W - 1) / W);
   dim3 grid(m * tiles, groups);
-  if (const_stride) {
-    auto kern = lut_build_kernel<W, 1024>;
+  const float one = e->one;  // run-time 1.0f (see common.cuh: keeps ptxas from contracting the packed chain)
+  if (const_stride && e->packed_fp32) {
+    auto kern = lut_build_kernel<W, 1024, true>;
     FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
+  } else if (const_stride) {
+    auto kern = lut_build_kernel<W, 1024, false>;
+    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
   } else {
-    auto kern = lut_build_kernel<W, 0>;
+    auto kern = lut_build_kernel<W, 0, false>;
     FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut);
+    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
   }
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -808,6 +815,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
   switch (option) {
     case FB_OPT_FORCE_EXACT_PATH: e->force_exact = value != 0; return FB_OK;
     case FB_OPT_PROFILE: e->profile = value != 0; return FB_OK;
+    case FB_OPT_PACKED_FP32: e->packed_fp32 = value != 0; return FB_OK;
     case FB_OPT_QSCAN_MIN_QUERIES:
       e->qscan_min_queries = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
       return FB_OK;

@@ -168,7 +168,9 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
 // ---------------------------------------------------------------------------
 // TKS > 0: the shared-memory row stride of the codebook slice is the compile-time
 // constant TKS (immediate LDS offsets in the unrolled loop); TKS == 0: stride = TK.
-template <int W, int TKS>
+// PACKED: the W chains run two per instruction (FADD2/FMUL2/FFMA2, see common.cuh);
+// `one` must be 1.0f and must reach the kernel as a run-time value.
+template <int W, int TKS, bool PACKED>
 __global__ void __launch_bounds__(1024, 1)
 lut_build_kernel(const float* __restrict__ queries, int d,
                  const float* __restrict__ coarse,        // [C][d] row-major or nullptr
@@ -176,7 +178,8 @@ lut_build_kernel(const float* __restrict__ queries, int d,
                  int jobs_per_query, int njobs,
                  const float* __restrict__ cbT,           // [m][sub][K]
                  int m, int K, int sub, int TK,
-                 float* __restrict__ lut) {               // [njobs][m][K]
+                 float* __restrict__ lut,                 // [njobs][m][K]
+                 float one) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   float* cbs = reinterpret_cast<float*>(smem_raw);        // [sub][stride]
@@ -248,37 +251,75 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       __syncthreads();
     }
     if (tid < ncodes) {
-      float acc[W];
-#pragma unroll
-      for (int jj = 0; jj < W; jj++) acc[jj] = 0.0f;
-      // one dimension of the chain for all W jobs: r - c, squared, accumulated (3 rounded ops)
-      auto step = [&](const float* pc, const float* pr) {
-        const float cv = *pc;
-        const float4* rrow4 = reinterpret_cast<const float4*>(pr);   // broadcast 16-byte reads
-        float rv[WS];
-#pragma unroll
-        for (int v = 0; v < WS / 4; v++) {
-          float4 t4 = rrow4[v];
-          rv[4 * v + 0] = t4.x; rv[4 * v + 1] = t4.y; rv[4 * v + 2] = t4.z; rv[4 * v + 3] = t4.w;
-        }
-#pragma unroll
-        for (int jj = 0; jj < W; jj++) {
-          float t = xsub(rv[jj], cv);
-          acc[jj] = xadd(acc[jj], xmul(t, t));
-        }
-      };
       const float* pc = cbs + tid;
       const float* pr = rsc;
       int i = 0;
-      for (; i + 5 <= sub; i += 5, pc += 5 * stride, pr += 5 * WS) {
+      if (PACKED) {
+        constexpr int NP = (W + 1) / 2;                     // chain pairs (a padding chain, if any, is never stored)
+        const u64 one2 = pack2(one, one);
+        u64 acc2[NP];
 #pragma unroll
-        for (int u = 0; u < 5; u++) step(pc + u * stride, pr + u * WS);
-      }
-      for (; i < sub; i++, pc += stride, pr += WS) step(pc, pr);
+        for (int p2 = 0; p2 < NP; p2++) acc2[p2] = 0ull;    // (+0.0f, +0.0f)
+        auto step2 = [&](const float* pcc, const float* prr) {
+          const float cv = *pcc;
+          const u64 cv2 = pack2(cv, cv);
+          const ulonglong2* rrow = reinterpret_cast<const ulonglong2*>(prr);   // broadcast 16-byte reads
 #pragma unroll
-      for (int jj = 0; jj < W; jj++) {
-        int job = job0 + jj;
-        if (job < njobs) lut[((size_t)job * m + pos) * K + code0 + tid] = acc[jj];
+          for (int v = 0; v < WS / 4; v++) {
+            const ulonglong2 r4 = rrow[v];
+            if (2 * v < NP) {
+              const u64 t0 = xsub2(r4.x, cv2);
+              acc2[2 * v] = xacc2(xmul2(t0, t0), one2, acc2[2 * v]);
+            }
+            if (2 * v + 1 < NP) {
+              const u64 t1 = xsub2(r4.y, cv2);
+              acc2[2 * v + 1] = xacc2(xmul2(t1, t1), one2, acc2[2 * v + 1]);
+            }
+          }
+        };
+        for (; i + 5 <= sub; i += 5, pc += 5 * stride, pr += 5 * WS) {
+#pragma unroll
+          for (int u = 0; u < 5; u++) step2(pc + u * stride, pr + u * WS);
+        }
+        for (; i < sub; i++, pc += stride, pr += WS) step2(pc, pr);
+#pragma unroll
+        for (int p2 = 0; p2 < NP; p2++) {
+          float lo, hi;
+          unpack2(acc2[p2], lo, hi);
+          const int j0 = job0 + 2 * p2;
+          if (2 * p2 < W && j0 < njobs) lut[((size_t)j0 * m + pos) * K + code0 + tid] = lo;
+          if (2 * p2 + 1 < W && j0 + 1 < njobs) lut[((size_t)(j0 + 1) * m + pos) * K + code0 + tid] = hi;
+        }
+      } else {
+        float acc[W];
+#pragma unroll
+        for (int jj = 0; jj < W; jj++) acc[jj] = 0.0f;
+        // one dimension of the chain for all W jobs: r - c, squared, accumulated (3 rounded ops)
+        auto step = [&](const float* pcc, const float* prr) {
+          const float cv = *pcc;
+          const float4* rrow4 = reinterpret_cast<const float4*>(prr);   // broadcast 16-byte reads
+          float rv[WS];
+#pragma unroll
+          for (int v = 0; v < WS / 4; v++) {
+            float4 t4 = rrow4[v];
+            rv[4 * v + 0] = t4.x; rv[4 * v + 1] = t4.y; rv[4 * v + 2] = t4.z; rv[4 * v + 3] = t4.w;
+          }
+#pragma unroll
+          for (int jj = 0; jj < W; jj++) {
+            float t = xsub(rv[jj], cv);
+            acc[jj] = xadd(acc[jj], xmul(t, t));
+          }
+        };
+        for (; i + 5 <= sub; i += 5, pc += 5 * stride, pr += 5 * WS) {
+#pragma unroll
+          for (int u = 0; u < 5; u++) step(pc + u * stride, pr + u * WS);
+        }
+        for (; i < sub; i++, pc += stride, pr += WS) step(pc, pr);
+#pragma unroll
+        for (int jj = 0; jj < W; jj++) {
+          int job = job0 + jj;
+          if (job < njobs) lut[((size_t)job * m + pos) * K + code0 + tid] = acc[jj];
+        }
       }
     }
     if (pipelined) cur ^= 1;

@@ -101,13 +101,21 @@ def test_generic_m(eng, oracle_mod):
     assert_same_topk(ids, d, eids, ed, "m=10")
 
 
-def test_readme_shape(eng, oracle_mod):
-    """d=300, m=12, K=1024 (README.md:125-128) on a 60k-row table"""
+@pytest.mark.parametrize("packed", [1, 0])
+def test_readme_shape(eng, oracle_mod, packed):
+    """d=300, m=12, K=1024 (README.md:125-128) on a 60k-row table; LUT build with the
+    packed f32x2 and the scalar forms of the same rounded operations"""
+    from freddy_b200 import _lib
     ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)
     q = queries_from(ix, 150, seed=6)
-    for qmin in (0, 1 << 30):
-        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, 10, qscan_min=qmin)
-        assert_same_topk(ids, d, eids, ed, f"d=300 K=1024 qscan_min={qmin}")
+    eng.set_option(_lib.FB_OPT_PACKED_FP32, packed)
+    try:
+        for qmin in (0, 1 << 30):
+            for w in (10, 3, 7):       # even / odd numbers of chains per thread
+                ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 5, w, qscan_min=qmin)
+                assert_same_topk(ids, d, eids, ed, f"d=300 K=1024 qscan_min={qmin} w={w} packed={packed}")
+    finally:
+        eng.set_option(_lib.FB_OPT_PACKED_FP32, 1)
 
 
 def test_edge_cases(eng, oracle_mod):
