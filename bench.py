@@ -56,6 +56,7 @@ def parse():
                     help="cluster-size skew of the synthetic vectors: size ~ 1/(10+rank)^zipf")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lut-tile", type=int, default=None, help="codes per LUT-build CTA (256/512/1024)")
     ap.add_argument("--scalar-lut", action="store_true", help="LUT build with scalar instead of packed f32x2 ops")
     return ap.parse_args()
 
@@ -223,6 +224,8 @@ def main():
     assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.set_option(_lib.FB_OPT_PROFILE, 1)
+    if a.lut_tile is not None:
+        eng.set_option(_lib.FB_OPT_LUT_TILE, a.lut_tile)
     if a.scalar_lut:
         eng.set_option(_lib.FB_OPT_PACKED_FP32, 0)
 

@@ -113,6 +113,8 @@ enum {
                                   chunk * w * m * K * 4 bytes)                */
   FB_OPT_PACKED_FP32 = 5,      /* 1 (default): LUT build uses the packed f32x2
                                   forms of the same rounded operations; 0: scalar */
+  FB_OPT_LUT_TILE = 6,         /* codes per LUT-build CTA: 256 / 512 / 1024 (then
+                                  4 / 2 / 1 CTAs per SM); anything else: generic  */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

@@ -104,6 +104,7 @@ struct fb_engine {
   int64_t query_chunk = 2048;
   int qscan_min_queries = 64;
   bool packed_fp32 = true;
+  int lut_tile = 512;
   volatile float one = 1.0f;
 
   // profiling
@@ -276,43 +277,54 @@ int launch_coarse(fb_engine* e, const float* d_q, int nq, int w, int k) {
   return fail(e, FB_ERR_UNSUPPORTED, "coarse table too large for shared memory (C=%d d=%d)", e->C, e->d);
 }
 
-template <int W>
-int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
-                 int jobs_per_query, int njobs, float* d_lut) {
-  const int K = cb.K, sub = cb.sub, m = cb.m;
-  constexpr int WS = (W + 3) & ~3;
-  const size_t budget = std::min<size_t>(e->smem_optin, 200 * 1024) - 4096;
-  const size_t rs_bytes = 2 * (size_t)sub * WS * sizeof(float);
-  int TK = std::min(1024, (K + 31) / 32 * 32);
-  // constant row stride (immediate shared-memory offsets) whenever the padded slice fits
-  const bool const_stride = (size_t)sub * 1024 * sizeof(float) + rs_bytes <= budget;
-  if (!const_stride) {
-    while ((size_t)sub * TK * sizeof(float) + rs_bytes > budget && TK > 32) TK -= 32;
-    if ((size_t)sub * TK * sizeof(float) + rs_bytes > budget)
-      return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
-  }
-  const int tiles = (K + TK - 1) / TK;
-  const size_t smem = (size_t)sub * (const_stride ? 1024 : TK) * sizeof(float) + rs_bytes;
-  int groups = std::max(1, e->num_sms / std::max(1, m * tiles));
+template <int W, int TKS, bool PACKED>
+int launch_lut_cfg(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
+                   int jobs_per_query, int njobs, float* d_lut, int TK, size_t smem) {
+  const int tiles = (cb.K + TK - 1) / TK;
+  const int per_sm = TKS > 0 ? 1024 / TKS : 1;
+  int groups = std::max(1, e->num_sms * per_sm / std::max(1, cb.m * tiles));
   groups = std::min(groups, (njobs + W - 1) / W);
-  dim3 grid(m * tiles, groups);
-  const float one = e->one;  // run-time 1.0f (see common.cuh: keeps ptxas from contracting the packed chain)
-  if (const_stride && e->packed_fp32) {
-    auto kern = lut_build_kernel<W, 1024, true>;
-    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
-  } else if (const_stride) {
-    auto kern = lut_build_kernel<W, 1024, false>;
-    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
-  } else {
-    auto kern = lut_build_kernel<W, 0, false>;
-    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, m, K, sub, TK, d_lut, one);
-  }
+  dim3 grid(cb.m * tiles, groups);
+  auto kern = lut_build_kernel<W, TKS, PACKED>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // e->one: run-time 1.0f (common.cuh: keeps ptxas from contracting the packed chain)
+  kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, cb.m, cb.K, cb.sub,
+                                      TK, d_lut, e->one);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
+}
+
+template <int W>
+int launch_lut_w(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
+                 int jobs_per_query, int njobs, float* d_lut) {
+  const int K = cb.K, sub = cb.sub;
+  constexpr int WS = (W + 3) & ~3;
+  const size_t rs_bytes = 2 * (size_t)sub * WS * sizeof(float);
+  // preferred: TKS codes per CTA, 1024/TKS CTAs per SM, constant row stride
+  const int tks = e->lut_tile;
+  if ((tks == 256 || tks == 512 || tks == 1024) && K % 4 == 0) {
+    const int TK = std::min(tks, (K + 31) / 32 * 32);
+    const size_t smem = (size_t)sub * tks * sizeof(float) + rs_bytes;
+    const size_t per_sm_budget = (e->smem_optin - 2048) / (1024 / tks);
+    if (smem + 1024 <= per_sm_budget) {
+#define FB_LUT_GO(T_) \
+  return e->packed_fp32 ? launch_lut_cfg<W, T_, true>(e, cb, d_q, d_coarse, d_probes, jobs_per_query, njobs, d_lut, TK, smem) \
+                        : launch_lut_cfg<W, T_, false>(e, cb, d_q, d_coarse, d_probes, jobs_per_query, njobs, d_lut, TK, smem)
+      if (tks == 256) FB_LUT_GO(256);
+      if (tks == 512) FB_LUT_GO(512);
+      FB_LUT_GO(1024);
+#undef FB_LUT_GO
+    }
+  }
+  // generic: shrink the code tile until the slice fits
+  const size_t budget = std::min<size_t>(e->smem_optin, 200 * 1024) - 4096;
+  int TK = std::min(1024, (K + 31) / 32 * 32);
+  while ((size_t)sub * TK * sizeof(float) + rs_bytes > budget && TK > 32) TK -= 32;
+  if ((size_t)sub * TK * sizeof(float) + rs_bytes > budget)
+    return fail(e, FB_ERR_UNSUPPORTED, "sub-vector too long for shared memory (sub=%d)", sub);
+  return launch_lut_cfg<W, 0, false>(e, cb, d_q, d_coarse, d_probes, jobs_per_query, njobs, d_lut, TK,
+                                     (size_t)sub * TK * sizeof(float) + rs_bytes);
 }
 
 int launch_lut(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,
@@ -816,6 +828,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_FORCE_EXACT_PATH: e->force_exact = value != 0; return FB_OK;
     case FB_OPT_PROFILE: e->profile = value != 0; return FB_OK;
     case FB_OPT_PACKED_FP32: e->packed_fp32 = value != 0; return FB_OK;
+    case FB_OPT_LUT_TILE: e->lut_tile = (int)value; return FB_OK;
     case FB_OPT_QSCAN_MIN_QUERIES:
       e->qscan_min_queries = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
       return FB_OK;

@@ -166,12 +166,18 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
 // for every job the CTA processes; one thread = one code, W jobs at a time = W
 // independent accumulation chains fed by broadcast reads of the residuals.
 // ---------------------------------------------------------------------------
-// TKS > 0: the shared-memory row stride of the codebook slice is the compile-time
-// constant TKS (immediate LDS offsets in the unrolled loop); TKS == 0: stride = TK.
+// TKS > 0: one CTA owns TKS codes, the shared-memory row stride of its codebook slice is
+// the compile-time constant TKS (immediate LDS offsets in the unrolled loop) and
+// 1024/TKS CTAs share an SM so that one CTA's per-group barrier/prologue bubbles are
+// filled by the others; TKS == 0: generic (stride = TK, one CTA per SM).
+template <int TKS> struct LutCfg {
+  static constexpr int kThreads = (TKS > 0) ? TKS : 1024;
+  static constexpr int kPerSm = (TKS > 0) ? (1024 / TKS) : 1;
+};
 // PACKED: the W chains run two per instruction (FADD2/FMUL2/FFMA2, see common.cuh);
 // `one` must be 1.0f and must reach the kernel as a run-time value.
 template <int W, int TKS, bool PACKED>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__((LutCfg<TKS>::kThreads), (LutCfg<TKS>::kPerSm))
 lut_build_kernel(const float* __restrict__ queries, int d,
                  const float* __restrict__ coarse,        // [C][d] row-major or nullptr
                  const int32_t* __restrict__ probes,      // [njobs] centroid per job or nullptr
@@ -207,22 +213,36 @@ lut_build_kernel(const float* __restrict__ queries, int d,
 
   // Residuals of the next job group are fetched (two dependent global loads) while the
   // current group is being computed; rs is double-buffered so one barrier per group suffices.
+  // Ownership of the residual elements is fixed per thread, so all index arithmetic is
+  // hoisted out of the group loop; only warps that own elements take part.
   constexpr int kPre = 4;                                  // residual elements a thread may own
   const int n_res = sub * W;
   const bool pipelined = n_res <= kPre * (int)blockDim.x;
+  const bool aligned = (W % jobs_per_query) == 0;          // then job0 is a multiple of jobs_per_query
   float pre_q[kPre], pre_c[kPre];
+  int e_dst[kPre], e_jj[kPre], e_qoff[kPre], e_src[kPre];
+#pragma unroll
+  for (int e = 0; e < kPre; e++) {
+    const int idx = tid + e * (int)blockDim.x;
+    const int i = idx / W, jj = idx % W;
+    e_jj[e] = (idx < n_res) ? jj : -1;
+    e_dst[e] = i * WS + jj;
+    e_qoff[e] = jj / jobs_per_query;
+    e_src[e] = pos * sub + i;
+    pre_q[e] = 0.0f;
+    pre_c[e] = 0.0f;
+  }
+  const bool owner_warp = (tid & ~31) < n_res;
   auto prefetch = [&](int job0) {
+    if (!owner_warp) return;
+    const int q0 = job0 / jobs_per_query;
 #pragma unroll
     for (int e = 0; e < kPre; e++) {
-      const int idx = tid + e * (int)blockDim.x;
-      pre_q[e] = 0.0f;
-      pre_c[e] = 0.0f;
-      if (idx < n_res) {
-        const int i = idx / W, jj = idx % W;
-        const int job = min(job0 + jj, njobs - 1);
-        const int q = job / jobs_per_query;
-        pre_q[e] = queries[(size_t)q * d + pos * sub + i];
-        if (probes != nullptr) pre_c[e] = coarse[(size_t)probes[job] * d + pos * sub + i];
+      if (e_jj[e] >= 0) {
+        const int job = min(job0 + e_jj[e], njobs - 1);
+        const int q = aligned ? min(q0 + e_qoff[e], (njobs - 1) / jobs_per_query) : job / jobs_per_query;
+        pre_q[e] = queries[(size_t)q * d + e_src[e]];
+        if (probes != nullptr) pre_c[e] = coarse[(size_t)probes[job] * d + e_src[e]];
       }
     }
   };
@@ -231,10 +251,10 @@ lut_build_kernel(const float* __restrict__ queries, int d,
   for (int job0 = blockIdx.y * W; job0 < njobs; job0 += gridDim.y * W) {
     float* rsc = cur ? rs + (size_t)sub * WS : rs;
     if (pipelined) {
+      if (owner_warp) {
 #pragma unroll
-      for (int e = 0; e < kPre; e++) {
-        const int idx = tid + e * (int)blockDim.x;
-        if (idx < n_res) rsc[(idx / W) * WS + (idx % W)] = (probes != nullptr) ? xsub(pre_q[e], pre_c[e]) : pre_q[e];
+        for (int e = 0; e < kPre; e++)
+          if (e_jj[e] >= 0) rsc[e_dst[e]] = (probes != nullptr) ? xsub(pre_q[e], pre_c[e]) : pre_q[e];
       }
       __syncthreads();
       const int next = job0 + gridDim.y * W;
@@ -250,6 +270,9 @@ lut_build_kernel(const float* __restrict__ queries, int d,
       }
       __syncthreads();
     }
+    float* const out = lut + ((size_t)job0 * m + pos) * K + code0 + tid;   // + j * m * K for job j of the group
+    const size_t job_stride = (size_t)m * K;
+    const bool full = job0 + W <= njobs;
     if (tid < ncodes) {
       const float* pc = cbs + tid;
       const float* pr = rsc;
@@ -286,9 +309,8 @@ lut_build_kernel(const float* __restrict__ queries, int d,
         for (int p2 = 0; p2 < NP; p2++) {
           float lo, hi;
           unpack2(acc2[p2], lo, hi);
-          const int j0 = job0 + 2 * p2;
-          if (2 * p2 < W && j0 < njobs) lut[((size_t)j0 * m + pos) * K + code0 + tid] = lo;
-          if (2 * p2 + 1 < W && j0 + 1 < njobs) lut[((size_t)(j0 + 1) * m + pos) * K + code0 + tid] = hi;
+          if (2 * p2 < W && (full || job0 + 2 * p2 < njobs)) out[(size_t)(2 * p2) * job_stride] = lo;
+          if (2 * p2 + 1 < W && (full || job0 + 2 * p2 + 1 < njobs)) out[(size_t)(2 * p2 + 1) * job_stride] = hi;
         }
       } else {
         float acc[W];
@@ -316,10 +338,8 @@ lut_build_kernel(const float* __restrict__ queries, int d,
         }
         for (; i < sub; i++, pc += stride, pr += WS) step(pc, pr);
 #pragma unroll
-        for (int jj = 0; jj < W; jj++) {
-          int job = job0 + jj;
-          if (job < njobs) lut[((size_t)job * m + pos) * K + code0 + tid] = acc[jj];
-        }
+        for (int jj = 0; jj < W; jj++)
+          if (full || job0 + jj < njobs) out[(size_t)jj * job_stride] = acc[jj];
       }
     }
     if (pipelined) cur ^= 1;

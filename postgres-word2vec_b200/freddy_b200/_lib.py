@@ -13,6 +13,7 @@ FB_OK = 0
 FB_ERR_INVALID, FB_ERR_CUDA, FB_ERR_UNSUPPORTED, FB_ERR_REFERENCE_UB = -1, -2, -3, -4
 FB_CB_RESIDUAL, FB_CB_PQ = 0, 1
 FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK, FB_OPT_QSCAN_MIN_QUERIES, FB_OPT_PACKED_FP32 = 1, 2, 3, 4, 5
+FB_OPT_LUT_TILE = 6
 
 
 class Counters(C.Structure):
