@@ -37,7 +37,7 @@ UNIT = "queries/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=3_000_000)
@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -208,7 +208,7 @@ def main():
         for nm in names:
             shp, dt = shapes[nm]
             t = torch.from_numpy(ix[nm]).to(dev) if rank == 0 else torch.empty(shp, dtype=dt, device=dev)
-            dist.broadcast(t, 0)
+            dist.broadcast(t.view(torch.uint8), 0)      # NCCL has no int16: ship the raw bytes
             ix[nm] = t.cpu().numpy()
         if rank != 0:
             all_q = torch.empty(a.batch * world, a.d, device=dev)
@@ -278,12 +278,12 @@ def main():
             ms = float(t.item())
         return ms
 
+    clocks = ClockSampler(local_rank)   # samples through warm-up + timed region (same load in both)
+    clocks.start()
     for _ in range(max(3, a.warmup)):
         step_dev()
     eng.synchronize()
     eng.reset_counters()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ms_total = timed(step_dev, a.steps, True)
     clk = clocks.stop()
     c = eng.counters()
@@ -297,7 +297,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "adc_scan_kernel<12>", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "adc_scan_query_kernel<12,1024>", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, c["n_scan_launches"]),
                 "ms_per_launch": c["ms_scan"] / max(1, c["n_scan_launches"]),
