@@ -83,6 +83,126 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class ReferenceSession:
+    """The reference extension's OWN SRFs (freddy.c, ivpq_search_in.c, core_functions.c
+    compiled unmodified into oracle/_ref/libfreddy_ref.so) running on in-memory copies of
+    the index tables through the SPI/fmgr emulator oracle/pg_emul.c.  Plays one Postgres
+    backend with the tables `init()` names (freddy--0.0.1.sql:5-19)."""
+
+    T_COARSE, T_CODEBOOK, T_FINE, T_PQ, T_VECS, T_STATS = 1, 2, 3, 4, 5, 6
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise RuntimeError("oracle/_ref/libfreddy_ref.so not built (reference sources absent)")
+        R = C.CDLL(REF_SO)
+        R.ref_register_table.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_void_p]
+        R.ref_set_config.argtypes = [C.c_char_p, C.c_char_p]
+        R.ref_last_error.restype = C.c_char_p
+        R.ref_ivfadc_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_pq_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        R.ref_pq_search_in.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        R.ref_pq_search_in_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_cosine_similarity_bytea.restype = C.c_float
+        R.ref_cosine_similarity_bytea.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        for f in (R.ref_vec_minus_bytea, R.ref_vec_plus_bytea):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        R.ref_vec_normalize_bytea.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.R = R
+        self.keep = []
+        R.ref_reset()
+        self.d = None
+
+    def _err(self, what, n):
+        raise RuntimeError(f"{what} failed ({n}): {self.R.ref_last_error().decode()}")
+
+    def set_config(self, fn, value):
+        self.R.ref_set_config(fn.encode(), str(value).encode())
+
+    def _table(self, name, kind, n, ids=None, a=None, b=None, vec=None, freq=None):
+        arrs = [None if x is None else np.ascontiguousarray(x) for x in (ids, a, b, vec, freq)]
+        self.keep.append(arrs)
+        ids, a, b, vec, freq = arrs
+        vb = 0 if vec is None else vec.dtype.itemsize * int(np.prod(vec.shape[1:]))
+        pp = lambda x: None if x is None else _p(x)
+        rc = self.R.ref_register_table(name.encode(), kind, n, pp(ids), pp(a), pp(b), pp(vec), vb, pp(freq))
+        assert rc == 0
+
+    def load_ivfadc(self, index, w):
+        ix = index
+        self.d = int(ix["d"])
+        C_, m, K = int(ix["C"]), int(ix["m"]), int(ix["K"])
+        self._table("coarse_quantization", self.T_COARSE, C_, ids=np.arange(C_, dtype=np.int32),
+                    vec=np.asarray(ix["coarse"], np.float32))
+        pos = np.repeat(np.arange(m, dtype=np.int32), K)
+        code = np.tile(np.arange(K, dtype=np.int32), m)
+        self._table("residual_codebook", self.T_CODEBOOK, m * K, ids=np.arange(m * K, dtype=np.int32), a=pos, b=code,
+                    vec=np.asarray(ix["residual_codebook"], np.float32).reshape(m * K, -1))
+        self._table("fine_quantization", self.T_FINE, int(ix["N"]), ids=np.asarray(ix["ids"], np.int32),
+                    a=np.asarray(ix["coarse_ids"], np.int32), vec=np.asarray(ix["codes"], np.int16))
+        self.set_config("get_vecs_name()", "google_vecs_norm")
+        self.set_config("get_vecs_name_residual_codebook()", "residual_codebook")
+        self.set_config("get_vecs_name_residual_quantization()", "fine_quantization")
+        self.set_config("get_vecs_name_coarse_quantization()", "coarse_quantization")
+        self.set_config("get_w()", w)
+
+    def load_pq(self, index):
+        ix = index
+        self.d = int(ix["d"])
+        m, K = int(ix["m"]), int(ix["K"])
+        pos = np.repeat(np.arange(m, dtype=np.int32), K)
+        code = np.tile(np.arange(K, dtype=np.int32), m)
+        self._table("pq_codebook", self.T_CODEBOOK, m * K, ids=np.arange(m * K, dtype=np.int32), a=pos, b=code,
+                    vec=np.asarray(ix["pq_codebook"], np.float32).reshape(m * K, -1))
+        self._table("pq_quantization", self.T_PQ, int(ix["N"]), ids=np.asarray(ix["ids"], np.int32),
+                    vec=np.asarray(ix["pq_codes"], np.int16))
+        self.set_config("get_vecs_name()", "google_vecs_norm")
+        self.set_config("get_vecs_name_codebook()", "pq_codebook")
+        self.set_config("get_vecs_name_pq_quantization()", "pq_quantization")
+
+    def ivfadc_search(self, queries, k):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
+        ids = np.empty((len(q), k), np.int32)
+        raw = np.empty((len(q), k), np.float32)
+        txt = np.empty((len(q), k), np.float32)
+        for i in range(len(q)):
+            n = self.R.ref_ivfadc_search(_p(q[i]), self.d, k, _p(ids[i]), _p(raw[i]), _p(txt[i]))
+            if n != k:
+                self._err("ivfadc_search", n)
+        return ids, raw, txt
+
+    def pq_search(self, queries, k):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
+        ids, raw = np.empty((len(q), k), np.int32), np.empty((len(q), k), np.float32)
+        for i in range(len(q)):
+            n = self.R.ref_pq_search(_p(q[i]), self.d, k, _p(ids[i]), _p(raw[i]))
+            if n != k:
+                self._err("pq_search", n)
+        return ids, raw
+
+    def pq_search_in(self, query, k, targets):
+        q = np.ascontiguousarray(query, np.float32).reshape(self.d)
+        t = np.ascontiguousarray(targets, np.int32)
+        ids, raw = np.empty(k, np.int32), np.empty(k, np.float32)
+        n = self.R.ref_pq_search_in(_p(q), self.d, k, _p(t), len(t), _p(ids), _p(raw))
+        if n != k:
+            self._err("pq_search_in", n)
+        return ids, raw
+
+    def pq_search_in_batch(self, queries, query_ids, k, targets, use_targetlist):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
+        nq = len(q)
+        qi = np.ascontiguousarray(query_ids, np.int32)
+        t = np.ascontiguousarray(targets, np.int32)
+        qo, ids, raw = np.empty(nq * k, np.int32), np.empty(nq * k, np.int32), np.empty(nq * k, np.float32)
+        n = self.R.ref_pq_search_in_batch(_p(q), nq, self.d, _p(qi), k, _p(t), len(t), 1 if use_targetlist else 0,
+                                          _p(qo), _p(ids), _p(raw))
+        if n != nq * k:
+            self._err("pq_search_in_batch", n)
+        return qo.reshape(nq, k), ids.reshape(nq, k), raw.reshape(nq, k)
+
+
 class OracleIndex:
     """In-memory image of the index tables for the oracle (keeps arrays alive)."""
 

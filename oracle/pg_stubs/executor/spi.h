@@ -1,17 +1,15 @@
-/* stub (see ../postgres.h): SPI is never reachable from the arithmetic the
- * oracle exercises; the symbols exist so the reference file links. */
+/* stub of executor/spi.h, backed by the in-memory tables of oracle/pg_emul.c */
 #ifndef FB_STUB_SPI_H
 #define FB_STUB_SPI_H
-#include "postgres.h"
-typedef struct TupleDescData* TupleDesc;
-typedef struct HeapTupleData* HeapTuple;
+#include "funcapi.h"
 typedef struct SPITupleTable { TupleDesc tupdesc; HeapTuple* vals; } SPITupleTable;
-extern uint64_t SPI_processed;
+extern uint64 SPI_processed;
 extern SPITupleTable* SPI_tuptable;
 int SPI_connect(void);
 int SPI_finish(void);
 int SPI_exec(const char* src, long tcount);
+int SPI_execute(const char* src, bool read_only, long tcount);
 Datum SPI_getbinval(HeapTuple tuple, TupleDesc tupdesc, int fnumber, bool* isnull);
 char* SPI_getvalue(HeapTuple tuple, TupleDesc tupdesc, int fnumber);
-void* SPI_palloc(size_t size);
+void* SPI_palloc(Size size);
 #endif

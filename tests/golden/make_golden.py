@@ -66,6 +66,40 @@ def main():
     with open(os.path.join(HERE, "kernels_golden.json"), "w") as f:
         json.dump(out, f)
     print("wrote kernels_golden.json")
+    srf_golden()
+
+
+def srf_golden():
+    """outputs of the reference's OWN SRFs (freddy.c compiled unmodified, run through
+    oracle/pg_emul.c) on a tiny seeded index -> tests/golden/srf_golden.npz"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "postgres-word2vec_b200"))
+    from freddy_b200.index_build import make_synthetic_index
+    ix = make_synthetic_index(3000, d=24, m=6, K=16, C=12, n_train=3000, n_clusters=8, sigma=0.5, kmeans_iters=4,
+                              seed=99, device="cpu", with_pq=True, keep_vectors=True)
+    vec = ix.pop("vectors_t").numpy()
+    rng = np.random.default_rng(5)
+    q = vec[rng.choice(len(vec), 24, replace=False)] + 0.01 * rng.standard_normal((24, 24)).astype(np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    S = oracle.ReferenceSession()
+    S.load_ivfadc(ix, 3)
+    ids_a, raw_a, txt_a = S.ivfadc_search(q, 5)
+    S = oracle.ReferenceSession()
+    S.load_ivfadc(ix, 1)
+    ids_b, raw_b, _ = S.ivfadc_search(q, 12)
+    S = oracle.ReferenceSession()
+    S.load_pq(ix)
+    pq_ids, pq_raw = S.pq_search(q[:6], 4)
+    targets = rng.choice(np.arange(1, 3200), size=300, replace=True).astype(np.int32)
+    _, in_ids, in_raw = S.pq_search_in_batch(q, np.arange(len(q), dtype=np.int32), 5, targets, False)
+    np.savez_compressed(
+        os.path.join(HERE, "srf_golden.npz"),
+        d=ix["d"], m=ix["m"], K=ix["K"], C=ix["C"], N=ix["N"], coarse=ix["coarse"],
+        residual_codebook=ix["residual_codebook"], ids=ix["ids"], coarse_ids=ix["coarse_ids"], codes=ix["codes"],
+        pq_codebook=ix["pq_codebook"], pq_codes=ix["pq_codes"], queries=q, targets=targets,
+        ivfadc_k5_w3_ids=ids_a, ivfadc_k5_w3_dist=raw_a, ivfadc_k5_w3_text=txt_a,
+        ivfadc_k12_w1_ids=ids_b, ivfadc_k12_w1_dist=raw_b,
+        pq_search_k4_ids=pq_ids, pq_search_k4_dist=pq_raw, pq_in_k5_ids=in_ids, pq_in_k5_dist=in_raw)
+    print("wrote srf_golden.npz")
 
 
 if __name__ == "__main__":

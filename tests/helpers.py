@@ -29,3 +29,12 @@ def assert_same_topk(got_ids, got_d, exp_ids, exp_d, what=""):
     bad = np.nonzero((got_ids != exp_ids).any(axis=1))[0]
     assert bad.size == 0, f"{what}: {bad.size} queries differ in ids, first {bad[:5]}: got {got_ids[bad[:2]]} exp {exp_ids[bad[:2]]}"
     np.testing.assert_array_equal(got_d.view(np.uint32), exp_d.view(np.uint32), err_msg=f"{what}: distances differ")
+
+
+def srf_golden():
+    """index + outputs of the reference's own SRFs (tests/golden/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srf_golden.npz"))
+    ix = {k: (int(g[k]) if k in ("d", "m", "K", "C", "N") else g[k]) for k in
+          ("d", "m", "K", "C", "N", "coarse", "residual_codebook", "ids", "coarse_ids", "codes", "pq_codebook", "pq_codes")}
+    return ix, g

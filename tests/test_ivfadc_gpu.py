@@ -149,3 +149,19 @@ def test_flat_pq(eng, oracle_mod):
     ids, d = eng.pq_search_in_batch(q, 6, few)
     eids, ed = oi.pq_search_in_batch(q, 6, few)
     assert_same_topk(ids, d, eids, ed, "fewer targets than k")
+
+
+def test_against_reference_srf_golden(eng):
+    """the CUDA engine directly against committed outputs of the reference's own SRFs
+    (freddy.c run through the emulator, tests/golden/make_golden.py)"""
+    from helpers import srf_golden
+    ix, g = srf_golden()
+    eng.load_ivfadc_index(ix)
+    for k, w, tag in ((5, 3, "ivfadc_k5_w3"), (12, 1, "ivfadc_k12_w1")):
+        ids, d = eng.ivfadc_search(g["queries"], k, w)
+        assert_same_topk(ids, d, g[tag + "_ids"], g[tag + "_dist"], tag)
+    eng.load_pq_index(ix)
+    ids, d = eng.pq_search(g["queries"][:6], 4)
+    assert_same_topk(ids, d, g["pq_search_k4_ids"], g["pq_search_k4_dist"], "pq_search")
+    ids, d = eng.pq_search_in_batch(g["queries"], 5, g["targets"])
+    assert_same_topk(ids, d, g["pq_in_k5_ids"], g["pq_in_k5_dist"], "pq_search_in_batch")

@@ -124,3 +124,25 @@ def test_golden_vectors(oracle_mod):
             c = np.array(codes, np.int16)
             got = np.float32(L.fo_pq_distance_int16(_p(lut), _p(c), m, K)).view(np.uint32)
             assert int(got) == out
+
+
+def test_srf_golden_vectors(oracle_mod):
+    """the oracle's drivers against committed outputs of the reference's own SRFs"""
+    from helpers import srf_golden
+    ix, g = srf_golden()
+    oi = oracle_mod.OracleIndex(ix)
+    for k, w, tag in ((5, 3, "ivfadc_k5_w3"), (12, 1, "ivfadc_k12_w1")):
+        ids, d, rc, _ = oi.ivfadc_search(g["queries"], k, w)
+        assert rc == 0
+        np.testing.assert_array_equal(ids, g[tag + "_ids"])
+        np.testing.assert_array_equal(d.view(np.uint32), g[tag + "_dist"].view(np.uint32))
+    L = oracle_mod.lib()
+    txt = np.array([L.fo_round_through_text(float(x)) for x in g["ivfadc_k5_w3_dist"].ravel()], np.float32)
+    np.testing.assert_array_equal(txt.view(np.uint32), g["ivfadc_k5_w3_text"].ravel().view(np.uint32))
+    op = oracle_mod.OracleIndex(ix, flat_pq=True)
+    ids, d = op.pq_search(g["queries"][:6], 4)
+    np.testing.assert_array_equal(ids, g["pq_search_k4_ids"])
+    np.testing.assert_array_equal(d.view(np.uint32), g["pq_search_k4_dist"].view(np.uint32))
+    ids, d = op.pq_search_in_batch(g["queries"], 5, g["targets"])
+    np.testing.assert_array_equal(ids, g["pq_in_k5_ids"])
+    np.testing.assert_array_equal(d.view(np.uint32), g["pq_in_k5_dist"].view(np.uint32))

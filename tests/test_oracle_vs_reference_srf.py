@@ -1,0 +1,89 @@
+"""Pins the oracle's DRIVER restatements against the reference extension's own SRFs:
+freddy.c is compiled unmodified (oracle/Makefile `ref`) and run in-process on
+in-memory tables through the SPI/fmgr emulator oracle/pg_emul.c.  ids and raw fp32
+distances must agree bit for bit; the SRF's "%f" text output must equal
+fo_round_through_text of the oracle's distance."""
+import numpy as np
+import pytest
+
+from helpers import queries_from, small_index
+
+
+@pytest.fixture(scope="module")
+def ref(oracle_mod):
+    if oracle_mod.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (reference sources absent and no prebuilt .so)")
+    return oracle_mod.ReferenceSession
+
+
+def _same(a, b):
+    np.testing.assert_array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+
+
+@pytest.mark.parametrize("k,w", [(5, 4), (1, 1), (10, 3), (7, 10)])
+def test_ivfadc_search_driver(ref, oracle_mod, k, w):
+    ix = small_index()
+    q = queries_from(ix, 40, seed=21, noise=0.02)
+    s = ref()
+    s.load_ivfadc(ix, w)
+    rids, rraw, rtxt = s.ivfadc_search(q, k)
+    oids, od, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(q, k, w)
+    assert rc == 0
+    np.testing.assert_array_equal(oids, rids)
+    _same(od, rraw)
+    L = oracle_mod.lib()
+    _same(np.array([L.fo_round_through_text(float(x)) for x in od.ravel()], np.float32), rtxt.ravel())
+
+
+def test_ivfadc_search_ties_and_reprobe(ref, oracle_mod):
+    # duplicate-heavy table: ties straddle the k-th place constantly
+    ix = small_index(N=6000, d=8, m=2, K=4, C=8, seed=3, n_clusters=5)
+    q = queries_from(ix, 60, seed=9)
+    for k, w in ((5, 2), (3, 8), (20, 3)):
+        s = ref()
+        s.load_ivfadc(ix, w)
+        rids, rraw, _ = s.ivfadc_search(q, k)
+        oids, od, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(q, k, w)
+        assert rc == 0
+        np.testing.assert_array_equal(oids, rids)
+        _same(od, rraw)
+    # lists shorter than k: the re-probe loop with its blacklist (freddy.c:262-293)
+    ix = small_index(N=150, d=24, m=12, K=8, C=64, seed=5, n_clusters=20)
+    q = queries_from(ix, 30, seed=2)
+    s = ref()
+    s.load_ivfadc(ix, 2)
+    rids, rraw, _ = s.ivfadc_search(q, 12)
+    oids, od, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(q, 12, 2)
+    assert rc == 0
+    np.testing.assert_array_equal(oids, rids)
+    _same(od, rraw)
+
+
+def test_flat_pq_drivers(ref, oracle_mod):
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    q = queries_from(ix, 12, seed=13)
+    s = ref()
+    s.load_pq(ix)
+    oi = oracle_mod.OracleIndex(ix, flat_pq=True)
+    rids, rraw = s.pq_search(q[:4], 5)
+    oids, od = oi.pq_search(q[:4], 5)
+    np.testing.assert_array_equal(oids, rids)
+    _same(od, rraw)
+    rng = np.random.default_rng(0)
+    targets = rng.choice(np.arange(1, ix["N"] + 500), size=2000, replace=True).astype(np.int32)
+    rids, rraw = s.pq_search_in(q[0], 6, targets)
+    oids, od = oi.pq_search_in_batch(q[:1], 6, targets)
+    np.testing.assert_array_equal(oids[0], rids)
+    _same(od[0], rraw)
+    qids = np.arange(100, 100 + len(q), dtype=np.int32)
+    for tl in (False, True):
+        rq, rids, rraw = s.pq_search_in_batch(q, qids, 6, targets, tl)
+        oids, od = oi.pq_search_in_batch(q, 6, targets, use_target_lists=tl)
+        np.testing.assert_array_equal(rq, np.repeat(qids[:, None], 6, 1))
+        np.testing.assert_array_equal(oids, rids)
+        _same(od, rraw)
+    few = targets[:3]   # fewer rows than k: padded with id -1 / sentinel
+    rq, rids, rraw = s.pq_search_in_batch(q, qids, 6, few, False)
+    oids, od = oi.pq_search_in_batch(q, 6, few)
+    np.testing.assert_array_equal(oids, rids)
+    _same(od, rraw)
