@@ -97,6 +97,29 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k,
                           const int32_t* targets, int n_targets, int use_target_lists,
                           int32_t* out_ids, float* out_dists);
 
+/* ---- dense word-vector UDFs ------------------------------------------------ */
+/* word-vector table (google_vecs / google_vecs_norm: id, vector bytea = float4[d],
+ * vec2database.py:25) in table order; pinned in HBM, dimension-major in 32-row blocks */
+int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int64_t N, int d);
+/* n independent pairs a[i], b[i] of d floats -> out[i]
+ *   variant 0: cosine_similarity(float4[], float4[]) -> float8   core_functions.c:23-42, cosine_similarity.c:12-37
+ *   variant 1: cosine_similarity_norm                -> float8   core_functions.c:44-63, cosine_similarity.c:39-45
+ *   variant 2: cosine_similarity_bytea               -> float4 (widened)   core_functions.c:65-81 */
+int fb_cosine_similarity(fb_engine* e, int variant, const float* a, const float* b, int n, int d, double* out);
+/* vec_minus_bytea / vec_plus_bytea / vec_normalize_bytea on n vectors
+ * (core_functions.c:120-139, :179-196, :243-269); op 0: a-b, 1: a+b, 2: normalize(a) (b ignored) */
+int fb_vec_op(fb_engine* e, int op, const float* a, const float* b, int n, int d, float* out);
+/* analogy_3cosadd(w1, w2, w3) (freddy--0.0.1.sql:1270-1288) for nq triples of word ids
+ * (a, b, c): arg-max over the whole table, rows of the three ids excluded, of
+ * cosine_similarity_bytea(vec_plus_bytea(vec_minus_bytea(v_c, v_a), v_b), v_row); the first
+ * table row reaching the maximum wins (ORDER BY ... DESC FETCH FIRST 1).
+ * out_ids[q] = id of the winner (-1 if none), out_scores[q] = its score. */
+int fb_analogy_3cosadd(fb_engine* e, const int32_t* ids_abc, int nq, int32_t* out_ids, float* out_scores);
+/* same scan with explicit query vectors [nq][d] and up to three excluded ids per query
+ * (-1 = none): the building block for vocabulary-sharded multi-GPU runs */
+int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids, int nq,
+                    int32_t* out_ids, float* out_scores);
+
 int fb_synchronize(fb_engine* e);
 /* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL restores the engine's own stream).  Lets a host runtime order the

@@ -9,6 +9,7 @@
  */
 #include "freddy_oracle.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -367,4 +368,100 @@ int fo_ivfadc_search_many(const FoIndex* ix, const float* queries, int nq, int k
   if (rows_scanned) *rows_scanned = rows;
   free(th); free(args);
   return rc;
+}
+
+/* ------------------------------------------------------------------------- */
+/* vector UDFs                                                                */
+/* ------------------------------------------------------------------------- */
+
+/* ref: cosine_similarity.c:12-37 cosine_similarity_simple: three double accumulators,
+ * each term a double product of float inputs; 0 when either squared norm is 0. */
+double fo_cosine_similarity(const float* v1, const float* v2, int n) {
+  double scalar = 0, sq1 = 0, sq2 = 0;
+  for (int i = 0; i < n; i++) {
+    scalar += ((double)v1[i]) * ((double)v2[i]);
+    sq2 += ((double)v2[i]) * ((double)v2[i]);
+    sq1 += ((double)v1[i]) * ((double)v1[i]);
+  }
+  if (sq1 > 0 && sq2 > 0) return scalar / (sqrt(sq1) * sqrt(sq2));
+  return 0;
+}
+
+/* ref: cosine_similarity.c:39-45 cosine_similarity_simple_norm: plain double dot */
+double fo_cosine_similarity_norm(const float* v1, const float* v2, int n) {
+  double scalar = 0;
+  for (int i = 0; i < n; i++) scalar += ((double)v1[i]) * ((double)v2[i]);
+  return scalar;
+}
+
+/* ref: core_functions.c:67-81 cosine_similarity_bytea: fp32 dot, product and sum rounded
+ * separately, no normalisation */
+float fo_cosine_similarity_bytea(const float* v1, const float* v2, int n) {
+  float scalar = 0;
+  for (int i = 0; i < n; i++) {
+    float prod = v1[i] * v2[i];
+    scalar = scalar + prod;
+  }
+  return scalar;
+}
+
+/* ref: core_functions.c:120-139 / :179-196 */
+void fo_vec_minus(const float* a, const float* b, int n, float* out) {
+  for (int i = 0; i < n; i++) out[i] = a[i] - b[i];
+}
+void fo_vec_plus(const float* a, const float* b, int n, float* out) {
+  for (int i = 0; i < n; i++) out[i] = a[i] + b[i];
+}
+
+/* ref: core_functions.c:243-269 vec_normalize_bytea: fp32 sum of squares, sqrt through
+ * double (the C library sqrt), fp32 division */
+void fo_vec_normalize(const float* a, int n, float* out) {
+  float sq = 0;
+  for (int i = 0; i < n; i++) {
+    float p = a[i] * a[i];
+    sq = sq + p;
+  }
+  float length = (float)sqrt((double)sq);
+  for (int i = 0; i < n; i++) out[i] = a[i] / length;
+}
+
+/* ref: freddy--0.0.1.sql:1270-1288 analogy_3cosadd */
+int fo_analogy_3cosadd(const float* vectors, int N, int d, int row_a, int row_b, int row_c, float* score) {
+  float* q = malloc(sizeof(float) * (size_t)d);
+  float* t = malloc(sizeof(float) * (size_t)d);
+  fo_vec_minus(vectors + (size_t)row_c * d, vectors + (size_t)row_a * d, d, t);   /* v3 - v1 */
+  fo_vec_plus(t, vectors + (size_t)row_b * d, d, q);                               /* + v2    */
+  int best = -1;
+  float best_s = 0;
+  for (int r = 0; r < N; r++) {
+    if (r == row_a || r == row_b || r == row_c) continue;                          /* word NOT IN (...) */
+    float s = fo_cosine_similarity_bytea(q, vectors + (size_t)r * d, d);
+    if (best < 0 || s > best_s) { best = r; best_s = s; }                          /* DESC, first row wins ties */
+  }
+  if (score) *score = best_s;
+  free(q); free(t);
+  return best;
+}
+
+typedef struct { const float* v; int N, d; const int32_t* abc; int begin, end; int32_t* rows; float* scores; } AnaArgs;
+static void* ana_worker(void* p) {
+  AnaArgs* a = p;
+  for (int q = a->begin; q < a->end; q++)
+    a->rows[q] = fo_analogy_3cosadd(a->v, a->N, a->d, a->abc[3 * q], a->abc[3 * q + 1], a->abc[3 * q + 2], &a->scores[q]);
+  return NULL;
+}
+int fo_analogy_3cosadd_many(const float* vectors, int N, int d, const int32_t* rows_abc, int nq, int n_threads,
+                            int32_t* out_rows, float* out_scores) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > nq) n_threads = nq > 0 ? nq : 1;
+  pthread_t* th = malloc(sizeof(pthread_t) * (size_t)n_threads);
+  AnaArgs* args = malloc(sizeof(AnaArgs) * (size_t)n_threads);
+  for (int t = 0; t < n_threads; t++) {
+    args[t] = (AnaArgs){vectors, N, d, rows_abc, (int)((int64_t)nq * t / n_threads),
+                        (int)((int64_t)nq * (t + 1) / n_threads), out_rows, out_scores};
+    pthread_create(&th[t], NULL, ana_worker, &args[t]);
+  }
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  free(th); free(args);
+  return 0;
 }

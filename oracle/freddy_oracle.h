@@ -76,6 +76,22 @@ int fo_pq_search_in_batch(const FoIndex* ix, const float* queries, int nq, int k
                           const int32_t* targets, int n_targets, int use_target_lists,
                           FoTopKEntry* out_topk);
 
+/* ---- vector UDFs (core_functions.c, cosine_similarity.c) ---- */
+double fo_cosine_similarity(const float* v1, const float* v2, int n);      /* cosine_similarity.c:12-37 */
+double fo_cosine_similarity_norm(const float* v1, const float* v2, int n); /* cosine_similarity.c:39-45 */
+float fo_cosine_similarity_bytea(const float* v1, const float* v2, int n); /* core_functions.c:67-81 */
+void fo_vec_minus(const float* a, const float* b, int n, float* out);      /* core_functions.c:120-139 */
+void fo_vec_plus(const float* a, const float* b, int n, float* out);       /* core_functions.c:179-196 */
+void fo_vec_normalize(const float* a, int n, float* out);                  /* core_functions.c:243-269 */
+/* analogy_3cosadd (freddy--0.0.1.sql:1270-1288) over an in-memory word-vector table:
+ * argmax over rows r (table order, rows a/b/c excluded) of
+ * cosine_similarity_bytea(vec_plus_bytea(vec_minus_bytea(v[c], v[a]), v[b]), v[r]);
+ * ORDER BY ... DESC FETCH FIRST 1: the first row reaching the maximum wins.
+ * rows are table row numbers; returns the winning row (or -1), score in *score. */
+int fo_analogy_3cosadd(const float* vectors, int N, int d, int row_a, int row_b, int row_c, float* score);
+int fo_analogy_3cosadd_many(const float* vectors, int N, int d, const int32_t* rows_abc, int nq, int n_threads,
+                            int32_t* out_rows, float* out_scores);
+
 /* Run fo_ivfadc_search over nq queries on n_threads host threads (disjoint
  * query shards = n_threads concurrent backends).  out_topk is [nq][k]. */
 int fo_ivfadc_search_many(const FoIndex* ix, const float* queries, int nq, int k, int w,

@@ -61,8 +61,27 @@ def lib():
                                             C.c_int, C.c_void_p]
         L.fo_ivfadc_search_many.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_void_p]
+        L.fo_cosine_similarity.restype = C.c_double
+        L.fo_cosine_similarity.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.fo_cosine_similarity_norm.restype = C.c_double
+        L.fo_cosine_similarity_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.fo_cosine_similarity_bytea.restype = C.c_float
+        L.fo_cosine_similarity_bytea.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.fo_vec_minus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_vec_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_vec_normalize.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_analogy_3cosadd_many.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def analogy_3cosadd(vectors, rows_abc, threads=1):
+    """oracle: winning table row and score per (a, b, c) row triple"""
+    v = np.ascontiguousarray(vectors, np.float32)
+    t = np.ascontiguousarray(rows_abc, np.int32).reshape(-1, 3)
+    rows, scores = np.empty(len(t), np.int32), np.empty(len(t), np.float32)
+    lib().fo_analogy_3cosadd_many(_p(v), v.shape[0], v.shape[1], _p(t), len(t), threads, _p(rows), _p(scores))
+    return rows, scores
 
 
 def ref_lib():
@@ -76,6 +95,15 @@ def ref_lib():
     R.computePQDistanceInt16.restype = C.c_float
     R.computePQDistanceInt16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     R.getPrecomputedDistances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    R.cosine_similarity_simple.restype = C.c_double
+    R.cosine_similarity_simple.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.cosine_similarity_simple_norm.restype = C.c_double
+    R.cosine_similarity_simple_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_cosine_similarity_bytea.restype = C.c_float
+    R.ref_cosine_similarity_bytea.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_vec_minus_bytea.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    R.ref_vec_plus_bytea.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    R.ref_vec_normalize_bytea.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     return R
 
 

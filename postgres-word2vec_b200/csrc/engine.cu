@@ -17,6 +17,7 @@
 #include "../../include/freddy_b200.h"
 #include "exact_kernels.cuh"
 #include "ivfadc_kernels.cuh"
+#include "vector_kernels.cuh"
 
 using namespace fb;
 
@@ -89,6 +90,19 @@ struct fb_engine {
   bool pq_ids_sorted = true;
   std::unordered_map<int32_t, int32_t> pq_id_to_row;
   DevBuf<int32_t> iota_lists;
+  // word-vector table (analogy / exact rerank)
+  DevBuf<float> vecT;
+  DevBuf<int32_t> vec_ids;
+  std::vector<int32_t> vec_ids_host;
+  bool vec_ids_sorted = true;
+  std::unordered_map<int32_t, int32_t> vec_id_to_row;
+  int64_t vec_N = 0;
+  int vec_d = 0;
+  bool vec_loaded = false;
+  DevBuf<float> va, vb, vo;
+  DevBuf<double> vdo;
+  DevBuf<int32_t> ana_rows;
+  DevBuf<u64> ana_partial;
 
   // scratch
   DevBuf<float> lut, exact_lut, q_stage, dist_stage;
@@ -636,6 +650,8 @@ void fb_destroy(fb_engine* e) {
   for (auto& c : e->cb) c.cbT.release();
   e->fine.release(); e->pq.release(); e->tmp.release();
   e->iota_lists.release();
+  e->vecT.release(); e->vec_ids.release(); e->va.release(); e->vb.release(); e->vo.release(); e->vdo.release();
+  e->ana_rows.release(); e->ana_partial.release();
   e->lut.release(); e->exact_lut.release(); e->q_stage.release(); e->dist_stage.release();
   e->probes.release(); e->exact_list.release(); e->id_stage.release(); e->sel_rows.release();
   e->qflags.release(); e->partial.release(); e->kth.release(); e->small.release(); e->counters64.release();
@@ -876,6 +892,173 @@ float fb_round_through_text(float distance) {
   char buf[16];
   snprintf(buf, sizeof buf, "%f", distance);
   return strtof(buf, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int vec_row_of(const fb_engine* e, int32_t id) {
+  if (id < 0) return -1;
+  if (e->vec_ids_sorted) {
+    auto it = std::lower_bound(e->vec_ids_host.begin(), e->vec_ids_host.end(), id);
+    return (it != e->vec_ids_host.end() && *it == id) ? (int)(it - e->vec_ids_host.begin()) : -1;
+  }
+  auto it = e->vec_id_to_row.find(id);
+  return it == e->vec_id_to_row.end() ? -1 : it->second;
+}
+
+// d_q: device [nq][d] query vectors; h_rows: host [nq][3] excluded table rows
+int analogy_scan_dev(fb_engine* e, const float* d_q, const std::vector<int32_t>& h_rows, int nq, int32_t* d_out_ids,
+                     float* d_out_scores) {
+  const int d = e->vec_d;
+  const int64_t N = e->vec_N;
+  const int tiles = (nq + kAnaQT - 1) / kAnaQT, nq_pad = tiles * kAnaQT;
+  const int64_t n_blocks = (N + 31) / 32;
+  const int blocks_per_slab = kAnaWarps * 8;
+  const int n_slabs = (int)((n_blocks + blocks_per_slab - 1) / blocks_per_slab);
+  FB_CUDA(e, e->ana_rows.ensure((size_t)nq * 3));
+  FB_CUDA(e, e->ana_partial.ensure((size_t)std::max(1, n_slabs) * nq_pad));
+  FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, h_rows.data(), (size_t)nq * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));  // h_rows is the caller's stack/heap
+  const size_t smem = ((size_t)d * kAnaQT + (size_t)kAnaWarps * 32 * 33) * sizeof(float);
+  if (smem > e->smem_optin - 2048) return fail(e, FB_ERR_UNSUPPORTED, "d=%d too large for the analogy scan", d);
+  FB_CUDA(e, cudaFuncSetAttribute(analogy_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (n_slabs > 0) {
+    StageTimer t(e, ST_SCAN);
+    dim3 grid(tiles, n_slabs);
+    analogy_scan_kernel<<<grid, kAnaThreads, smem, e->stream>>>(e->vecT.p, N, d, blocks_per_slab, d_q, nq, e->ana_rows.p,
+                                                                e->ana_partial.p, nq_pad, e->one);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  analogy_reduce_kernel<<<(nq + 127) / 128, 128, 0, e->stream>>>(e->ana_partial.p, n_slabs, nq, nq_pad, e->vec_ids.p, 0,
+                                                                d_out_ids, d_out_scores, nullptr);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  e->host_rows += (int64_t)nq * N;
+  e->bytes_per_row = d * 4;
+  return FB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int64_t N, int d) {
+  if (!e || N < 0 || d < 1 || (N > 0 && (!ids || !vectors))) return fail(e, FB_ERR_INVALID, "fb_load_vectors: bad arguments");
+  if (N >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int64_t n_blocks = std::max<int64_t>(1, (N + 31) / 32);
+  FB_CUDA(e, e->vecT.ensure((size_t)n_blocks * d * 32));
+  FB_CUDA(e, e->vec_ids.ensure((size_t)std::max<int64_t>(1, N)));
+  // stage row-major through a temporary device buffer in slices, transpose on the device
+  const int64_t slice_rows = 32 * 8192;
+  DevBuf<float> stage;
+  FB_CUDA(e, stage.ensure((size_t)std::min<int64_t>(std::max<int64_t>(N, 1), slice_rows) * d));
+  for (int64_t r0 = 0; r0 < N; r0 += slice_rows) {
+    const int64_t n = std::min(slice_rows, N - r0);
+    FB_CUDA(e, cudaMemcpyAsync(stage.p, vectors + (size_t)r0 * d, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    transpose_rows_kernel<<<(unsigned)((n + 31) / 32), 256, 0, e->stream>>>(stage.p, n, d, e->vecT.p + (size_t)(r0 / 32) * d * 32);
+    FB_CUDA(e, cudaGetLastError());
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
+  stage.release();
+  if (N > 0) FB_CUDA(e, cudaMemcpy(e->vec_ids.p, ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->vec_ids_host.assign(ids, ids + N);
+  e->vec_ids_sorted = std::is_sorted(e->vec_ids_host.begin(), e->vec_ids_host.end());
+  e->vec_id_to_row.clear();
+  if (!e->vec_ids_sorted)
+    for (int64_t r = 0; r < N; r++) e->vec_id_to_row.emplace(ids[r], (int32_t)r);
+  e->vec_N = N; e->vec_d = d; e->vec_loaded = true;
+  return FB_OK;
+}
+
+int fb_cosine_similarity(fb_engine* e, int variant, const float* a, const float* b, int n, int d, double* out) {
+  if (!e || variant < 0 || variant > 2 || n < 0 || d < 1) return fail(e, FB_ERR_INVALID, "fb_cosine_similarity: bad arguments");
+  if (n == 0) return FB_OK;
+  if (!a || !b || !out) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->va.ensure((size_t)n * d));
+  FB_CUDA(e, e->vb.ensure((size_t)n * d));
+  FB_CUDA(e, e->vdo.ensure((size_t)n));
+  FB_CUDA(e, cudaMemcpyAsync(e->va.p, a, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(e->vb.p, b, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  cosine_pairs_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->va.p, e->vb.p, n, d, variant, e->vdo.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaMemcpyAsync(out, e->vdo.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
+int fb_vec_op(fb_engine* e, int op, const float* a, const float* b, int n, int d, float* out) {
+  if (!e || op < 0 || op > 2 || n < 0 || d < 1) return fail(e, FB_ERR_INVALID, "fb_vec_op: bad arguments");
+  if (n == 0) return FB_OK;
+  if (!a || !out || (op != 2 && !b)) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->va.ensure((size_t)n * d));
+  FB_CUDA(e, e->vb.ensure((size_t)n * d));
+  FB_CUDA(e, e->vo.ensure((size_t)n * d));
+  FB_CUDA(e, cudaMemcpyAsync(e->va.p, a, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if (op != 2) FB_CUDA(e, cudaMemcpyAsync(e->vb.p, b, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  vec_ops_kernel<<<n, 128, 0, e->stream>>>(e->va.p, e->vb.p, n, d, op, e->vo.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaMemcpyAsync(out, e->vo.p, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
+int fb_analogy_3cosadd(fb_engine* e, const int32_t* ids_abc, int nq, int32_t* out_ids, float* out_scores) {
+  if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_analogy_3cosadd: bad arguments");
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "word-vector table not loaded (fb_load_vectors)");
+  if (nq == 0) return FB_OK;
+  if (!ids_abc || !out_ids || !out_scores) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int32_t> rows((size_t)nq * 3);
+  for (int i = 0; i < nq * 3; i++) {
+    rows[i] = vec_row_of(e, ids_abc[i]);
+    // the SQL inner joins on the three words: an unknown word yields no row at all
+    if (rows[i] < 0) return fail(e, FB_ERR_INVALID, "analogy: id %d is not in the word-vector table", ids_abc[i]);
+  }
+  const int d = e->vec_d;
+  FB_CUDA(e, e->ana_rows.ensure((size_t)nq * 3));
+  FB_CUDA(e, e->vo.ensure((size_t)nq * d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq));
+  FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  analogy_query_kernel<<<nq, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, nq, e->vo.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  int rc = analogy_scan_dev(e, e->vo.p, rows, nq, e->id_stage.p, e->dist_stage.p);
+  if (rc) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_scores, e->dist_stage.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->queries_done += nq;
+  return FB_OK;
+}
+
+int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids, int nq, int32_t* out_ids, float* out_scores) {
+  if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_analogy_scan: bad arguments");
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "word-vector table not loaded (fb_load_vectors)");
+  if (nq == 0) return FB_OK;
+  if (!qvecs || !out_ids || !out_scores) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int32_t> rows((size_t)nq * 3, -1);
+  if (exclude_ids)
+    for (int i = 0; i < nq * 3; i++) rows[i] = vec_row_of(e, exclude_ids[i]);  // ids living on another shard: no local row
+  const int d = e->vec_d;
+  FB_CUDA(e, e->va.ensure((size_t)nq * d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq));
+  FB_CUDA(e, cudaMemcpyAsync(e->va.p, qvecs, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  int rc = analogy_scan_dev(e, e->va.p, rows, nq, e->id_stage.p, e->dist_stage.p);
+  if (rc) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_scores, e->dist_stage.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->queries_done += nq;
+  return FB_OK;
 }
 
 }  // extern "C"

@@ -41,6 +41,11 @@ SIGNATURES = {
     "fb_ivfadc_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search_in_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
+    "fb_cosine_similarity": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "fb_vec_op": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
+    "fb_analogy_3cosadd": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "fb_analogy_scan": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "fb_synchronize": (C.c_int, [_P]),
     "fb_set_stream": (C.c_int, [_P, _P]),
     "fb_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),

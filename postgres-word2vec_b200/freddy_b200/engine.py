@@ -126,6 +126,40 @@ class Engine:
         """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream) or 0/None"""
         self._check(self._lib.fb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    # ---- dense word-vector UDFs -----------------------------------------
+    def load_vectors(self, ids, vectors):
+        ids = _i32(ids)
+        v = _f32(vectors)
+        self.vec_d = v.shape[1]
+        self._check(self._lib.fb_load_vectors(self._h, _ptr(ids), _ptr(v), v.shape[0], v.shape[1]))
+
+    def cosine_similarity(self, a, b, variant=0):
+        a, b = _f32(a), _f32(b)
+        n, d = a.shape
+        out = np.empty(n, np.float64)
+        self._check(self._lib.fb_cosine_similarity(self._h, variant, _ptr(a), _ptr(b), n, d, _ptr(out)))
+        return out
+
+    def vec_op(self, op, a, b=None):
+        a = _f32(a)
+        b = _f32(b) if b is not None else None
+        out = np.empty_like(a)
+        self._check(self._lib.fb_vec_op(self._h, op, _ptr(a), _ptr(b), a.shape[0], a.shape[1], _ptr(out)))
+        return out
+
+    def analogy_3cosadd(self, ids_abc):
+        t = _i32(ids_abc).reshape(-1, 3)
+        out_ids, out_s = np.empty(len(t), np.int32), np.empty(len(t), np.float32)
+        self._check(self._lib.fb_analogy_3cosadd(self._h, _ptr(t), len(t), _ptr(out_ids), _ptr(out_s)))
+        return out_ids, out_s
+
+    def analogy_scan(self, qvecs, exclude_ids=None):
+        q = _f32(qvecs)
+        ex = _i32(exclude_ids).reshape(-1, 3) if exclude_ids is not None else None
+        out_ids, out_s = np.empty(len(q), np.int32), np.empty(len(q), np.float32)
+        self._check(self._lib.fb_analogy_scan(self._h, _ptr(q), _ptr(ex), len(q), _ptr(out_ids), _ptr(out_s)))
+        return out_ids, out_s
+
     def synchronize(self):
         self._check(self._lib.fb_synchronize(self._h))
 
