@@ -465,3 +465,293 @@ int fo_analogy_3cosadd_many(const float* vectors, int N, int d, const int32_t* r
   free(th); free(args);
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* kNN-join: ivpq_search_in                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* ref: index_utils.c:673-682 getConfidenceHyp — normal approximation of a
+ * hypergeometric tail; float/double mix kept exactly as written there. */
+float fo_confidence_hyp(int expect, int size, float p, int stat_size) {
+  if (expect > size) return 0;
+  float mu = size * p;
+  float sig = sqrt(size * p * (1.0 - p)) * (((float)stat_size - size) / ((float)stat_size - 1.0));
+  return 1.0 - 0.5 * (1.0 + erf((((float)expect) - 0.5 - mu) / (sig * sqrt(2))));
+}
+
+typedef struct { int id; float distance; int pos0, pos1; } HeapNode;   /* index_utils.h:33-37 QueueEntry */
+
+/* ref: index_utils.c:118-131 push — sift up while the parent is strictly larger */
+static void heap_push(HeapNode* nodes, int* len, float distance, int id, int p0, int p1) {
+  int i = *len;
+  int parent = (i - 1) / 2;
+  while (i > 0 && nodes[parent].distance > distance) {
+    nodes[i] = nodes[parent];
+    i = parent;
+    parent = (parent - 1) / 2;
+  }
+  nodes[i].distance = distance; nodes[i].id = id; nodes[i].pos0 = p0; nodes[i].pos1 = p1;
+  (*len)++;
+}
+
+/* ref: index_utils.c:133-155 pop — the old last element (still readable at nodes[len])
+ * is sifted down from the root through a hole; a child moves up only if strictly
+ * smaller; note the reference also reads nodes[j+1] when j+1 == len (the stale copy). */
+static HeapNode heap_pop(HeapNode* nodes, int* len) {
+  HeapNode result = nodes[0];
+  nodes[0] = nodes[*len - 1];
+  (*len)--;
+  int i = 0;
+  while (i != *len) {
+    int pick = *len;
+    int j = 1 + 2 * i;
+    if (j <= *len - 1 && nodes[j].distance < nodes[pick].distance) pick = j;
+    if (j <= *len - 1 && nodes[j + 1].distance < nodes[pick].distance) pick = j + 1;
+    nodes[i] = nodes[pick];
+    i = pick;
+  }
+  return result;
+}
+
+static int cmp_topk_dist(const void* a, const void* b) {   /* index_utils.c:111-116 cmpTopKEntry */
+  float x = ((const FoTopKEntry*)a)->distance, y = ((const FoTopKEntry*)b)->distance;
+  return (x > y) - (x < y);
+}
+
+typedef struct { int id; float distance; const float* vector; } PvEntry;   /* index_utils.h:27-31 TopKPVEntry */
+static int cmp_pv_dist(const void* a, const void* b) {      /* index_utils.c:104-109 cmpTopKPVEntry */
+  float x = ((const PvEntry*)a)->distance, y = ((const PvEntry*)b)->distance;
+  return (x > y) - (x < y);
+}
+
+/* ref: ivpq_search_in.c:40-44 reorderTopKPV */
+static void pv_reorder(PvEntry* tk, int kk, int* fill, float* max_dist) {
+  qsort(tk, (size_t)*fill, sizeof(PvEntry), cmp_pv_dist);
+  *fill = kk;
+  *max_dist = tk[kk - 1].distance;
+}
+/* ref: ivpq_search_in.c:46-57 updateTopKPVFast */
+static void pv_append(PvEntry* tk, int batch, int kk, int* fill, float* max_dist, int id, float distance, const float* vec) {
+  tk[*fill].id = id; tk[*fill].distance = distance; tk[*fill].vector = vec;
+  (*fill)++;
+  if (*fill == batch - 1) pv_reorder(tk, kk, fill, max_dist);
+}
+static void pv_init(PvEntry* tk, int n, float max_dist) {   /* index_utils.c:84-92 initTopKPV */
+  for (int i = 0; i < n; i++) { tk[i].distance = max_dist; tk[i].id = -1; tk[i].vector = NULL; }
+}
+
+/* ref: index_utils.c:252-443 determineCoarseIdsMultiWithStatisticsMulti (USE_PROPERTY_QUEUE,
+ * two positions): per active query, multi-sequence traversal of the Kc x Kc grid in ascending
+ * d0 + d1 until getConfidenceHyp(minTarget, |targets|, sum freq, total) >= confidence.
+ * Registers query q with every visited cell (cell_q[cell] in registration order). */
+static int ivpq_select_cells(const FoIvpqIndex* ix, const float* queries, const int* active, int n_active,
+                             int n_targets, int min_target, float confidence,
+                             int** cell_q, int* cell_n) {
+  const int Kc = ix->Kc, cells = Kc * Kc, half = ix->d / 2;
+  int last_iteration = 1;
+  FoTopKEntry* md0 = malloc(sizeof(FoTopKEntry) * (size_t)Kc);
+  FoTopKEntry* md1 = malloc(sizeof(FoTopKEntry) * (size_t)Kc);
+  float* all = malloc(sizeof(float) * (size_t)cells);
+  HeapNode* heap = malloc(sizeof(HeapNode) * (size_t)(cells + 2));
+  unsigned char* traversed = malloc((size_t)cells);
+  unsigned char* in_queue = malloc((size_t)cells);
+  for (int c = 0; c < cells; c++) cell_n[c] = 0;
+  for (int x = 0; x < n_active; x++) {
+    const int q = active[x];
+    const float* qv = queries + (size_t)q * ix->d;
+    int visited = 0;
+    float prob = 0.0f;
+    for (int j = 0; j < Kc; j++) {                                             /* :296-305 */
+      md0[j].id = j; md0[j].distance = fo_square_distance(qv, ix->coarse_multi + (size_t)j * half, half);
+      md1[j].id = j; md1[j].distance = fo_square_distance(qv + half, ix->coarse_multi + (size_t)(Kc + j) * half, half);
+    }
+    for (int i = 0; i < cells; i++) {                                          /* :306-313 */
+      float s = 0;
+      s += md0[i % Kc].distance;
+      s += md1[i / Kc].distance;
+      all[i] = s;
+    }
+    qsort(md0, (size_t)Kc, sizeof(FoTopKEntry), cmp_topk_dist);                 /* :317-319 */
+    qsort(md1, (size_t)Kc, sizeof(FoTopKEntry), cmp_topk_dist);
+    memset(traversed, 0, (size_t)cells);
+    memset(in_queue, 0, (size_t)cells);
+    int len = 0;
+    {
+      int first = md0[0].id + Kc * md1[0].id;                                   /* :342-348 */
+      heap[0].pos0 = 0; heap[0].pos1 = 0; heap[0].id = first; heap[0].distance = all[first];
+      len = 1;
+    }
+    while (fo_confidence_hyp(min_target, n_targets, prob, (int)ix->stats[cells]) < confidence && visited < cells) { /* :349-351 */
+      HeapNode next = heap_pop(heap, &len);
+      traversed[next.pos0 + Kc * next.pos1] = 1;
+      if (next.pos0 < Kc - 1 &&
+          (next.pos1 == 0 || traversed[next.pos0 + 1 + Kc * (next.pos1 - 1)])) {      /* :356-372 */
+        int np = (next.pos0 + 1) + Kc * next.pos1;
+        if (!in_queue[np]) {
+          int nid = md0[next.pos0 + 1].id + Kc * md1[next.pos1].id;
+          heap_push(heap, &len, all[nid], nid, next.pos0 + 1, next.pos1);
+          in_queue[np] = 1;
+        }
+      }
+      if (next.pos1 < Kc - 1 &&
+          (next.pos0 == 0 || traversed[next.pos0 - 1 + Kc * (next.pos1 + 1)])) {      /* :373-392 */
+        int np = next.pos0 + Kc * (next.pos1 + 1);
+        if (!in_queue[np]) {
+          int nid = md0[next.pos0].id + Kc * md1[next.pos1 + 1].id;
+          heap_push(heap, &len, all[nid], nid, next.pos0, next.pos1 + 1);
+          in_queue[np] = 1;
+        }
+      }
+      prob += ix->stats[next.id];                                               /* :394 */
+      visited++;
+      cell_q[next.id][cell_n[next.id]++] = q;                                   /* :398-402 */
+    }
+    if (visited < cells) last_iteration = 0;                                    /* :404-406 */
+  }
+  free(md0); free(md1); free(all); free(heap); free(traversed); free(in_queue);
+  return last_iteration;
+}
+
+static const float* ivpq_vector_of(const FoIvpqIndex* ix, int32_t id) {   /* INNER JOIN vecs ON fq.id = vecs.id */
+  int lo = 0, hi = ix->Nv - 1;
+  while (lo <= hi) {
+    int mid = lo + (hi - lo) / 2;
+    if (ix->vec_ids[mid] < id) lo = mid + 1; else if (ix->vec_ids[mid] > id) hi = mid - 1;
+    else return ix->vectors + (size_t)mid * ix->d;
+  }
+  return NULL;
+}
+
+/* ref: ivpq_search_in.c:197-684 (first-call body).  The target-list mode only reorders the
+ * loop nest (row-major collect, then query-major evaluate, :546-607) except for the
+ * `targetCounts < k*alpha_original` skip (:553-557), which is kept. */
+int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                      int alpha_original, int pvf, int method, int use_tl, float confidence, int double_threshold,
+                      FoTopKEntry* topks, int64_t* stats_out) {
+  const float MAX_DIST = 1000.0f;                    /* :62 */
+  const int BATCH = 200;                             /* :63 TOPK_BATCH_SIZE */
+  const int d = ix->d, m = ix->m, K = ix->K, sub = d / m, cells = ix->Kc * ix->Kc;
+  int alpha = alpha_original;
+  if (pvf < 1) pvf = 1;                              /* :206-208 */
+  if ((method == 0 || method == 2) && alpha * k > double_threshold) return -10;   /* pair-LUT variant (:261-275) not restated */
+  const int kk = k * pvf;
+  int64_t rounds = 0, pairs = 0;
+
+  float* max_dists = malloc(sizeof(float) * (size_t)(nq ? nq : 1));
+  int* target_counts = calloc((size_t)(nq ? nq : 1), sizeof(int));
+  int* fill = calloc((size_t)(nq ? nq : 1), sizeof(int));
+  PvEntry* pv = NULL;
+  float* luts = NULL;
+  for (int i = 0; i < nq; i++) { fo_init_topk(topks + (size_t)i * k, k, MAX_DIST); max_dists[i] = MAX_DIST; }   /* :238 */
+  if (method == 2) {                                 /* :243-251 */
+    pv = malloc(sizeof(PvEntry) * (size_t)(nq ? nq : 1) * (BATCH + kk));
+    for (int i = 0; i < nq; i++) pv_init(pv + (size_t)i * (BATCH + kk), BATCH + kk, MAX_DIST);
+  }
+  if (method == 0 || method == 2) {                  /* :279-290 */
+    luts = malloc(sizeof(float) * (size_t)(nq ? nq : 1) * m * K);
+    for (int i = 0; i < nq; i++) fo_precomputed_distances(luts + (size_t)i * m * K, m, K, sub, queries + (size_t)i * d, ix->codebook);
+  }
+  /* rows selected by `fq.id IN (targets)`, table order */
+  int32_t* tsorted = malloc(sizeof(int32_t) * (size_t)(n_targets ? n_targets : 1));
+  memcpy(tsorted, targets, sizeof(int32_t) * (size_t)n_targets);
+  qsort(tsorted, (size_t)n_targets, sizeof(int32_t), cmp_i32);
+
+  int* active = malloc(sizeof(int) * (size_t)(nq ? nq : 1));
+  int n_active = nq;
+  for (int i = 0; i < nq; i++) active[i] = i;
+  int** cell_q = malloc(sizeof(int*) * (size_t)cells);
+  for (int c = 0; c < cells; c++) cell_q[c] = malloc(sizeof(int) * (size_t)(nq ? nq : 1));
+  int* cell_n = malloc(sizeof(int) * (size_t)cells);
+  /* per-query candidate lists for the target-list mode (query-major evaluation) */
+  int** tl_rows = NULL; int* tl_n = NULL; int* tl_cap = NULL;
+  if (use_tl) { tl_rows = calloc((size_t)(nq ? nq : 1), sizeof(int*)); tl_n = calloc((size_t)(nq ? nq : 1), sizeof(int)); tl_cap = calloc((size_t)(nq ? nq : 1), sizeof(int)); }
+
+  while (n_active > 0) {                              /* :299 */
+    rounds++;
+    int last_iteration = ivpq_select_cells(ix, queries, active, n_active, n_targets, k * alpha, confidence, cell_q, cell_n);
+    if (use_tl) for (int i = 0; i < nq; i++) tl_n[i] = 0;
+    for (int r = 0; r < ix->N; r++) {                 /* rows: coarse_id IN (cells with queries) AND id IN (targets) */
+      const int cell = ix->coarse_ids[r];
+      if (cell_n[cell] == 0) continue;
+      if (!bsearch(&ix->ids[r], tsorted, (size_t)n_targets, sizeof(int32_t), cmp_i32)) continue;
+      const float* vec = NULL;
+      if (method != 0) { vec = ivpq_vector_of(ix, ix->ids[r]); if (!vec) continue; }
+      const int16_t* codes = ix->codes + (size_t)r * m;
+      for (int j = 0; j < cell_n[cell]; j++) {        /* :459-541 */
+        const int q = cell_q[cell][j];
+        target_counts[q] += 1;
+        pairs++;
+        if (use_tl) {
+          if (tl_n[q] == tl_cap[q]) { tl_cap[q] = tl_cap[q] ? 2 * tl_cap[q] : 256; tl_rows[q] = realloc(tl_rows[q], sizeof(int) * (size_t)tl_cap[q]); }
+          tl_rows[q][tl_n[q]++] = r;
+          continue;
+        }
+        float dist;
+        if (method == 1) dist = fo_square_distance(queries + (size_t)q * d, vec, d);
+        else dist = fo_pq_distance_int16(luts + (size_t)q * m * K, codes, m, K);
+        if (dist < max_dists[q]) {
+          if (method == 2) pv_append(pv + (size_t)q * (BATCH + kk), BATCH + kk, kk, &fill[q], &max_dists[q], ix->ids[r], dist, vec);
+          else { fo_update_topk(topks + (size_t)q * k, dist, ix->ids[r], k); max_dists[q] = topks[(size_t)q * k + k - 1].distance; }
+        }
+      }
+    }
+    if (use_tl) {                                      /* :546-607 */
+      for (int x = 0; x < n_active; x++) {
+        const int q = active[x];
+        if (target_counts[q] < k * alpha_original && !last_iteration) { target_counts[q] = 0; continue; }   /* :553-557 */
+        for (int t = 0; t < tl_n[q]; t++) {
+          const int r = tl_rows[q][t];
+          const float* vec = (method != 0) ? ivpq_vector_of(ix, ix->ids[r]) : NULL;
+          float dist;
+          if (method == 1) dist = fo_square_distance(queries + (size_t)q * d, vec, d);
+          else dist = fo_pq_distance_int16(luts + (size_t)q * m * K, ix->codes + (size_t)r * m, m, K);
+          if (dist < max_dists[q]) {
+            if (method == 2) pv_append(pv + (size_t)q * (BATCH + kk), BATCH + kk, kk, &fill[q], &max_dists[q], ix->ids[r], dist, vec);
+            else { fo_update_topk(topks + (size_t)q * k, dist, ix->ids[r], k); max_dists[q] = topks[(size_t)q * k + k - 1].distance; }
+          }
+        }
+      }
+    }
+    if (method == 2) {                                 /* :611-629 + index_utils.c:477-498 postverify */
+      for (int x = 0; x < n_active; x++) {
+        const int q = active[x];
+        pv_reorder(pv + (size_t)q * (BATCH + kk), kk, &fill[q], &max_dists[q]);
+      }
+      for (int x = 0; x < n_active; x++) {
+        const int q = active[x];
+        PvEntry* tk = pv + (size_t)q * (BATCH + kk);
+        float md = MAX_DIST;
+        for (int j = 0; j < kk; j++) {
+          if (tk[j].id != -1) {
+            float dist = fo_square_distance(queries + (size_t)q * d, tk[j].vector, d);
+            if (dist < md) { fo_update_topk(topks + (size_t)q * k, dist, tk[j].id, k); md = topks[(size_t)q * k + k - 1].distance; }
+          }
+        }
+      }
+    }
+    if (!last_iteration) {                             /* :639-666 */
+      int n_new = 0;
+      int* next = malloc(sizeof(int) * (size_t)n_active);
+      for (int x = 0; x < n_active; x++) {
+        const int q = active[x];
+        if (topks[(size_t)q * k + k - 1].distance == MAX_DIST) {
+          next[n_new++] = q;
+          fo_init_topk(topks + (size_t)q * k, k, MAX_DIST);
+          max_dists[q] = MAX_DIST;
+          if (method == 2) { pv_init(pv + (size_t)q * (BATCH + kk), BATCH + kk, MAX_DIST); fill[x] = 0; /* sic: :654 indexes by x */ }
+        }
+      }
+      memcpy(active, next, sizeof(int) * (size_t)n_new);
+      free(next);
+      n_active = n_new;
+    } else {
+      n_active = 0;
+    }
+    alpha += alpha;                                    /* :680 */
+  }
+  if (stats_out) { stats_out[0] = rounds; stats_out[1] = pairs; }
+  for (int c = 0; c < cells; c++) free(cell_q[c]);
+  free(cell_q); free(cell_n); free(active); free(tsorted); free(max_dists); free(target_counts); free(fill); free(pv); free(luts);
+  if (use_tl) { for (int i = 0; i < nq; i++) free(tl_rows[i]); free(tl_rows); free(tl_n); free(tl_cap); }
+  return 0;
+}

@@ -92,6 +92,28 @@ int fo_analogy_3cosadd(const float* vectors, int N, int d, int row_a, int row_b,
 int fo_analogy_3cosadd_many(const float* vectors, int N, int d, const int32_t* rows_abc, int nq, int n_threads,
                             int32_t* out_rows, float* out_scores);
 
+/* ---- kNN-join: ivpq_search_in (ivpq_search_in.c:61-721) ---- */
+typedef struct {
+  int d, m, K;                  /* fine PQ over the raw vectors (codebook_ivpq)              */
+  int Kc;                       /* codes per half of the 2-way multi-index coarse quantizer   */
+  int N;                        /* rows of fine_quantization_ivpq                             */
+  const float* coarse_multi;    /* [2][Kc][d/2]  coarse_quantization_ivpq rows by (pos, code) */
+  const float* codebook;        /* [m][K][d/m]                                                */
+  const int32_t* ids;           /* [N] table order                                            */
+  const int32_t* coarse_ids;    /* [N] c0 + Kc*c1 (ivpq.py:18)                                 */
+  const int16_t* codes;         /* [N][m]                                                     */
+  const float* stats;           /* [Kc*Kc + 1] cell frequencies, last entry = total count     */
+  int Nv;                       /* rows of the normalized word-vector table                   */
+  const int32_t* vec_ids;       /* [Nv] ascending                                             */
+  const float* vectors;         /* [Nv][d]                                                    */
+} FoIvpqIndex;
+/* method: 0 PQ, 1 exact, 2 PQ + post verification.  out_topk is [nq][k].
+ * stats_out (optional): [0] rounds of the retry loop, [1] candidate (query,row) pairs. */
+int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                      int alpha, int pvf, int method, int use_target_lists, float confidence, int double_threshold,
+                      FoTopKEntry* out_topk, int64_t* stats_out);
+float fo_confidence_hyp(int expect, int size, float p, int stat_size);   /* index_utils.c:673-682 */
+
 /* Run fo_ivfadc_search over nq queries on n_threads host threads (disjoint
  * query shards = n_threads concurrent backends).  out_topk is [nq][k]. */
 int fo_ivfadc_search_many(const FoIndex* ix, const float* queries, int nq, int k, int w,

@@ -75,6 +75,42 @@ def lib():
     return _lib
 
 
+class FoIvpqIndex(C.Structure):
+    _fields_ = [("d", C.c_int), ("m", C.c_int), ("K", C.c_int), ("Kc", C.c_int), ("N", C.c_int),
+                ("coarse_multi", C.c_void_p), ("codebook", C.c_void_p), ("ids", C.c_void_p), ("coarse_ids", C.c_void_p),
+                ("codes", C.c_void_p), ("stats", C.c_void_p), ("Nv", C.c_int), ("vec_ids", C.c_void_p),
+                ("vectors", C.c_void_p)]
+
+
+class OracleIvpq:
+    """oracle kNN-join (fo_ivpq_search_in) over an IVPQ index + the normalized vector table"""
+
+    def __init__(self, ivpq, vectors, vec_ids):
+        self.keep = [np.ascontiguousarray(ivpq["coarse_multi"], np.float32), np.ascontiguousarray(ivpq["ivpq_codebook"], np.float32),
+                     np.ascontiguousarray(ivpq["ids"], np.int32), np.ascontiguousarray(ivpq["ivpq_coarse_ids"], np.int32),
+                     np.ascontiguousarray(ivpq["ivpq_codes"], np.int16), np.ascontiguousarray(ivpq["stats"], np.float32),
+                     np.ascontiguousarray(vec_ids, np.int32), np.ascontiguousarray(vectors, np.float32)]
+        ix = FoIvpqIndex()
+        ix.d, ix.m, ix.K, ix.Kc, ix.N = int(ivpq["d"]), int(ivpq["m"]), int(ivpq["K"]), int(ivpq["Kc"]), int(ivpq["N"])
+        (ix.coarse_multi, ix.codebook, ix.ids, ix.coarse_ids, ix.codes, ix.stats, ix.vec_ids, ix.vectors) = [_p(a) for a in self.keep]
+        ix.Nv = len(self.keep[6])
+        self.ix = ix
+        L = lib()
+        L.fo_ivpq_search_in.argtypes = [C.POINTER(FoIvpqIndex), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+
+    def search_in(self, queries, k, targets, alpha, pvf, method, use_targetlist, confidence, dbl_threshold=10_000_000):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.ix.d)
+        t = np.ascontiguousarray(targets, np.int32)
+        nq = len(q)
+        tk = (TopKEntry * (nq * k))()
+        st = (C.c_int64 * 2)()
+        rc = lib().fo_ivpq_search_in(C.byref(self.ix), _p(q), nq, k, _p(t), len(t), alpha, pvf, method,
+                                     1 if use_targetlist else 0, confidence, dbl_threshold, tk, st)
+        a = np.frombuffer(tk, dtype=[("id", np.int32), ("distance", np.float32)]).reshape(nq, k)
+        return a["id"].copy(), a["distance"].copy(), rc, (st[0], st[1])
+
+
 def analogy_3cosadd(vectors, rows_abc, threads=1):
     """oracle: winning table row and score per (a, b, c) row triple"""
     v = np.ascontiguousarray(vectors, np.float32)
@@ -188,6 +224,43 @@ class ReferenceSession:
         self.set_config("get_vecs_name()", "google_vecs_norm")
         self.set_config("get_vecs_name_codebook()", "pq_codebook")
         self.set_config("get_vecs_name_pq_quantization()", "pq_quantization")
+
+    def load_ivpq(self, ivpq, vectors, vec_ids):
+        """ivpq: dict from freddy_b200.index_build.make_ivpq_index; vectors: the normalized table"""
+        self.d = int(ivpq["d"])
+        m, K, Kc, N = int(ivpq["m"]), int(ivpq["K"]), int(ivpq["Kc"]), int(ivpq["N"])
+        self._table("codebook_ivpq", self.T_CODEBOOK, m * K, ids=np.arange(m * K, dtype=np.int32),
+                    a=np.repeat(np.arange(m, dtype=np.int32), K), b=np.tile(np.arange(K, dtype=np.int32), m),
+                    vec=np.asarray(ivpq["ivpq_codebook"], np.float32).reshape(m * K, -1))
+        self._table("coarse_quantization_ivpq", self.T_CODEBOOK, 2 * Kc, ids=np.arange(2 * Kc, dtype=np.int32),
+                    a=np.repeat(np.arange(2, dtype=np.int32), Kc), b=np.tile(np.arange(Kc, dtype=np.int32), 2),
+                    vec=np.asarray(ivpq["coarse_multi"], np.float32).reshape(2 * Kc, -1))
+        self._table("fine_quantization_ivpq", self.T_FINE, N, ids=np.asarray(ivpq["ids"], np.int32),
+                    a=np.asarray(ivpq["ivpq_coarse_ids"], np.int32), vec=np.asarray(ivpq["ivpq_codes"], np.int16))
+        self._table("google_vecs_norm", self.T_VECS, len(vec_ids), ids=np.asarray(vec_ids, np.int32),
+                    vec=np.asarray(vectors, np.float32))
+        st = np.asarray(ivpq["stats"], np.float32)
+        self._table("stat_table", self.T_STATS, len(st), ids=np.arange(len(st), dtype=np.int32), freq=st)
+        self.set_config("get_vecs_name()", "google_vecs_norm")
+        self.set_config("get_vecs_name_ivpq_codebook()", "codebook_ivpq")
+        self.set_config("get_vecs_name_ivpq_quantization()", "fine_quantization_ivpq")
+        self.set_config("get_vecs_name_coarse_quantization_multi()", "coarse_quantization_ivpq")
+        self.set_config("get_statistics_table()", "stat_table")
+        self.R.ref_ivpq_search_in.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def ivpq_search_in(self, queries, query_ids, k, targets, alpha, pvf, method, use_targetlist, confidence, dbl_threshold):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
+        nq = len(q)
+        qi = np.ascontiguousarray(query_ids, np.int32)
+        t = np.ascontiguousarray(targets, np.int32)
+        qo, ids, raw = np.empty(nq * k, np.int32), np.empty(nq * k, np.int32), np.empty(nq * k, np.float32)
+        n = self.R.ref_ivpq_search_in(_p(q), nq, self.d, _p(qi), k, _p(t), len(t), alpha, pvf, method,
+                                      1 if use_targetlist else 0, confidence, dbl_threshold, _p(qo), _p(ids), _p(raw))
+        if n != nq * k:
+            self._err("ivpq_search_in", n)
+        return qo.reshape(nq, k), ids.reshape(nq, k), raw.reshape(nq, k)
 
     def ivfadc_search(self, queries, k):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)

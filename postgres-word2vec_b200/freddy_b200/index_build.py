@@ -117,3 +117,40 @@ def sample_queries(index, vectors_t, n, seed=4321):
     g.manual_seed(seed)
     sel = torch.randperm(vectors_t.shape[0], generator=g)[:n]
     return vectors_t[sel.to(vectors_t.device)].cpu().numpy(), (sel + 1).numpy().astype(np.int32)
+
+
+def make_ivpq_index(vectors_t, m=12, K=1024, Kc=32, n_train=100_000, kmeans_iters=10, seed=77, target_rows=None):
+    """IVPQ (inverted multi-index + PQ) tables for the kNN-join path, from normalised vectors:
+      coarse_multi [2][Kc][d/2]   2-way product quantizer of the halves      ivpq.py:220-223
+      codebook     [m][K][d/m]    PQ on the RAW vectors (not residuals)      ivpq.py:232-236
+      coarse_ids   c0 + Kc*c1                                                 ivpq.py:18, :79
+      stats        [Kc*Kc + 1]    relative cell frequency over `target_rows` (all rows if None),
+                                  last entry = their count                    freddy--0.0.1.sql:150-171
+    """
+    dev = vectors_t.device
+    N, d = vectors_t.shape
+    assert d % 2 == 0 and d % m == 0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    ntr = min(n_train, N)
+    train = vectors_t[:ntr]
+    half, sub = d // 2, d // m
+    cm = torch.stack([_kmeans(train[:, h * half:(h + 1) * half].contiguous(), Kc, kmeans_iters, gen) for h in range(2)])
+    cb = torch.stack([_kmeans(train[:, p * sub:(p + 1) * sub].contiguous(), K, kmeans_iters, gen) for p in range(m)])
+    step = 262144
+    cids = torch.empty(N, dtype=torch.int32, device=dev)
+    codes = torch.empty(N, m, dtype=torch.int16, device=dev)
+    for s in range(0, N, step):
+        v = vectors_t[s:s + step]
+        c0 = _nearest(v[:, :half].contiguous(), cm[0])
+        c1 = _nearest(v[:, half:].contiguous(), cm[1])
+        cids[s:s + step] = (c0 + Kc * c1).to(torch.int32)
+        for p in range(m):
+            codes[s:s + step, p] = _nearest(v[:, p * sub:(p + 1) * sub].contiguous(), cb[p]).to(torch.int16)
+    sel = cids if target_rows is None else cids[torch.as_tensor(target_rows, device=dev, dtype=torch.long)]
+    counts = torch.bincount(sel.to(torch.long), minlength=Kc * Kc).to(torch.float64)
+    total = float(sel.numel())
+    stats = torch.cat([(counts / total).to(torch.float32), torch.tensor([total], dtype=torch.float32, device=dev)])
+    return {"d": d, "m": m, "K": K, "Kc": Kc, "N": N, "coarse_multi": cm.cpu().numpy(), "ivpq_codebook": cb.cpu().numpy(),
+            "ids": np.arange(1, N + 1, dtype=np.int32), "ivpq_coarse_ids": cids.cpu().numpy(),
+            "ivpq_codes": codes.cpu().numpy(), "stats": stats.cpu().numpy()}

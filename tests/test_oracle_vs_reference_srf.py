@@ -87,3 +87,58 @@ def test_flat_pq_drivers(ref, oracle_mod):
     oids, od = oi.pq_search_in_batch(q, 6, few)
     np.testing.assert_array_equal(oids, rids)
     _same(od, rraw)
+
+
+def _ivpq_setup(N=12000, d=48, m=12, K=64, Kc=8, nt=3000, seed=5):
+    import torch
+    from freddy_b200.index_build import make_ivpq_index
+    ix = small_index(N=20000, d=d, m=12, K=64, C=40, seed=7)
+    vec = np.ascontiguousarray(ix["vectors"][:N])
+    rng = np.random.default_rng(seed)
+    trows = np.sort(rng.choice(N, nt, replace=False))
+    ivpq = make_ivpq_index(torch.from_numpy(vec), m=m, K=K, Kc=Kc, n_train=N, kmeans_iters=4, seed=3, target_rows=trows)
+    vec_ids = np.arange(1, N + 1, dtype=np.int32)
+    targets = (trows + 1).astype(np.int32)
+    q = vec[rng.choice(N, 30, replace=False)] + 0.02 * rng.standard_normal((30, d)).astype(np.float32)
+    return ivpq, vec, vec_ids, targets, np.ascontiguousarray(q, np.float32)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("use_tl", [False, True])
+def test_ivpq_search_in_driver(ref, oracle_mod, method, use_tl):
+    """kNN-join driver (ivpq_search_in.c) incl. confidence stop, PV buffer, retry loop"""
+    ivpq, vec, vec_ids, targets, q = _ivpq_setup()
+    oi = oracle_mod.OracleIvpq(ivpq, vec, vec_ids)
+    qids = np.arange(500, 500 + len(q), dtype=np.int32)
+    for (k, alpha, pvf, conf) in ((5, 3, 4, 0.8), (5, 1, 2, 0.5), (3, 40, 20, 0.8)):
+        s = ref()
+        s.load_ivpq(ivpq, vec, vec_ids)
+        rq, rids, rraw = s.ivpq_search_in(q, qids, k, targets, alpha, pvf, method, use_tl, conf, 10_000_000)
+        oids, od, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf)
+        assert rc == 0
+        np.testing.assert_array_equal(rq, np.repeat(qids[:, None], k, 1))
+        np.testing.assert_array_equal(oids, rids, err_msg=f"method={method} tl={use_tl} k={k} alpha={alpha} rounds={st[0]}")
+        _same(od, rraw)
+
+
+@pytest.mark.parametrize("method", [0, 2])
+def test_ivpq_search_in_retry_loop(ref, oracle_mod, method):
+    """few targets: the first rounds find < k candidates, alpha doubles until enough cells are probed
+    (ivpq_search_in.c:639-680), incl. the target-list skip rule (:553-557)"""
+    ivpq, vec, vec_ids, targets, q = _ivpq_setup()
+    rng = np.random.default_rng(1)
+    few = np.sort(rng.choice(targets, 60, replace=False)).astype(np.int32)
+    oi = oracle_mod.OracleIvpq(ivpq, vec, vec_ids)
+    qids = np.arange(len(q), dtype=np.int32)
+    seen_retry = False
+    for use_tl in (False, True):
+        for (k, alpha, pvf, conf) in ((10, 1, 2, 0.5), (8, 2, 3, 0.8), (70, 1, 1, 0.5)):
+            s = ref()
+            s.load_ivpq(ivpq, vec, vec_ids)
+            rq, rids, rraw = s.ivpq_search_in(q, qids, k, few, alpha, pvf, method, use_tl, conf, 10_000_000)
+            oids, od, rc, st = oi.search_in(q, k, few, alpha, pvf, method, use_tl, conf)
+            assert rc == 0
+            seen_retry |= st[0] > 1
+            np.testing.assert_array_equal(oids, rids, err_msg=f"method={method} tl={use_tl} k={k} rounds={st[0]}")
+            _same(od, rraw)
+    assert seen_retry
