@@ -48,7 +48,8 @@ enum {
 enum {
   FB_CB_RESIDUAL = 0,  /* residual_codebook  + fine_quantization  (IVFADC)   */
   FB_CB_PQ = 1,        /* pq_codebook        + pq_quantization    (flat PQ)  */
-  FB_CB_KINDS = 2
+  FB_CB_IVPQ = 2,      /* codebook_ivpq      + fine_quantization_ivpq (kNN-join) */
+  FB_CB_KINDS = 3
 };
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -96,6 +97,24 @@ int fb_pq_search(fb_engine* e, const float* queries, int nq, int k,
 int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k,
                           const int32_t* targets, int n_targets, int use_target_lists,
                           int32_t* out_ids, float* out_dists);
+
+/* ---- kNN-join ------------------------------------------------------------------ */
+/* IVPQ index: 2-way multi-index coarse quantizer coarse_multi [2][Kc][d/2]
+ * (coarse_quantization_ivpq, ivpq.py:27-30), fine_quantization_ivpq rows in table order
+ * (id, coarse_id = c0 + Kc*c1, int2[m] codes over the RAW vectors; ivpq.py:35, :18) and the
+ * statistics table stats[Kc*Kc + 1] (cell frequencies, last = total; freddy--0.0.1.sql:150-171).
+ * The fine codebook goes through fb_load_codebook(FB_CB_IVPQ) first; post verification /
+ * exact mode read the word vectors of fb_load_vectors (the `vecs` side of the SQL join). */
+int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const int32_t* ids,
+                 const int32_t* coarse_ids, const int16_t* codes, int64_t N, int m, const float* stats);
+/* ivpq_search_in(bytea[] q, int[] qids, k, int[] targets, alpha, pvf, method, use_targetlist,
+ * confidence, double_threshold) (ivpq_search_in.c:61-721), the C side of knn_join /
+ * knn_in_ivpq_batch.  method 0 = PQ, 1 = exact, 2 = PQ + post verification.  Returns the
+ * [nq][k] (target id, distance) rows; the caller pairs them with its query ids.
+ * alpha*k > double_threshold (pair-LUT variant, off by default) is FB_ERR_UNSUPPORTED. */
+int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                      int alpha, int pvf, int method, int use_target_lists, float confidence,
+                      int double_threshold, int32_t* out_ids, float* out_dists);
 
 /* ---- dense word-vector UDFs ------------------------------------------------ */
 /* word-vector table (google_vecs / google_vecs_norm: id, vector bytea = float4[d],

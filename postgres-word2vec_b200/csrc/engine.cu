@@ -18,6 +18,7 @@
 #include "exact_kernels.cuh"
 #include "ivfadc_kernels.cuh"
 #include "vector_kernels.cuh"
+#include "knn_join_kernels.cuh"
 
 using namespace fb;
 
@@ -90,6 +91,19 @@ struct fb_engine {
   bool pq_ids_sorted = true;
   std::unordered_map<int32_t, int32_t> pq_id_to_row;
   DevBuf<int32_t> iota_lists;
+  // IVPQ index (kNN-join)
+  CodeTable ivpq, jtmp;
+  DevBuf<float> coarse_multi, ivpq_stats;
+  DevBuf<int32_t> ivpq_cells;
+  std::vector<int32_t> ivpq_ids_host, ivpq_cells_host;
+  std::vector<float> ivpq_stats_host;
+  bool ivpq_ids_sorted = true;
+  std::unordered_map<int32_t, int32_t> ivpq_id_to_row;
+  int ivpq_Kc = 0, ivpq_d = 0;
+  bool ivpq_loaded = false;
+  DevBuf<int32_t> j_cell, j_vrow, j_id, j_active, j_ncells, j_filled, j_tcounts;
+  DevBuf<uint32_t> j_bitmaps;
+  DevBuf<u64> j_keys;
   // word-vector table (analogy / exact rerank)
   DevBuf<float> vecT;
   DevBuf<int32_t> vec_ids;
@@ -650,6 +664,9 @@ void fb_destroy(fb_engine* e) {
   for (auto& c : e->cb) c.cbT.release();
   e->fine.release(); e->pq.release(); e->tmp.release();
   e->iota_lists.release();
+  e->ivpq.release(); e->jtmp.release(); e->coarse_multi.release(); e->ivpq_stats.release(); e->ivpq_cells.release();
+  e->j_cell.release(); e->j_vrow.release(); e->j_id.release(); e->j_active.release(); e->j_ncells.release();
+  e->j_filled.release(); e->j_tcounts.release(); e->j_bitmaps.release(); e->j_keys.release();
   e->vecT.release(); e->vec_ids.release(); e->va.release(); e->vb.release(); e->vo.release(); e->vdo.release();
   e->ana_rows.release(); e->ana_partial.release();
   e->lut.release(); e->exact_lut.release(); e->q_stage.release(); e->dist_stage.release();
@@ -1058,6 +1075,186 @@ int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids
   FB_CUDA(e, cudaMemcpyAsync(out_scores, e->dist_stage.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
   e->queries_done += nq;
+  return FB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const int32_t* ids, const int32_t* coarse_ids,
+                 const int16_t* codes, int64_t N, int m, const float* stats) {
+  if (!e || !coarse_multi || !stats || Kc < 1 || d < 2 || (N > 0 && (!ids || !coarse_ids || !codes)))
+    return fail(e, FB_ERR_INVALID, "fb_load_ivpq: bad arguments");
+  if (Kc > 32) return fail(e, FB_ERR_UNSUPPORTED, "Kc=%d: the cell-selection kernel handles up to 32 x 32 cells", Kc);
+  if (d % 2) return fail(e, FB_ERR_INVALID, "d must be even for the 2-way multi-index");
+  if (!e->cb[FB_CB_IVPQ].loaded) return fail(e, FB_ERR_INVALID, "fb_load_ivpq: load the ivpq codebook first");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int cells = Kc * Kc;
+  for (int64_t r = 0; r < N; r++)
+    if (coarse_ids[r] < 0 || coarse_ids[r] >= cells) return fail(e, FB_ERR_INVALID, "row %lld: coarse_id %d out of range", (long long)r, coarse_ids[r]);
+  int rc = build_table(e, e->ivpq, ids, nullptr, 0, 8192, codes, N, m, e->cb[FB_CB_IVPQ].K);
+  if (rc) return rc;
+  FB_CUDA(e, e->coarse_multi.ensure((size_t)2 * Kc * (d / 2)));
+  FB_CUDA(e, e->ivpq_stats.ensure((size_t)cells + 1));
+  FB_CUDA(e, e->ivpq_cells.ensure((size_t)std::max<int64_t>(1, N)));
+  FB_CUDA(e, cudaMemcpy(e->coarse_multi.p, coarse_multi, (size_t)2 * Kc * (d / 2) * sizeof(float), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(e->ivpq_stats.p, stats, ((size_t)cells + 1) * sizeof(float), cudaMemcpyHostToDevice));
+  if (N > 0) FB_CUDA(e, cudaMemcpy(e->ivpq_cells.p, coarse_ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->ivpq_ids_host.assign(ids, ids + N);
+  e->ivpq_cells_host.assign(coarse_ids, coarse_ids + N);
+  e->ivpq_stats_host.assign(stats, stats + cells + 1);
+  e->ivpq_ids_sorted = std::is_sorted(e->ivpq_ids_host.begin(), e->ivpq_ids_host.end());
+  e->ivpq_id_to_row.clear();
+  if (!e->ivpq_ids_sorted)
+    for (int64_t r = 0; r < N; r++) e->ivpq_id_to_row.emplace(ids[r], (int32_t)r);
+  e->ivpq_Kc = Kc; e->ivpq_d = d; e->ivpq_loaded = true;
+  return FB_OK;
+}
+
+int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets, int alpha,
+                      int pvf, int method, int use_target_lists, float confidence, int double_threshold,
+                      int32_t* out_ids, float* out_dists) {
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if (!e->ivpq_loaded) return fail(e, FB_ERR_INVALID, "IVPQ index not loaded (fb_load_ivpq)");
+  if (method < 0 || method > 2) return fail(e, FB_ERR_INVALID, "Unknown computation method!");   // ivpq_search_in.c:376
+  if (n_targets < 0 || (n_targets > 0 && !targets)) return fail(e, FB_ERR_INVALID, "bad target array");
+  if (alpha < 1) return fail(e, FB_ERR_INVALID, "alpha=%d", alpha);
+  if (method != 0 && !e->vec_loaded) return fail(e, FB_ERR_INVALID, "methods 1/2 join the word-vector table: fb_load_vectors first");
+  if (pvf < 1) pvf = 1;                                                                           // :206-208
+  const Codebook& cb = e->cb[FB_CB_IVPQ];
+  const int d = e->ivpq_d, m = cb.m, K = cb.K, Kc = e->ivpq_Kc, cells = Kc * Kc;
+  if (cb.m != e->ivpq.m || cb.m * cb.sub != d) return fail(e, FB_ERR_INVALID, "ivpq codebook / table shape mismatch");
+  if (method != 0 && e->vec_d != d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, index d=%d", e->vec_d, d);
+  if (method != 1 && (int64_t)alpha * k > double_threshold)
+    return fail(e, FB_ERR_UNSUPPORTED, "alpha*k > double_threshold selects the pair-LUT variant (index_utils.c:457-475), not built");
+  if ((int64_t)k * pvf > kJoinMaxP) return fail(e, FB_ERR_UNSUPPORTED, "k*pvf=%lld > %d", (long long)k * pvf, kJoinMaxP);
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  e->d = d;
+
+  // rows selected by `fq.id IN (targets)` in table order (ivpq_search_in.c:352-401)
+  std::vector<int32_t> rows;
+  rows.reserve(n_targets);
+  for (int i = 0; i < n_targets; i++) {
+    if (e->ivpq_ids_sorted) {
+      auto it = std::lower_bound(e->ivpq_ids_host.begin(), e->ivpq_ids_host.end(), targets[i]);
+      if (it != e->ivpq_ids_host.end() && *it == targets[i]) rows.push_back((int32_t)(it - e->ivpq_ids_host.begin()));
+    } else {
+      auto it = e->ivpq_id_to_row.find(targets[i]);
+      if (it != e->ivpq_id_to_row.end()) rows.push_back(it->second);
+    }
+  }
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+  const int nt = (int)rows.size();
+  std::vector<int32_t> h_cell(std::max(1, nt)), h_vrow(std::max(1, nt)), h_id(std::max(1, nt));
+  for (int t = 0; t < nt; t++) {
+    h_cell[t] = e->ivpq_cells_host[rows[t]];
+    h_id[t] = e->ivpq_ids_host[rows[t]];
+    h_vrow[t] = (method != 0) ? vec_row_of(e, h_id[t]) : -1;
+  }
+  // temporary blocked table over the target rows (arrival order = slot order)
+  CodeTable& tmp = e->jtmp;
+  const int U = e->ivpq.U;
+  const int n_slots = std::max(1, (nt + 31) / 32) * 32;
+  FB_CUDA(e, tmp.units.ensure((size_t)n_slots * U));
+  FB_CUDA(e, tmp.rowno.ensure((size_t)n_slots));
+  FB_CUDA(e, e->sel_rows.ensure((size_t)std::max(1, nt)));
+  FB_CUDA(e, e->j_cell.ensure(h_cell.size()));
+  FB_CUDA(e, e->j_vrow.ensure(h_vrow.size()));
+  FB_CUDA(e, e->j_id.ensure(h_id.size()));
+  if (nt > 0) {
+    FB_CUDA(e, cudaMemcpyAsync(e->sel_rows.p, rows.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(e, cudaMemcpyAsync(e->j_cell.p, h_cell.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(e, cudaMemcpyAsync(e->j_vrow.p, h_vrow.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(e, cudaMemcpyAsync(e->j_id.p, h_id.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  }
+  gather_rows_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->ivpq.units.p, U, e->sel_rows.p, nt, tmp.units.p, tmp.rowno.p, n_slots);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  CodeTableDev ttab;
+  ttab.units = tmp.units.p; ttab.rowno = tmp.rowno.p; ttab.list_blk = nullptr; ttab.list_len = nullptr;
+  ttab.ids = nullptr; ttab.m = m; ttab.U = U; ttab.n_lists = 1;
+
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->j_active.ensure((size_t)nq));
+  FB_CUDA(e, e->j_ncells.ensure((size_t)nq));
+  FB_CUDA(e, e->j_filled.ensure((size_t)nq));
+  FB_CUDA(e, e->j_tcounts.ensure((size_t)nq));
+  FB_CUDA(e, e->j_bitmaps.ensure((size_t)nq * 32));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  FB_CUDA(e, cudaMemsetAsync(e->j_tcounts.p, 0, (size_t)nq * sizeof(int32_t), e->stream));
+  if (method != 1) {   // LUT per query on the raw query (ivpq_search_in.c:279-290)
+    FB_CUDA(e, e->lut.ensure((size_t)nq * m * K));
+    if ((rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, nq, e->lut.p))) return rc;
+  }
+  const size_t smem = sizeof(u64) * kJoinSortN + (sizeof(float) * 2 + sizeof(int32_t)) * kJoinMaxP +
+                      (method != 1 ? (size_t)m * K * sizeof(float) : 0);
+  if (smem > e->smem_optin - 4096) return fail(e, FB_ERR_UNSUPPORTED, "LUT too large for the join kernel");
+  FB_CUDA(e, cudaFuncSetAttribute(ivpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t key_budget = (size_t)512 << 20;
+  const int q_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, key_budget / (sizeof(u64) * (size_t)std::max(1, nt))));
+  FB_CUDA(e, e->j_keys.ensure((size_t)q_chunk * std::max(1, nt)));
+
+  std::vector<int32_t> active(nq), n_cells(nq), filled(nq);
+  for (int i = 0; i < nq; i++) active[i] = i;
+  int n_active = nq;
+  int64_t cur_alpha = alpha;
+  JoinParams prm;
+  prm.d = d; prm.m = m; prm.K = K; prm.Kc = Kc; prm.k = k; prm.pvf = pvf; prm.method = method;
+  prm.n_targets_sql = n_targets; prm.confidence = confidence; prm.stat_total = (int)e->ivpq_stats_host[cells];
+  prm.skip_below = use_target_lists ? k * alpha : 0;
+  while (n_active > 0) {                                                                        // :299
+    prm.min_target = (int)std::min<int64_t>((int64_t)k * cur_alpha, 0x7fffffff);
+    FB_CUDA(e, cudaMemcpyAsync(e->j_active.p, active.data(), (size_t)n_active * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    {
+      StageTimer t(e, ST_COARSE);
+      ivpq_select_kernel<<<n_active, 1024, 0, e->stream>>>(e->q_stage.p, e->j_active.p, d, Kc, e->coarse_multi.p,
+                                                           e->ivpq_stats.p, prm, e->j_bitmaps.p, e->j_ncells.p);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
+    FB_CUDA(e, cudaMemcpyAsync(n_cells.data(), e->j_ncells.p, (size_t)n_active * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+    bool last = true;                                                                           // index_utils.c:404-406
+    for (int i = 0; i < n_active; i++) last = last && (n_cells[i] >= cells);
+    prm.last_iteration = last ? 1 : 0;
+    {
+      StageTimer t(e, ST_SCAN);
+      for (int c0 = 0; c0 < n_active; c0 += q_chunk) {
+        const int nc = std::min(q_chunk, n_active - c0);
+        ivpq_scan_kernel<<<nc, kJoinThreads, smem, e->stream>>>(
+            e->q_stage.p, e->j_active.p + c0, prm, ttab, nt, e->j_cell.p, e->j_vrow.p, e->j_id.p, e->vecT.p, e->lut.p,
+            e->j_bitmaps.p + (size_t)c0 * 32, e->j_tcounts.p, e->j_keys.p, e->id_stage.p, e->dist_stage.p,
+            e->j_filled.p + c0);
+        e->launches++;
+        e->n_scan_launches++;
+        FB_CUDA(e, cudaGetLastError());
+      }
+    }
+    FB_CUDA(e, cudaMemcpyAsync(filled.data(), e->j_filled.p, (size_t)n_active * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (!last) {                                                                                // :639-666
+      int n_new = 0;
+      for (int i = 0; i < n_active; i++)
+        if (!filled[i]) active[n_new++] = active[i];
+      n_active = n_new;
+    } else {
+      n_active = 0;
+    }
+    cur_alpha += cur_alpha;                                                                     // :680
+  }
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->queries_done += nq;
+  e->bytes_per_row = 2 * m + 4;
   return FB_OK;
 }
 

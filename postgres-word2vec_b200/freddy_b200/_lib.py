@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfreddy_b200.so")
 
 FB_OK = 0
 FB_ERR_INVALID, FB_ERR_CUDA, FB_ERR_UNSUPPORTED, FB_ERR_REFERENCE_UB = -1, -2, -3, -4
-FB_CB_RESIDUAL, FB_CB_PQ = 0, 1
+FB_CB_RESIDUAL, FB_CB_PQ, FB_CB_IVPQ = 0, 1, 2
 FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK, FB_OPT_QSCAN_MIN_QUERIES, FB_OPT_PACKED_FP32 = 1, 2, 3, 4, 5
 FB_OPT_LUT_TILE = 6
 
@@ -41,6 +41,9 @@ SIGNATURES = {
     "fb_ivfadc_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search_in_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "fb_load_ivpq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "fb_ivpq_search_in": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_int, _P, _P]),
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "fb_cosine_similarity": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "fb_vec_op": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),

@@ -126,6 +126,29 @@ class Engine:
         """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream) or 0/None"""
         self._check(self._lib.fb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    # ---- kNN-join ----------------------------------------------------------
+    def load_ivpq_index(self, ivpq):
+        """ivpq: dict from index_build.make_ivpq_index"""
+        self.load_codebook(_lib.FB_CB_IVPQ, ivpq["ivpq_codebook"])
+        cm = _f32(ivpq["coarse_multi"])
+        ids, cids = _i32(ivpq["ids"]), _i32(ivpq["ivpq_coarse_ids"])
+        codes = np.ascontiguousarray(ivpq["ivpq_codes"], dtype=np.int16)
+        st = _f32(ivpq["stats"])
+        self.d = int(ivpq["d"])
+        self._check(self._lib.fb_load_ivpq(self._h, _ptr(cm), int(ivpq["Kc"]), self.d, _ptr(ids), _ptr(cids),
+                                           _ptr(codes), codes.shape[0], codes.shape[1], _ptr(st)))
+
+    def ivpq_search_in(self, queries, k, targets, alpha, pvf, method, use_target_lists, confidence,
+                       double_threshold=10_000_000):
+        q = _f32(queries).reshape(-1, self.d)
+        nq = q.shape[0]
+        t = _i32(targets)
+        ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
+        self._check(self._lib.fb_ivpq_search_in(self._h, _ptr(q), nq, k, _ptr(t), t.shape[0], alpha, pvf, method,
+                                                1 if use_target_lists else 0, confidence, double_threshold,
+                                                _ptr(ids), _ptr(dists)))
+        return ids, dists
+
     # ---- dense word-vector UDFs -----------------------------------------
     def load_vectors(self, ids, vectors):
         ids = _i32(ids)

@@ -1,0 +1,63 @@
+"""kNN-join (ivpq_search_in) on the GPU vs the oracle (which is pinned to the real SRF in
+tests/test_oracle_vs_reference_srf.py)."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_topk
+from test_oracle_vs_reference_srf import _ivpq_setup
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(oracle_mod):
+    from freddy_b200 import Engine
+    ivpq, vec, vec_ids, targets, q = _ivpq_setup()
+    e = Engine(0)
+    e.load_ivpq_index(ivpq)
+    e.load_vectors(vec_ids, vec)
+    oi = oracle_mod.OracleIvpq(ivpq, vec, vec_ids)
+    yield e, oi, targets, q
+    e.close()
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("use_tl", [False, True])
+def test_knn_join_parity(setup, method, use_tl):
+    e, oi, targets, q = setup
+    for (k, alpha, pvf, conf) in ((5, 3, 4, 0.8), (5, 1, 2, 0.5), (3, 40, 20, 0.8), (5, 100, 20, 0.8)):
+        ids, d = e.ivpq_search_in(q, k, targets, alpha, pvf, method, use_tl, conf)
+        eids, ed, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf)
+        assert rc == 0
+        assert_same_topk(ids, d, eids, ed, f"method={method} tl={use_tl} k={k} alpha={alpha} pvf={pvf}")
+
+
+@pytest.mark.parametrize("method", [0, 2])
+def test_knn_join_retry_loop(setup, method):
+    e, oi, targets, q = setup
+    rng = np.random.default_rng(1)
+    few = np.sort(rng.choice(targets, 60, replace=False)).astype(np.int32)
+    seen_retry = False
+    for use_tl in (False, True):
+        for (k, alpha, pvf, conf) in ((10, 1, 2, 0.5), (8, 2, 3, 0.8), (70, 1, 1, 0.5)):
+            ids, d = e.ivpq_search_in(q, k, few, alpha, pvf, method, use_tl, conf)
+            eids, ed, rc, st = oi.search_in(q, k, few, alpha, pvf, method, use_tl, conf)
+            assert rc == 0
+            seen_retry |= st[0] > 1
+            assert_same_topk(ids, d, eids, ed, f"retry method={method} tl={use_tl} k={k}")
+    assert seen_retry
+
+
+def test_knn_join_edge_cases(setup):
+    from freddy_b200 import FreddyError, _lib
+    e, oi, targets, q = setup
+    ids, d = e.ivpq_search_in(q[:3], 4, np.zeros(0, np.int32), 3, 2, 0, False, 0.8)      # no targets at all
+    eids, ed, rc, _ = oi.search_in(q[:3], 4, np.zeros(0, np.int32), 3, 2, 0, False, 0.8)
+    assert_same_topk(ids, d, eids, ed, "empty target set")
+    dup = np.concatenate([targets[:50], targets[:50], [10 ** 7]]).astype(np.int32)          # duplicates + unknown id
+    ids, d = e.ivpq_search_in(q, 5, dup, 2, 2, 2, True, 0.6)
+    eids, ed, rc, _ = oi.search_in(q, 5, dup, 2, 2, 2, True, 0.6)
+    assert_same_topk(ids, d, eids, ed, "duplicate / unknown targets")
+    with pytest.raises(FreddyError) as ei:
+        e.ivpq_search_in(q, 5, targets, 3, 2, 0, False, 0.8, double_threshold=10)            # pair-LUT variant
+    assert ei.value.code == _lib.FB_ERR_UNSUPPORTED
