@@ -86,6 +86,14 @@ int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w,
 int fb_ivfadc_search_dev(fb_engine* e, const float* d_queries, int nq, int k, int w,
                          int32_t* d_out_ids, float* d_out_dists);
 
+/* ivfadc_batch_search(int[] ids, int k) (freddy.c:677-1024): the query vectors are the rows of the
+ * word-vector table (fb_load_vectors) whose id is in query_ids, in table order, each once
+ * (freddy.c:767-804); per query one list per round, nearest unprobed first, until k rows were seen;
+ * sentinel distance 100.0.  out_query_ids[n], out_ids/out_dists [n][k] with n = *n_queries_out
+ * <= n_ids (buffers sized for n_ids). */
+int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, int k, int32_t* out_query_ids,
+                           int32_t* out_ids, float* out_dists, int* n_queries_out);
+
 /* pq_search(bytea, int) (freddy.c:28-170): exhaustive ADC over pq_quantization,
  * sentinel distance 100.0. */
 int fb_pq_search(fb_engine* e, const float* queries, int nq, int k,

@@ -250,6 +250,23 @@ class ReferenceSession:
                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
 
+    def load_vectors_table(self, vectors, vec_ids, name="google_vecs_norm"):
+        self._table(name, self.T_VECS, len(vec_ids), ids=np.asarray(vec_ids, np.int32), vec=np.asarray(vectors, np.float32))
+        self.set_config("get_vecs_name()", name)
+
+    def ivfadc_batch_search(self, query_ids, k):
+        qi = np.ascontiguousarray(query_ids, np.int32)
+        n = len(qi)
+        self.R.ref_ivfadc_batch_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p,
+                                                   C.c_void_p, C.c_void_p]
+        qo, ids, raw = np.empty(n * k, np.int32), np.empty(n * k, np.int32), np.empty(n * k, np.float32)
+        nq = C.c_int(0)
+        r = self.R.ref_ivfadc_batch_search(_p(qi), n, k, n, C.byref(nq), _p(qo), _p(ids), _p(raw))
+        if r < 0:
+            self._err("ivfadc_batch_search", r)
+        m = nq.value
+        return qo[:m * k].reshape(m, k)[:, 0].copy(), ids[:m * k].reshape(m, k), raw[:m * k].reshape(m, k)
+
     def ivpq_search_in(self, queries, query_ids, k, targets, alpha, pvf, method, use_targetlist, confidence, dbl_threshold):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
         nq = len(q)

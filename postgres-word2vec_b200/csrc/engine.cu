@@ -456,7 +456,8 @@ size_t exact_smem_bytes(const fb_engine* e, int w) {
 }
 
 // ---- the IVFADC pipeline on device pointers --------------------------------
-int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists) {
+int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists,
+               float sentinel = 1000.0f) {
   int rc = check_common(e, nq, k);
   if (rc) return rc;
   if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded || !e->fine.loaded)
@@ -507,12 +508,12 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       float* od = d_out_dists + (size_t)q0 * k;
       if ((rc = launch_lut(e, cb, dq, e->coarse.p, pr, w, n * w, e->lut.p))) return rc;          // HOT(2)
       // HOT(3)+(4): one CTA per query when the chunk fills the GPU, else one CTA per (query, list)
-      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, e->lut.p, K, KK, k, 1000.0f, oi, od)
+      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, e->lut.p, K, KK, k, sentinel, oi, od)
                                        : FB_ERR_UNSUPPORTED;
       if (rc == FB_ERR_UNSUPPORTED) {
         FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
         if ((rc = launch_scan(e, e->fine, pr, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
-        if ((rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, 1000.0f, true, oi, od))) return rc;
+        if ((rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, sentinel, true, oi, od))) return rc;
       } else if (rc) {
         return rc;
       }
@@ -529,7 +530,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
         d_q, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
         e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
-        fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage);
+        fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage, sentinel);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
   }
@@ -1256,6 +1257,57 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
   e->queries_done += nq;
   e->bytes_per_row = 2 * m + 4;
   return FB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+__global__ void gather_vec_rows_kernel(const float* __restrict__ vT, int d, const int32_t* __restrict__ rows, int n,
+                                       float* __restrict__ out) {
+  const int q = blockIdx.x;
+  if (q >= n) return;
+  const int r = rows[q];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) out[(size_t)q * d + i] = vT[((size_t)(r >> 5) * d + i) * 32 + (r & 31)];
+}
+
+int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, int k, int32_t* out_query_ids,
+                           int32_t* out_ids, float* out_dists, int* n_queries_out) {
+  if (!e || n_ids < 0 || !n_queries_out) return fail(e, FB_ERR_INVALID, "fb_ivfadc_batch_search: bad arguments");
+  int rc = check_common(e, n_ids, k);
+  if (rc) return rc;
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "ivfadc_batch_search reads the query vectors from the word-vector table: fb_load_vectors first");
+  *n_queries_out = 0;
+  if (n_ids == 0) return FB_OK;
+  if (!query_ids || !out_query_ids || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  // `SELECT id, vector FROM <normalized> WHERE id IN (...)` (freddy.c:767-804): table order, each id once
+  std::vector<int32_t> rows;
+  for (int i = 0; i < n_ids; i++) { int r = vec_row_of(e, query_ids[i]); if (r >= 0) rows.push_back(r); }
+  std::sort(rows.begin(), rows.end());
+  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+  const int nq = (int)rows.size();
+  *n_queries_out = nq;
+  if (nq == 0) return FB_OK;
+  if (e->vec_d != e->d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, IVFADC index d=%d", e->vec_d, e->d);
+  const int d = e->vec_d;
+  FB_CUDA(e, e->ana_rows.ensure((size_t)nq));
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, rows.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  gather_vec_rows_kernel<<<nq, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, nq, e->q_stage.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));   // rows is a local
+  // one list per round, argmin with the first minimum winning (freddy.c:846-866) == the w = 1 case of
+  // ivfadc_search's selection; rounds continue until k rows were seen; sentinel 100.0 (:823-827)
+  if ((rc = ivfadc_dev(e, e->q_stage.p, nq, k, 1, e->id_stage.p, e->dist_stage.p, 100.0f))) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < nq; i++) out_query_ids[i] = e->vec_ids_host[rows[i]];
+  return check_error_flag(e);
 }
 
 }  // extern "C"

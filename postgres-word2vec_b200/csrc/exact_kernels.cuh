@@ -287,7 +287,8 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     const uint32_t* __restrict__ qflags, const int32_t* __restrict__ probes,   // [nq][w]
                     const u64* __restrict__ kth_key,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
-                    int32_t* __restrict__ error_flag, int lut_stage_floats) {
+                    int32_t* __restrict__ error_flag, int lut_stage_floats,
+                    float sentinel) {                    // 1000.0 (freddy.c:184) / 100.0 (freddy.c:823-827)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ExactShared sh = exact_carve(smem_raw, k, lut_stage_floats);
   unsigned char* p = smem_raw + kExactFixedSmem + sizeof(float) * (size_t)lut_stage_floats;
@@ -301,7 +302,7 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
   const int m = tab.m;
   const size_t lut_stride = (size_t)m * K;
   float* my_luts = lut_scratch + (size_t)blockIdx.x * w * lut_stride;
-  const float MAX_DIST = 1000.0f;                       // freddy.c:184
+  const float MAX_DIST = sentinel;
 
   while (true) {
     __syncthreads();

@@ -39,6 +39,7 @@ SIGNATURES = {
     "fb_load_pq": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "fb_ivfadc_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_ivfadc_search_dev": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "fb_ivfadc_batch_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]),
     "fb_pq_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "fb_pq_search_in_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "fb_load_ivpq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P]),

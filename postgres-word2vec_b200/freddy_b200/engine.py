@@ -106,6 +106,14 @@ class Engine:
         self._check(self._lib.fb_ivfadc_search_dev(self._h, C.c_void_p(d_queries_ptr), nq, k, w,
                                                    C.c_void_p(d_ids_ptr), C.c_void_p(d_dists_ptr)))
 
+    def ivfadc_batch_search(self, query_ids, k):
+        qi = _i32(query_ids)
+        n = qi.shape[0]
+        oq, ids, dists = np.empty(n, np.int32), np.empty((n, k), np.int32), np.empty((n, k), np.float32)
+        nout = C.c_int(0)
+        self._check(self._lib.fb_ivfadc_batch_search(self._h, _ptr(qi), n, k, _ptr(oq), _ptr(ids), _ptr(dists), C.byref(nout)))
+        return oq[:nout.value], ids[:nout.value], dists[:nout.value]
+
     def pq_search(self, queries, k):
         q = _f32(queries).reshape(-1, self.d)
         nq = q.shape[0]

@@ -66,6 +66,29 @@ class Session:
         ids, d = self.engine.ivfadc_search(q[None, :], int(k), self._w)
         return self._rows(ids, d)
 
+    def ivfadc_batch_search(self, ids, k):
+        """ivfadc_batch_search(int[], int) -> SETOF (query_id, id, distance)   freddy.c:677-1024"""
+        oq, ri, rd = self.engine.ivfadc_batch_search(np.asarray(ids, np.int32), int(k))
+        rd = round_through_text(rd)
+        return [(int(q), int(i), float(x)) for q, a, b in zip(oq, ri, rd) for i, x in zip(a, b)]
+
+    def ivpq_search_in(self, query_byteas, query_ids, k, input_ids, alpha, pvf, method, use_targetlist, confidence,
+                       double_threshold):
+        """ivpq_search_in(bytea[], int[], int, int[], int, int, int, bool, float4, int)
+        -> SETOF (query_id, target_id, distance)   ivpq_search_in.c:61-721"""
+        if len(query_byteas) != len(query_ids):
+            raise ValueError(f"Number of query vectors and query vector ids differs! ( {len(query_ids)}, {len(query_byteas)})")
+        q = np.stack([bytea_to_vec(b) for b in query_byteas])
+        ids, d = self.engine.ivpq_search_in(q, int(k), np.asarray(input_ids, np.int32), int(alpha), int(pvf), int(method),
+                                            bool(use_targetlist), float(confidence), int(double_threshold))
+        d = round_through_text(d)
+        return [(int(qid), int(i), float(x)) for qid, ri, rd in zip(query_ids, ids, d) for i, x in zip(ri, rd)]
+
+    def analogy_3cosadd(self, id1, id2, id3):
+        """analogy_3cosadd(w1, w2, w3) by word ids -> id of the answer   freddy--0.0.1.sql:1270-1288"""
+        ids, _ = self.engine.analogy_3cosadd(np.array([[id1, id2, id3]], np.int32))
+        return int(ids[0])
+
     def pq_search(self, query_bytea, k):
         """pq_search(bytea, int) -> SETOF (id, distance)   freddy.c:28-170"""
         q = bytea_to_vec(query_bytea)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Secondary BASELINE.json configs (bench.py carries the headline one):
   config 3  pq_search_in_batch  5k queries x 100k targets, m=12, K=1024        (freddy.c:414-675)
+  config 4  knn_join / ivpq_search_in  5k x 100k, k=5, alpha=100, pvf=20, method 2 (PQ + post verification)
+                                                                                  (ivpq_search_in.c:61-721)
   config 5  analogy_3cosadd     1k triples, exact scan over the full 3M vocab    (freddy--0.0.1.sql:1270-1288)
 Each prints one JSON line: GPU time through the host-buffer C-ABI call (H2D/D2H included),
 the CPU oracle on a bounded sample with all host threads, and a parity check on that sample."""
@@ -22,7 +24,7 @@ from oracle import oracle  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=3_000_000)
-ap.add_argument("--which", default="3,5")
+ap.add_argument("--which", default="3,4,5")
 ap.add_argument("--reps", type=int, default=5)
 a = ap.parse_args()
 threads = os.cpu_count() or 1
@@ -65,6 +67,35 @@ if "3" in a.which.split(","):
                       "gpu_lookups_per_s": lookups / t_gpu, "queries_per_s": nq / t_gpu,
                       "cpu_oracle": {"sample_queries": ns, "seconds": t_cpu, "queries_per_s_1thread": ns / t_cpu, "kind": "port"},
                       "parity_on_sample": ok, "reference_published_s": 14.4}))
+
+if "4" in a.which.split(","):
+    from freddy_b200.index_build import make_ivpq_index
+    nq, nt, k, alpha, pvf, method, conf = 5000, 100_000, 5, 100, 20, 2, 0.8
+    perm = torch.randperm(a.n, generator=g)
+    trows = np.sort(perm[nq:nq + nt].numpy())
+    ivpq = make_ivpq_index(vec_t, m=12, K=1024, Kc=32, n_train=100_000, kmeans_iters=10, seed=77, target_rows=trows)
+    vec = vec_t.cpu().numpy()
+    q = vec[perm[:nq].numpy()]
+    targets = (trows + 1).astype(np.int32)
+    eng.load_ivpq_index(ivpq)
+    eng.load_vectors(ivpq["ids"], vec)
+    res = {}
+    for use_tl in (True,):
+        t_gpu = timed(lambda: res.__setitem__("r", eng.ivpq_search_in(q, k, targets, alpha, pvf, method, use_tl, conf)), a.reps)
+        ids, d = res["r"]
+        oi = oracle.OracleIvpq(ivpq, vec, ivpq["ids"])
+        ns = 32
+        t0 = time.perf_counter()
+        eids, ed, rc, st = oi.search_in(q[:ns], k, targets, alpha, pvf, method, use_tl, conf)
+        t_cpu = time.perf_counter() - t0
+        same_ids = (ids[:ns] == eids).all(axis=1)
+        ok = bool(same_ids.all() and (d[:ns].view(np.uint32) == ed.view(np.uint32)).all())
+        print(json.dumps({"config": f"knn_join ivpq_search_in 5k x 100k, k=5, alpha=100, pvf=20, method=2, use_targetlist={use_tl}, m=12 K=1024 Kc=32",
+                          "gpu_seconds_e2e": t_gpu, "queries_per_s": nq / t_gpu,
+                          "cpu_oracle": {"sample_queries": ns, "seconds": t_cpu, "queries_per_s_1thread": ns / t_cpu,
+                                         "rounds": int(st[0]), "candidate_pairs_per_query": st[1] / ns, "kind": "port"},
+                          "parity_on_sample": ok, "sample_queries_with_identical_ids": int(same_ids.sum()),
+                          "reference_published_s": "8.4-12.2 (PQ+PV, alpha=1000)"}))
 
 if "5" in a.which.split(","):
     nq = 1000

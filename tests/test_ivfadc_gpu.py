@@ -165,3 +165,22 @@ def test_against_reference_srf_golden(eng):
     assert_same_topk(ids, d, g["pq_search_k4_ids"], g["pq_search_k4_dist"], "pq_search")
     ids, d = eng.pq_search_in_batch(g["queries"], 5, g["targets"])
     assert_same_topk(ids, d, g["pq_in_k5_ids"], g["pq_in_k5_dist"], "pq_search_in_batch")
+
+
+def test_ivfadc_batch_search(eng, oracle_mod):
+    """fb_ivfadc_batch_search: vectors fetched by id in table order, one list per round, sentinel 100.0
+    (equivalence with the w = 1 search is pinned against the real SRF in test_oracle_vs_reference_srf.py)"""
+    for ix, k in ((small_index(), 5), (small_index(N=150, d=24, m=12, K=8, C=64, seed=5, n_clusters=20), 12)):
+        vec_ids = np.asarray(ix["ids"], np.int32)
+        eng.load_ivfadc_index(ix)
+        eng.load_vectors(vec_ids, ix["vectors"])
+        rng = np.random.default_rng(2)
+        qids = rng.choice(vec_ids, min(40, len(vec_ids)), replace=False).astype(np.int32)
+        qids = np.concatenate([qids, qids[:2], [10 ** 8]]).astype(np.int32)
+        oq, ids, d = eng.ivfadc_batch_search(qids, k)
+        order = np.sort(np.unique(qids[qids < 10 ** 8]))
+        np.testing.assert_array_equal(oq, order)
+        eids, ed, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(ix["vectors"][order - 1], k, 1)
+        assert rc == 0
+        ed = np.where(eids == -1, np.float32(100.0), ed)
+        assert_same_topk(ids, d, eids, ed, "ivfadc_batch_search")

@@ -142,3 +142,38 @@ def test_ivpq_search_in_retry_loop(ref, oracle_mod, method):
             np.testing.assert_array_equal(oids, rids, err_msg=f"method={method} tl={use_tl} k={k} rounds={st[0]}")
             _same(od, rraw)
     assert seen_retry
+
+
+def test_ivfadc_batch_search_equals_w1_search(ref, oracle_mod):
+    """ivfadc_batch_search (freddy.c:677-1024) == per fetched vector ivfadc_search with w = 1
+    (one list per round until k rows were seen), sentinel 100.0, vectors fetched in table order"""
+    ix = small_index()
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    rng = np.random.default_rng(8)
+    qids = rng.choice(vec_ids, 25, replace=False).astype(np.int32)
+    qids = np.concatenate([qids, qids[:3], [10 ** 8]]).astype(np.int32)          # duplicates + unknown id
+    for k in (5, 1, 12):
+        s = ref()
+        s.load_ivfadc(ix, 3)
+        s.load_vectors_table(ix["vectors"], vec_ids)
+        rq, rids, rraw = s.ivfadc_batch_search(qids, k)
+        order = np.sort(np.unique(qids[qids < 10 ** 8]))
+        np.testing.assert_array_equal(rq, order)
+        q = ix["vectors"][order - 1]
+        oids, od, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(q, k, 1)
+        assert rc == 0
+        np.testing.assert_array_equal(oids, rids)
+        od = np.where(oids == -1, np.float32(100.0), od)
+        _same(od, rraw)
+    # lists shorter than k: several rounds
+    ix = small_index(N=150, d=24, m=12, K=8, C=64, seed=5, n_clusters=20)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    s = ref()
+    s.load_ivfadc(ix, 3)
+    s.load_vectors_table(ix["vectors"], vec_ids)
+    qids = vec_ids[::7].copy()
+    rq, rids, rraw = s.ivfadc_batch_search(qids, 12)
+    oids, od, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(ix["vectors"][rq - 1], 12, 1)
+    assert rc == 0
+    np.testing.assert_array_equal(oids, rids)
+    _same(np.where(oids == -1, np.float32(100.0), od), rraw)
