@@ -311,6 +311,19 @@ def main():
     ms_e2e = timed(step_e2e, a.steps, False)
     e2e_value = world * nq * a.steps / (ms_e2e / 1e3)
 
+    # single-query latency through the same host-buffer call (the form config[1] names)
+    lat_us = None
+    if rank == 0:
+        one_q, one_i, one_d = h_q[:1].clone().pin_memory(), h_ids[:1].clone().pin_memory(), h_dist[:1].clone().pin_memory()
+        for _ in range(20):
+            eng.ivfadc_search_ptr(one_q.data_ptr(), 1, k, w, one_i.data_ptr(), one_d.data_ptr())
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            eng.ivfadc_search_ptr(one_q.data_ptr(), 1, k, w, one_i.data_ptr(), one_d.data_ptr())
+            ts.append(time.perf_counter() - t0)
+        lat_us = float(np.median(ts) * 1e6)
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_arm(a, ix, h_q.numpy(), a.cpu_seconds)
@@ -323,6 +336,7 @@ def main():
                "config": {"workload": workload_name(a), "parallelism": f"replicated index, queries sharded x{world}",
                           "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1),
                           "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]),
+                          "single_query_latency_us": lat_us,
                           "exact_path_queries_per_step": exact_q / a.steps,
                           "exact_path_reasons_per_step": {r: c["exact_" + r] / a.steps for r in
                                                           ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")}},

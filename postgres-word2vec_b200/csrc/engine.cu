@@ -469,8 +469,8 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   if (w > e->C) return fail(e, FB_ERR_REFERENCE_UB, "w=%d > %d coarse centroids: the reference indexes cq[-1] (freddy.c:296-302)", w, e->C);
   if (nq == 0) return FB_OK;
   const int m = cb.m, K = cb.K;
-  const bool fast = (k <= 31 && w <= 31);
-  const int KK = k + 1;
+  const bool fast = (k <= 30 && w <= 31);
+  const int KK = k + 2;   // k + 2 keys: enough to settle a boundary tie in the merge (warp_emit_topk)
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
   const size_t lut_per_query = (size_t)w * m * K;
 
@@ -555,8 +555,8 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
            int32_t* d_out_ids, float* d_out_dists) {
   const Codebook& cb = e->cb[FB_CB_PQ];
   const int m = cb.m, K = cb.K;
-  const bool fast = (k <= 31);
-  const int KK = k + 1;
+  const bool fast = (k <= 30);
+  const int KK = k + 2;
   const int nl = tab.n_lists;
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
   // bound the per-warp partial lists (chunk * nl * 8 * KK keys)

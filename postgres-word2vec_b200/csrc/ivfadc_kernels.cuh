@@ -305,12 +305,23 @@ lut_build_kernel(const float* __restrict__ queries, int d,
           for (int u = 0; u < 5; u++) step2(pc + u * stride, pr + u * WS);
         }
         for (; i < sub; i++, pc += stride, pr += WS) step2(pc, pr);
+        float* o = out;   // one pointer bump per job instead of a 64-bit multiply per store
+        if (full) {
 #pragma unroll
-        for (int p2 = 0; p2 < NP; p2++) {
-          float lo, hi;
-          unpack2(acc2[p2], lo, hi);
-          if (2 * p2 < W && (full || job0 + 2 * p2 < njobs)) out[(size_t)(2 * p2) * job_stride] = lo;
-          if (2 * p2 + 1 < W && (full || job0 + 2 * p2 + 1 < njobs)) out[(size_t)(2 * p2 + 1) * job_stride] = hi;
+          for (int p2 = 0; p2 < NP; p2++) {
+            float lo, hi;
+            unpack2(acc2[p2], lo, hi);
+            if (2 * p2 < W) { *o = lo; o += job_stride; }
+            if (2 * p2 + 1 < W) { *o = hi; o += job_stride; }
+          }
+        } else {
+#pragma unroll
+          for (int p2 = 0; p2 < NP; p2++) {
+            float lo, hi;
+            unpack2(acc2[p2], lo, hi);
+            if (2 * p2 < W && job0 + 2 * p2 < njobs) o[(size_t)(2 * p2) * job_stride] = lo;
+            if (2 * p2 + 1 < W && job0 + 2 * p2 + 1 < njobs) o[(size_t)(2 * p2 + 1) * job_stride] = hi;
+          }
         }
       } else {
         float acc[W];
@@ -453,6 +464,25 @@ adc_scan_kernel(CodeTableDev tab,
   if (lane < KK) partial[((size_t)task * kScanWarps + warp) * KK + lane] = mine;
 }
 
+// same chain from units already in registers (software-pipelined scan, M > 0)
+template <int M, int KC>
+__device__ __forceinline__ float adc_units(const uint2 (&v)[(M + 3) / 4 > 0 ? (M + 3) / 4 : 1], const char* lut_base,
+                                           uint32_t row_stride_rt) {
+  constexpr int UU = (M + 3) / 4;
+  const uint32_t rs = (KC > 0) ? (uint32_t)KC * 4u : row_stride_rt;
+  float acc = 0.0f;
+#pragma unroll
+  for (int u = 0; u < UU; u++) {
+    const uint32_t wlo = v[u].x, whi = v[u].y;
+    const char* base = lut_base + (size_t)(4 * u) * rs;
+    if (4 * u + 0 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + (wlo & 0xFFFFu)));
+    if (4 * u + 1 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + rs + (wlo >> 16)));
+    if (4 * u + 2 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 2 * rs + (whi & 0xFFFFu)));
+    if (4 * u + 3 < M) acc = xadd(acc, *reinterpret_cast<const float*>(base + 3 * rs + (whi >> 16)));
+  }
+  return acc;
+}
+
 // Write the k results of one query in the reference's order (ascending distance,
 // later arrival first among equal distances, index_utils.c:19-33) from an ascending
 // key list held one key per lane, or flag the query for the general kernel when a
@@ -464,9 +494,37 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_
                                                int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                                                int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
                                                u64* __restrict__ exact_total, u64* __restrict__ kth_key) {
-  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
-  if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) flags |= kFlagExact | kWhyScanTie;
-  if (lane == 0) { kth_key[q] = kk1; qflags[q] = flags; }
+  // lanes hold the k+2 smallest keys (lane i = i-th).  A distance tie across the k-th place makes the
+  // reference's result depend on arrival order (strict `<` admission + insert-before-equal,
+  // index_utils.c:19-33).  If every row tied with the k-th distance is among the k+1 smallest keys
+  // (the (k+2)-th key is larger), the outcome is those k+1 rows minus one tied row: the tied row that
+  // arrived last if it is the latest arrival of all k+1, else the one that arrived first
+  // (tests/test_topk_semantics.py, fact C).  Longer tie groups go to the general kernel.
+  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1), kk2 = shfl_u64(mine, k + 1);
+  if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) {
+    if (kk2 != kKeyInf && key_dbits(kk2) == key_dbits(kk1)) {
+      flags |= kFlagExact | kWhyScanTie;
+    } else {
+      const uint32_t v = key_dbits(kk1);
+      const bool member = lane <= k;
+      const bool is_tie = member && key_dbits(mine) == v;
+      // latest arrival among the k+1 members (arrival = low word, unique)
+      uint32_t tmax = member ? key_t(mine) : 0u;
+      int lmax = lane;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t ot = __shfl_xor_sync(0xffffffffu, tmax, s);
+        const int ol = __shfl_xor_sync(0xffffffffu, lmax, s);
+        if (ot > tmax || (ot == tmax && ol < lmax)) { tmax = ot; lmax = ol; }
+      }
+      const unsigned tie_mask = __ballot_sync(0xffffffffu, is_tie);
+      const int first_tie = __ffs(tie_mask) - 1;
+      const int drop = ((tie_mask >> lmax) & 1u) ? lmax : first_tie;
+      const u64 next = __shfl_down_sync(0xffffffffu, mine, 1);
+      if (lane >= drop && lane < 31) mine = next;          // close the gap: lanes 0..k-1 now hold the result
+    }
+  }
+  if (lane == 0) { kth_key[q] = kk1; qflags[q] = flags; }   // kk1: the k-th smallest key = the general kernel's bound
   if (flags & kFlagExact) {
     if (lane == 0) {
       exact_list[atomicAdd(exact_count, 1)] = q + q_base;
@@ -551,9 +609,30 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
     const int nblk = (len + 31) >> 5;
     mbar_wait(&bar[j & 1], (uint32_t)((j >> 1) & 1));
     const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)(j & 1) * lut_bytes;
+    constexpr int UU = (M > 0) ? (M + 3) / 4 : 1;
+    uint2 cur[UU], nxt[UU];
+    if (M > 0 && warp < nblk) {
+      const uint2* up0 = tab.units + ((size_t)(blk0 + warp) * U) * 32 + lane;
+#pragma unroll
+      for (int u = 0; u < UU; u++) cur[u] = __ldg(up0 + u * 32);
+    }
     for (int b = warp; b < nblk; b += kQScanWarps) {
-      const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
-      const float acc = adc_block_row<M, KC>(up, lut_base, m, U, row_stride);
+      float acc;
+      if (M > 0) {
+        // the next block's codes are requested before this block's gathers: their latency hides behind them
+        const int bn = b + kQScanWarps;
+        if (bn < nblk) {
+          const uint2* upn = tab.units + ((size_t)(blk0 + bn) * U) * 32 + lane;
+#pragma unroll
+          for (int u = 0; u < UU; u++) nxt[u] = __ldg(upn + u * 32);
+        }
+        acc = adc_units<M, KC>(cur, lut_base, row_stride);
+#pragma unroll
+        for (int u = 0; u < UU; u++) cur[u] = nxt[u];
+      } else {
+        const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
+        acc = adc_block_row<M, KC>(up, lut_base, m, U, row_stride);
+      }
       const uint32_t thr = min(my_thr, *reinterpret_cast<volatile uint32_t*>(&s_thr));
       const uint32_t dbits = __float_as_uint(acc);
       const bool cand = ((b * 32 + lane) < len) && (dbits <= thr);

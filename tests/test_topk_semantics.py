@@ -64,3 +64,26 @@ def test_fact_B_filtered_replay_with_carried_state(ds0, ds1, k):
     else:
         s = second
     assert literal(s, k, state) == want
+
+
+@settings(max_examples=600, deadline=None)
+@given(streams, st.integers(1, 8))
+def test_fact_C_boundary_tie_resolved_from_k_plus_one_keys(ds, k):
+    """(warp_emit_topk) if the rows tied with the k-th distance are all among the k+1 smallest keys
+    (i.e. the (k+2)-th key, if any, has a larger distance), the reference's result is those k+1 rows
+    minus ONE tied row: the tied row that arrived last if it is the latest arrival of all k+1,
+    else the tied row that arrived first."""
+    stream = [(float(x) / 4, t) for t, x in enumerate(ds)]
+    keys = sorted(stream)
+    if len(keys) < k + 1 or keys[k][0] != keys[k - 1][0]:
+        return                                   # no tie across the k-th place
+    v = keys[k - 1][0]
+    if len(keys) > k + 1 and keys[k + 1][0] == v:
+        return                                   # tie group reaches beyond k+1 keys: general kernel
+    S = keys[:k + 1]
+    ties = [e for e in S if e[0] == v]           # ascending arrival
+    latest = max(S, key=lambda e: e[1])
+    drop = latest if latest[0] == v else ties[0]
+    kept = [e for e in S if e != drop]
+    out = sorted(kept, key=lambda e: (e[0], -e[1]))
+    assert out == literal(stream, k)
