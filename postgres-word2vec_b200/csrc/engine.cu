@@ -530,7 +530,8 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     ivfadc_exact_kernel<<<exact_ctas, kExactThreads, ex_smem, e->stream>>>(
         d_q, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
         e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
-        fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage, sentinel);
+        fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage, sentinel,
+        fast ? nullptr : e->counters64.p + 0);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
   }

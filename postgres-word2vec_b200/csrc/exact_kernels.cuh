@@ -288,7 +288,8 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     const u64* __restrict__ kth_key,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                     int32_t* __restrict__ error_flag, int lut_stage_floats,
-                    float sentinel) {                    // 1000.0 (freddy.c:184) / 100.0 (freddy.c:823-827)
+                    float sentinel,                      // 1000.0 (freddy.c:184) / 100.0 (freddy.c:823-827)
+                    u64* __restrict__ rows_counter) {    // statistics (rows whose ADC distance was computed), or nullptr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ExactShared sh = exact_carve(smem_raw, k, lut_stage_floats);
   unsigned char* p = smem_raw + kExactFixedSmem + sizeof(float) * (size_t)lut_stage_floats;
@@ -385,6 +386,7 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
       for (int j = 0; j < w; j++) found += tab.list_len[sel[j]];   // freddy.c:377
       __syncthreads();
     }
+    if (tid == 0 && rows_counter != nullptr) atomicAdd(rows_counter, (u64)found);
     if (failed) {
       if (tid == 0) atomicExch(error_flag, 1);
       for (int i = tid; i < k; i += kExactThreads) { sh.tk_d[i] = MAX_DIST; sh.tk_t[i] = kNoRow; }
