@@ -431,6 +431,41 @@ int launch_qscan(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, cons
 #undef FB_QS
 }
 
+__global__ void collect_flagged_kernel(const uint32_t* __restrict__ qflags, int n, int q_base, int32_t* __restrict__ exact_list,
+                                       int32_t* __restrict__ exact_count, u64* __restrict__ exact_total) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t f = qflags[q];
+  if (f & kFlagExact) {
+    exact_list[atomicAdd(exact_count, 1)] = q + q_base;
+    atomicAdd(exact_total, 1ull);
+    for (int b = 1; b <= 5; b++)
+      if (f & (1u << b)) atomicAdd(exact_total + b, 1ull);
+  }
+}
+
+template <int M, int KC>
+int launch_scan_keys_mk(fb_engine* e, const CodeTable& tab, const int32_t* d_probes, int nq, int w, const float* d_lut, int K,
+                        u64* d_keys, size_t stride, int32_t* d_nkeys) {
+  size_t smem = 2 * (size_t)tab.m * K * sizeof(float);
+  if (smem > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT too large for shared memory");
+  auto kern = adc_scan_keys_kernel<M, KC>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab.dev(), d_probes, w, d_lut, K, d_keys, stride, d_nkeys);
+  e->launches++;
+  e->n_scan_launches++;
+  FB_CUDA(e, cudaGetLastError());
+  return FB_OK;
+}
+
+int launch_scan_keys(fb_engine* e, const CodeTable& tab, const int32_t* d_probes, int nq, int w, const float* d_lut, int K,
+                     u64* d_keys, size_t stride, int32_t* d_nkeys) {
+  StageTimer t(e, ST_SCAN);
+  if (K == 1024 && tab.m == 12) return launch_scan_keys_mk<12, 1024>(e, tab, d_probes, nq, w, d_lut, K, d_keys, stride, d_nkeys);
+  if (K == 256 && tab.m == 12) return launch_scan_keys_mk<12, 256>(e, tab, d_probes, nq, w, d_lut, K, d_keys, stride, d_nkeys);
+  return launch_scan_keys_mk<0, 0>(e, tab, d_probes, nq, w, d_lut, K, d_keys, stride, d_nkeys);
+}
+
 int launch_finalize(fb_engine* e, const CodeTable& tab, int q0, int lists_per_query, int KK, int k, int nq, float sentinel,
                     bool has_input_flags, int32_t* d_out_ids, float* d_out_dists) {
   StageTimer t(e, ST_FINALIZE);
@@ -470,9 +505,19 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   if (nq == 0) return FB_OK;
   const int m = cb.m, K = cb.K;
   const bool fast = (k <= 30 && w <= 31);
+  const bool large_k = (!fast && w <= 31);   // k in 31..1024: materialised-key path (scan -> keys -> reference top-k)
   const int KK = k + 2;   // k + 2 keys: enough to settle a boundary tie in the merge (warp_emit_topk)
-  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
   const size_t lut_per_query = (size_t)w * m * K;
+  size_t key_cap = 0;   // keys one query can produce: the w longest lists
+  if (large_k) {
+    std::vector<int32_t> lens = e->fine.h_list_len;
+    std::sort(lens.begin(), lens.end(), std::greater<int32_t>());
+    for (int j = 0; j < w && j < (int)lens.size(); j++) key_cap += (size_t)lens[j];
+    key_cap = std::max<size_t>(key_cap, 1);
+    const size_t budget = (size_t)1 << 30;
+    chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, (int64_t)(budget / (key_cap * sizeof(u64)))));
+  }
 
   // per-query products of the streaming pass live for the whole call (the general
   // kernel runs once at the end); only the LUT scratch is per chunk
@@ -480,9 +525,11 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   FB_CUDA(e, e->qflags.ensure((size_t)nq));
   FB_CUDA(e, e->exact_list.ensure((size_t)nq));
   FB_CUDA(e, e->kth.ensure((size_t)nq));
-  if (fast) {
-    FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
-    if (chunk < e->qscan_min_queries) FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+  if (fast || large_k) FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
+  if (fast && chunk < e->qscan_min_queries) FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+  if (large_k) {
+    FB_CUDA(e, e->j_keys.ensure((size_t)chunk * key_cap));
+    FB_CUDA(e, e->j_ncells.ensure((size_t)chunk));
   }
   // general-kernel scratch: one LUT set per resident CTA
   int exact_ctas = 2 * e->num_sms;
@@ -518,6 +565,24 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
         return rc;
       }
     }
+  } else if (large_k) {
+    if ((rc = launch_coarse(e, d_q, nq, w, k))) return rc;
+    count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, nq * w, e->fine.list_len.p, e->counters64.p + 0);
+    collect_flagged_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>(e->qflags.p, nq, 0, e->exact_list.p, e->small.p + 0,
+                                                                    e->counters64.p + 1);
+    e->launches += 2;
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+      const int n = (int)std::min<int64_t>(chunk, nq - q0);
+      const int32_t* pr = e->probes.p + (size_t)q0 * w;
+      if ((rc = launch_lut(e, cb, d_q + (size_t)q0 * e->d, e->coarse.p, pr, w, n * w, e->lut.p))) return rc;
+      if ((rc = launch_scan_keys(e, e->fine, pr, n, w, e->lut.p, K, e->j_keys.p, key_cap, e->j_ncells.p))) return rc;
+      StageTimer t(e, ST_FINALIZE);
+      topk_from_keys_kernel<<<n, kJoinThreads, 0, e->stream>>>(e->j_keys.p, key_cap, e->j_ncells.p, k, sentinel, e->fine.ids.p,
+                                                              e->qflags.p + q0, d_out_ids + (size_t)q0 * k,
+                                                              d_out_dists + (size_t)q0 * k);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
   } else {
     iota_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, nq);
     int32_t cnt = nq;
@@ -531,7 +596,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
         d_q, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
         e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
         fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage, sentinel,
-        fast ? nullptr : e->counters64.p + 0);
+        (fast || large_k) ? nullptr : e->counters64.p + 0);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
   }

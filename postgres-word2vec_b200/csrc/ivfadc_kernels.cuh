@@ -671,6 +671,67 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
 }
 
 // ---------------------------------------------------------------------------
+// Large-k form (k > 30, e.g. ivfadc_search(v, pvf*k) of the post-verification wrappers,
+// freddy--0.0.1.sql:556-591): the same walk over the query's w lists, but every row's key
+// (ADC distance bits, table row) is written out; topk_from_keys_kernel (knn_join_kernels.cuh)
+// then applies the reference's top-k to the materialised stream.
+// ---------------------------------------------------------------------------
+template <int M, int KC>
+__global__ void __launch_bounds__(kQScanThreads, 2)
+adc_scan_keys_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int w,
+                     const float* __restrict__ lut, int K,
+                     u64* __restrict__ key_base, size_t stride, int32_t* __restrict__ n_keys) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int m = (M > 0) ? M : tab.m;
+  const int U = (M > 0) ? (M + 3) / 4 : tab.U;
+  const int Kc = (KC > 0) ? KC : K;
+  const size_t lut_floats = (size_t)m * Kc;
+  const uint32_t lut_bytes = (uint32_t)(lut_floats * sizeof(float));
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* qlut = lut + (size_t)q * w * lut_floats;
+  u64* keys = key_base + (size_t)q * stride;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], lut_bytes);
+    bulk_g2s(smem_raw, qlut, lut_bytes, &bar[0]);
+    if (w > 1) {
+      mbar_expect_tx(&bar[1], lut_bytes);
+      bulk_g2s(smem_raw + lut_bytes, qlut + lut_floats, lut_bytes, &bar[1]);
+    }
+  }
+  const uint32_t row_stride = (uint32_t)Kc * 4u;
+  int base = 0;
+  for (int j = 0; j < w; j++) {
+    const int list = probes[(size_t)q * w + j];
+    const int blk0 = tab.list_blk[list];
+    const int len = tab.list_len[list];
+    const int nblk = (len + 31) >> 5;
+    mbar_wait(&bar[j & 1], (uint32_t)((j >> 1) & 1));
+    const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)(j & 1) * lut_bytes;
+    for (int b = warp; b < nblk; b += kQScanWarps) {
+      const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
+      const float acc = adc_block_row<M, KC>(up, lut_base, m, U, row_stride);
+      const int r = b * 32 + lane;
+      if (r < len) keys[base + r] = make_key(acc, (uint32_t)tab.rowno[(size_t)(blk0 + b) * 32 + lane]);
+    }
+    base += len;
+    __syncthreads();
+    if (tid == 0 && j + 2 < w) {
+      mbar_expect_tx(&bar[j & 1], lut_bytes);
+      bulk_g2s(smem_raw + (size_t)(j & 1) * lut_bytes, qlut + (size_t)(j + 2) * lut_floats, lut_bytes, &bar[j & 1]);
+    }
+  }
+  if (tid == 0) n_keys[q] = base;
+}
+
+// ---------------------------------------------------------------------------
 // finalize: one warp per query merges its n_lists per-warp key lists, checks the
 // tie condition, and writes the k results in the reference's order: ascending
 // distance, later arrival first among equal distances (index_utils.c:19-33).

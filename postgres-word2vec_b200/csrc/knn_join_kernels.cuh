@@ -244,6 +244,83 @@ __device__ int block_select_smallest(const u64* __restrict__ keys, int n, int wa
   return n_out;
 }
 
+// Reference top-k (strict `<` admission, insert before equal entries; index_utils.c:19-33) of a
+// candidate stream given as keys (distance bits << 32 | arrival) in global memory, arrival = position in
+// the stream's order.  Fills tk_d / tk_t (shared, k entries; tk_t = arrival of the winner or 0xFFFFFFFF).
+//   no tie across the k-th place  -> the k smallest keys, equal-distance runs reversed (fact A)
+//   otherwise                     -> literal replay, in arrival order, of the rows with d <= v and of the
+//                                    k earliest rows tied at v (fact B)
+// All threads of the CTA (kJoinThreads) call it.
+__device__ void block_reference_topk(const u64* __restrict__ keys, int n, int k, float sentinel,
+                                     u64* sbuf, unsigned* hist, int* misc, float* tk_d, uint32_t* tk_t) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < k; i += kJoinThreads) { tk_d[i] = sentinel; tk_t[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  if (n <= 0) return;
+  const int n_s = block_select_smallest(keys, n, k, true, k, sbuf, hist, misc);
+  __syncthreads();
+  const bool boundary_tie = n_s > k && key_dbits(sbuf[k]) == key_dbits(sbuf[k - 1]);
+  if (!boundary_tie) {
+    const int n_out = min(n_s, k);
+    for (int i = tid; i < n_out; i += kJoinThreads) {
+      const uint32_t db = key_dbits(sbuf[i]);
+      int s0 = i, e0 = i;
+      while (s0 > 0 && key_dbits(sbuf[s0 - 1]) == db) s0--;
+      while (e0 + 1 < n_out && key_dbits(sbuf[e0 + 1]) == db) e0++;
+      const int pos = s0 + (e0 - i);                       // later arrival first inside a run
+      tk_d[pos] = __uint_as_float(db);
+      tk_t[pos] = key_t(sbuf[i]);
+    }
+    __syncthreads();
+    return;
+  }
+  int n_pad = 32;
+  while (n_pad < n_s) n_pad <<= 1;
+  for (int i = tid; i < n_pad; i += kJoinThreads) {
+    const u64 e = sbuf[i];
+    sbuf[i] = (i < n_s) ? (((u64)key_t(e) << 32) | key_dbits(e)) : kKeyInf;   // re-key by arrival
+  }
+  __syncthreads();
+  block_bitonic_sort(sbuf, n_pad);
+  if (tid == 0) {
+    float max_dist = sentinel;
+    for (int i = 0; i < n_s; i++) {
+      const float dist = __uint_as_float((uint32_t)sbuf[i]);
+      if (dist < max_dist) {
+        int slot = k;
+        while (slot > 0 && !(tk_d[slot - 1] < dist)) slot--;
+        if (slot < k) {
+          for (int j = k - 1; j > slot; j--) { tk_d[j] = tk_d[j - 1]; tk_t[j] = tk_t[j - 1]; }
+          tk_d[slot] = dist;
+          tk_t[slot] = (uint32_t)(sbuf[i] >> 32);
+        }
+        max_dist = tk_d[k - 1];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// top-k of a materialised key stream per query (the large-k form of ivfadc_search / pq_search*):
+// keys[q] = key_base + q * stride, n[q] keys; arrival values are table rows -> ids[]
+__global__ void __launch_bounds__(kJoinThreads)
+topk_from_keys_kernel(const u64* __restrict__ key_base, size_t stride, const int32_t* __restrict__ n_keys, int k,
+                      float sentinel, const int32_t* __restrict__ ids, const uint32_t* __restrict__ qflags,
+                      int32_t* __restrict__ out_ids, float* __restrict__ out_dists) {
+  __shared__ u64 sbuf[kJoinSortN];
+  __shared__ float tk_d[kJoinMaxP];
+  __shared__ uint32_t tk_t[kJoinMaxP];
+  __shared__ unsigned s_hist[256];
+  __shared__ int s_misc[8];
+  const int q = blockIdx.x;
+  if (qflags != nullptr && (qflags[q] & kFlagExact)) return;   // re-done by the general kernel
+  block_reference_topk(key_base + (size_t)q * stride, n_keys[q], k, sentinel, sbuf, s_hist, s_misc, tk_d, tk_t);
+  for (int i = threadIdx.x; i < k; i += kJoinThreads) {
+    out_ids[(size_t)q * k + i] = (tk_t[i] == 0xFFFFFFFFu) ? -1 : ids[tk_t[i]];
+    out_dists[(size_t)q * k + i] = tk_d[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // candidate scan + selection: one CTA per active query
 // ---------------------------------------------------------------------------------------
