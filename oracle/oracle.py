@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libfreddy_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libfreddy_ref.so")
+SHIM_SO = os.path.join(_HERE, "_ref", "libfreddy_shim_emul.so")
 
 
 def build(quiet=True):
@@ -155,10 +156,16 @@ class ReferenceSession:
 
     T_COARSE, T_CODEBOOK, T_FINE, T_PQ, T_VECS, T_STATS = 1, 2, 3, 4, 5, 6
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
-            raise RuntimeError("oracle/_ref/libfreddy_ref.so not built (reference sources absent)")
-        R = C.CDLL(REF_SO)
+    def __init__(self, lib_path=None):
+        """lib_path=None: the reference's own SRFs.  lib_path=SHIM_SO: OUR Postgres-side shim
+        (postgres-word2vec_b200/shim/freddy_shim.c -> libfreddy_b200.so) behind the same emulated
+        fmgr/SPI boundary."""
+        path = lib_path or REF_SO
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (reference sources absent)")
+        R = C.CDLL(path)
+        if lib_path is not None:
+            R.freddy_shim_reset()
         R.ref_register_table.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p]
         R.ref_set_config.argtypes = [C.c_char_p, C.c_char_p]
