@@ -90,6 +90,8 @@ float fo_round_through_text(float distance) {
 int fo_index_prepare(FoIndex* ix) {
   ix->list_offsets = NULL;
   ix->list_rows = NULL;
+  ix->list_codes = NULL;
+  ix->list_ids = NULL;
   if (ix->C <= 0 || ix->coarse_ids == NULL) return 0;
   ix->list_offsets = calloc((size_t)ix->C + 1, sizeof(int32_t));
   ix->list_rows = malloc(sizeof(int32_t) * (size_t)(ix->N > 0 ? ix->N : 1));
@@ -104,14 +106,27 @@ int fo_index_prepare(FoIndex* ix) {
   memcpy(cursor, ix->list_offsets, sizeof(int32_t) * (size_t)ix->C);
   for (int r = 0; r < ix->N; r++) ix->list_rows[cursor[ix->coarse_ids[r]]++] = r; /* stays id-ascending */
   free(cursor);
+  /* list-contiguous copies so that the CPU baseline streams each list instead of chasing table rows */
+  ix->list_codes = malloc(sizeof(int16_t) * (size_t)(ix->N > 0 ? ix->N : 1) * ix->m);
+  ix->list_ids = malloc(sizeof(int32_t) * (size_t)(ix->N > 0 ? ix->N : 1));
+  if (!ix->list_codes || !ix->list_ids) return -1;
+  for (int s = 0; s < ix->N; s++) {
+    const int r = ix->list_rows[s];
+    memcpy(ix->list_codes + (size_t)s * ix->m, ix->codes + (size_t)r * ix->m, sizeof(int16_t) * (size_t)ix->m);
+    ix->list_ids[s] = ix->ids[r];
+  }
   return 0;
 }
 
 void fo_index_release(FoIndex* ix) {
   free(ix->list_offsets);
   free(ix->list_rows);
+  free(ix->list_codes);
+  free(ix->list_ids);
   ix->list_offsets = NULL;
   ix->list_rows = NULL;
+  ix->list_codes = NULL;
+  ix->list_ids = NULL;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -193,13 +208,13 @@ static int ivfadc_search_ws(const FoIndex* ix, const float* query, int k, int w,
           if (best < 0 || row < best_row) { best = j; best_row = row; }
         }
       }
-      cursor[best]++;
-      const int16_t* codes = ix->codes + (size_t)best_row * m;
+      const int slot = cursor[best]++;
+      const int16_t* codes = ix->list_codes + (size_t)slot * m;
       const float* lut = luts + (size_t)best * m * K;
       float dist = 0;                                /* ref: :364-368 */
       for (int l = 0; l < m; l++) dist = dist + lut[l * K + codes[l]];
       if (dist < max_dist) {                         /* ref: :369-372 */
-        fo_update_topk(topk, dist, ix->ids[best_row], k);
+        fo_update_topk(topk, dist, ix->list_ids[slot], k);
         max_dist = topk[k - 1].distance;
       }
     }

@@ -44,6 +44,8 @@ typedef struct {
   /* derived by fo_index_prepare(): CSR over coarse_id (rows stay id-ascending) */
   int32_t* list_offsets;      /* [C+1] */
   int32_t* list_rows;         /* [N] row numbers grouped by coarse id */
+  int16_t* list_codes;        /* [N][m] codes in list_rows order (contiguous per list: what a clustered scan reads) */
+  int32_t* list_ids;          /* [N] ids in list_rows order */
 } FoIndex;
 
 int fo_index_prepare(FoIndex* ix);   /* builds the CSR; returns 0 on success */

@@ -32,7 +32,8 @@ class FoIndex(C.Structure):
     _fields_ = [("d", C.c_int), ("m", C.c_int), ("K", C.c_int), ("C", C.c_int), ("N", C.c_int),
                 ("coarse", C.c_void_p), ("codebook", C.c_void_p), ("ids", C.c_void_p),
                 ("coarse_ids", C.c_void_p), ("codes", C.c_void_p),
-                ("list_offsets", C.c_void_p), ("list_rows", C.c_void_p)]
+                ("list_offsets", C.c_void_p), ("list_rows", C.c_void_p),
+                ("list_codes", C.c_void_p), ("list_ids", C.c_void_p)]
 
 
 _lib = None
