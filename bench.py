@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lut-tile", type=int, default=None, help="codes per LUT-build CTA (256/512/1024)")
+    ap.add_argument("--overlap", type=int, default=None, help="1: overlap LUT build and scan of consecutive chunks")
+    ap.add_argument("--lut-ctas", type=int, default=None, help="cap on LUT-build CTAs per SM")
+    ap.add_argument("--chunk", type=int, default=None, help="queries per pipeline chunk")
     ap.add_argument("--scalar-lut", action="store_true", help="LUT build with scalar instead of packed f32x2 ops")
     return ap.parse_args()
 
@@ -226,6 +229,12 @@ def main():
     eng.set_option(_lib.FB_OPT_PROFILE, 1)
     if a.lut_tile is not None:
         eng.set_option(_lib.FB_OPT_LUT_TILE, a.lut_tile)
+    if a.overlap is not None:
+        eng.set_option(_lib.FB_OPT_OVERLAP, a.overlap)
+    if a.lut_ctas is not None:
+        eng.set_option(_lib.FB_OPT_LUT_CTAS_PER_SM, a.lut_ctas)
+    if a.chunk is not None:
+        eng.set_option(_lib.FB_OPT_QUERY_CHUNK, a.chunk)
     if a.scalar_lut:
         eng.set_option(_lib.FB_OPT_PACKED_FP32, 0)
 

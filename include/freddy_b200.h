@@ -165,6 +165,8 @@ enum {
                                   forms of the same rounded operations; 0: scalar */
   FB_OPT_LUT_TILE = 6,         /* codes per LUT-build CTA: 256 / 512 / 1024 (then
                                   4 / 2 / 1 CTAs per SM); anything else: generic  */
+  FB_OPT_LUT_CTAS_PER_SM = 7,  /* cap on resident LUT-build CTAs per SM (0 = as many as fit)      */
+  FB_OPT_OVERLAP = 8,          /* 1: LUT build of chunk c+1 overlaps the scan of chunk c (two streams) */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

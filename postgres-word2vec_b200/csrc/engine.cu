@@ -133,6 +133,11 @@ struct fb_engine {
   int qscan_min_queries = 64;
   bool packed_fp32 = true;
   int lut_tile = 512;
+  int lut_ctas_per_sm = 0;   // 0: as many as fit; overlap mode leaves room for scan CTAs
+  int overlap = 0;           // 1: LUT build of chunk c+1 runs concurrently with the scan of chunk c (two streams)
+  cudaStream_t s_lut = nullptr, s_scan = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_all = nullptr, ev_lut_done[2] = {nullptr, nullptr}, ev_scan_done[2] = {nullptr, nullptr};
+  DevBuf<float> lut2;
   volatile float one = 1.0f;
 
   // profiling
@@ -310,7 +315,8 @@ int launch_lut_cfg(fb_engine* e, const Codebook& cb, const float* d_q, const flo
                    int jobs_per_query, int njobs, float* d_lut, int TK, size_t smem) {
   const int tiles = (cb.K + TK - 1) / TK;
   const int per_sm = TKS > 0 ? 1024 / TKS : 1;
-  int groups = std::max(1, e->num_sms * per_sm / std::max(1, cb.m * tiles));
+  const int ctas_per_sm = (e->lut_ctas_per_sm > 0) ? std::min(e->lut_ctas_per_sm, per_sm) : per_sm;
+  int groups = std::max(1, e->num_sms * ctas_per_sm / std::max(1, cb.m * tiles));
   groups = std::min(groups, (njobs + W - 1) / W);
   dim3 grid(cb.m * tiles, groups);
   auto kern = lut_build_kernel<W, TKS, PACKED>;
@@ -547,23 +553,50 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     if ((rc = launch_coarse(e, d_q, nq, w, k))) return rc;   // HOT(1) for the whole batch
     count_rows_kernel<<<64, 256, 0, e->stream>>>(e->probes.p, nq * w, e->fine.list_len.p, e->counters64.p + 0);
     e->launches++;
-    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+    // With overlap on, the LUT build of chunk c+1 (fp32-pipe bound) runs on its own stream while the
+    // scan of chunk c (shared-memory / LSU bound) runs on another; two LUT buffers alternate.
+    const bool overlap = e->overlap && nq > chunk && chunk >= e->qscan_min_queries;
+    cudaStream_t main_stream = e->stream;
+    if (overlap) {
+      FB_CUDA(e, e->lut2.ensure((size_t)chunk * lut_per_query));
+      FB_CUDA(e, cudaEventRecord(e->ev_main, main_stream));
+      FB_CUDA(e, cudaStreamWaitEvent(e->s_lut, e->ev_main, 0));
+      FB_CUDA(e, cudaStreamWaitEvent(e->s_scan, e->ev_main, 0));
+    }
+    int c = 0;
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
       const int n = (int)std::min<int64_t>(chunk, nq - q0);
       const float* dq = d_q + (size_t)q0 * e->d;
       const int32_t* pr = e->probes.p + (size_t)q0 * w;
       int32_t* oi = d_out_ids + (size_t)q0 * k;
       float* od = d_out_dists + (size_t)q0 * k;
-      if ((rc = launch_lut(e, cb, dq, e->coarse.p, pr, w, n * w, e->lut.p))) return rc;          // HOT(2)
+      float* lutbuf = (overlap && (c & 1)) ? e->lut2.p : e->lut.p;
+      if (overlap) {
+        if (c >= 2) FB_CUDA(e, cudaStreamWaitEvent(e->s_lut, e->ev_scan_done[c & 1], 0));   // buffer free again
+        e->stream = e->s_lut;
+      }
+      rc = launch_lut(e, cb, dq, e->coarse.p, pr, w, n * w, lutbuf);                               // HOT(2)
+      if (overlap) {
+        cudaEventRecord(e->ev_lut_done[c & 1], e->s_lut);
+        cudaStreamWaitEvent(e->s_scan, e->ev_lut_done[c & 1], 0);
+        e->stream = e->s_scan;
+      }
+      if (rc) { e->stream = main_stream; return rc; }
       // HOT(3)+(4): one CTA per query when the chunk fills the GPU, else one CTA per (query, list)
-      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, e->lut.p, K, KK, k, sentinel, oi, od)
+      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, lutbuf, K, KK, k, sentinel, oi, od)
                                        : FB_ERR_UNSUPPORTED;
       if (rc == FB_ERR_UNSUPPORTED) {
-        FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
-        if ((rc = launch_scan(e, e->fine, pr, n * w, 1, 1, e->lut.p, K, KK, e->partial.p))) return rc;
-        if ((rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, sentinel, true, oi, od))) return rc;
-      } else if (rc) {
-        return rc;
+        rc = e->partial.ensure((size_t)chunk * w * kScanWarps * KK) == cudaSuccess ? FB_OK : FB_ERR_CUDA;
+        if (!rc) rc = launch_scan(e, e->fine, pr, n * w, 1, 1, lutbuf, K, KK, e->partial.p);
+        if (!rc) rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, sentinel, true, oi, od);
       }
+      if (overlap) cudaEventRecord(e->ev_scan_done[c & 1], e->s_scan);
+      e->stream = main_stream;
+      if (rc) return rc;
+    }
+    if (overlap) {
+      FB_CUDA(e, cudaEventRecord(e->ev_all, e->s_scan));
+      FB_CUDA(e, cudaStreamWaitEvent(main_stream, e->ev_all, 0));
     }
   } else if (large_k) {
     if ((rc = launch_coarse(e, d_q, nq, w, k))) return rc;
@@ -716,6 +749,14 @@ int fb_create(int device, fb_engine** out) {
     return fail(nullptr, FB_ERR_CUDA, "engine setup: %s", cudaGetErrorString(err));
   }
   e->stream = e->own_stream;
+  cudaStreamCreateWithFlags(&e->s_lut, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&e->s_scan, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_all, cudaEventDisableTiming);
+  for (int i = 0; i < 2; i++) {
+    cudaEventCreateWithFlags(&e->ev_lut_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->ev_scan_done[i], cudaEventDisableTiming);
+  }
   cudaMemset(e->small.p, 0, 4 * sizeof(int32_t));
   cudaMemset(e->counters64.p, 0, 8 * sizeof(u64));
   *out = e;
@@ -740,6 +781,10 @@ void fb_destroy(fb_engine* e) {
   e->probes.release(); e->exact_list.release(); e->id_stage.release(); e->sel_rows.release();
   e->qflags.release(); e->partial.release(); e->kth.release(); e->small.release(); e->counters64.release();
   cudaStreamDestroy(e->own_stream);
+  cudaStreamDestroy(e->s_lut); cudaStreamDestroy(e->s_scan);
+  cudaEventDestroy(e->ev_main); cudaEventDestroy(e->ev_all);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(e->ev_lut_done[i]); cudaEventDestroy(e->ev_scan_done[i]); }
+  e->lut2.release();
   delete e;
 }
 
@@ -929,6 +974,8 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_PROFILE: e->profile = value != 0; return FB_OK;
     case FB_OPT_PACKED_FP32: e->packed_fp32 = value != 0; return FB_OK;
     case FB_OPT_LUT_TILE: e->lut_tile = (int)value; return FB_OK;
+    case FB_OPT_LUT_CTAS_PER_SM: e->lut_ctas_per_sm = (int)value; return FB_OK;
+    case FB_OPT_OVERLAP: e->overlap = value != 0; return FB_OK;
     case FB_OPT_QSCAN_MIN_QUERIES:
       e->qscan_min_queries = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
       return FB_OK;

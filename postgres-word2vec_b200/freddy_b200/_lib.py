@@ -14,6 +14,7 @@ FB_ERR_INVALID, FB_ERR_CUDA, FB_ERR_UNSUPPORTED, FB_ERR_REFERENCE_UB = -1, -2, -
 FB_CB_RESIDUAL, FB_CB_PQ, FB_CB_IVPQ = 0, 1, 2
 FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK, FB_OPT_QSCAN_MIN_QUERIES, FB_OPT_PACKED_FP32 = 1, 2, 3, 4, 5
 FB_OPT_LUT_TILE = 6
+FB_OPT_LUT_CTAS_PER_SM, FB_OPT_OVERLAP = 7, 8
 
 
 class Counters(C.Structure):

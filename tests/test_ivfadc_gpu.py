@@ -52,16 +52,24 @@ def test_parity_general_kernel(eng, oracle_mod):
     assert eng.counters()["exact_path_queries"] == 120
 
 
-def test_parity_noisy_queries_and_chunks(eng, oracle_mod):
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_parity_noisy_queries_and_chunks(eng, oracle_mod, overlap):
+    """several pipeline chunks (last one ragged); overlap=1: LUT build of chunk c+1 runs on a second
+    stream concurrently with the scan of chunk c (two alternating LUT buffers)"""
     from freddy_b200 import _lib
     ix = small_index()
-    q = queries_from(ix, 257, seed=3, noise=0.05)
-    eng.set_option(_lib.FB_OPT_QUERY_CHUNK, 100)   # 3 chunks, last one ragged
+    q = queries_from(ix, 457, seed=3, noise=0.05)
+    eng.set_option(_lib.FB_OPT_QUERY_CHUNK, 100)   # 5 chunks, last one ragged
+    eng.set_option(_lib.FB_OPT_OVERLAP, overlap)
+    eng.set_option(_lib.FB_OPT_LUT_CTAS_PER_SM, 1 if overlap else 0)
     try:
-        ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 7, 5)
+        for _ in range(3):
+            ids, d, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, 7, 5)
+            assert_same_topk(ids, d, eids, ed, f"chunked overlap={overlap}")
     finally:
         eng.set_option(_lib.FB_OPT_QUERY_CHUNK, 2048)
-    assert_same_topk(ids, d, eids, ed, "chunked")
+        eng.set_option(_lib.FB_OPT_OVERLAP, 0)
+        eng.set_option(_lib.FB_OPT_LUT_CTAS_PER_SM, 0)
 
 
 def test_ties_everywhere(eng, oracle_mod):
