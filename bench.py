@@ -61,6 +61,10 @@ def parse():
     ap.add_argument("--lut-ctas", type=int, default=None, help="cap on LUT-build CTAs per SM")
     ap.add_argument("--chunk", type=int, default=None, help="queries per pipeline chunk")
     ap.add_argument("--scalar-lut", action="store_true", help="LUT build with scalar instead of packed f32x2 ops")
+    ap.add_argument("--pipeline", type=int, default=None, help="0: separate LUT/scan kernels instead of the pipeline kernel")
+    ap.add_argument("--pipe-chunk", type=int, default=None, help="queries per pipeline beat")
+    ap.add_argument("--placement", type=int, default=None, help="window of the conflict-aware row placement (0 = arrival order)")
+    ap.add_argument("--pipe-debug", type=int, default=None, help="timing aid (invalid results): 1 producers only, 2 scan only")
     return ap.parse_args()
 
 
@@ -221,7 +225,11 @@ def main():
     my_q = all_q[rank * a.batch:(rank + 1) * a.batch].contiguous()
 
     eng = Engine(local_rank)
+    if a.placement is not None:
+        eng.set_option(_lib.FB_OPT_PLACEMENT_WINDOW, a.placement)
+    t_load = time.time()
     eng.load_ivfadc_index(ix)
+    t_load = time.time() - t_load
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: events and kernels share it
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -237,6 +245,10 @@ def main():
         eng.set_option(_lib.FB_OPT_QUERY_CHUNK, a.chunk)
     if a.scalar_lut:
         eng.set_option(_lib.FB_OPT_PACKED_FP32, 0)
+    if a.pipeline is not None:
+        eng.set_option(_lib.FB_OPT_PIPELINE, a.pipeline)
+    if a.pipe_chunk is not None:
+        eng.set_option(_lib.FB_OPT_PIPE_CHUNK, a.pipe_chunk)
 
     nq, k, w = a.batch, a.k, a.w
     d_ids = torch.empty(nq, k, dtype=torch.int32, device=dev)
@@ -292,6 +304,8 @@ def main():
     for _ in range(max(3, a.warmup)):
         step_dev()
     eng.synchronize()
+    if a.pipe_debug is not None:    # after the warm-up: the LUT scratch then holds valid LUTs for the scan-only mode
+        eng.set_option(_lib.FB_OPT_PIPE_DEBUG, a.pipe_debug)
     eng.reset_counters()
     ms_total = timed(step_dev, a.steps, True)
     clk = clocks.stop()
@@ -300,17 +314,24 @@ def main():
 
     # roofline of the dominant kernel (ADC scan): algorithmic bytes / event time of its launches
     peak, peak_src = peaks()
-    scan_gbs = (c["scan_bytes"] / 1e9) / (c["ms_scan"] / 1e3) if c["ms_scan"] > 0 else None
+    piped = c["n_pipe_launches"] > 0
+    # pipeline mode: ONE kernel does the ADC scan of chunk c and the LUT build of chunk c+1; its launches
+    # carry all the scan bytes (the LUT build rides along on the fp32 pipe), n_chunks + 1 launches per step
+    ms_dom = c["ms_pipe"] if piped else c["ms_scan"]
+    n_dom = c["n_pipe_launches"] if piped else c["n_scan_launches"]
+    scan_gbs = (c["scan_bytes"] / 1e9) / (ms_dom / 1e3) if ms_dom > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        traffic = tj["pipe_dram_bytes_per_launch" if piped else "dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "adc_scan_query_kernel<12,1024>", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "ivfadc_pipe_kernel<12,1024,25>" if piped else "adc_scan_query_kernel<12,1024>",
+                "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, c["n_scan_launches"]),
-                "ms_per_launch": c["ms_scan"] / max(1, c["n_scan_launches"]),
-                "stage_ms_per_step": {s: c["ms_" + s] / a.steps for s in ("coarse", "lut", "scan", "finalize", "exact")}}
+                "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, n_dom),
+                "ms_per_launch": ms_dom / max(1, n_dom),
+                "stage_ms_per_step": {s: c["ms_" + s] / a.steps for s in ("coarse", "lut", "scan", "pipe", "finalize", "exact")}}
     launches = c["kernel_launches"]
     exact_q = c["exact_path_queries"]
 
@@ -343,7 +364,7 @@ def main():
                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": workload_name(a), "parallelism": f"replicated index, queries sharded x{world}",
-                          "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1),
+                          "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1), "index_upload_s": round(t_load, 1),
                           "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]),
                           "single_query_latency_us": lat_us,
                           "exact_path_queries_per_step": exact_q / a.steps,

@@ -167,6 +167,17 @@ enum {
                                   4 / 2 / 1 CTAs per SM); anything else: generic  */
   FB_OPT_LUT_CTAS_PER_SM = 7,  /* cap on resident LUT-build CTAs per SM (0 = as many as fit)      */
   FB_OPT_OVERLAP = 8,          /* 1: LUT build of chunk c+1 overlaps the scan of chunk c (two streams) */
+  FB_OPT_PIPELINE = 9,         /* 1 (default): large batches of the headline shapes run the warp-
+                                  specialised pipeline kernel (LUT build of chunk c+1 and ADC scan of
+                                  chunk c share every SM inside one launch); 0: separate kernels   */
+  FB_OPT_PIPE_CHUNK = 10,      /* queries per pipeline beat (default 1024)                         */
+  FB_OPT_PLACEMENT_WINDOW = 12, /* fb_load_fine: rows of a list are placed into 32-row blocks so that
+                                  the lanes of a warp hit different shared-memory banks of the LUT as
+                                  far as possible (arrival order travels with each row, results do
+                                  not change); value = candidate rows examined per slot (default 256,
+                                  0/1 = keep arrival order).  Applies to the next fb_load_fine.      */
+  FB_OPT_PIPE_DEBUG = 11,      /* timing aid, results are NOT valid: 1 = producers only (no scan),
+                                  2 = scan only (LUT scratch left as is)                           */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */
@@ -183,9 +194,16 @@ typedef struct {
   int64_t n_scan_launches;
   /* why queries took the general kernel (a query can have several reasons) */
   int64_t exact_coarse_tie, exact_coarse_far, exact_few_rows, exact_scan_tie, exact_forced;
+  double ms_pipe;           /* pipeline-kernel launches (LUT build + scan in one) */
+  int64_t n_pipe_launches;
 } fb_counters;
 int fb_get_counters(fb_engine* e, fb_counters* out);  /* synchronizes the stream */
 int fb_reset_counters(fb_engine* e);
+
+/* Host-only helper (no device needed): the slot order fb_load_fine gives the rows of ONE inverted list
+ * under FB_OPT_PLACEMENT_WINDOW = window.  codes = [n][m] int16 of that list in arrival order;
+ * order_out[s] = arrival index of the row placed in slot s (a permutation of 0..n-1).            */
+int fb_placement_order(const int16_t* codes, int n, int m, int K, int window, int32_t* order_out);
 
 /* snprintf("%f") -> float4in, as every SRF returns distances (freddy.c:401-408) */
 float fb_round_through_text(float distance);

@@ -10,7 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -19,6 +21,7 @@
 #include "ivfadc_kernels.cuh"
 #include "vector_kernels.cuh"
 #include "knn_join_kernels.cuh"
+#include "pipeline_kernels.cuh"
 
 using namespace fb;
 
@@ -69,7 +72,7 @@ struct Codebook {
   bool loaded = false;
 };
 
-enum Stage { ST_COARSE = 0, ST_LUT, ST_SCAN, ST_FINALIZE, ST_EXACT, ST_COUNT };
+enum Stage { ST_COARSE = 0, ST_LUT, ST_SCAN, ST_FINALIZE, ST_EXACT, ST_PIPE, ST_COUNT };
 
 }  // namespace
 
@@ -138,14 +141,20 @@ struct fb_engine {
   cudaStream_t s_lut = nullptr, s_scan = nullptr;
   cudaEvent_t ev_main = nullptr, ev_all = nullptr, ev_lut_done[2] = {nullptr, nullptr}, ev_scan_done[2] = {nullptr, nullptr};
   DevBuf<float> lut2;
+  int pipeline = 1;          // 1: warp-specialised pipeline kernel for large batches of the headline shapes
+  int64_t pipe_chunk = 1024; // queries per pipeline beat
+  DevBuf<int32_t> pipe_counters;
+  int pipe_debug = 0;
+  int placement_window = 256; // rows considered per slot by the conflict-aware placement of the fine table (<= 1: off)
   volatile float one = 1.0f;
 
   // profiling
   struct Ev { cudaEvent_t a, b; int stage; };
   std::vector<Ev> events;
   size_t events_used = 0;
-  double ms[ST_COUNT] = {0, 0, 0, 0, 0};
+  double ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
   int64_t n_scan_launches = 0;
+  int64_t n_pipe_launches = 0;
   int64_t launches = 0;
   int64_t queries_done = 0;
   int bytes_per_row = 0;
@@ -201,8 +210,69 @@ void drain_events(fb_engine* e) {
 }
 
 // ---- host-side layout transform of a code table ---------------------------
+// Bank-conflict-aware row placement.  The ADC scan gathers LUT[pos][code] from shared memory with one
+// row per lane; lanes whose codes differ but share a bank (code % 32: every LUT row starts on a 128-byte
+// boundary) serialise, and a gather costs max-over-banks(distinct codes) data-pipe cycles (measured:
+// scripts/microbench_smem.cu).  Rows of a list may sit in any slot — arrival order travels in rowno —
+// so each 32-row block is filled greedily from a window of the list's remaining rows with the row that
+// raises the fewest per-position bank maxima.  `order` receives, per list, the table rows in slot order.
+void place_rows_of_list(const int16_t* codes, int m, int K, const std::vector<int32_t>& rows, int window,
+                        std::vector<int32_t>& order) {
+  const int n = (int)rows.size();
+  order.clear();
+  order.reserve(n);
+  if (n <= 32 || m > 64) { order = rows; return; }
+  std::vector<int32_t> rem(rows);
+  size_t head = 0;                                  // rem[head..) are unplaced, in arrival order
+  std::vector<uint8_t> cnt((size_t)m * 32);         // distinct codes per (pos, bank) in the open block
+  std::vector<uint8_t> mx(m);
+  std::vector<uint32_t> seen((size_t)m * ((K + 31) / 32));
+  const int kw = (K + 31) / 32;
+  while (head < rem.size()) {
+    std::fill(cnt.begin(), cnt.end(), 0);
+    std::fill(mx.begin(), mx.end(), 0);
+    std::fill(seen.begin(), seen.end(), 0u);
+    for (int slot = 0; slot < 32 && head < rem.size(); slot++) {
+      const size_t avail = std::min<size_t>(window, rem.size() - head);
+      size_t best = 0;
+      if (slot > 0) {
+        int best_cost = 1 << 30;
+        for (size_t c = 0; c < avail; c++) {
+          const int16_t* cr = codes + (size_t)rem[head + c] * m;
+          int raises = 0, load = 0;
+          for (int p = 0; p < m; p++) {
+            const int code = cr[p];
+            if (seen[(size_t)p * kw + (code >> 5)] >> (code & 31) & 1u) continue;   // same address: merged
+            const int l = cnt[(size_t)p * 32 + (code & 31)];
+            raises += (l + 1 > mx[p]);
+            load += l;
+          }
+          const int cost = raises * 4096 + load;
+          if (cost < best_cost) { best_cost = cost; best = c; if (cost == 0) break; }
+        }
+      }
+      const int32_t r = rem[head + best];
+      // keep the window in arrival order: shift the skipped rows up by one
+      for (size_t c = best; c > 0; c--) rem[head + c] = rem[head + c - 1];
+      head++;
+      order.push_back(r);
+      const int16_t* cr = codes + (size_t)r * m;
+      for (int p = 0; p < m; p++) {
+        const int code = cr[p];
+        uint32_t& wd = seen[(size_t)p * kw + (code >> 5)];
+        if (wd >> (code & 31) & 1u) continue;
+        wd |= 1u << (code & 31);
+        uint8_t& l = cnt[(size_t)p * 32 + (code & 31)];
+        l++;
+        if (l > mx[p]) mx[p] = l;
+      }
+    }
+  }
+}
+
 int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
-                int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K) {
+                int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K,
+                int placement_window = 0) {
   if (N < 0 || m <= 0) return fail(e, FB_ERR_INVALID, "bad table shape N=%lld m=%d", (long long)N, m);
   if (N >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
   const int U = (m + 3) / 4;
@@ -217,10 +287,41 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
   for (int c = 0; c < n_lists; c++) { blk[c] = (int32_t)n_blocks; n_blocks += (len[c] + 31) / 32; }
   std::vector<uint2> units((size_t)std::max<int64_t>(1, n_blocks) * U * 32, make_uint2(0, 0));
   std::vector<int32_t> rowno((size_t)std::max<int64_t>(1, n_blocks) * 32, -1);
-  std::vector<int32_t> cursor(n_lists, 0);
+  for (int64_t r = 0; r < N; r++)
+    for (int p = 0; p < m; p++) {
+      const int code = codes[(size_t)r * m + p];
+      if (code < 0 || code >= K) return fail(e, FB_ERR_INVALID, "row %lld pos %d: code %d out of range [0,%d)", (long long)r, p, code, K);
+    }
+  // slot of every row inside its list: arrival order, or the conflict-aware placement
+  std::vector<int32_t> slot_of((size_t)std::max<int64_t>(1, N));
+  {
+    std::vector<int32_t> cursor(n_lists, 0);
+    for (int64_t r = 0; r < N; r++) {
+      int c = list_of_row ? list_of_row[r] : (int)(r / rows_per_pseudo_list);
+      slot_of[r] = cursor[c]++;
+    }
+  }
+  if (placement_window > 1 && list_of_row != nullptr && K <= 65536) {
+    std::vector<std::vector<int32_t>> rows_of(n_lists);
+    for (int c = 0; c < n_lists; c++) rows_of[c].reserve(len[c]);
+    for (int64_t r = 0; r < N; r++) rows_of[list_of_row[r]].push_back((int32_t)r);
+    const int n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+      std::vector<int32_t> order;
+      for (int c = next.fetch_add(1); c < n_lists; c = next.fetch_add(1)) {
+        place_rows_of_list(codes, m, K, rows_of[c], placement_window, order);
+        for (size_t s = 0; s < order.size(); s++) slot_of[order[s]] = (int32_t)s;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+  }
   for (int64_t r = 0; r < N; r++) {
     int c = list_of_row ? list_of_row[r] : (int)(r / rows_per_pseudo_list);
-    int slot = cursor[c]++;
+    int slot = slot_of[r];
     int64_t b = blk[c] + slot / 32;
     int L = slot % 32;
     const int16_t* cr = codes + (size_t)r * m;
@@ -230,7 +331,6 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
         int p = 4 * u + t;
         if (p < m) {
           int code = cr[p];
-          if (code < 0 || code >= K) return fail(e, FB_ERR_INVALID, "row %lld pos %d: code %d out of range [0,%d)", (long long)r, p, code, K);
           f[t] = (uint32_t)code * 4u;  // pre-scaled: byte offset into a K-float LUT row
         }
       }
@@ -496,6 +596,85 @@ size_t exact_smem_bytes(const fb_engine* e, int w) {
          (sizeof(float) + sizeof(int)) * ((w + 3) & ~3) + (size_t)e->C + 16;
 }
 
+// ---- throughput form: warp-specialised pipeline (pipeline_kernels.cuh) ------
+// Beat c (= one launch) builds the LUTs of chunk c+1 and scans chunk c; two LUT
+// buffers alternate.  nchunks + 1 launches on the engine stream.
+template <int M, int KC, int SUB>
+int run_pipeline_t(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int k, int w, int KK, float sentinel,
+                   int32_t* d_out_ids, float* d_out_dists, int64_t chunk) {
+  using L = PipeSmem<M, KC, SUB>;
+  auto kern = ivfadc_pipe_kernel<M, KC, SUB>;
+  FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+  const int nchunks = (int)((nq + chunk - 1) / chunk);
+  const size_t lut_per_query = (size_t)w * M * KC;
+  FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
+  FB_CUDA(e, e->lut2.ensure((size_t)chunk * lut_per_query));
+  FB_CUDA(e, e->pipe_counters.ensure((size_t)nchunks + 1));
+  FB_CUDA(e, cudaMemsetAsync(e->pipe_counters.p, 0, ((size_t)nchunks + 1) * sizeof(int32_t), e->stream));
+  const int tiles = (KC + kPipeTile - 1) / kPipeTile;
+  PipeArgs a;
+  memset(&a, 0, sizeof a);
+  a.jobs_per_query = w;
+  a.coarse = e->coarse.p;
+  a.cbT = cb.cbT.p;
+  a.d = e->d;
+  a.K = KC;
+  a.tiles = tiles;
+  a.n_slices = M * tiles;
+  a.n_groups = std::max(1, e->num_sms / a.n_slices);
+  a.one = e->one;
+  a.tab = e->fine.dev();
+  a.w = w; a.KK = KK; a.k = k;
+  a.sentinel = sentinel;
+  a.exact_list = e->exact_list.p;
+  a.exact_count = e->small.p + 0;
+  a.exact_total = e->counters64.p + 1;
+  const int grid = std::max(e->num_sms, a.n_slices);   // one CTA per SM; producers beyond n_groups * n_slices idle
+  if (grid > e->num_sms) a.n_groups = 1;
+  for (int c = -1; c < nchunks; c++) {
+    // producer half: chunk c + 1
+    const int64_t p0 = (int64_t)(c + 1) * chunk;
+    const int pn = (c + 1 < nchunks) ? (int)std::min<int64_t>(chunk, nq - p0) : 0;
+    a.lut_queries = d_q + (size_t)std::min<int64_t>(p0, nq) * e->d;
+    a.lut_probes = e->probes.p + (size_t)std::min<int64_t>(p0, nq) * w;
+    a.lut_out = ((c + 1) & 1) ? e->lut2.p : e->lut.p;
+    a.lut_njobs = pn * w;
+    // scan half: chunk c
+    const int64_t s0 = (int64_t)std::max(c, 0) * chunk;
+    const int sn = (c >= 0) ? (int)std::min<int64_t>(chunk, nq - s0) : 0;
+    a.scan_probes = e->probes.p + (size_t)s0 * w;
+    a.scan_lut = (c & 1) ? e->lut2.p : e->lut.p;
+    a.scan_nq = sn;
+    a.qflags = e->qflags.p + s0;
+    a.out_ids = d_out_ids + (size_t)s0 * k;
+    a.out_dists = d_out_dists + (size_t)s0 * k;
+    a.kth_key = e->kth.p + s0;
+    a.q_base = (int)s0;
+    a.work_counter = e->pipe_counters.p + (c + 1);
+    if (e->pipe_debug == 1) a.scan_nq = 0;
+    if (e->pipe_debug == 2) a.lut_njobs = 0;
+    StageTimer t(e, ST_PIPE);
+    kern<<<grid, kPipeThreads, L::total, e->stream>>>(a);
+    e->launches++;
+    e->n_pipe_launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  return FB_OK;
+}
+
+// FB_ERR_UNSUPPORTED: shape not covered by the pipeline kernel (caller uses the separate kernels)
+int run_pipeline(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int k, int w, int KK, float sentinel,
+                 int32_t* d_out_ids, float* d_out_dists) {
+  if (!e->pipeline || nq < 512 || cb.m != 12 || cb.sub != 25) return FB_ERR_UNSUPPORTED;
+  int64_t chunk = std::max<int64_t>(128, std::min<int64_t>(e->pipe_chunk, (nq + 3) / 4));
+  if (cb.K == 1024) {
+    if (PipeSmem<12, 1024, 25>::total > e->smem_optin) return FB_ERR_UNSUPPORTED;
+    return run_pipeline_t<12, 1024, 25>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists, chunk);
+  }
+  if (cb.K == 256) return run_pipeline_t<12, 256, 25>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists, chunk);
+  return FB_ERR_UNSUPPORTED;
+}
+
 // ---- the IVFADC pipeline on device pointers --------------------------------
 int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists,
                float sentinel = 1000.0f) {
@@ -557,14 +736,17 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     // scan of chunk c (shared-memory / LSU bound) runs on another; two LUT buffers alternate.
     const bool overlap = e->overlap && nq > chunk && chunk >= e->qscan_min_queries;
     cudaStream_t main_stream = e->stream;
-    if (overlap) {
+    rc = run_pipeline(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists);
+    if (rc != FB_OK && rc != FB_ERR_UNSUPPORTED) return rc;
+    const bool piped = (rc == FB_OK);
+    if (overlap && !piped) {
       FB_CUDA(e, e->lut2.ensure((size_t)chunk * lut_per_query));
       FB_CUDA(e, cudaEventRecord(e->ev_main, main_stream));
       FB_CUDA(e, cudaStreamWaitEvent(e->s_lut, e->ev_main, 0));
       FB_CUDA(e, cudaStreamWaitEvent(e->s_scan, e->ev_main, 0));
     }
     int c = 0;
-    for (int64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
+    for (int64_t q0 = 0; q0 < nq && !piped; q0 += chunk, c++) {
       const int n = (int)std::min<int64_t>(chunk, nq - q0);
       const float* dq = d_q + (size_t)q0 * e->d;
       const int32_t* pr = e->probes.p + (size_t)q0 * w;
@@ -594,7 +776,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       e->stream = main_stream;
       if (rc) return rc;
     }
-    if (overlap) {
+    if (overlap && !piped) {
       FB_CUDA(e, cudaEventRecord(e->ev_all, e->s_scan));
       FB_CUDA(e, cudaStreamWaitEvent(main_stream, e->ev_all, 0));
     }
@@ -824,7 +1006,7 @@ int fb_load_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids, co
   if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded)
     return fail(e, FB_ERR_INVALID, "fb_load_fine: load the coarse table and the residual codebook first");
   FB_CUDA(e, cudaSetDevice(e->device));
-  return build_table(e, e->fine, ids, coarse_ids, e->C, 0, codes, N, m, e->cb[FB_CB_RESIDUAL].K);
+  return build_table(e, e->fine, ids, coarse_ids, e->C, 0, codes, N, m, e->cb[FB_CB_RESIDUAL].K, e->placement_window);
 }
 
 int fb_load_pq(fb_engine* e, const int32_t* ids, const int16_t* codes, int64_t N, int m) {
@@ -976,6 +1158,13 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_LUT_TILE: e->lut_tile = (int)value; return FB_OK;
     case FB_OPT_LUT_CTAS_PER_SM: e->lut_ctas_per_sm = (int)value; return FB_OK;
     case FB_OPT_OVERLAP: e->overlap = value != 0; return FB_OK;
+    case FB_OPT_PIPELINE: e->pipeline = value != 0; return FB_OK;
+    case FB_OPT_PIPE_DEBUG: e->pipe_debug = (int)value; return FB_OK;
+    case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
+    case FB_OPT_PIPE_CHUNK:
+      if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");
+      e->pipe_chunk = value;
+      return FB_OK;
     case FB_OPT_QSCAN_MIN_QUERIES:
       e->qscan_min_queries = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
       return FB_OK;
@@ -1005,6 +1194,8 @@ int fb_get_counters(fb_engine* e, fb_counters* out) {
   out->ms_coarse = e->ms[ST_COARSE]; out->ms_lut = e->ms[ST_LUT]; out->ms_scan = e->ms[ST_SCAN];
   out->ms_finalize = e->ms[ST_FINALIZE]; out->ms_exact = e->ms[ST_EXACT];
   out->n_scan_launches = e->n_scan_launches;
+  out->ms_pipe = e->ms[ST_PIPE];
+  out->n_pipe_launches = e->n_pipe_launches;
   return FB_OK;
 }
 
@@ -1015,7 +1206,19 @@ int fb_reset_counters(fb_engine* e) {
   drain_events(e);
   FB_CUDA(e, cudaMemset(e->counters64.p, 0, 8 * sizeof(u64)));
   for (double& v : e->ms) v = 0;
-  e->launches = 0; e->queries_done = 0; e->n_scan_launches = 0; e->host_rows = 0;
+  e->launches = 0; e->queries_done = 0; e->n_scan_launches = 0; e->n_pipe_launches = 0; e->host_rows = 0;
+  return FB_OK;
+}
+
+int fb_placement_order(const int16_t* codes, int n, int m, int K, int window, int32_t* order_out) {
+  if (!codes || !order_out || n < 0 || m <= 0 || K <= 0) return FB_ERR_INVALID;
+  for (int64_t i = 0; i < (int64_t)n * m; i++)
+    if (codes[i] < 0 || codes[i] >= K) return FB_ERR_INVALID;
+  std::vector<int32_t> rows(n), order;
+  for (int i = 0; i < n; i++) rows[i] = i;
+  if (window > 1) place_rows_of_list(codes, m, K, rows, window, order);
+  else order = rows;
+  memcpy(order_out, order.data(), (size_t)n * sizeof(int32_t));
   return FB_OK;
 }
 

@@ -1,0 +1,350 @@
+// pipeline_kernels.cuh — the throughput form of the IVFADC hot path as ONE
+// warp-specialised kernel per pipeline beat (sm_100a).
+//
+// The two heavy stages of ivfadc_search (freddy.c:247-378) stress different parts
+// of an SM: the residual LUT build (freddy.c:295-314, index_utils.c:445-455) is
+// bound by the fp32 pipe, the ADC scan (freddy.c:347-372) by shared-memory gathers
+// (LSU).  Launch c of this kernel therefore does both at once on every SM:
+//
+//   producer warps (the last kPipeProdWarps warps of the CTA — highest warp ids win
+//       issue arbitration) build the LUTs of query chunk c+1 into global scratch;
+//   scan warps walk the probed lists of query chunk c, LUTs streamed through a ring
+//       of shared-memory buffers by a loader thread (1-D bulk async copies +
+//       mbarriers), a merger warp writes each query's k results;
+//
+// and the only dependency between the roles is launch order on the stream (chunk
+// c+1's LUTs are complete when launch c ends), so there is no cross-CTA waiting.
+//
+// Exactness is unchanged: every distance is the reference's own chain of
+// individually rounded fp32 operations (common.cuh), selection and tie handling are
+// warp_emit_topk's (ivfadc_kernels.cuh).
+#pragma once
+#include "common.cuh"
+#include "ivfadc_kernels.cuh"
+
+namespace fb {
+
+constexpr int kPipeThreads = 1024;
+constexpr int kPipeWarps = kPipeThreads / kWarp;
+constexpr int kPipeProdWarps = 8;                    // 256 producer threads = 2 job halves x 128 threads x 4 codes
+constexpr int kPipeGroup = 16;                       // jobs per producer group (8 per job half)
+constexpr int kPipeProdThreads = kPipeProdWarps * kWarp;
+constexpr int kPipeTile = 4 * (kPipeProdThreads / 2); // codes per producer CTA slice
+constexpr int kPipeScanWarps = kPipeWarps - kPipeProdWarps - 2;   // 22 (+ loader warp + merger warp)
+constexpr int kPipeBufs = 3;                         // LUT ring depth in shared memory
+constexpr int kPipeScanRegs = 40, kPipeProdRegs = 136;   // registers per thread after setmaxnreg
+static_assert((kPipeThreads - kPipeProdThreads) * kPipeScanRegs + kPipeProdThreads * kPipeProdRegs <= 65536, "register file");
+static_assert(kPipeProdWarps % 4 == 0, "roles must be whole warpgroups");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct PipeArgs {
+  // producer half: LUTs of `lut_njobs` jobs (job = query * jobs_per_query + probe)
+  const float* lut_queries;     // [lut_nq][d]
+  const int32_t* lut_probes;    // [lut_njobs] coarse centroid per job
+  float* lut_out;               // [lut_njobs][m][K]
+  int lut_njobs;
+  int jobs_per_query;
+  const float* coarse;          // [C][d]
+  const float* cbT;             // [m][sub][K]
+  int d, K;
+  int n_slices, n_groups, tiles;
+  float one;
+  // scan half: queries [0, scan_nq) of the previous chunk
+  CodeTableDev tab;
+  const int32_t* scan_probes;   // [scan_nq][w]
+  const float* scan_lut;        // [scan_nq][w][m][K]
+  int scan_nq, w, KK, k;
+  float sentinel;
+  uint32_t* qflags;
+  int32_t* out_ids;
+  float* out_dists;
+  int32_t* exact_list;
+  int32_t* exact_count;
+  u64* exact_total;
+  u64* kth_key;
+  int q_base;
+  int32_t* work_counter;        // zeroed before the launch
+};
+
+// shared-memory plan (dynamic): [kPipeBufs][M*KC] LUT ring | [SUB][kPipeTile] codebook slice |
+// 2 x [SUB][kPipeGroup] residual pairs | 2 x [kPipeScanWarps][32] key staging | control block
+template <int M, int KC, int SUB>
+struct PipeSmem {
+  static constexpr size_t lut_bytes = (size_t)M * KC * sizeof(float);
+  static constexpr size_t off_cb = kPipeBufs * lut_bytes;
+  static constexpr size_t cb_bytes = (size_t)SUB * kPipeTile * sizeof(float);
+  static constexpr size_t off_rs = off_cb + cb_bytes;
+  static constexpr size_t rs_bytes = 2 * (size_t)SUB * kPipeGroup * sizeof(u64);
+  static constexpr size_t off_stage = off_rs + rs_bytes;
+  static constexpr size_t stage_bytes = 2 * (size_t)kPipeScanWarps * 32 * sizeof(u64);
+  static constexpr size_t off_ctl = off_stage + stage_bytes;
+  static constexpr size_t total = off_ctl + 256;
+};
+
+struct PipeCtl {
+  uint64_t full[kPipeBufs], empty[kPipeBufs], stg_full[2], stg_empty[2], cb_bar;   // mbarriers
+  int4 desc[kPipeBufs];        // {first block, rows, query, probe index} of the task in each ring slot
+  int stage_q[2];
+  uint32_t thr[2];
+};
+static_assert(sizeof(PipeCtl) <= 256, "control block");
+
+template <int M, int KC, int SUB>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+ivfadc_pipe_kernel(const PipeArgs a) {
+  using L = PipeSmem<M, KC, SUB>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + L::off_ctl);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t lut_bytes = (uint32_t)L::lut_bytes;
+  constexpr size_t lut_floats = (size_t)M * KC;
+
+  if (tid == 0) {
+    for (int b = 0; b < kPipeBufs; b++) {
+      mbar_init(&ctl->full[b], 1);
+      mbar_init(&ctl->empty[b], kPipeScanWarps);
+    }
+    for (int p = 0; p < 2; p++) {
+      mbar_init(&ctl->stg_full[p], kPipeScanWarps);
+      mbar_init(&ctl->stg_empty[p], 1);
+      ctl->thr[p] = 0xFFFFFFFFu;
+      ctl->stage_q[p] = -1;
+    }
+    mbar_init(&ctl->cb_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Register re-balancing between the roles (warpgroup-wide setmaxnreg): the CTA is launched with
+  // 64 registers per thread; the six scan-side warpgroups give 24 each back, the two producer warpgroups
+  // take them (768 * 40 + 256 * 136 = 64 K), so the LUT build can keep its operands for several
+  // dimensions in flight while the scan warps only need a few dozen registers.
+  if (warp >= kPipeWarps - kPipeProdWarps) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeProdRegs));
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeScanRegs));
+  }
+
+  // ============================================================ producers
+  // 8 warps = 2 job halves x 4 warps; a thread owns 4 adjacent codes (two packed pairs) x 8 jobs of the
+  // 16-job group: per dimension one 16-byte read of its codes and four broadcast 16-byte reads of
+  // residual pairs feed 48 packed operations (shared-memory wavefronts per operation: 0.25).
+  if (warp >= kPipeWarps - kPipeProdWarps) {
+    const int pt = tid - (kPipeWarps - kPipeProdWarps) * kWarp;        // 0..255
+    const int half = pt >> 7, ct = pt & 127;
+    const int slice = blockIdx.x % a.n_slices, group = blockIdx.x / a.n_slices;
+    if (a.lut_njobs <= 0 || group >= a.n_groups) return;
+    const int pos = slice / a.tiles, tile = slice % a.tiles;
+    const int code0 = tile * kPipeTile;
+    const int ncodes = min(kPipeTile, a.K - code0);
+    float* cbs = reinterpret_cast<float*>(smem_raw + L::off_cb);       // [SUB][kPipeTile]
+    u64* rs2 = reinterpret_cast<u64*>(smem_raw + L::off_rs);           // 2 x [SUB][kPipeGroup] pairs (r, r)
+    if (pt == 0) {
+      mbar_expect_tx(&ctl->cb_bar, (uint32_t)(SUB * ncodes * sizeof(float)));
+      for (int i = 0; i < SUB; i++)
+        bulk_g2s(cbs + (size_t)i * kPipeTile, a.cbT + ((size_t)pos * SUB + i) * a.K + code0,
+                 (uint32_t)(ncodes * sizeof(float)), &ctl->cb_bar);
+    }
+    // residual element ownership: element e = i * kPipeGroup + jj of a group, kPre per thread
+    constexpr int n_res = SUB * kPipeGroup;
+    constexpr int kPre = (n_res + kPipeProdThreads - 1) / kPipeProdThreads;
+    const int jpq = a.jobs_per_query;
+    const int last_job = a.lut_njobs - 1;
+    float pre_q[kPre], pre_c[kPre];
+    auto prefetch = [&](int job0) {
+#pragma unroll
+      for (int e = 0; e < kPre; e++) {
+        const int idx = pt + e * kPipeProdThreads;
+        if (idx < n_res) {
+          const int i = idx / kPipeGroup, jj = idx % kPipeGroup;
+          const int job = min(job0 + jj, last_job);
+          const int q = job / jpq;
+          pre_q[e] = a.lut_queries[(size_t)q * a.d + pos * SUB + i];
+          pre_c[e] = a.coarse[(size_t)a.lut_probes[job] * a.d + pos * SUB + i];
+        }
+      }
+    };
+    const int job_step = a.n_groups * kPipeGroup;
+    int cur = 0;
+    prefetch(group * kPipeGroup);
+    mbar_wait(&ctl->cb_bar, 0);
+    const u64 one2 = pack2(a.one, a.one);
+    const bool active = 4 * ct < ncodes;
+    const float* pc = cbs + 4 * ct;
+    constexpr int WJ = kPipeGroup / 2;                                   // jobs per thread
+    for (int job0 = group * kPipeGroup; job0 < a.lut_njobs; job0 += job_step) {
+      u64* rsc = rs2 + (size_t)cur * n_res;
+#pragma unroll
+      for (int e = 0; e < kPre; e++) {
+        const int idx = pt + e * kPipeProdThreads;
+        if (idx < n_res) {
+          const float r = xsub(pre_q[e], pre_c[e]);
+          rsc[idx] = pack2(r, r);
+        }
+      }
+      named_bar_sync(1, kPipeProdThreads);   // rs2[cur] complete; rs2[cur^1] readers (previous group) are done
+      if (job0 + job_step < a.lut_njobs) prefetch(job0 + job_step);
+      if (active) {
+        u64 acc[WJ][2];
+#pragma unroll
+        for (int j = 0; j < WJ; j++) acc[j][0] = acc[j][1] = 0ull;
+        const u64* rh = rsc + half * WJ;
+#pragma unroll
+        for (int i = 0; i < SUB; i++) {
+          const ulonglong2 cv = *reinterpret_cast<const ulonglong2*>(pc + i * kPipeTile);   // codes 4ct..4ct+3, dimension i
+          const ulonglong2* rr = reinterpret_cast<const ulonglong2*>(rh + i * kPipeGroup);    // broadcast reads
+#pragma unroll
+          for (int j2 = 0; j2 < WJ / 2; j2++) {
+            const ulonglong2 r4 = rr[j2];
+            u64 t;
+            t = xsub2(r4.x, cv.x); acc[2 * j2][0] = xacc2(xmul2(t, t), one2, acc[2 * j2][0]);
+            t = xsub2(r4.x, cv.y); acc[2 * j2][1] = xacc2(xmul2(t, t), one2, acc[2 * j2][1]);
+            t = xsub2(r4.y, cv.x); acc[2 * j2 + 1][0] = xacc2(xmul2(t, t), one2, acc[2 * j2 + 1][0]);
+            t = xsub2(r4.y, cv.y); acc[2 * j2 + 1][1] = xacc2(xmul2(t, t), one2, acc[2 * j2 + 1][1]);
+          }
+        }
+        const int jb = job0 + half * WJ;
+        ulonglong2* o = reinterpret_cast<ulonglong2*>(a.lut_out + ((size_t)jb * M + pos) * a.K + code0) + ct;
+        constexpr size_t job_stride = (size_t)M * KC / 4;          // in 16-byte units
+        if (jb + WJ <= a.lut_njobs) {
+#pragma unroll
+          for (int j = 0; j < WJ; j++) o[(size_t)j * job_stride] = make_ulonglong2(acc[j][0], acc[j][1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < WJ; j++)
+            if (jb + j < a.lut_njobs) o[(size_t)j * job_stride] = make_ulonglong2(acc[j][0], acc[j][1]);
+        }
+      }
+      cur ^= 1;
+    }
+    return;
+  }
+
+  // ============================================================ loader (one thread)
+  if (warp == kPipeScanWarps) {
+    if (lane != 0) return;
+    int t = 0;
+    for (;;) {
+      const int q = (a.scan_nq > 0) ? atomicAdd(a.work_counter, 1) : 0x7fffffff;
+      const bool end = q >= a.scan_nq;
+      const int nj = end ? 1 : a.w;
+      for (int j = 0; j < nj; j++, t++) {
+        const int b = t % kPipeBufs, use = t / kPipeBufs;
+        if (use > 0) mbar_wait(&ctl->empty[b], (uint32_t)((use - 1) & 1));
+        if (end) {
+          ctl->desc[b] = make_int4(0, 0, -1, 0);
+          mbar_arrive(&ctl->full[b]);
+        } else {
+          const int list = a.scan_probes[(size_t)q * a.w + j];
+          ctl->desc[b] = make_int4(a.tab.list_blk[list], a.tab.list_len[list], q, j);
+          mbar_expect_tx(&ctl->full[b], lut_bytes);
+          bulk_g2s(smem_raw + (size_t)b * lut_bytes, a.scan_lut + ((size_t)q * a.w + j) * lut_floats, lut_bytes,
+                   &ctl->full[b]);
+        }
+      }
+      if (end) return;
+    }
+  }
+
+  // ============================================================ merger (one warp)
+  if (warp == kPipeScanWarps + 1) {
+    const u64* stage = reinterpret_cast<const u64*>(smem_raw + L::off_stage);
+    for (int n = 0;; n++) {
+      const int p = n & 1;
+      mbar_wait(&ctl->stg_full[p], (uint32_t)((n >> 1) & 1));
+      const int q = ctl->stage_q[p];
+      if (q < 0) return;
+      const u64* sp = stage + (size_t)p * kPipeScanWarps * 32;
+      u64 mine = sp[lane];
+      for (int l = 1; l < kPipeScanWarps; l++) {
+        const u64 other = sp[l * 32 + lane];
+        if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, a.KK - 1)) == 0) continue;
+        warp_list_merge(mine, other, lane);
+      }
+      warp_emit_topk(mine, lane, q, a.q_base, a.k, a.qflags[q], a.tab.ids, a.sentinel, a.qflags, a.out_ids, a.out_dists,
+                     a.exact_list, a.exact_count, a.exact_total, a.kth_key);
+      if (lane == 0) ctl->thr[p] = 0xFFFFFFFFu;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->stg_empty[p]);
+    }
+  }
+
+  // ============================================================ scan warps
+  {
+    u64* stage = reinterpret_cast<u64*>(smem_raw + L::off_stage);
+    constexpr int UU = (M + 3) / 4;
+    u64 mine = kKeyInf;
+    uint32_t my_thr = 0xFFFFFFFFu;
+    int nq_seen = 0, p = 0;
+    for (int t = 0;; t++) {
+      const int b = t % kPipeBufs;
+      mbar_wait(&ctl->full[b], (uint32_t)((t / kPipeBufs) & 1));
+      const int4 ds = ctl->desc[b];
+      if (ds.w == 0) {   // first list of a query (or the end marker): staging slot and threshold of parity p must be free
+        p = nq_seen & 1;
+        if (nq_seen >= 2) mbar_wait(&ctl->stg_empty[p], (uint32_t)(((nq_seen >> 1) - 1) & 1));
+        mine = kKeyInf;
+        my_thr = 0xFFFFFFFFu;
+      }
+      if (ds.z < 0) {
+        if (warp == 0 && lane == 0) ctl->stage_q[p] = -1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->stg_full[p]);
+        return;
+      }
+      const int blk0 = ds.x, len = ds.y;
+      const int nblk = (len + 31) >> 5;
+      const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)b * lut_bytes;
+      volatile uint32_t* s_thr = &ctl->thr[p];
+      uint2 cur[UU], nxt[UU];
+      if (warp < nblk) {
+        const uint2* up0 = a.tab.units + ((size_t)(blk0 + warp) * UU) * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < UU; u++) cur[u] = __ldg(up0 + u * 32);
+      }
+      for (int blk = warp; blk < nblk; blk += kPipeScanWarps) {
+        const int bn = blk + kPipeScanWarps;
+        if (bn < nblk) {
+          const uint2* upn = a.tab.units + ((size_t)(blk0 + bn) * UU) * 32 + lane;
+#pragma unroll
+          for (int u = 0; u < UU; u++) nxt[u] = __ldg(upn + u * 32);
+        }
+        const float acc = adc_units<M, KC>(cur, lut_base, (uint32_t)KC * 4u);
+#pragma unroll
+        for (int u = 0; u < UU; u++) cur[u] = nxt[u];
+        const uint32_t thr = min(my_thr, *s_thr);
+        const uint32_t dbits = __float_as_uint(acc);
+        const bool cand = ((blk * 32 + lane) < len) && (dbits <= thr);
+        unsigned mask = __ballot_sync(0xffffffffu, cand);
+        if (mask) {
+          u64 key = kKeyInf;
+          if (cand) key = make_key(acc, (uint32_t)a.tab.rowno[(size_t)(blk0 + blk) * 32 + lane]);
+          while (mask) {
+            const int src = __ffs(mask) - 1;
+            warp_list_insert(mine, shfl_u64(key, src), lane);
+            mask &= mask - 1;
+          }
+          my_thr = key_dbits(shfl_u64(mine, a.KK - 1));
+          if (lane == 0 && my_thr < thr) atomicMin(const_cast<uint32_t*>(s_thr), my_thr);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->empty[b]);   // this warp is done with ring slot b
+      if (ds.w == a.w - 1) {                        // last list of the query: hand the warp's keys to the merger
+        stage[((size_t)p * kPipeScanWarps + warp) * 32 + lane] = mine;
+        if (warp == 0 && lane == 0) ctl->stage_q[p] = ds.z;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->stg_full[p]);
+        nq_seen++;
+      }
+    }
+  }
+}
+
+}  // namespace fb

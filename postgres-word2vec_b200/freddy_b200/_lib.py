@@ -15,6 +15,7 @@ FB_CB_RESIDUAL, FB_CB_PQ, FB_CB_IVPQ = 0, 1, 2
 FB_OPT_FORCE_EXACT_PATH, FB_OPT_PROFILE, FB_OPT_QUERY_CHUNK, FB_OPT_QSCAN_MIN_QUERIES, FB_OPT_PACKED_FP32 = 1, 2, 3, 4, 5
 FB_OPT_LUT_TILE = 6
 FB_OPT_LUT_CTAS_PER_SM, FB_OPT_OVERLAP = 7, 8
+FB_OPT_PIPELINE, FB_OPT_PIPE_CHUNK, FB_OPT_PIPE_DEBUG, FB_OPT_PLACEMENT_WINDOW = 9, 10, 11, 12
 
 
 class Counters(C.Structure):
@@ -25,6 +26,7 @@ class Counters(C.Structure):
         ("ms_finalize", C.c_double), ("ms_exact", C.c_double), ("n_scan_launches", C.c_int64),
         ("exact_coarse_tie", C.c_int64), ("exact_coarse_far", C.c_int64), ("exact_few_rows", C.c_int64),
         ("exact_scan_tie", C.c_int64), ("exact_forced", C.c_int64),
+        ("ms_pipe", C.c_double), ("n_pipe_launches", C.c_int64),
     ]
 
 
@@ -32,6 +34,7 @@ class Counters(C.Structure):
 _P = C.c_void_p
 SIGNATURES = {
     "fb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "fb_placement_order": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "fb_destroy": (None, [_P]),
     "fb_last_error": (C.c_char_p, [_P]),
     "fb_load_coarse": (C.c_int, [_P, _P, C.c_int, C.c_int]),
