@@ -92,6 +92,22 @@ __device__ __forceinline__ void warp_list_merge(u64& mine, u64 other, int lane) 
   }
 }
 
+// Full ascending sort of 32 keys, one per lane (bitonic network, 15 exchange steps).
+__device__ __forceinline__ u64 warp_sort_u64(u64 v, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int s = size >> 1; s >= 1; s >>= 1) {
+      const u64 partner = shfl_xor_u64(v, s);
+      const bool up = ((lane & size) == 0) || size == 32;      // direction of this lane's subsequence
+      const bool lower = (lane & s) == 0;
+      const bool take_min = (lower == up);
+      v = take_min ? (partner < v ? partner : v) : (partner > v ? partner : v);
+    }
+  }
+  return v;
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP / SYNCS) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

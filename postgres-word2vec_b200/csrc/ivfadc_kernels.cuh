@@ -493,35 +493,50 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_
                                                uint32_t* __restrict__ qflags,
                                                int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                                                int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count,
-                                               u64* __restrict__ exact_total, u64* __restrict__ kth_key) {
-  // lanes hold the k+2 smallest keys (lane i = i-th).  A distance tie across the k-th place makes the
-  // reference's result depend on arrival order (strict `<` admission + insert-before-equal,
-  // index_utils.c:19-33).  If every row tied with the k-th distance is among the k+1 smallest keys
-  // (the (k+2)-th key is larger), the outcome is those k+1 rows minus one tied row: the tied row that
-  // arrived last if it is the latest arrival of all k+1, else the one that arrived first
-  // (tests/test_topk_semantics.py, fact C).  Longer tie groups go to the general kernel.
-  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1), kk2 = shfl_u64(mine, k + 1);
+                                               u64* __restrict__ exact_total, u64* __restrict__ kth_key,
+                                               int n_valid) {
+  // lanes 0..n_valid-1 hold the n_valid smallest keys (lane i = i-th; n_valid = 32 when the warp lists were
+  // merged untruncated, k+2 when they went through the partial-list buffer; every row whose distance is <=
+  // the (k+2)-th smallest distance was admitted by the scan).  A distance tie across the k-th place makes the reference's result
+  // depend on arrival order (strict `<` admission + insert-before-equal, index_utils.c:19-33).  With v = the
+  // k-th smallest distance, rows with d > v can neither enter nor rearrange the entries <= v (fact B,
+  // tests/test_topk_semantics.py), so the literal loop over S = {rows with d <= v} in arrival order gives
+  // the reference's result.  S is complete in this list iff some lane < n_valid holds a key with d > v (or none):
+  // then the warp replays it here (fact D).  Tie groups too long for that go to the general kernel.
+  const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
+  bool replayed = false;
   if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) {
-    if (kk2 != kKeyInf && key_dbits(kk2) == key_dbits(kk1)) {
+    const uint32_t v = key_dbits(kk1);
+    const bool member = lane < n_valid && (mine != kKeyInf) && key_dbits(mine) <= v;
+    const unsigned members = __ballot_sync(0xffffffffu, member);
+    if (members == (n_valid >= 32 ? 0xffffffffu : ((1u << n_valid) - 1u))) {
       flags |= kFlagExact | kWhyScanTie;
     } else {
-      const uint32_t v = key_dbits(kk1);
-      const bool member = lane <= k;
-      const bool is_tie = member && key_dbits(mine) == v;
-      // latest arrival among the k+1 members (arrival = low word, unique)
-      uint32_t tmax = member ? key_t(mine) : 0u;
-      int lmax = lane;
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        const uint32_t ot = __shfl_xor_sync(0xffffffffu, tmax, s);
-        const int ol = __shfl_xor_sync(0xffffffffu, lmax, s);
-        if (ot > tmax || (ot == tmax && ol < lmax)) { tmax = ot; lmax = ol; }
+      // S by arrival: (arrival << 32 | distance bits), non-members last
+      u64 byt = member ? (((u64)key_t(mine) << 32) | (u64)key_dbits(mine)) : kKeyInf;
+      byt = warp_sort_u64(byt, lane);
+      const int n_s = __popc(members);
+      // literal updateTopK on lanes 0..k-1 (lane i = tk[i]), starting from k sentinel entries
+      float tk_d = sentinel;
+      uint32_t tk_t = 0xFFFFFFFFu;
+      for (int s_i = 0; s_i < n_s; s_i++) {
+        const u64 e = shfl_u64(byt, s_i);
+        const float dist = __uint_as_float((uint32_t)e);
+        const uint32_t t = (uint32_t)(e >> 32);
+        const float max_dist = __shfl_sync(0xffffffffu, tk_d, k - 1);
+        const float up_d = __shfl_up_sync(0xffffffffu, tk_d, 1);
+        const uint32_t up_t = __shfl_up_sync(0xffffffffu, tk_t, 1);
+        const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && tk_d < dist));   // entries strictly smaller
+        if (dist < max_dist) {
+          if (lane == pos) { tk_d = dist; tk_t = t; }
+          else if (lane > pos && lane < k) { tk_d = up_d; tk_t = up_t; }
+        }
       }
-      const unsigned tie_mask = __ballot_sync(0xffffffffu, is_tie);
-      const int first_tie = __ffs(tie_mask) - 1;
-      const int drop = ((tie_mask >> lmax) & 1u) ? lmax : first_tie;
-      const u64 next = __shfl_down_sync(0xffffffffu, mine, 1);
-      if (lane >= drop && lane < 31) mine = next;          // close the gap: lanes 0..k-1 now hold the result
+      if (lane < k) {
+        out_ids[(size_t)q * k + lane] = (tk_t == 0xFFFFFFFFu) ? -1 : ids[tk_t];
+        out_dists[(size_t)q * k + lane] = tk_d;
+      }
+      replayed = true;
     }
   }
   if (lane == 0) { kth_key[q] = kk1; qflags[q] = flags; }   // kk1: the k-th smallest key = the general kernel's bound
@@ -534,6 +549,7 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_
     }
     return;
   }
+  if (replayed) return;
   const uint32_t dbits = key_dbits(mine);
   const uint32_t prev = __shfl_up_sync(0xffffffffu, dbits, 1);
   const bool in_range = lane < k;
@@ -662,11 +678,11 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
   if (warp == 0) {
     for (int l = 1; l < kQScanWarps; l++) {
       const u64 other = stage[l * 32 + lane];
-      if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
+      if (__ballot_sync(0xffffffffu, other <= (shfl_u64(mine, KK - 1) | 0xFFFFFFFFull)) == 0) continue;   // keeps distance ties
       warp_list_merge(mine, other, lane);
     }
     warp_emit_topk(mine, lane, q, q_base, k, qflags[q], tab.ids, sentinel, qflags, out_ids, out_dists,
-                   exact_list, exact_count, exact_total, kth_key);
+                   exact_list, exact_count, exact_total, kth_key, 32);
   }
 }
 
@@ -752,12 +768,12 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
   const u64* base = partial + (size_t)q * lists_per_query * KK;
   for (int l = 0; l < lists_per_query; l++) {
     u64 other = (lane < KK) ? base[(size_t)l * KK + lane] : kKeyInf;
-    if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, KK - 1)) == 0) continue;
+    if (__ballot_sync(0xffffffffu, other <= (shfl_u64(mine, KK - 1) | 0xFFFFFFFFull)) == 0) continue;   // keeps distance ties
     warp_list_merge(mine, other, lane);
   }
   const uint32_t flags = has_input_flags ? qflags[q] : 0u;
   warp_emit_topk(mine, lane, q, q_base, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
-                 exact_total, kth_key);
+                 exact_total, kth_key, KK);
 }
 
 }  // namespace fb

@@ -32,12 +32,23 @@ constexpr int kPipeProdThreads = kPipeProdWarps * kWarp;
 constexpr int kPipeTile = 4 * (kPipeProdThreads / 2); // codes per producer CTA slice
 constexpr int kPipeScanWarps = kPipeWarps - kPipeProdWarps - 2;   // 22 (+ loader warp + merger warp)
 constexpr int kPipeBufs = 3;                         // LUT ring depth in shared memory
-constexpr int kPipeScanRegs = 40, kPipeProdRegs = 136;   // registers per thread after setmaxnreg
+constexpr int kPipeScanRegs = 56, kPipeProdRegs = 88;   // registers per thread after setmaxnreg
 static_assert((kPipeThreads - kPipeProdThreads) * kPipeScanRegs + kPipeProdThreads * kPipeProdRegs <= 65536, "register file");
 static_assert(kPipeProdWarps % 4 == 0, "roles must be whole warpgroups");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32-bit shared-window loads (constant offsets fold into LDS [R + imm]; no generic-address arithmetic)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -264,11 +275,11 @@ ivfadc_pipe_kernel(const PipeArgs a) {
       u64 mine = sp[lane];
       for (int l = 1; l < kPipeScanWarps; l++) {
         const u64 other = sp[l * 32 + lane];
-        if (__ballot_sync(0xffffffffu, other < shfl_u64(mine, a.KK - 1)) == 0) continue;
+        if (__ballot_sync(0xffffffffu, other <= (shfl_u64(mine, a.KK - 1) | 0xFFFFFFFFull)) == 0) continue;   // keeps distance ties
         warp_list_merge(mine, other, lane);
       }
       warp_emit_topk(mine, lane, q, a.q_base, a.k, a.qflags[q], a.tab.ids, a.sentinel, a.qflags, a.out_ids, a.out_dists,
-                     a.exact_list, a.exact_count, a.exact_total, a.kth_key);
+                     a.exact_list, a.exact_count, a.exact_total, a.kth_key, 32);
       if (lane == 0) ctl->thr[p] = 0xFFFFFFFFu;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->stg_empty[p]);
@@ -279,6 +290,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
   {
     u64* stage = reinterpret_cast<u64*>(smem_raw + L::off_stage);
     constexpr int UU = (M + 3) / 4;
+    const uint32_t smem_base = smem_u32(smem_raw);
     u64 mine = kKeyInf;
     uint32_t my_thr = 0xFFFFFFFFu;
     int nq_seen = 0, p = 0;
@@ -300,26 +312,32 @@ ivfadc_pipe_kernel(const PipeArgs a) {
       }
       const int blk0 = ds.x, len = ds.y;
       const int nblk = (len + 31) >> 5;
-      const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)b * lut_bytes;
-      volatile uint32_t* s_thr = &ctl->thr[p];
-      uint2 cur[UU], nxt[UU];
-      if (warp < nblk) {
-        const uint2* up0 = a.tab.units + ((size_t)(blk0 + warp) * UU) * 32 + lane;
+      const uint32_t lut_s = smem_base + (uint32_t)b * lut_bytes;        // shared-window address of this task's LUT
+      const uint32_t thr_s = smem_u32(&ctl->thr[p]);
+      // this warp's blocks: warp, warp + S, ...; their codes travel through three register stages
+      // (A, B, C) so that two blocks are always in flight behind the one being gathered
+      const int n_mine = (nblk > warp) ? (nblk - warp + kPipeScanWarps - 1) / kPipeScanWarps : 0;
+      const uint2* ubase = a.tab.units + ((size_t)(blk0 + warp) * UU) * 32 + lane;
+      constexpr size_t ustep = (size_t)kPipeScanWarps * UU * 32;           // uint2 elements between a warp's blocks
+      uint2 sa[UU], sb[UU], sc[UU];
+      auto load = [&](uint2 (&v)[UU], int i) {
+        const uint2* up = ubase + (size_t)i * ustep;
 #pragma unroll
-        for (int u = 0; u < UU; u++) cur[u] = __ldg(up0 + u * 32);
-      }
-      for (int blk = warp; blk < nblk; blk += kPipeScanWarps) {
-        const int bn = blk + kPipeScanWarps;
-        if (bn < nblk) {
-          const uint2* upn = a.tab.units + ((size_t)(blk0 + bn) * UU) * 32 + lane;
+        for (int u = 0; u < UU; u++) v[u] = __ldg(up + u * 32);
+      };
+      auto process = [&](const uint2 (&v)[UU], int i) {
+        float acc = 0.0f;
 #pragma unroll
-          for (int u = 0; u < UU; u++) nxt[u] = __ldg(upn + u * 32);
+        for (int u = 0; u < UU; u++) {
+          const uint32_t wlo = v[u].x, whi = v[u].y;
+          if (4 * u + 0 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 0) * KC * 4) + lut_s + (wlo & 0xFFFFu)));
+          if (4 * u + 1 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 1) * KC * 4) + lut_s + (wlo >> 16)));
+          if (4 * u + 2 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 2) * KC * 4) + lut_s + (whi & 0xFFFFu)));
+          if (4 * u + 3 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 3) * KC * 4) + lut_s + (whi >> 16)));
         }
-        const float acc = adc_units<M, KC>(cur, lut_base, (uint32_t)KC * 4u);
-#pragma unroll
-        for (int u = 0; u < UU; u++) cur[u] = nxt[u];
-        const uint32_t thr = min(my_thr, *s_thr);
+        const uint32_t thr = min(my_thr, lds_u32(thr_s));
         const uint32_t dbits = __float_as_uint(acc);
+        const int blk = warp + i * kPipeScanWarps;
         const bool cand = ((blk * 32 + lane) < len) && (dbits <= thr);
         unsigned mask = __ballot_sync(0xffffffffu, cand);
         if (mask) {
@@ -331,8 +349,20 @@ ivfadc_pipe_kernel(const PipeArgs a) {
             mask &= mask - 1;
           }
           my_thr = key_dbits(shfl_u64(mine, a.KK - 1));
-          if (lane == 0 && my_thr < thr) atomicMin(const_cast<uint32_t*>(s_thr), my_thr);
+          if (lane == 0 && my_thr < thr) atomicMin(&ctl->thr[p], my_thr);
         }
+      };
+      if (n_mine > 0) load(sa, 0);
+      if (n_mine > 1) load(sb, 1);
+      for (int i = 0; i < n_mine; i += 3) {
+        if (i + 2 < n_mine) load(sc, i + 2);
+        process(sa, i);
+        if (i + 1 >= n_mine) break;
+        if (i + 3 < n_mine) load(sa, i + 3);
+        process(sb, i + 1);
+        if (i + 2 >= n_mine) break;
+        if (i + 4 < n_mine) load(sb, i + 4);
+        process(sc, i + 2);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->empty[b]);   // this warp is done with ring slot b

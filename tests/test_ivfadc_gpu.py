@@ -75,13 +75,17 @@ def test_parity_noisy_queries_and_chunks(eng, oracle_mod, overlap):
 def test_ties_everywhere(eng, oracle_mod):
     """m=2 (or 4) positions x K=4 codes: every list holds only 16 (256) distinct
     code vectors, so distance ties straddle the k-th place all the time."""
+    general = 0
     for (d, m) in ((8, 2), (16, 4)):
         ix = small_index(N=6000, d=d, m=m, K=4, C=8, seed=3, n_clusters=5)
         q = queries_from(ix, 200, seed=9)
         for k, w in ((5, 2), (3, 8), (20, 3)):
             ids, d_, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, k, w, qscan_min=(1 << 30) if k == 3 else 0)
             assert_same_topk(ids, d_, eids, ed, f"ties m={m} k={k} w={w}")
-            assert eng.counters()["exact_path_queries"] > 0
+            general += eng.counters()["exact_path_queries"]
+    # short tie groups are replayed inside the merging warp (warp_emit_topk); groups that do not fit
+    # the warp's 32 keys (m=2: about 47 duplicates per distinct code vector) still reach the general kernel
+    assert general > 0
 
 
 def test_reprobe_loop(eng, oracle_mod):

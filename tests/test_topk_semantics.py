@@ -87,3 +87,21 @@ def test_fact_C_boundary_tie_resolved_from_k_plus_one_keys(ds, k):
     kept = [e for e in S if e != drop]
     out = sorted(kept, key=lambda e: (e[0], -e[1]))
     assert out == literal(stream, k)
+
+
+@settings(max_examples=600, deadline=None)
+@given(streams, st.integers(1, 8), st.integers(9, 14))
+def test_fact_D_replay_of_the_complete_tie_set(ds, k, cap):
+    """(warp_emit_topk) v = k-th smallest distance.  If fewer than `cap` rows have d <= v (cap = 32 lanes
+    on the GPU), those rows are all among the cap smallest keys, and the literal loop over just them, in
+    arrival order, from the initial sentinel state, is the reference's result."""
+    stream = [(float(x) / 4, t) for t, x in enumerate(ds)]
+    keys = sorted(stream)[:cap]
+    if len(keys) < k:
+        return
+    v = keys[k - 1][0]
+    s = [e for e in keys if e[0] <= v]
+    if len(s) == cap:
+        return                                   # cannot prove completeness: general kernel
+    assert len(s) == sum(1 for e in stream if e[0] <= v)
+    assert literal(sorted(s, key=lambda e: e[1]), k) == literal(stream, k)
