@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--pipeline", type=int, default=None, help="0: separate LUT/scan kernels instead of the pipeline kernel")
     ap.add_argument("--pipe-chunk", type=int, default=None, help="queries per pipeline beat")
     ap.add_argument("--placement", type=int, default=None, help="window of the conflict-aware row placement (0 = arrival order)")
+    ap.add_argument("--pipe-shape", type=int, default=None, help="role split of the pipeline CTA (FB_OPT_PIPE_SHAPE)")
+    ap.add_argument("--pipe-ramp", type=int, default=None, help="0: uniform pipeline chunks")
     ap.add_argument("--pipe-debug", type=int, default=None, help="timing aid (invalid results): 1 producers only, 2 scan only")
     return ap.parse_args()
 
@@ -249,6 +251,10 @@ def main():
         eng.set_option(_lib.FB_OPT_PIPELINE, a.pipeline)
     if a.pipe_chunk is not None:
         eng.set_option(_lib.FB_OPT_PIPE_CHUNK, a.pipe_chunk)
+    if a.pipe_ramp is not None:
+        eng.set_option(_lib.FB_OPT_PIPE_RAMP, a.pipe_ramp)
+    if a.pipe_shape is not None:
+        eng.set_option(_lib.FB_OPT_PIPE_SHAPE, a.pipe_shape)
 
     nq, k, w = a.batch, a.k, a.w
     d_ids = torch.empty(nq, k, dtype=torch.int32, device=dev)
@@ -326,7 +332,7 @@ def main():
         traffic = tj["pipe_dram_bytes_per_launch" if piped else "dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "ivfadc_pipe_kernel<12,1024,25>" if piped else "adc_scan_query_kernel<12,1024>",
+    roofline = {"bound": "hbm", "kernel": "ivfadc_pipe_kernel<12,1024,25,...>" if piped else "adc_scan_query_kernel<12,1024>",
                 "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, n_dom),

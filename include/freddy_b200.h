@@ -170,12 +170,14 @@ enum {
   FB_OPT_PIPELINE = 9,         /* 1 (default): large batches of the headline shapes run the warp-
                                   specialised pipeline kernel (LUT build of chunk c+1 and ADC scan of
                                   chunk c share every SM inside one launch); 0: separate kernels   */
-  FB_OPT_PIPE_CHUNK = 10,      /* queries per pipeline beat (default 1024)                         */
+  FB_OPT_PIPE_CHUNK = 10,      /* queries per pipeline beat (default 2048)                         */
   FB_OPT_PLACEMENT_WINDOW = 12, /* fb_load_fine: rows of a list are placed into 32-row blocks so that
                                   the lanes of a warp hit different shared-memory banks of the LUT as
                                   far as possible (arrival order travels with each row, results do
                                   not change); value = candidate rows examined per slot (default 256,
                                   0/1 = keep arrival order).  Applies to the next fb_load_fine.      */
+  FB_OPT_PIPE_SHAPE = 13,      /* role split of the pipeline CTA (producer warps, scan warps): 0 = (8,18), 1 = (8,22), 2 = (8,14) */
+  FB_OPT_PIPE_RAMP = 14,       /* 1: the first and last pipeline chunks are shortened (quarter, half); default 0  */
   FB_OPT_PIPE_DEBUG = 11,      /* timing aid, results are NOT valid: 1 = producers only (no scan),
                                   2 = scan only (LUT scratch left as is)                           */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the

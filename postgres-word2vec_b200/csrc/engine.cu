@@ -142,9 +142,11 @@ struct fb_engine {
   cudaEvent_t ev_main = nullptr, ev_all = nullptr, ev_lut_done[2] = {nullptr, nullptr}, ev_scan_done[2] = {nullptr, nullptr};
   DevBuf<float> lut2;
   int pipeline = 1;          // 1: warp-specialised pipeline kernel for large batches of the headline shapes
-  int64_t pipe_chunk = 1024; // queries per pipeline beat
+  int64_t pipe_chunk = 2048; // queries per pipeline beat
   DevBuf<int32_t> pipe_counters;
   int pipe_debug = 0;
+  int pipe_shape = 0;
+  int pipe_ramp = 0;
   int placement_window = 256; // rows considered per slot by the conflict-aware placement of the fine table (<= 1: off)
   volatile float one = 1.0f;
 
@@ -389,11 +391,11 @@ __global__ void gather_rows_kernel(const uint2* __restrict__ src_units, int U, c
 template <int QT>
 int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k) {
   size_t smem = ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float);
-  auto kern = coarse_select_kernel_t<QT>;
+  auto kern = e->packed_fp32 ? coarse_select_kernel_t<QT, true> : coarse_select_kernel_t<QT, false>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nq + QT - 1) / QT, kCoarseThreads, smem, e->stream>>>(
       d_q, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k, e->probes.p, e->qflags.p,
-      e->force_exact ? 1 : 0);
+      e->force_exact ? 1 : 0, e->one);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
@@ -599,13 +601,32 @@ size_t exact_smem_bytes(const fb_engine* e, int w) {
 // ---- throughput form: warp-specialised pipeline (pipeline_kernels.cuh) ------
 // Beat c (= one launch) builds the LUTs of chunk c+1 and scans chunk c; two LUT
 // buffers alternate.  nchunks + 1 launches on the engine stream.
-template <int M, int KC, int SUB>
+template <int M, int KC, int SUB, class Cfg>
 int run_pipeline_t(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int k, int w, int KK, float sentinel,
                    int32_t* d_out_ids, float* d_out_dists, int64_t chunk) {
-  using L = PipeSmem<M, KC, SUB>;
-  auto kern = ivfadc_pipe_kernel<M, KC, SUB>;
+  using L = PipeSmem<M, KC, SUB, Cfg>;
+  auto kern = ivfadc_pipe_kernel<M, KC, SUB, Cfg>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-  const int nchunks = (int)((nq + chunk - 1) / chunk);
+  // Chunk boundaries.  The first launch only builds LUTs and the last one only scans, so the chunks ramp
+  // up at the start and down at the end (quarter, half, full ... half, quarter of `chunk`): the two
+  // un-overlapped launches become short.
+  std::vector<int64_t> bounds{0};
+  {
+    const int64_t ramp_up[2] = {std::max<int64_t>(64, chunk / 4), std::max<int64_t>(64, chunk / 2)};
+    const int64_t tail = ramp_up[0] + ramp_up[1];
+    int64_t pos = 0;
+    if (e->pipe_ramp && nq >= 2 * tail + chunk) {
+      for (int i = 0; i < 2; i++) { pos += ramp_up[i]; bounds.push_back(pos); }
+      while (nq - pos > tail + chunk) { pos += chunk; bounds.push_back(pos); }
+      const int64_t mid = nq - pos - tail;            // in (0, chunk]
+      if (mid > 0) { pos += mid; bounds.push_back(pos); }
+      pos += ramp_up[1]; bounds.push_back(pos);
+      bounds.push_back(nq);
+    } else {
+      while (pos < nq) { pos = std::min<int64_t>(nq, pos + chunk); bounds.push_back(pos); }
+    }
+  }
+  const int nchunks = (int)bounds.size() - 1;
   const size_t lut_per_query = (size_t)w * M * KC;
   FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
   FB_CUDA(e, e->lut2.ensure((size_t)chunk * lut_per_query));
@@ -633,15 +654,15 @@ int run_pipeline_t(fb_engine* e, const Codebook& cb, const float* d_q, int nq, i
   if (grid > e->num_sms) a.n_groups = 1;
   for (int c = -1; c < nchunks; c++) {
     // producer half: chunk c + 1
-    const int64_t p0 = (int64_t)(c + 1) * chunk;
-    const int pn = (c + 1 < nchunks) ? (int)std::min<int64_t>(chunk, nq - p0) : 0;
-    a.lut_queries = d_q + (size_t)std::min<int64_t>(p0, nq) * e->d;
-    a.lut_probes = e->probes.p + (size_t)std::min<int64_t>(p0, nq) * w;
+    const int64_t p0 = (c + 1 < nchunks) ? bounds[c + 1] : nq;
+    const int pn = (c + 1 < nchunks) ? (int)(bounds[c + 2] - bounds[c + 1]) : 0;
+    a.lut_queries = d_q + (size_t)p0 * e->d;
+    a.lut_probes = e->probes.p + (size_t)p0 * w;
     a.lut_out = ((c + 1) & 1) ? e->lut2.p : e->lut.p;
     a.lut_njobs = pn * w;
     // scan half: chunk c
-    const int64_t s0 = (int64_t)std::max(c, 0) * chunk;
-    const int sn = (c >= 0) ? (int)std::min<int64_t>(chunk, nq - s0) : 0;
+    const int64_t s0 = (c >= 0) ? bounds[c] : 0;
+    const int sn = (c >= 0) ? (int)(bounds[c + 1] - bounds[c]) : 0;
     a.scan_probes = e->probes.p + (size_t)s0 * w;
     a.scan_lut = (c & 1) ? e->lut2.p : e->lut.p;
     a.scan_nq = sn;
@@ -654,7 +675,7 @@ int run_pipeline_t(fb_engine* e, const Codebook& cb, const float* d_q, int nq, i
     if (e->pipe_debug == 1) a.scan_nq = 0;
     if (e->pipe_debug == 2) a.lut_njobs = 0;
     StageTimer t(e, ST_PIPE);
-    kern<<<grid, kPipeThreads, L::total, e->stream>>>(a);
+    kern<<<grid, Cfg::kThreads, L::total, e->stream>>>(a);
     e->launches++;
     e->n_pipe_launches++;
     FB_CUDA(e, cudaGetLastError());
@@ -667,11 +688,21 @@ int run_pipeline(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int
                  int32_t* d_out_ids, float* d_out_dists) {
   if (!e->pipeline || nq < 512 || cb.m != 12 || cb.sub != 25) return FB_ERR_UNSUPPORTED;
   int64_t chunk = std::max<int64_t>(128, std::min<int64_t>(e->pipe_chunk, (nq + 3) / 4));
+#define FB_PIPE_GO(K_, ...)                                                                              \
+  do {                                                                                                   \
+    if (PipeSmem<12, K_, 25, PipeCfg<__VA_ARGS__>>::total > e->smem_optin) return FB_ERR_UNSUPPORTED;    \
+    return run_pipeline_t<12, K_, 25, PipeCfg<__VA_ARGS__>>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, \
+                                                            d_out_dists, chunk);                         \
+  } while (0)
   if (cb.K == 1024) {
-    if (PipeSmem<12, 1024, 25>::total > e->smem_optin) return FB_ERR_UNSUPPORTED;
-    return run_pipeline_t<12, 1024, 25>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists, chunk);
+    switch (e->pipe_shape) {   // (producer warps, scan warps): tuning knob, FB_OPT_PIPE_SHAPE
+      case 1: FB_PIPE_GO(1024, 8, 22);
+      case 2: FB_PIPE_GO(1024, 8, 14);
+      default: FB_PIPE_GO(1024, 8, 18);
+    }
   }
-  if (cb.K == 256) return run_pipeline_t<12, 256, 25>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists, chunk);
+  if (cb.K == 256) FB_PIPE_GO(256, 8, 18);
+#undef FB_PIPE_GO
   return FB_ERR_UNSUPPORTED;
 }
 
@@ -1160,6 +1191,8 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_OVERLAP: e->overlap = value != 0; return FB_OK;
     case FB_OPT_PIPELINE: e->pipeline = value != 0; return FB_OK;
     case FB_OPT_PIPE_DEBUG: e->pipe_debug = (int)value; return FB_OK;
+    case FB_OPT_PIPE_SHAPE: e->pipe_shape = (int)value; return FB_OK;
+    case FB_OPT_PIPE_RAMP: e->pipe_ramp = value != 0; return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");

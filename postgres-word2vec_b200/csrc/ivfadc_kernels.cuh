@@ -52,14 +52,18 @@ constexpr int kLutMaxJobs = 16;
 // table transposed ([d][Cs]) so the per-dimension load is coalesced and shared
 // by the QT queries.  Selection: one warp per query keeps an ascending key list.
 // ---------------------------------------------------------------------------
-template <int QT>
+// PACKED: a thread owns two adjacent centroids as one f32x2 pair (FADD2/FMUL2/FFMA2, common.cuh); the
+// query values enter as scalar-broadcast operands, so one 8-byte coalesced load and QT/4 broadcast
+// 16-byte reads feed 3*QT packed operations per dimension (half the shared-memory traffic per
+// operation of the scalar form).  `one` must be 1.0f supplied at run time.
+template <int QT, bool PACKED>
 __global__ void __launch_bounds__(kCoarseThreads, 2)
 coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
                      const float* __restrict__ coarseT, int C, int Cs,
                      const int32_t* __restrict__ list_len, int w, int k,
                      int32_t* __restrict__ probes,      // [nq][w]
                      uint32_t* __restrict__ qflags,      // [nq]
-                     int force_exact) {
+                     int force_exact, float one) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qs = reinterpret_cast<float*>(smem_raw);     // [d][QT]
   float* dist = qs + (size_t)d * QT;           // [QT][Cs]
@@ -73,6 +77,44 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
   }
   __syncthreads();
 
+  if (PACKED && QT % 4 == 0) {
+    const u64 one2 = pack2(one, one);
+    const int Ch = Cs >> 1;                                   // Cs is a multiple of 32
+    for (int c2 = tid; c2 < Ch; c2 += kCoarseThreads) {
+      u64 acc[QT];
+#pragma unroll
+      for (int qq = 0; qq < QT; qq++) acc[qq] = 0ull;
+      const u64* col = reinterpret_cast<const u64*>(coarseT) + c2;
+      constexpr int PF = 2;
+      u64 cur[PF], nxt[PF];
+#pragma unroll
+      for (int u = 0; u < PF; u++) cur[u] = (u < d) ? __ldg(col + (size_t)u * Ch) : 0ull;
+      for (int i0 = 0; i0 < d; i0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) nxt[u] = (i0 + PF + u < d) ? __ldg(col + (size_t)(i0 + PF + u) * Ch) : 0ull;
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+          const int i = i0 + u;
+          if (i >= d) break;
+          const u64 cv2 = cur[u];
+          const float4* qrow = reinterpret_cast<const float4*>(qs + i * QT);
+#pragma unroll
+          for (int v = 0; v < QT / 4; v++) {
+            const float4 qv = qrow[v];
+            u64 t;
+            t = xsub2(pack2(qv.x, qv.x), cv2); acc[4 * v + 0] = xacc2(xmul2(t, t), one2, acc[4 * v + 0]);
+            t = xsub2(pack2(qv.y, qv.y), cv2); acc[4 * v + 1] = xacc2(xmul2(t, t), one2, acc[4 * v + 1]);
+            t = xsub2(pack2(qv.z, qv.z), cv2); acc[4 * v + 2] = xacc2(xmul2(t, t), one2, acc[4 * v + 2]);
+            t = xsub2(pack2(qv.w, qv.w), cv2); acc[4 * v + 3] = xacc2(xmul2(t, t), one2, acc[4 * v + 3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; u++) cur[u] = nxt[u];
+      }
+#pragma unroll
+      for (int qq = 0; qq < QT; qq++) reinterpret_cast<u64*>(dist + (size_t)qq * Cs)[c2] = acc[qq];
+    }
+  } else
   for (int c = tid; c < Cs; c += kCoarseThreads) {
     float acc[QT];
 #pragma unroll

@@ -6,8 +6,7 @@
 // bound by the fp32 pipe, the ADC scan (freddy.c:347-372) by shared-memory gathers
 // (LSU).  Launch c of this kernel therefore does both at once on every SM:
 //
-//   producer warps (the last kPipeProdWarps warps of the CTA — highest warp ids win
-//       issue arbitration) build the LUTs of query chunk c+1 into global scratch;
+//   producer warps (the last warps of the CTA) build the LUTs of query chunk c+1 into global scratch;
 //   scan warps walk the probed lists of query chunk c, LUTs streamed through a ring
 //       of shared-memory buffers by a loader thread (1-D bulk async copies +
 //       mbarriers), a merger warp writes each query's k results;
@@ -24,17 +23,28 @@
 
 namespace fb {
 
-constexpr int kPipeThreads = 1024;
-constexpr int kPipeWarps = kPipeThreads / kWarp;
-constexpr int kPipeProdWarps = 8;                    // 256 producer threads = 2 job halves x 128 threads x 4 codes
-constexpr int kPipeGroup = 16;                       // jobs per producer group (8 per job half)
-constexpr int kPipeProdThreads = kPipeProdWarps * kWarp;
-constexpr int kPipeTile = 4 * (kPipeProdThreads / 2); // codes per producer CTA slice
-constexpr int kPipeScanWarps = kPipeWarps - kPipeProdWarps - 2;   // 22 (+ loader warp + merger warp)
+constexpr int kPipeTile = 512;                       // codes per producer CTA slice: 128 code threads x 4 codes
 constexpr int kPipeBufs = 3;                         // LUT ring depth in shared memory
-constexpr int kPipeScanRegs = 56, kPipeProdRegs = 88;   // registers per thread after setmaxnreg
-static_assert((kPipeThreads - kPipeProdThreads) * kPipeScanRegs + kPipeProdThreads * kPipeProdRegs <= 65536, "register file");
-static_assert(kPipeProdWarps % 4 == 0, "roles must be whole warpgroups");
+
+// Role split of the CTA.  PW producer warps (a multiple of 4: one job split of 8 jobs per 4 warps),
+// SW scan warps, one loader warp, one merger warp; roles are whole warpgroups so that setmaxnreg can
+// move registers from the scan side to the producers.
+template <int PW, int SW>
+struct PipeCfg {
+  static constexpr int kProdWarps = PW, kScanWarps = SW;
+  static constexpr int kWarps = PW + SW + 2;
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kProdThreads = PW * 32;
+  static constexpr int kSplits = PW / 4;             // job splits: 4 warps = 128 threads x 4 codes = one 512-code slice
+  static constexpr int kGroup = 8 * kSplits;         // jobs per producer group (8 per thread)
+  static constexpr int kLaunchRegs = ((65536 / kThreads) & ~7) > 255 ? 248 : ((65536 / kThreads) & ~7);
+  static constexpr int kScanRegs = 56;
+  static constexpr int kProdRegsRaw = ((kLaunchRegs * kThreads - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
+  static constexpr int kProdRegs = kProdRegsRaw > 232 ? 232 : kProdRegsRaw;
+  static_assert(PW % 4 == 0 && (SW + 2) % 4 == 0, "roles must be whole warpgroups");
+  static_assert(kThreads <= 1024, "CTA too large");
+  static_assert(kProdRegs >= 72, "producers need about 80 registers");
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -84,16 +94,16 @@ struct PipeArgs {
 };
 
 // shared-memory plan (dynamic): [kPipeBufs][M*KC] LUT ring | [SUB][kPipeTile] codebook slice |
-// 2 x [SUB][kPipeGroup] residual pairs | 2 x [kPipeScanWarps][32] key staging | control block
-template <int M, int KC, int SUB>
+// 2 x [SUB][jobs per group] residuals | 2 x [scan warps][32] key staging | control block
+template <int M, int KC, int SUB, class Cfg>
 struct PipeSmem {
   static constexpr size_t lut_bytes = (size_t)M * KC * sizeof(float);
   static constexpr size_t off_cb = kPipeBufs * lut_bytes;
   static constexpr size_t cb_bytes = (size_t)SUB * kPipeTile * sizeof(float);
   static constexpr size_t off_rs = off_cb + cb_bytes;
-  static constexpr size_t rs_bytes = 2 * (size_t)SUB * kPipeGroup * sizeof(u64);
+  static constexpr size_t rs_bytes = 2 * (size_t)SUB * Cfg::kGroup * sizeof(float);
   static constexpr size_t off_stage = off_rs + rs_bytes;
-  static constexpr size_t stage_bytes = 2 * (size_t)kPipeScanWarps * 32 * sizeof(u64);
+  static constexpr size_t stage_bytes = 2 * (size_t)Cfg::kScanWarps * 32 * sizeof(u64);
   static constexpr size_t off_ctl = off_stage + stage_bytes;
   static constexpr size_t total = off_ctl + 256;
 };
@@ -106,10 +116,13 @@ struct PipeCtl {
 };
 static_assert(sizeof(PipeCtl) <= 256, "control block");
 
-template <int M, int KC, int SUB>
-__global__ void __launch_bounds__(kPipeThreads, 1)
+template <int M, int KC, int SUB, class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, 1)
 ivfadc_pipe_kernel(const PipeArgs a) {
-  using L = PipeSmem<M, KC, SUB>;
+  using L = PipeSmem<M, KC, SUB, Cfg>;
+  constexpr int kPipeWarps = Cfg::kWarps, kPipeProdWarps = Cfg::kProdWarps, kPipeProdThreads = Cfg::kProdThreads;
+  constexpr int kPipeScanWarps = Cfg::kScanWarps, kPipeGroup = Cfg::kGroup;
+  constexpr int kPipeProdRegs = Cfg::kProdRegs, kPipeScanRegs = Cfg::kScanRegs;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + L::off_ctl);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -133,29 +146,29 @@ ivfadc_pipe_kernel(const PipeArgs a) {
   __syncthreads();
 
   // Register re-balancing between the roles (warpgroup-wide setmaxnreg): the CTA is launched with
-  // 64 registers per thread; the six scan-side warpgroups give 24 each back, the two producer warpgroups
-  // take them (768 * 40 + 256 * 136 = 64 K), so the LUT build can keep its operands for several
-  // dimensions in flight while the scan warps only need a few dozen registers.
+  // Cfg::kLaunchRegs registers per thread; the scan-side warpgroups give theirs back down to kScanRegs,
+  // the producer warpgroups take them (e.g. 768 * 56 + 256 * 88 = 64 K), so the LUT build can keep its
+  // operands for several dimensions in flight while the scan warps only need a few dozen registers.
   if (warp >= kPipeWarps - kPipeProdWarps) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeProdRegs));
+    if constexpr (kPipeProdRegs > Cfg::kLaunchRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeProdRegs));
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeScanRegs));
+    if constexpr (kPipeScanRegs < Cfg::kLaunchRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeScanRegs));
   }
 
   // ============================================================ producers
   // 8 warps = 2 job halves x 4 warps; a thread owns 4 adjacent codes (two packed pairs) x 8 jobs of the
-  // 16-job group: per dimension one 16-byte read of its codes and four broadcast 16-byte reads of
-  // residual pairs feed 48 packed operations (shared-memory wavefronts per operation: 0.25).
+  // 16-job group: per dimension one 16-byte read of its codes and two broadcast 16-byte reads of
+  // residuals feed 48 packed operations (shared-memory wavefronts per operation: 0.17).
   if (warp >= kPipeWarps - kPipeProdWarps) {
-    const int pt = tid - (kPipeWarps - kPipeProdWarps) * kWarp;        // 0..255
-    const int half = pt >> 7, ct = pt & 127;
+    const int pt = (warp - (kPipeWarps - kPipeProdWarps)) * kWarp + lane;   // 0..255
+    const int half = pt >> 7, ct = pt & 127;            // job split (8 jobs each), code thread
     const int slice = blockIdx.x % a.n_slices, group = blockIdx.x / a.n_slices;
     if (a.lut_njobs <= 0 || group >= a.n_groups) return;
     const int pos = slice / a.tiles, tile = slice % a.tiles;
     const int code0 = tile * kPipeTile;
     const int ncodes = min(kPipeTile, a.K - code0);
     float* cbs = reinterpret_cast<float*>(smem_raw + L::off_cb);       // [SUB][kPipeTile]
-    u64* rs2 = reinterpret_cast<u64*>(smem_raw + L::off_rs);           // 2 x [SUB][kPipeGroup] pairs (r, r)
+    float* rs2 = reinterpret_cast<float*>(smem_raw + L::off_rs);       // 2 x [SUB][kPipeGroup] residuals
     if (pt == 0) {
       mbar_expect_tx(&ctl->cb_bar, (uint32_t)(SUB * ncodes * sizeof(float)));
       for (int i = 0; i < SUB; i++)
@@ -188,15 +201,14 @@ ivfadc_pipe_kernel(const PipeArgs a) {
     const u64 one2 = pack2(a.one, a.one);
     const bool active = 4 * ct < ncodes;
     const float* pc = cbs + 4 * ct;
-    constexpr int WJ = kPipeGroup / 2;                                   // jobs per thread
+    constexpr int WJ = 8;                                                // jobs per thread
     for (int job0 = group * kPipeGroup; job0 < a.lut_njobs; job0 += job_step) {
-      u64* rsc = rs2 + (size_t)cur * n_res;
+      float* rsc = rs2 + (size_t)cur * n_res;
 #pragma unroll
       for (int e = 0; e < kPre; e++) {
         const int idx = pt + e * kPipeProdThreads;
         if (idx < n_res) {
-          const float r = xsub(pre_q[e], pre_c[e]);
-          rsc[idx] = pack2(r, r);
+          rsc[idx] = xsub(pre_q[e], pre_c[e]);
         }
       }
       named_bar_sync(1, kPipeProdThreads);   // rs2[cur] complete; rs2[cur^1] readers (previous group) are done
@@ -205,19 +217,23 @@ ivfadc_pipe_kernel(const PipeArgs a) {
         u64 acc[WJ][2];
 #pragma unroll
         for (int j = 0; j < WJ; j++) acc[j][0] = acc[j][1] = 0ull;
-        const u64* rh = rsc + half * WJ;
+        const float* rh = rsc + half * WJ;
 #pragma unroll
         for (int i = 0; i < SUB; i++) {
           const ulonglong2 cv = *reinterpret_cast<const ulonglong2*>(pc + i * kPipeTile);   // codes 4ct..4ct+3, dimension i
-          const ulonglong2* rr = reinterpret_cast<const ulonglong2*>(rh + i * kPipeGroup);    // broadcast reads
+          const float4* rr = reinterpret_cast<const float4*>(rh + i * kPipeGroup);            // broadcast reads, 4 jobs each
 #pragma unroll
-          for (int j2 = 0; j2 < WJ / 2; j2++) {
-            const ulonglong2 r4 = rr[j2];
-            u64 t;
-            t = xsub2(r4.x, cv.x); acc[2 * j2][0] = xacc2(xmul2(t, t), one2, acc[2 * j2][0]);
-            t = xsub2(r4.x, cv.y); acc[2 * j2][1] = xacc2(xmul2(t, t), one2, acc[2 * j2][1]);
-            t = xsub2(r4.y, cv.x); acc[2 * j2 + 1][0] = xacc2(xmul2(t, t), one2, acc[2 * j2 + 1][0]);
-            t = xsub2(r4.y, cv.y); acc[2 * j2 + 1][1] = xacc2(xmul2(t, t), one2, acc[2 * j2 + 1][1]);
+          for (int j4 = 0; j4 < WJ / 4; j4++) {
+            const float4 r4 = rr[j4];
+            const float rj[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              // pack2(r, r) costs nothing: FADD2 takes the scalar as a broadcast operand (R.F32)
+              const u64 r2 = pack2(rj[jj], rj[jj]);
+              u64 t;
+              t = xsub2(r2, cv.x); acc[4 * j4 + jj][0] = xacc2(xmul2(t, t), one2, acc[4 * j4 + jj][0]);
+              t = xsub2(r2, cv.y); acc[4 * j4 + jj][1] = xacc2(xmul2(t, t), one2, acc[4 * j4 + jj][1]);
+            }
           }
         }
         const int jb = job0 + half * WJ;

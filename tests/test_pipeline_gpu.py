@@ -17,17 +17,21 @@ def eng():
     e.close()
 
 
-def _search(eng, q, k, w, pipeline, pipe_chunk=1024):
+def _search(eng, q, k, w, pipeline, pipe_chunk=2048, shape=0, ramp=0):
     from freddy_b200 import _lib
     eng.set_option(_lib.FB_OPT_PIPELINE, pipeline)
     eng.set_option(_lib.FB_OPT_PIPE_CHUNK, pipe_chunk)
+    eng.set_option(_lib.FB_OPT_PIPE_SHAPE, shape)
+    eng.set_option(_lib.FB_OPT_PIPE_RAMP, ramp)
     eng.reset_counters()
     try:
         ids, d = eng.ivfadc_search(q, k, w)
         c = eng.counters()
     finally:
         eng.set_option(_lib.FB_OPT_PIPELINE, 1)
-        eng.set_option(_lib.FB_OPT_PIPE_CHUNK, 1024)
+        eng.set_option(_lib.FB_OPT_PIPE_CHUNK, 2048)
+        eng.set_option(_lib.FB_OPT_PIPE_SHAPE, 0)
+        eng.set_option(_lib.FB_OPT_PIPE_RAMP, 0)
     return ids, d, c
 
 
@@ -37,12 +41,14 @@ def test_pipeline_parity(eng, oracle_mod, K):
     eng.load_ivfadc_index(ix)
     oi = oracle_mod.OracleIndex(ix)
     q = queries_from(ix, 1300, seed=6, noise=0.02)
-    for k, w, chunk in ((5, 10, 1024), (5, 10, 300), (1, 1, 1024), (7, 3, 200), (30, 7, 1024), (5, 16, 500)):
-        ids, d, c = _search(eng, q, k, w, 1, chunk)
+    cases = ((5, 10, 1024, 0, 0), (5, 10, 300, 1, 1), (1, 1, 1024, 2, 0), (7, 3, 200, 0, 1), (30, 7, 1024, 1, 0),
+             (5, 16, 500, 2, 1))
+    for k, w, chunk, shape, ramp in cases:
+        ids, d, c = _search(eng, q, k, w, 1, chunk, shape if K == 1024 else 0, ramp)
         assert c["n_pipe_launches"] >= 2, "pipeline kernel did not run"
         eids, ed, rc, rows = oi.ivfadc_search(q, k, w, threads=8)
         assert rc == 0
-        assert_same_topk(ids, d, eids, ed, f"pipeline K={K} k={k} w={w} chunk={chunk}")
+        assert_same_topk(ids, d, eids, ed, f"pipeline K={K} k={k} w={w} chunk={chunk} shape={shape} ramp={ramp}")
         assert c["rows_scanned"] == rows
         ids2, d2, c2 = _search(eng, q, k, w, 0)
         assert c2["n_pipe_launches"] == 0
