@@ -147,6 +147,18 @@ int fb_analogy_3cosadd(fb_engine* e, const int32_t* ids_abc, int nq, int32_t* ou
 int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids, int nq,
                     int32_t* out_ids, float* out_scores);
 
+/* ---- exact cosine k-NN and post-verification ----------
+ * fb_knn_exact: k_nearest_neighbour(bytea, k) (freddy--0.0.1.sql:426-439) when targets == NULL, else
+ * knn_in_exact(bytea, k, int[]) (:1026-1038): similarity = cosine_similarity_bytea (core_functions.c:67-81,
+ * sequential float4 dot), ORDER BY similarity DESC FETCH FIRST k.  Equal similarities are ordered by table
+ * row (SQL leaves that order to the executor).  Fewer than k rows: id -1, similarity 0.  k <= 32.
+ * fb_ivfadc_search_pv: k_nearest_neighbour_ivfadc_pv(bytea, k) (:574-591) with pvf = get_pvf(), w = get_w():
+ * ivfadc_search(v, pvf*k) INNER JOIN vectors ON idx = id, re-ranked by cosine_similarity_bytea.          */
+int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                 int32_t* out_ids, float* out_sims);
+int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int w,
+                        int32_t* out_ids, float* out_sims);
+
 int fb_synchronize(fb_engine* e);
 /* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL restores the engine's own stream).  Lets a host runtime order the

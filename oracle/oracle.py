@@ -395,3 +395,59 @@ class OracleIndex:
         tk = (TopKEntry * (nq * k))()
         lib().fo_pq_search_in_batch(C.byref(self.ix), _p(q), nq, k, _p(t), t.shape[0], 1 if use_target_lists else 0, tk)
         return self._unpack(tk, nq, k)
+
+
+# ---- exact cosine k-NN and post-verification (SQL-level functions) ----------------
+def cosine_similarity_bytea_many(q, vectors):
+    """core_functions.c:67-81 for one query against many rows: `scalar += v1[i] * v2[i]` in float4, product and
+    sum rounded separately, left to right (vectorised over rows, sequential over dimensions)"""
+    v = np.ascontiguousarray(vectors, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    acc = np.zeros(v.shape[0], np.float32)
+    for i in range(v.shape[1]):
+        acc = acc + q[i] * v[:, i]          # float32 * float32 -> float32, + float32 -> float32
+    return acc
+
+
+def _order_desc(sims, rows, k):
+    """ORDER BY similarity DESC FETCH FIRST k; equal similarities by table row (the engine's stated rule)"""
+    order = np.lexsort((rows, -sims.astype(np.float64)))
+    return order[:k]
+
+
+def knn_exact(vectors, vec_ids, queries, k, targets=None):
+    """k_nearest_neighbour(bytea, k) / knn_in_exact(bytea, k, int[])   freddy--0.0.1.sql:426-439, :1026-1038"""
+    v = np.ascontiguousarray(vectors, np.float32)
+    ids = np.asarray(vec_ids, np.int32)
+    rows = np.arange(len(v))
+    if targets is not None:
+        rows = np.nonzero(np.isin(ids, np.asarray(targets, np.int32)))[0]       # WHERE id = ANY(...): table order, once
+    out_ids = np.full((len(queries), k), -1, np.int32)
+    out_s = np.zeros((len(queries), k), np.float32)
+    for qi, q in enumerate(np.ascontiguousarray(queries, np.float32)):
+        s = cosine_similarity_bytea_many(q, v[rows])
+        sel = _order_desc(s, rows, k)
+        out_ids[qi, :len(sel)] = ids[rows[sel]]
+        out_s[qi, :len(sel)] = s[sel]
+    return out_ids, out_s
+
+
+def ivfadc_search_pv(oracle_index, vectors, vec_ids, queries, k, pvf, w, threads=4):
+    """k_nearest_neighbour_ivfadc_pv(bytea, k)   freddy--0.0.1.sql:574-591: candidates = ivfadc_search(v, pvf*k),
+    INNER JOIN vectors ON idx = id, ORDER BY cosine_similarity_bytea DESC FETCH FIRST k"""
+    v = np.ascontiguousarray(vectors, np.float32)
+    ids = np.asarray(vec_ids, np.int32)
+    row_of = {int(i): r for r, i in enumerate(ids)}
+    cand, _, rc, _ = oracle_index.ivfadc_search(queries, k * pvf, w, threads=threads)
+    assert rc == 0
+    out_ids = np.full((len(queries), k), -1, np.int32)
+    out_s = np.zeros((len(queries), k), np.float32)
+    for qi, q in enumerate(np.ascontiguousarray(queries, np.float32)):
+        rows = np.array([row_of[int(c)] for c in cand[qi] if int(c) in row_of], np.int64)
+        if len(rows) == 0:
+            continue
+        s = cosine_similarity_bytea_many(q, v[rows])
+        sel = _order_desc(s, rows, k)
+        out_ids[qi, :len(sel)] = ids[rows[sel]]
+        out_s[qi, :len(sel)] = s[sel]
+    return out_ids, out_s

@@ -22,6 +22,7 @@
 #include "vector_kernels.cuh"
 #include "knn_join_kernels.cuh"
 #include "pipeline_kernels.cuh"
+#include "rerank_kernels.cuh"
 
 using namespace fb;
 
@@ -109,7 +110,10 @@ struct fb_engine {
   DevBuf<u64> j_keys;
   // word-vector table (analogy / exact rerank)
   DevBuf<float> vecT;
-  DevBuf<int32_t> vec_ids;
+  DevBuf<int32_t> vec_ids, vec_sorted_ids, vec_sorted_rows;   // sorted (id, row) pairs: id -> row on the device
+  DevBuf<float> sub_vT;                                        // gathered subset (knn_in_exact)
+  DevBuf<int32_t> sub_rows, pv_cand;
+  DevBuf<u64> knn_partial;
   std::vector<int32_t> vec_ids_host;
   bool vec_ids_sorted = true;
   std::unordered_map<int32_t, int32_t> vec_id_to_row;
@@ -1335,6 +1339,18 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   e->vec_id_to_row.clear();
   if (!e->vec_ids_sorted)
     for (int64_t r = 0; r < N; r++) e->vec_id_to_row.emplace(ids[r], (int32_t)r);
+  {
+    std::vector<int32_t> order((size_t)N), sid((size_t)N);
+    for (int64_t r = 0; r < N; r++) order[r] = (int32_t)r;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ids[a] < ids[b]; });
+    for (int64_t r = 0; r < N; r++) sid[r] = ids[order[r]];
+    FB_CUDA(e, e->vec_sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
+    FB_CUDA(e, e->vec_sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
+    if (N > 0) {
+      FB_CUDA(e, cudaMemcpy(e->vec_sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+      FB_CUDA(e, cudaMemcpy(e->vec_sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+  }
   e->vec_N = N; e->vec_d = d; e->vec_loaded = true;
   return FB_OK;
 }
@@ -1431,6 +1447,118 @@ int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids
 }  // extern "C"
 
 extern "C" {
+
+// exact cosine top-k over a dimension-major blocked table (the whole word-vector table or a gathered subset)
+static int knn_exact_dev(fb_engine* e, const float* vT, int64_t N, const int32_t* d_row_map, const float* d_q, int nq, int k,
+                         int32_t* d_out_ids, float* d_out_sims) {
+  const int d = e->vec_d;
+  const int tiles = (nq + kAnaQT - 1) / kAnaQT, nq_pad = tiles * kAnaQT;
+  const int64_t n_blocks = (N + 31) / 32;
+  const int blocks_per_slab = kAnaWarps * 8;
+  const int n_slabs = (int)((n_blocks + blocks_per_slab - 1) / blocks_per_slab);
+  FB_CUDA(e, e->knn_partial.ensure((size_t)std::max(1, n_slabs) * nq_pad * k));
+  const size_t smem = ((size_t)d * kAnaQT + (size_t)kAnaWarps * 32 * 33) * sizeof(float) + (size_t)kAnaWarps * 32 * k * sizeof(u64);
+  if (smem > e->smem_optin - 2048) return fail(e, FB_ERR_UNSUPPORTED, "d=%d, k=%d too large for the exact scan", d, k);
+  FB_CUDA(e, cudaFuncSetAttribute(exact_knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (n_slabs > 0) {
+    StageTimer t(e, ST_SCAN);
+    dim3 grid(tiles, n_slabs);
+    exact_knn_scan_kernel<<<grid, kAnaThreads, smem, e->stream>>>(vT, N, d, blocks_per_slab, d_q, nq, k, e->knn_partial.p,
+                                                                  nq_pad, e->one);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  exact_knn_reduce_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->knn_partial.p, n_slabs, nq, nq_pad, k, e->vec_ids.p,
+                                                               d_row_map, d_out_ids, d_out_sims);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  e->host_rows += (int64_t)nq * N;
+  e->bytes_per_row = d * 4;
+  return FB_OK;
+}
+
+int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                 int32_t* out_ids, float* out_sims) {
+  if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_knn_exact: bad arguments");
+  if (k < 1 || k > kKnnMaxK) return fail(e, FB_ERR_UNSUPPORTED, "fb_knn_exact: k=%d outside [1,%d]", k, kKnnMaxK);
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "word-vector table not loaded (fb_load_vectors)");
+  if (n_targets < 0 || (n_targets > 0 && !targets)) return fail(e, FB_ERR_INVALID, "bad target array");
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_sims) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int d = e->vec_d;
+  FB_CUDA(e, e->va.ensure((size_t)nq * d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->va.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  int rc;
+  if (targets == nullptr) {
+    rc = knn_exact_dev(e, e->vecT.p, e->vec_N, nullptr, e->va.p, nq, k, e->id_stage.p, e->dist_stage.p);
+  } else {
+    // WHERE id = ANY(targets): the matching rows in table order, each once (freddy--0.0.1.sql:1026-1038)
+    std::vector<int32_t> rows;
+    rows.reserve(n_targets);
+    for (int i = 0; i < n_targets; i++) { const int r = vec_row_of(e, targets[i]); if (r >= 0) rows.push_back(r); }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const int n = (int)rows.size();
+    const int nb = std::max(1, (n + 31) / 32);
+    FB_CUDA(e, e->sub_rows.ensure((size_t)std::max(1, n)));
+    FB_CUDA(e, e->sub_vT.ensure((size_t)nb * d * 32));
+    if (n > 0) {
+      FB_CUDA(e, cudaMemcpyAsync(e->sub_rows.p, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+      gather_vec_blocks_kernel<<<nb, 256, 0, e->stream>>>(e->vecT.p, d, e->sub_rows.p, n, e->sub_vT.p);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+      FB_CUDA(e, cudaStreamSynchronize(e->stream));   // rows is a local
+    }
+    rc = knn_exact_dev(e, e->sub_vT.p, n, e->sub_rows.p, e->va.p, nq, k, e->id_stage.p, e->dist_stage.p);
+  }
+  if (rc) return rc;
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_sims, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->queries_done += nq;
+  return FB_OK;
+}
+
+int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int w, int32_t* out_ids, float* out_sims) {
+  if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_ivfadc_search_pv: bad arguments");
+  if (k < 1 || pvf < 1) return fail(e, FB_ERR_INVALID, "fb_ivfadc_search_pv: k=%d pvf=%d", k, pvf);
+  const int64_t kp64 = (int64_t)k * pvf;
+  if (kp64 > kExactMaxK || kp64 > kPvMaxCand) return fail(e, FB_ERR_UNSUPPORTED, "pvf*k=%lld outside [1,%d]", (long long)kp64, kExactMaxK);
+  const int kp = (int)kp64;
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "post-verification joins the word-vector table: fb_load_vectors first");
+  if (e->vec_d != e->d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, IVFADC index d=%d", e->vec_d, e->d);
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_sims) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int d = e->d;
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
+  FB_CUDA(e, e->pv_cand.ensure((size_t)nq * kp));
+  FB_CUDA(e, e->vo.ensure((size_t)nq * kp));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  // candidates: ivfadc_search(v, pvf * k)  (freddy--0.0.1.sql:583-584)
+  int rc = ivfadc_dev(e, e->q_stage.p, nq, kp, w, e->pv_cand.p, e->vo.p);
+  if (rc) return rc;
+  int n_pad = 32;
+  while (n_pad < kp) n_pad <<= 1;
+  const size_t smem = (size_t)((d + 3) & ~3) * sizeof(float) + (size_t)n_pad * sizeof(u64);
+  {
+    StageTimer t(e, ST_FINALIZE);
+    pv_rerank_kernel<<<nq, kPvThreads, smem, e->stream>>>(e->q_stage.p, d, e->pv_cand.p, kp, k, e->vecT.p, e->vec_ids.p,
+                                                          e->vec_sorted_ids.p, e->vec_sorted_rows.p, (int)e->vec_N,
+                                                          e->id_stage.p, e->dist_stage.p);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_sims, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return check_error_flag(e);
+}
 
 int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const int32_t* ids, const int32_t* coarse_ids,
                  const int16_t* codes, int64_t N, int m, const float* stats) {

@@ -51,6 +51,8 @@ SIGNATURES = {
     "fb_ivpq_search_in": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_int, _P, _P]),
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
+    "fb_knn_exact": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "fb_ivfadc_search_pv": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_cosine_similarity": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "fb_vec_op": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "fb_analogy_3cosadd": (C.c_int, [_P, _P, C.c_int, _P, _P]),

@@ -191,6 +191,22 @@ class Engine:
         self._check(self._lib.fb_analogy_scan(self._h, _ptr(q), _ptr(ex), len(q), _ptr(out_ids), _ptr(out_s)))
         return out_ids, out_s
 
+    def knn_exact(self, queries, k, targets=None):
+        """k_nearest_neighbour(bytea, k) / knn_in_exact(bytea, k, int[]) for a batch of query vectors"""
+        q = _f32(queries).reshape(-1, self.vec_d)
+        t = _i32(targets) if targets is not None else None
+        ids, sims = np.empty((len(q), k), np.int32), np.empty((len(q), k), np.float32)
+        self._check(self._lib.fb_knn_exact(self._h, _ptr(q), len(q), k, _ptr(t), 0 if t is None else len(t),
+                                           _ptr(ids), _ptr(sims)))
+        return ids, sims
+
+    def ivfadc_search_pv(self, queries, k, pvf, w):
+        """k_nearest_neighbour_ivfadc_pv(bytea, k) for a batch: ivfadc_search(v, pvf*k) re-ranked exactly"""
+        q = _f32(queries).reshape(-1, self.d)
+        ids, sims = np.empty((len(q), k), np.int32), np.empty((len(q), k), np.float32)
+        self._check(self._lib.fb_ivfadc_search_pv(self._h, _ptr(q), len(q), k, pvf, w, _ptr(ids), _ptr(sims)))
+        return ids, sims
+
     def synchronize(self):
         self._check(self._lib.fb_synchronize(self._h))
 

@@ -89,6 +89,24 @@ class Session:
         ids, _ = self.engine.analogy_3cosadd(np.array([[id1, id2, id3]], np.int32))
         return int(ids[0])
 
+    # ---- SQL-level functions around the SRFs (plpgsql in the reference) ----
+    def k_nearest_neighbour(self, query_bytea, k):
+        """k_nearest_neighbour(bytea, int) -> TABLE (id, similarity float4)   freddy--0.0.1.sql:426-439
+        (the SQL returns the word; this mirror returns the row's id)"""
+        ids, s = self.engine.knn_exact(bytea_to_vec(query_bytea)[None, :], int(k))
+        return [(int(i), float(x)) for i, x in zip(ids[0], s[0]) if i >= 0]
+
+    def knn_in_exact(self, query_bytea, k, input_ids):
+        """knn_in_exact(bytea, int, int[]) -> TABLE (id, similarity float4)   freddy--0.0.1.sql:1026-1038"""
+        ids, s = self.engine.knn_exact(bytea_to_vec(query_bytea)[None, :], int(k), np.asarray(input_ids, np.int32))
+        return [(int(i), float(x)) for i, x in zip(ids[0], s[0]) if i >= 0]
+
+    def k_nearest_neighbour_ivfadc_pv(self, query_bytea, k):
+        """k_nearest_neighbour_ivfadc_pv(bytea, int) -> TABLE (id, similarity float4)   freddy--0.0.1.sql:574-591,
+        post-verification factor get_pvf(), probes get_w()"""
+        ids, s = self.engine.ivfadc_search_pv(bytea_to_vec(query_bytea)[None, :], int(k), self._pvf, self._w)
+        return [(int(i), float(x)) for i, x in zip(ids[0], s[0]) if i >= 0]
+
     def pq_search(self, query_bytea, k):
         """pq_search(bytea, int) -> SETOF (id, distance)   freddy.c:28-170"""
         q = bytea_to_vec(query_bytea)
