@@ -393,28 +393,39 @@ __global__ void gather_rows_kernel(const uint2* __restrict__ src_units, int U, c
 
 // ---- kernel launch helpers -------------------------------------------------
 template <int QT>
-int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k) {
+int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k, int64_t q0) {
   size_t smem = ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float);
   auto kern = e->packed_fp32 ? coarse_select_kernel_t<QT, true> : coarse_select_kernel_t<QT, false>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nq + QT - 1) / QT, kCoarseThreads, smem, e->stream>>>(
-      d_q, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k, e->probes.p, e->qflags.p,
-      e->force_exact ? 1 : 0, e->one);
+      d_q + (size_t)q0 * e->d, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k, e->probes.p + (size_t)q0 * w,
+      e->qflags.p + q0, e->force_exact ? 1 : 0, e->one);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
 }
 
-int launch_coarse(fb_engine* e, const float* d_q, int nq, int w, int k) {
+int launch_coarse_range(fb_engine* e, const float* d_q, int nq, int w, int k, int64_t q0) {
   StageTimer t(e, ST_COARSE);
   auto need = [&](int QT) { return ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float); };
   const size_t two_per_sm = 100 * 1024;
-  if (need(16) <= two_per_sm) return launch_coarse_t<16>(e, d_q, nq, w, k);
-  if (need(8) <= two_per_sm) return launch_coarse_t<8>(e, d_q, nq, w, k);
-  if (need(4) <= e->smem_optin) return launch_coarse_t<4>(e, d_q, nq, w, k);
-  if (need(1) <= e->smem_optin) return launch_coarse_t<1>(e, d_q, nq, w, k);
+  if (need(16) <= two_per_sm) {
+    // all tiles cost the same, so the launch takes ceil(tiles / resident CTAs) rounds of one tile time
+    // (about QT + 1.5 units): pick the tile height that wastes the least of the last round
+    const int slots = 2 * e->num_sms;
+    auto cost = [&](int QT) { const int tiles = (nq + QT - 1) / QT; return (double)((tiles + slots - 1) / slots) * (QT + 1.5); };
+    const double c16 = cost(16), c12 = cost(12), c8 = cost(8);
+    if (c12 < c16 && c12 <= c8) return launch_coarse_t<12>(e, d_q, nq, w, k, q0);
+    if (c8 < c16) return launch_coarse_t<8>(e, d_q, nq, w, k, q0);
+    return launch_coarse_t<16>(e, d_q, nq, w, k, q0);
+  }
+  if (need(8) <= two_per_sm) return launch_coarse_t<8>(e, d_q, nq, w, k, q0);
+  if (need(4) <= e->smem_optin) return launch_coarse_t<4>(e, d_q, nq, w, k, q0);
+  if (need(1) <= e->smem_optin) return launch_coarse_t<1>(e, d_q, nq, w, k, q0);
   return fail(e, FB_ERR_UNSUPPORTED, "coarse table too large for shared memory (C=%d d=%d)", e->C, e->d);
 }
+
+int launch_coarse(fb_engine* e, const float* d_q, int nq, int w, int k) { return launch_coarse_range(e, d_q, nq, w, k, 0); }
 
 template <int W, int TKS, bool PACKED>
 int launch_lut_cfg(fb_engine* e, const Codebook& cb, const float* d_q, const float* d_coarse, const int32_t* d_probes,

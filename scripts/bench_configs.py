@@ -117,3 +117,50 @@ if "5" in a.which.split(","):
                       "table_bytes": a.n * 1200, "cpu_oracle": {"sample_queries": ns, "threads": threads, "seconds": t_cpu,
                                                                 "queries_per_s": ns / t_cpu, "kind": "port"},
                       "parity_on_sample": ok}))
+
+if "6" in a.which.split(","):
+    # k_nearest_neighbour_ivfadc_pv, batch form: ivfadc_search(v, pvf*k) + exact re-rank  (freddy--0.0.1.sql:574-591)
+    nq, k, pvf, w = 5000, 5, 20, 10
+    vec = vec_t.cpu().numpy()
+    ids_all = ix["ids"]
+    eng.load_ivfadc_index(ix)
+    eng.load_vectors(ids_all, vec)
+    perm = torch.randperm(a.n, generator=g)
+    q = vec[perm[:nq].numpy()]
+    res = {}
+    t_gpu = timed(lambda: res.__setitem__("r", eng.ivfadc_search_pv(q, k, pvf, w)), a.reps)
+    ids, s = res["r"]
+    ns = 32
+    t0 = time.perf_counter()
+    eids, es = oracle.ivfadc_search_pv(oracle.OracleIndex(ix), vec, ids_all, q[:ns], k, pvf, w, threads=threads)
+    t_cpu = time.perf_counter() - t0
+    ok = bool((ids[:ns] == eids).all() and (s[:ns].view(np.uint32) == es.view(np.uint32)).all())
+    # recall of the exact neighbours on the sample (the README's precision column)
+    xids, _ = eng.knn_exact(q[:ns], k)
+    prec = float(np.mean([len(set(ids[i]) & set(xids[i])) / k for i in range(ns)]))
+    print(json.dumps({"config": f"k_nearest_neighbour_ivfadc_pv batch: {nq} queries, k={k}, pvf={pvf}, w={w}, 3M x 300",
+                      "gpu_seconds_e2e": t_gpu, "queries_per_s": nq / t_gpu,
+                      "cpu_oracle": {"sample_queries": ns, "threads": threads, "seconds": t_cpu, "queries_per_s": ns / t_cpu, "kind": "port"},
+                      "parity_on_sample": ok, "precision_at_k_vs_exact_on_sample": prec}))
+
+if "7" in a.which.split(","):
+    # k_nearest_neighbour (exact): cosine_similarity_bytea over all 3M rows, top-k  (freddy--0.0.1.sql:426-439)
+    nq, k = 1000, 5
+    vec = vec_t.cpu().numpy()
+    ids_all = ix["ids"]
+    eng.load_vectors(ids_all, vec)
+    perm = torch.randperm(a.n, generator=g)
+    q = vec[perm[:nq].numpy()]
+    res = {}
+    t_gpu = timed(lambda: res.__setitem__("r", eng.knn_exact(q, k)), a.reps)
+    ids, s = res["r"]
+    ns = 4
+    t0 = time.perf_counter()
+    eids, es = oracle.knn_exact(vec, ids_all, q[:ns], k)
+    t_cpu = time.perf_counter() - t0
+    ok = bool((ids[:ns] == eids).all() and (s[:ns].view(np.uint32) == es.view(np.uint32)).all())
+    print(json.dumps({"config": f"k_nearest_neighbour exact: {nq} queries, k={k}, scan over 3M x 300", "gpu_seconds_e2e": t_gpu,
+                      "queries_per_s": nq / t_gpu, "rounded_fp32_ops_per_s": 2.0 * nq * a.n * 300 / t_gpu,
+                      "cpu_oracle": {"sample_queries": ns, "threads": 1, "seconds": t_cpu, "queries_per_s": ns / t_cpu,
+                                     "kind": "port (numpy, vectorised over rows)"},
+                      "parity_on_sample": ok, "reference_published_s_per_query": 8.79}))

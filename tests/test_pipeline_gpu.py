@@ -90,3 +90,20 @@ def test_pipeline_repeatable(eng):
             ref = (ids.copy(), d.copy())
         np.testing.assert_array_equal(ids, ref[0])
         np.testing.assert_array_equal(d.view(np.uint32), ref[1].view(np.uint32))
+
+
+def test_host_buffer_call_matches_device_path(eng):
+    """fb_ivfadc_search (host buffers) and fb_ivfadc_search_dev (device pointers) give the same bits"""
+    import torch
+    ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)
+    eng.load_ivfadc_index(ix)
+    q = queries_from(ix, 5000, seed=12, noise=0.02)
+    for _ in range(2):
+        ids, d = eng.ivfadc_search(q, 5, 10)
+        dq = torch.from_numpy(q).cuda()
+        oi = torch.empty(len(q), 5, dtype=torch.int32, device="cuda")
+        od = torch.empty(len(q), 5, dtype=torch.float32, device="cuda")
+        eng.ivfadc_search_dev(dq.data_ptr(), len(q), 5, 10, oi.data_ptr(), od.data_ptr())
+        eng.synchronize()
+        np.testing.assert_array_equal(ids, oi.cpu().numpy())
+        np.testing.assert_array_equal(d.view(np.uint32), od.cpu().numpy().view(np.uint32))
