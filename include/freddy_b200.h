@@ -159,6 +159,16 @@ int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_
 int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int w,
                         int32_t* out_ids, float* out_sims);
 
+/* ---- quantisation of new rows (the encode step of index build / insert_batch) ------
+ * As insert_batch assigns them: nearest coarse centroid with strict `<` from 100, first minimum wins
+ * (freddy.c:1567-1577), residual = row - centroid (:1578-1581), then per position the nearest codeword of the
+ * residual codebook, same rule in (pos, code) table order (updateCodebook, index_utils.c:923-939).
+ * fb_encode_pq quantises the raw rows with the pq / ivpq codebook (kind = FB_CB_PQ / FB_CB_IVPQ).
+ * out_codes = [n][m] int16.  FB_ERR_REFERENCE_UB where every candidate distance is >= 100 (the reference
+ * then reads an uninitialised assignment).  The codebook drift update of insert_batch is not done here. */
+int fb_encode_ivfadc(fb_engine* e, const float* vectors, int64_t n, int32_t* out_coarse_ids, int16_t* out_codes);
+int fb_encode_pq(fb_engine* e, int kind, const float* vectors, int64_t n, int16_t* out_codes);
+
 int fb_synchronize(fb_engine* e);
 /* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL restores the engine's own stream).  Lets a host runtime order the

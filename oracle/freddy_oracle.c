@@ -770,3 +770,41 @@ int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k
   if (use_tl) { for (int i = 0; i < nq; i++) free(tl_rows[i]); free(tl_rows); free(tl_n); free(tl_cap); }
   return 0;
 }
+
+
+/* ref: freddy.c:1567-1582 (coarse assignment + residual of insert_batch) and index_utils.c:923-939
+ * (updateCodebook's nearest-centroid loop; its codebook drift update is not part of the quantisation). */
+int fo_encode(const float* vectors, int n, int d, const float* coarse, int C,
+              const float* codebook, int m, int K, int32_t* out_coarse_ids, int16_t* out_codes) {
+  const int sub = d / m;
+  float* res = malloc(sizeof(float) * (size_t)d);
+  int rc = 0;
+  for (int i = 0; i < n; i++) {
+    const float* raw = vectors + (size_t)i * d;
+    const float* v = raw;
+    if (coarse != NULL) {
+      float min_dist = 100;
+      int best = -1;
+      for (int j = 0; j < C; j++) {
+        float dist = fo_square_distance(raw, coarse + (size_t)j * d, d);
+        if (dist < min_dist) { best = j; min_dist = dist; }
+      }
+      if (best < 0) { rc = -1; best = 0; }
+      out_coarse_ids[i] = best;
+      for (int j = 0; j < d; j++) res[j] = raw[j] - coarse[(size_t)best * d + j];
+      v = res;
+    }
+    for (int pos = 0; pos < m; pos++) {
+      float min_dist = 100;   /* "sufficient high value" */
+      int best = -1;
+      for (int code = 0; code < K; code++) {
+        float dist = fo_square_distance(v + pos * sub, codebook + ((size_t)pos * K + code) * sub, sub);
+        if (dist < min_dist) { best = code; min_dist = dist; }
+      }
+      if (best < 0) { rc = -1; best = 0; }
+      out_codes[(size_t)i * m + pos] = (int16_t)best;
+    }
+  }
+  free(res);
+  return rc;
+}

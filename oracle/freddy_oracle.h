@@ -78,6 +78,14 @@ int fo_pq_search_in_batch(const FoIndex* ix, const float* queries, int nq, int k
                           const int32_t* targets, int n_targets, int use_target_lists,
                           FoTopKEntry* out_topk);
 
+/* ---- quantisation of new rows (insert_batch) ---- */
+/* freddy.c:1567-1582: nearest coarse centroid (strict `<` from 100, first minimum wins) and residual;
+ * index_utils.c:923-939 (updateCodebook): nearest codeword per position (strict `<` from 100, table
+ * order = (pos, code) ascending).  coarse == NULL: the raw vectors are quantised (pq / ivpq tables).
+ * Returns 0, or -1 where the reference would read an uninitialised assignment (every distance >= 100). */
+int fo_encode(const float* vectors, int n, int d, const float* coarse, int C,
+              const float* codebook, int m, int K, int32_t* out_coarse_ids, int16_t* out_codes);
+
 /* ---- vector UDFs (core_functions.c, cosine_similarity.c) ---- */
 double fo_cosine_similarity(const float* v1, const float* v2, int n);      /* cosine_similarity.c:12-37 */
 double fo_cosine_similarity_norm(const float* v1, const float* v2, int n); /* cosine_similarity.c:39-45 */

@@ -72,6 +72,7 @@ def lib():
         L.fo_vec_minus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fo_vec_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fo_vec_normalize.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.fo_analogy_3cosadd_many.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -451,3 +452,47 @@ def ivfadc_search_pv(oracle_index, vectors, vec_ids, queries, k, pvf, w, threads
         out_ids[qi, :len(sel)] = ids[rows[sel]]
         out_s[qi, :len(sel)] = s[sel]
     return out_ids, out_s
+
+
+# ---- quantisation of new rows (insert_batch) -----------------------------------------------------------
+def encode(vectors, codebook, coarse=None):
+    """oracle: (coarse_ids or None, codes[n][m] int16, rc) as insert_batch assigns them (freddy.c:1567-1582,
+    index_utils.c:923-939)"""
+    v = np.ascontiguousarray(vectors, np.float32)
+    cb = np.ascontiguousarray(codebook, np.float32)            # [m][K][sub]
+    m, K, _ = cb.shape
+    n, d = v.shape
+    codes = np.empty((n, m), np.int16)
+    if coarse is not None:
+        cq = np.ascontiguousarray(coarse, np.float32)
+        cids = np.empty(n, np.int32)
+        rc = lib().fo_encode(_p(v), n, d, _p(cq), cq.shape[0], _p(cb), m, K, _p(cids), _p(codes))
+        return cids, codes, rc
+    rc = lib().fo_encode(_p(v), n, d, None, 0, _p(cb), m, K, None, _p(codes))
+    return None, codes, rc
+
+
+def reference_update_codebook_assignments(vectors, codebook):
+    """nearestCentroids of the reference's own updateCodebook (index_utils.c:908-957, compiled from
+    /root/reference into oracle/_ref) for raw vectors against a [m][K][sub] codebook"""
+    R = ref_lib()
+    v = np.ascontiguousarray(vectors, np.float32)
+    cb = np.ascontiguousarray(codebook, np.float32).copy()     # updateCodebook drifts the codebook in place
+    m, K, sub = cb.shape
+    n = v.shape[0]
+
+    class Entry(C.Structure):
+        _fields_ = [("pos", C.c_int), ("code", C.c_int), ("vector", C.POINTER(C.c_float)), ("count", C.c_int)]
+
+    entries = (Entry * (m * K))()
+    flat = cb.reshape(m * K, sub)
+    for j in range(m * K):
+        entries[j].pos, entries[j].code, entries[j].count = j // K, j % K, 1
+        entries[j].vector = flat[j].ctypes.data_as(C.POINTER(C.c_float))
+    rows = (C.POINTER(C.c_float) * n)(*[v[i].ctypes.data_as(C.POINTER(C.c_float)) for i in range(n)])
+    nearest = (C.POINTER(C.c_int) * n)()
+    incs = (C.c_int * (m * K))()
+    R.updateCodebook.restype = None
+    R.updateCodebook.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    R.updateCodebook(rows, n, sub, entries, m, K, nearest, incs)
+    return np.array([[nearest[i][p] for p in range(m)] for i in range(n)], np.int16)

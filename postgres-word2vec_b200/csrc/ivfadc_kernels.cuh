@@ -189,7 +189,7 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
     if (lane < w) {
       int cid = (int)key_t(mine);
       probes[(size_t)q * w + lane] = cid;
-      len = list_len[cid];
+      len = (list_len != nullptr) ? list_len[cid] : k;   // nullptr: quantisation only (fb_encode_*), no lists involved
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) len += __shfl_xor_sync(0xffffffffu, len, s);
@@ -816,6 +816,34 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
   const uint32_t flags = has_input_flags ? qflags[q] : 0u;
   warp_emit_topk(mine, lane, q, q_base, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
                  exact_total, kth_key, KK);
+}
+
+// ---------------------------------------------------------------------------
+// Quantisation of new rows (insert_batch): code[job][pos] = first minimum over the K entries of LUT row
+// (job, pos) with the reference's strict `<` from 100 (index_utils.c:926-939): key = (distance bits, code),
+// smallest key wins.  One warp per (job, pos).  A row whose distances are all >= 100 leaves the
+// reference's assignment uninitialised: error flag.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lut_argmin_kernel(const float* __restrict__ lut, int njobs, int m, int K, int16_t* __restrict__ codes, int32_t* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (int64_t)njobs * m) return;
+  const float* row = lut + (size_t)wid * K;
+  u64 best = kKeyInf;
+  for (int c = lane; c < K; c += 32) {
+    const u64 key = make_key(row[c], (uint32_t)c);
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const u64 o = shfl_xor_u64(best, s);
+    best = o < best ? o : best;
+  }
+  if (lane == 0) {
+    if (!(key_dist(best) < 100.0f)) atomicExch(err_flag, 1);
+    codes[wid] = (int16_t)key_t(best);
+  }
 }
 
 }  // namespace fb

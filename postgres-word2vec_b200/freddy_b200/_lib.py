@@ -51,6 +51,8 @@ SIGNATURES = {
     "fb_ivpq_search_in": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_int, _P, _P]),
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
+    "fb_encode_ivfadc": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "fb_encode_pq": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
     "fb_knn_exact": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "fb_ivfadc_search_pv": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_cosine_similarity": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),

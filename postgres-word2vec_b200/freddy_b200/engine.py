@@ -39,6 +39,7 @@ class Engine:
         self._h = h
         self.device = device
         self.d = None
+        self._cb_m = {}
 
     def close(self):
         if getattr(self, "_h", None):
@@ -67,6 +68,7 @@ class Engine:
         if self.d is None:
             self.d = m * sub
         self._check(self._lib.fb_load_codebook(self._h, kind, _ptr(cb), m, K, sub))
+        self._cb_m[kind] = m
 
     def load_fine(self, ids, coarse_ids, codes):
         ids, coarse_ids = _i32(ids), _i32(coarse_ids)
@@ -206,6 +208,24 @@ class Engine:
         ids, sims = np.empty((len(q), k), np.int32), np.empty((len(q), k), np.float32)
         self._check(self._lib.fb_ivfadc_search_pv(self._h, _ptr(q), len(q), k, pvf, w, _ptr(ids), _ptr(sims)))
         return ids, sims
+
+    def encode_ivfadc(self, vectors):
+        """(coarse_ids, codes) of new rows as insert_batch quantises them (coarse table + residual codebook loaded)"""
+        v = _f32(vectors)
+        n = v.shape[0]
+        m = self._cb_m[_lib.FB_CB_RESIDUAL]
+        cids, codes = np.empty(n, np.int32), np.empty((n, m), np.int16)
+        self._check(self._lib.fb_encode_ivfadc(self._h, _ptr(v), n, _ptr(cids), _ptr(codes)))
+        return cids, codes
+
+    def encode_pq(self, vectors, kind=None):
+        """codes of raw rows against the pq (default) / ivpq codebook"""
+        kind = _lib.FB_CB_PQ if kind is None else kind
+        v = _f32(vectors)
+        n = v.shape[0]
+        codes = np.empty((n, self._cb_m[kind]), np.int16)
+        self._check(self._lib.fb_encode_pq(self._h, kind, _ptr(v), n, _ptr(codes)))
+        return codes
 
     def synchronize(self):
         self._check(self._lib.fb_synchronize(self._h))

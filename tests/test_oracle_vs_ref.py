@@ -146,3 +146,22 @@ def test_srf_golden_vectors(oracle_mod):
     ids, d = op.pq_search_in_batch(g["queries"], 5, g["targets"])
     np.testing.assert_array_equal(ids, g["pq_in_k5_ids"])
     np.testing.assert_array_equal(d.view(np.uint32), g["pq_in_k5_dist"].view(np.uint32))
+
+
+def test_encode_against_reference_update_codebook():
+    """fo_encode's per-position assignment vs the nearestCentroids the reference's own updateCodebook
+    (index_utils.c:908-957) computes, incl. duplicate codewords (first minimum in table order wins)"""
+    from oracle import oracle
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    m, K, sub = 6, 32, 5
+    cb = rng.standard_normal((m, K, sub)).astype(np.float32) * 0.3
+    cb[:, 7] = cb[:, 3]                                        # duplicate codeword: ties
+    v = rng.standard_normal((300, m * sub)).astype(np.float32) * 0.3
+    v[:40] = cb[:, 7].reshape(-1)[None, :]                     # vectors exactly on the duplicated codeword
+    want = oracle.reference_update_codebook_assignments(v, cb)
+    _, got, rc = oracle.encode(v, cb)
+    assert rc == 0
+    np.testing.assert_array_equal(got, want)
+    assert (got[:40] == 3).all()
