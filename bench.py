@@ -338,6 +338,14 @@ def main():
                 "algorithmic_bytes_per_launch": c["scan_bytes"] / max(1, n_dom),
                 "ms_per_launch": ms_dom / max(1, n_dom),
                 "stage_ms_per_step": {s: c["ms_" + s] / a.steps for s in ("coarse", "lut", "scan", "pipe", "finalize", "exact")}}
+    # the same launches also carry the residual-LUT build (w*m*K*sub*3 individually rounded fp32
+    # operations per query); its bound is the fp32 pipe (measured: profiles/r1_microbench_fp32x2.txt)
+    lut_ops = 3.0 * a.w * a.m * a.K * (a.d // a.m) * nq * a.steps
+    ms_lut_host = ms_dom if piped else c["ms_lut"]
+    roofline["lut_build_fp32"] = {"bound": "fp32 pipe", "achieved": lut_ops / (ms_lut_host / 1e3) / 1e12 if ms_lut_host > 0 else None,
+                                  "peak": 36.8, "unit": "T rounded fp32 ops/s", "peak_source": "profiles/r1_microbench_fp32x2.txt",
+                                  "frac": lut_ops / (ms_lut_host / 1e3) / 1e12 / 36.8 if ms_lut_host > 0 else None,
+                                  "note": "same launches as the scan when the pipeline kernel runs: the two fractions add"}
     launches = c["kernel_launches"]
     exact_q = c["exact_path_queries"]
 
