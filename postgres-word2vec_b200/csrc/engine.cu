@@ -710,13 +710,13 @@ int run_pipeline(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int
                                                             d_out_dists, chunk);                         \
   } while (0)
   if (cb.K == 1024) {
-    switch (e->pipe_shape) {   // (producer warps, scan warps): tuning knob, FB_OPT_PIPE_SHAPE
-      case 1: FB_PIPE_GO(1024, 8, 22);
-      case 2: FB_PIPE_GO(1024, 8, 14);
-      default: FB_PIPE_GO(1024, 8, 18);
+    switch (e->pipe_shape) {   // (producer warps, scan warps[, jobs per producer thread]): tuning knob, FB_OPT_PIPE_SHAPE
+      case 1: FB_PIPE_GO(1024, 8, 18);
+      case 2: FB_PIPE_GO(1024, 8, 14, 16);
+      default: FB_PIPE_GO(1024, 12, 14);
     }
   }
-  if (cb.K == 256) FB_PIPE_GO(256, 8, 18);
+  if (cb.K == 256) FB_PIPE_GO(256, 12, 14);
 #undef FB_PIPE_GO
   return FB_ERR_UNSUPPORTED;
 }

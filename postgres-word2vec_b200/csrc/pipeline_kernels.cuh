@@ -29,16 +29,17 @@ constexpr int kPipeBufs = 3;                         // LUT ring depth in shared
 // Role split of the CTA.  PW producer warps (a multiple of 4: one job split of 8 jobs per 4 warps),
 // SW scan warps, one loader warp, one merger warp; roles are whole warpgroups so that setmaxnreg can
 // move registers from the scan side to the producers.
-template <int PW, int SW>
+template <int PW, int SW, int JT = 8>
 struct PipeCfg {
+  static constexpr int kJobsPerThread = JT;          // jobs per producer thread (8 or 16): 4 codes x JT jobs = 2*JT packed accumulators
   static constexpr int kProdWarps = PW, kScanWarps = SW;
   static constexpr int kWarps = PW + SW + 2;
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kProdThreads = PW * 32;
   static constexpr int kSplits = PW / 4;             // job splits: 4 warps = 128 threads x 4 codes = one 512-code slice
-  static constexpr int kGroup = 8 * kSplits;         // jobs per producer group (8 per thread)
+  static constexpr int kGroup = JT * kSplits;        // jobs per producer group
   static constexpr int kLaunchRegs = ((65536 / kThreads) & ~7) > 255 ? 248 : ((65536 / kThreads) & ~7);
-  static constexpr int kScanRegs = 56;
+  static constexpr int kScanRegs = 64;               // 56 left a loop bound of the scan warps in local memory (LDL in the hot loop)
   static constexpr int kProdRegsRaw = ((kLaunchRegs * kThreads - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
   static constexpr int kProdRegs = kProdRegsRaw > 232 ? 232 : kProdRegsRaw;
   static_assert(PW % 4 == 0 && (SW + 2) % 4 == 0, "roles must be whole warpgroups");
@@ -201,7 +202,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
     const u64 one2 = pack2(a.one, a.one);
     const bool active = 4 * ct < ncodes;
     const float* pc = cbs + 4 * ct;
-    constexpr int WJ = 8;                                                // jobs per thread
+    constexpr int WJ = Cfg::kJobsPerThread;                              // jobs per thread
     for (int job0 = group * kPipeGroup; job0 < a.lut_njobs; job0 += job_step) {
       float* rsc = rs2 + (size_t)cur * n_res;
 #pragma unroll
