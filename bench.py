@@ -358,6 +358,7 @@ def main():
     # single-query latency through the same host-buffer call (the form config[1] names)
     lat_us = None
     if rank == 0:
+        eng.set_option(_lib.FB_OPT_PROFILE, 0)      # no per-kernel events: small calls then replay a captured CUDA graph
         one_q, one_i, one_d = h_q[:1].clone().pin_memory(), h_ids[:1].clone().pin_memory(), h_dist[:1].clone().pin_memory()
         for _ in range(20):
             eng.ivfadc_search_ptr(one_q.data_ptr(), 1, k, w, one_i.data_ptr(), one_d.data_ptr())

@@ -200,6 +200,8 @@ enum {
                                   0/1 = keep arrival order).  Applies to the next fb_load_fine.      */
   FB_OPT_PIPE_SHAPE = 13,      /* role split of the pipeline CTA (producer warps, scan warps): 0 = (12,14), 1 = (8,18), 2 = (8,14) with a 4x16 producer tile */
   FB_OPT_PIPE_RAMP = 14,       /* 1: the first and last pipeline chunks are shortened (quarter, half); default 0  */
+  FB_OPT_CUDA_GRAPHS = 15,     /* 1 (default): host-buffer fb_ivfadc_search calls with <= 16 queries replay a
+                                  captured CUDA graph of the whole call (upload, kernels, download)      */
   FB_OPT_PIPE_DEBUG = 11,      /* timing aid, results are NOT valid: 1 = producers only (no scan),
                                   2 = scan only (LUT scratch left as is)                           */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the

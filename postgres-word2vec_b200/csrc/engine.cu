@@ -30,12 +30,16 @@ namespace {
 
 std::string g_create_error;
 
+// bumped whenever a device buffer moves: captured CUDA graphs hold raw pointers and are re-captured after that
+uint64_t g_alloc_generation = 0;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaError_t ensure(size_t count) {
     if (count <= n && p) return cudaSuccess;
+    g_alloc_generation++;
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
@@ -45,7 +49,7 @@ struct DevBuf {
     return err;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { cudaFree(p); g_alloc_generation++; }
     p = nullptr;
     n = 0;
   }
@@ -149,6 +153,13 @@ struct fb_engine {
   int64_t pipe_chunk = 2048; // queries per pipeline beat
   DevBuf<int32_t> pipe_counters;
   int pipe_debug = 0;
+  // small host-buffer calls (<= kGraphMaxQueries queries) replay a captured CUDA graph of the whole call
+  struct GraphEntry { int nq, k, w; uint64_t gen, epoch; cudaGraphExec_t exec; int launches; };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_epoch = 0;        // bumped by loads / option changes: kernel arguments are baked into a graph
+  int use_graphs = 1;
+  float* pin_q = nullptr; int32_t* pin_ids = nullptr; float* pin_d = nullptr; int32_t* pin_flag = nullptr;
+  size_t pin_q_floats = 0;
   int pipe_shape = 0;
   int pipe_ramp = 0;
   int placement_window = 256; // rows considered per slot by the conflict-aware placement of the fine table (<= 1: off)
@@ -877,6 +888,93 @@ int check_error_flag(fb_engine* e) {
   return FB_OK;
 }
 
+// ---- small host-buffer calls as one CUDA graph ------------------------------------------------
+// A single-query call is ~9 kernel launches and 4 copies: launch-bound.  The second call with the same
+// (nq, k, w) captures the whole sequence — upload from a pinned staging buffer, coarse, LUT, scan, finalize,
+// general kernel, download of ids / distances / error flag — and later calls replay it with one
+// cudaGraphLaunch.  A graph is dropped when a buffer moved (g_alloc_generation) or the index / options
+// changed (graph_epoch).  *handled = false: the caller runs the ordinary path.
+constexpr int kGraphMaxQueries = 16;
+
+void drop_graphs(fb_engine* e) {
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+int ivfadc_search_graph(fb_engine* e, const float* queries, int nq, int k, int w, int32_t* out_ids, float* out_dists,
+                        bool* handled) {
+  *handled = false;
+  fb_engine::GraphEntry* ent = nullptr;
+  for (auto& g : e->graphs)
+    if (g.nq == nq && g.k == k && g.w == w) ent = &g;
+  if (ent == nullptr) {   // first sighting: the ordinary path sizes every buffer
+    e->graphs.push_back({nq, k, w, 0, 0, nullptr, 0});
+    return FB_OK;
+  }
+  const size_t q_floats = (size_t)kGraphMaxQueries * e->d;
+  if (e->pin_q == nullptr || e->pin_q_floats < q_floats) {
+    if (e->pin_q) cudaFreeHost(e->pin_q);
+    e->pin_q = nullptr;
+    FB_CUDA(e, cudaMallocHost(&e->pin_q, q_floats * sizeof(float)));
+    e->pin_q_floats = q_floats;
+    drop_graphs(e);
+    e->graphs.push_back({nq, k, w, 0, 0, nullptr, 0});
+    ent = &e->graphs.back();
+  }
+  if (e->pin_ids == nullptr) {
+    FB_CUDA(e, cudaMallocHost(&e->pin_ids, (size_t)kGraphMaxQueries * 32 * sizeof(int32_t)));
+    FB_CUDA(e, cudaMallocHost(&e->pin_d, (size_t)kGraphMaxQueries * 32 * sizeof(float)));
+    FB_CUDA(e, cudaMallocHost(&e->pin_flag, sizeof(int32_t)));
+  }
+  if (ent->exec == nullptr || ent->gen != g_alloc_generation || ent->epoch != e->graph_epoch) {
+    if (ent->exec) { cudaGraphExecDestroy(ent->exec); ent->exec = nullptr; }
+    FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+    FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+    FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+    const uint64_t gen0 = g_alloc_generation;
+    const int64_t launches0 = e->launches, queries0 = e->queries_done;
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+    FB_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+    cudaMemcpyAsync(e->q_stage.p, e->pin_q, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    int rc = ivfadc_dev(e, e->q_stage.p, nq, k, w, e->id_stage.p, e->dist_stage.p);
+    cudaMemcpyAsync(e->pin_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->pin_d, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->pin_flag, e->small.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t cerr = cudaStreamEndCapture(e->stream, &graph);
+    const int n_launches = (int)(e->launches - launches0);
+    e->launches = launches0;             // nothing ran during the capture
+    e->queries_done = queries0;
+    if (rc != FB_OK || cerr != cudaSuccess || graph == nullptr || gen0 != g_alloc_generation) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ent->gen = 0;                      // try again on a later call; this one takes the ordinary path
+      return rc == FB_OK ? FB_OK : rc;
+    }
+    cerr = cudaGraphInstantiate(&ent->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (cerr != cudaSuccess) { ent->exec = nullptr; cudaGetLastError(); return FB_OK; }
+    ent->gen = g_alloc_generation;
+    ent->epoch = e->graph_epoch;
+    ent->launches = n_launches;
+  }
+  memcpy(e->pin_q, queries, (size_t)nq * e->d * sizeof(float));
+  FB_CUDA(e, cudaGraphLaunch(ent->exec, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  memcpy(out_ids, e->pin_ids, (size_t)nq * k * sizeof(int32_t));
+  memcpy(out_dists, e->pin_d, (size_t)nq * k * sizeof(float));
+  e->launches += ent->launches;
+  e->queries_done += nq;
+  *handled = true;
+  if (*e->pin_flag) {
+    cudaMemset(e->small.p + 2, 0, sizeof(int32_t));
+    return fail(e, FB_ERR_REFERENCE_UB,
+                "a query hit a state where the reference is undefined (fewer than w unprobed lists left, or a coarse distance >= 100)");
+  }
+  return FB_OK;
+}
+
 // ---- flat PQ pipeline over `tab` (the pq table or a per-call subset) --------
 int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, float sentinel,
            int32_t* d_out_ids, float* d_out_dists) {
@@ -995,6 +1093,11 @@ void fb_destroy(fb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  drop_graphs(e);
+  if (e->pin_q) cudaFreeHost(e->pin_q);
+  if (e->pin_ids) cudaFreeHost(e->pin_ids);
+  if (e->pin_d) cudaFreeHost(e->pin_d);
+  if (e->pin_flag) cudaFreeHost(e->pin_flag);
   for (auto& ev : e->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   e->coarse.release(); e->coarseT.release();
   for (auto& c : e->cb) c.cbT.release();
@@ -1017,6 +1120,7 @@ void fb_destroy(fb_engine* e) {
 }
 
 int fb_load_coarse(fb_engine* e, const float* coarse, int C, int d) {
+  if (e) e->graph_epoch++;
   if (!e || !coarse || C < 1 || d < 1) return fail(e, FB_ERR_INVALID, "fb_load_coarse: bad arguments");
   FB_CUDA(e, cudaSetDevice(e->device));
   const int Cs = (C + 31) / 32 * 32;
@@ -1032,6 +1136,7 @@ int fb_load_coarse(fb_engine* e, const float* coarse, int C, int d) {
 }
 
 int fb_load_codebook(fb_engine* e, int kind, const float* codebook, int m, int K, int sub) {
+  if (e) e->graph_epoch++;
   if (!e || !codebook || kind < 0 || kind >= FB_CB_KINDS || m < 1 || K < 1 || sub < 1)
     return fail(e, FB_ERR_INVALID, "fb_load_codebook: bad arguments");
   if (K % 4 != 0 || K > 16384) return fail(e, FB_ERR_UNSUPPORTED, "K=%d: need K %% 4 == 0 and K <= 16384", K);
@@ -1048,6 +1153,7 @@ int fb_load_codebook(fb_engine* e, int kind, const float* codebook, int m, int K
 }
 
 int fb_load_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids, const int16_t* codes, int64_t N, int m) {
+  if (e) e->graph_epoch++;
   if (!e || (N > 0 && (!ids || !coarse_ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_load_fine: bad arguments");
   if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded)
     return fail(e, FB_ERR_INVALID, "fb_load_fine: load the coarse table and the residual codebook first");
@@ -1082,6 +1188,12 @@ int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w, i
   if (nq == 0) return FB_OK;
   if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
+  if (e->use_graphs && !e->profile && nq <= kGraphMaxQueries && k <= 30 && w >= 1 && w <= 31 && w <= e->C &&
+      e->coarse_loaded && e->cb[FB_CB_RESIDUAL].loaded && e->fine.loaded) {
+    bool handled = false;
+    rc = ivfadc_search_graph(e, queries, nq, k, w, out_ids, out_dists, &handled);
+    if (rc || handled) return rc;
+  }
   FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
@@ -1187,6 +1299,7 @@ int fb_synchronize(fb_engine* e) {
 }
 
 int fb_set_stream(fb_engine* e, void* cuda_stream) {
+  if (e) e->graph_epoch++;
   if (!e) return FB_ERR_INVALID;
   FB_CUDA(e, cudaSetDevice(e->device));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1196,6 +1309,7 @@ int fb_set_stream(fb_engine* e, void* cuda_stream) {
 }
 
 int fb_set_option(fb_engine* e, int option, int64_t value) {
+  if (e) e->graph_epoch++;
   if (!e) return FB_ERR_INVALID;
   switch (option) {
     case FB_OPT_FORCE_EXACT_PATH: e->force_exact = value != 0; return FB_OK;
@@ -1208,6 +1322,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_PIPE_DEBUG: e->pipe_debug = (int)value; return FB_OK;
     case FB_OPT_PIPE_SHAPE: e->pipe_shape = (int)value; return FB_OK;
     case FB_OPT_PIPE_RAMP: e->pipe_ramp = value != 0; return FB_OK;
+    case FB_OPT_CUDA_GRAPHS: e->use_graphs = value != 0; return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");

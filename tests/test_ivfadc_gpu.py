@@ -196,3 +196,28 @@ def test_ivfadc_batch_search(eng, oracle_mod):
         assert rc == 0
         ed = np.where(eids == -1, np.float32(100.0), ed)
         assert_same_topk(ids, d, eids, ed, "ivfadc_batch_search")
+
+
+def test_small_calls_replay_a_cuda_graph(eng, oracle_mod):
+    """host-buffer calls with <= 16 queries: the first call runs the ordinary path, the second captures the
+    whole call as a CUDA graph, later ones replay it — all must give the oracle's bits, also after the index
+    or an option changed (re-capture), and for queries that need the general kernel (ties)"""
+    from freddy_b200 import _lib
+    for ix in (small_index(), small_index(N=6000, d=16, m=4, K=4, C=8, seed=3, n_clusters=5)):
+        eng.load_ivfadc_index(ix)
+        oi = oracle_mod.OracleIndex(ix)
+        for nq, k, w in ((1, 5, 4), (7, 3, 2), (16, 10, 3)):
+            for rep in range(4):
+                q = queries_from(ix, nq, seed=20 + rep)
+                ids, d = eng.ivfadc_search(q, k, w)
+                eids, ed, rc, _ = oi.ivfadc_search(q, k, w)
+                assert rc == 0
+                assert_same_topk(ids, d, eids, ed, f"graph nq={nq} k={k} w={w} rep={rep}")
+            eng.set_option(_lib.FB_OPT_CUDA_GRAPHS, 0)
+            q = queries_from(ix, nq, seed=99)
+            a = eng.ivfadc_search(q, k, w)
+            eng.set_option(_lib.FB_OPT_CUDA_GRAPHS, 1)
+            for _ in range(3):
+                b = eng.ivfadc_search(q, k, w)
+                np.testing.assert_array_equal(a[0], b[0])
+                np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
