@@ -154,6 +154,70 @@ def cpu_arm(a, ix, queries, seconds):
             "seconds": dt, "rows_per_query": rows / max(n, 1), "rc": rc}
 
 
+# ---- the reference's own SRF (oracle/_ref: freddy.c compiled unmodified, SPI/fmgr emulated) on all host cores:
+# one single-threaded "backend" process per core, each with the index tables registered (as one Postgres
+# connection per core would), each answering a slice of the sample.
+_REF = {}
+
+
+def _ref_worker_init(shm_dir, w):
+    from oracle import oracle
+    ix = {k: np.load(os.path.join(shm_dir, k + ".npy"), mmap_mode="r") for k in
+          ("coarse", "residual_codebook", "ids", "coarse_ids", "codes")}
+    meta = json.load(open(os.path.join(shm_dir, "meta.json")))
+    ix.update(meta)
+    rs = oracle.ReferenceSession()
+    rs.load_ivfadc(ix, w)
+    _REF["rs"] = rs
+
+
+def _ref_worker_run(args):
+    q, k = args
+    ids, raw, _ = _REF["rs"].ivfadc_search(q, k)
+    return ids, raw
+
+
+class ReferencePool:
+    def __init__(self, a, ix):
+        import multiprocessing as mp
+        import shutil
+        import tempfile
+        self.dir = tempfile.mkdtemp(prefix="fb_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self._rm = shutil.rmtree
+        for k in ("coarse", "residual_codebook", "ids", "coarse_ids", "codes"):
+            np.save(os.path.join(self.dir, k + ".npy"), np.ascontiguousarray(ix[k]))
+        json.dump({k: int(ix[k]) for k in ("d", "m", "K", "C", "N")}, open(os.path.join(self.dir, "meta.json"), "w"))
+        self.procs = os.cpu_count() or 1
+        self.k = a.k
+        self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_ref_worker_init, initargs=(self.dir, a.w))
+        self.pool.map(_ref_worker_run, [(np.zeros((1, a.d), np.float32) + 0.01, a.k)] * self.procs)   # every backend is up
+
+    def run(self, queries):
+        parts = [p for p in np.array_split(np.ascontiguousarray(queries, np.float32), self.procs) if len(p)]
+        t = time.time()
+        res = self.pool.map(_ref_worker_run, [(p, self.k) for p in parts], chunksize=1)
+        dt = time.time() - t
+        return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res]), dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        self._rm(self.dir, ignore_errors=True)
+
+
+def reference_arm(a, ix, queries, seconds, pool):
+    """times the reference's own ivfadc_search SRF (oracle/_ref) on all host cores"""
+    n0 = min(len(queries), 2 * pool.procs)
+    _, _, dt0 = pool.run(queries[:n0])
+    per_q = max(dt0 / n0, 1e-6)
+    n = int(max(n0, min(len(queries), seconds / per_q)))
+    ids, raw, dt = pool.run(queries[:n])
+    return {"value": n / dt, "unit": UNIT, "cores": pool.procs, "kind": "reference",
+            "sample": f"{n} of the step's queries, one pass, {pool.procs} single-threaded backends "
+                      "(oracle/_ref: the reference's freddy.c SRF, SPI emulated in memory)",
+            "seconds": dt, "ids": ids, "raw": raw}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -172,19 +236,35 @@ def main():
         sel = torch.randperm(a.n, generator=g)[:a.batch]
         queries = vec[sel.to(vec.device)].cpu().numpy()
         del vec
+        from oracle import oracle
+        use_ref = os.path.exists(oracle.REF_SO)
+        pool = ReferencePool(a, ix) if use_ref else None
         vals = []
+        budget = max(1.0, a.cpu_seconds / max(1, a.steps))
         for i in range(a.warmup + a.steps):
-            r = cpu_arm(a, ix, queries, max(1.0, a.cpu_seconds / max(1, a.steps)))
+            r = reference_arm(a, ix, queries, budget, pool) if use_ref else cpu_arm(a, ix, queries, budget)
             if i >= a.warmup:
                 vals.append(r)
+        port = cpu_arm(a, ix, queries, 3.0)
+        parity = None
+        if use_ref:      # the port answers the same sample: the two CPU implementations must agree bit for bit
+            n_chk = min(len(vals[-1]["ids"]), 64)
+            eids, ed, _, _ = oracle.OracleIndex(ix).ivfadc_search(queries[:n_chk], a.k, a.w, threads=os.cpu_count() or 1)
+            parity = bool((eids == vals[-1]["ids"][:n_chk]).all() and
+                          (ed.view(np.uint32) == vals[-1]["raw"][:n_chk].view(np.uint32)).all())
+            pool.close()
         v = float(np.mean([r["value"] for r in vals]))
         n_s = int(np.mean([r["value"] * r["seconds"] for r in vals]))
+        kind = vals[0]["kind"]
+        what = ("single-threaded backends running the reference's own freddy.c SRF (oracle/_ref)" if use_ref
+                else "host threads (oracle port)")
         out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": workload_name(a), "note": "each step = a bounded sample of the step's query batch"},
-               "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[0]["cores"], "kind": "port",
-                                "sample": f"~{n_s} queries per step on {vals[0]['cores']} host threads"},
+               "config": {"workload": workload_name(a), "note": "each step = a bounded sample of the step's query batch",
+                          "oracle_port_all_threads_queries_per_s": port["value"], "port_equals_reference_on_sample": parity},
+               "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[0]["cores"], "kind": kind,
+                                "sample": f"~{n_s} queries per step on {vals[0]['cores']} {what}"},
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return
@@ -371,8 +451,22 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_arm(a, ix, h_q.numpy(), a.cpu_seconds)
-        cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        from oracle import oracle
+        if os.path.exists(oracle.REF_SO):       # the reference's own SRF, one backend per core
+            pool = ReferencePool(a, ix)
+            cpu = reference_arm(a, ix, h_q.numpy(), a.cpu_seconds, pool)
+            pool.close()
+            n_chk = min(len(cpu["ids"]), 256)    # and our result for the same queries must be its result
+            cpu["gpu_equals_reference_on_sample"] = bool(
+                (cpu["ids"][:n_chk] == h_ids.numpy()[:n_chk]).all() and
+                (cpu["raw"][:n_chk].view(np.uint32) == h_dist.numpy()[:n_chk].view(np.uint32)).all())
+            port = cpu_arm(a, ix, h_q.numpy(), 3.0)
+            cpu["oracle_port_all_threads_queries_per_s"] = port["value"]
+            cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample", "gpu_equals_reference_on_sample",
+                                          "oracle_port_all_threads_queries_per_s")}
+        else:
+            cpu = cpu_arm(a, ix, h_q.numpy(), a.cpu_seconds)
+            cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
