@@ -130,7 +130,7 @@ struct fb_engine {
   DevBuf<u64> ana_partial;
 
   // scratch
-  DevBuf<float> lut, exact_lut, q_stage, dist_stage;
+  DevBuf<float> lut, exact_lut, q_stage, dist_stage, coarse_dist;
   DevBuf<int32_t> probes, exact_list, id_stage, sel_rows;
   DevBuf<uint32_t> qflags;
   DevBuf<u64> partial, kth;
@@ -418,6 +418,19 @@ int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k, int64_
 
 int launch_coarse_range(fb_engine* e, const float* d_q, int nq, int w, int k, int64_t q0) {
   StageTimer t(e, ST_COARSE);
+  if (nq <= 32 && (size_t)e->d * sizeof(float) <= 48 * 1024) {
+    // small batch: spread each query's C chains over C/128 CTAs, then one warp per query selects
+    if (e->coarse_dist.ensure((size_t)nq * e->Cs) != cudaSuccess) return fail(e, FB_ERR_CUDA, "out of device memory");
+    dim3 grid((e->Cs + kCoarseSmallThreads - 1) / kCoarseSmallThreads, nq);
+    coarse_dist_small_kernel<<<grid, kCoarseSmallThreads, (size_t)e->d * sizeof(float), e->stream>>>(
+        d_q + (size_t)q0 * e->d, e->d, e->coarseT.p, e->Cs, e->coarse_dist.p);
+    coarse_select_small_kernel<<<(nq + 3) / 4, 128, 0, e->stream>>>(e->coarse_dist.p, nq, e->C, e->Cs, e->fine.list_len.p, w, k,
+                                                                  e->probes.p + (size_t)q0 * w, e->qflags.p + q0,
+                                                                  e->force_exact ? 1 : 0);
+    e->launches += 2;
+    FB_CUDA(e, cudaGetLastError());
+    return FB_OK;
+  }
   auto need = [&](int QT) { return ((size_t)e->d * QT + (size_t)QT * e->Cs) * sizeof(float); };
   const size_t two_per_sm = 100 * 1024;
   if (need(16) <= two_per_sm) {
@@ -508,12 +521,12 @@ int launch_lut(fb_engine* e, const Codebook& cb, const float* d_q, const float* 
 
 template <int M>
 int launch_scan_m(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
-                  int list_mod, const float* d_lut, int K, int KK, u64* d_partial) {
-  size_t smem = (size_t)tab.m * K * sizeof(float);
+                  int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial) {
+  size_t smem = std::max<size_t>((size_t)tab.m * K * sizeof(float), (size_t)kScanWarps * 32 * sizeof(u64));
   if (smem > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT (%zu bytes) exceeds shared memory", smem);
   auto kern = adc_scan_kernel<M>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ntasks, kScanThreads, smem, e->stream>>>(tab.dev(), d_task_list, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+  kern<<<ntasks * segs, kScanThreads, smem, e->stream>>>(tab.dev(), d_task_list, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
   e->launches++;
   e->n_scan_launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -521,13 +534,13 @@ int launch_scan_m(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list
 }
 
 int launch_scan(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
-                int list_mod, const float* d_lut, int K, int KK, u64* d_partial) {
+                int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial) {
   StageTimer t(e, ST_SCAN);
   switch (tab.m) {
-    case 8: return launch_scan_m<8>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
-    case 12: return launch_scan_m<12>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
-    case 16: return launch_scan_m<16>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
-    default: return launch_scan_m<0>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, d_lut, K, KK, d_partial);
+    case 8: return launch_scan_m<8>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
+    case 12: return launch_scan_m<12>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
+    case 16: return launch_scan_m<16>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
+    default: return launch_scan_m<0>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
   }
 }
 
@@ -768,7 +781,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   FB_CUDA(e, e->exact_list.ensure((size_t)nq));
   FB_CUDA(e, e->kth.ensure((size_t)nq));
   if (fast || large_k) FB_CUDA(e, e->lut.ensure((size_t)chunk * lut_per_query));
-  if (fast && chunk < e->qscan_min_queries) FB_CUDA(e, e->partial.ensure((size_t)chunk * w * kScanWarps * KK));
+  if (fast && chunk < e->qscan_min_queries) FB_CUDA(e, e->partial.ensure((size_t)chunk * w * 16 * KK));
   if (large_k) {
     FB_CUDA(e, e->j_keys.ensure((size_t)chunk * key_cap));
     FB_CUDA(e, e->j_ncells.ensure((size_t)chunk));
@@ -825,9 +838,11 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, lutbuf, K, KK, k, sentinel, oi, od)
                                        : FB_ERR_UNSUPPORTED;
       if (rc == FB_ERR_UNSUPPORTED) {
-        rc = e->partial.ensure((size_t)chunk * w * kScanWarps * KK) == cudaSuccess ? FB_OK : FB_ERR_CUDA;
-        if (!rc) rc = launch_scan(e, e->fine, pr, n * w, 1, 1, lutbuf, K, KK, e->partial.p);
-        if (!rc) rc = launch_finalize(e, e->fine, (int)q0, w * kScanWarps, KK, k, n, sentinel, true, oi, od);
+        // few (query, list) tasks: split every list over `segs` CTAs so that the launch still fills the GPU
+        const int segs = std::max(1, std::min(16, (2 * e->num_sms) / std::max(1, n * w)));
+        rc = e->partial.ensure((size_t)chunk * w * 16 * KK) == cudaSuccess ? FB_OK : FB_ERR_CUDA;
+        if (!rc) rc = launch_scan(e, e->fine, pr, n * w, 1, 1, segs, lutbuf, K, KK, e->partial.p);
+        if (!rc) rc = launch_finalize(e, e->fine, (int)q0, w * segs, KK, k, n, sentinel, true, oi, od);
       }
       if (overlap) cudaEventRecord(e->ev_scan_done[c & 1], e->s_scan);
       e->stream = main_stream;
@@ -985,13 +1000,13 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
   const int nl = tab.n_lists;
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
   // bound the per-warp partial lists (chunk * nl * 8 * KK keys)
-  while (chunk > 1 && (size_t)chunk * nl * kScanWarps * KK * sizeof(u64) > ((size_t)1 << 30)) chunk /= 2;
+  while (chunk > 1 && (size_t)chunk * nl * KK * sizeof(u64) > ((size_t)1 << 30)) chunk /= 2;
   FB_CUDA(e, e->lut.ensure((size_t)chunk * m * K));
   FB_CUDA(e, e->qflags.ensure((size_t)chunk));
   FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
   FB_CUDA(e, e->kth.ensure((size_t)chunk));
   FB_CUDA(e, e->iota_lists.ensure((size_t)nl));
-  if (fast) FB_CUDA(e, e->partial.ensure((size_t)chunk * nl * kScanWarps * KK));
+  if (fast) FB_CUDA(e, e->partial.ensure((size_t)chunk * nl * KK));
   iota_kernel<<<(nl + 255) / 256, 256, 0, e->stream>>>(e->iota_lists.p, nl);
   e->launches++;
   size_t ex_smem = kExactFixedSmem;
@@ -1007,8 +1022,8 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
     FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
     if ((rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, n, e->lut.p))) return rc;   // freddy.c:519-525
     if (fast && !e->force_exact) {
-      if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, e->lut.p, K, KK, e->partial.p))) return rc;
-      if ((rc = launch_finalize(e, tab, 0, nl * kScanWarps, KK, k, n, sentinel, false, oi, od))) return rc;
+      if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, 1, e->lut.p, K, KK, e->partial.p))) return rc;
+      if ((rc = launch_finalize(e, tab, 0, nl, KK, k, n, sentinel, false, oi, od))) return rc;
     } else {
       iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
       int32_t cnt = n;

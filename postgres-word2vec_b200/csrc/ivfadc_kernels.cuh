@@ -44,6 +44,54 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / kWarp;
 constexpr int kLutMaxJobs = 16;
 
+// The w nearest lists of one query from its C coarse distances (one warp): top-(w+1) by (distance, centroid
+// id); lanes 0..w-1 hold the selection, lane w the runner-up; flags the rare cases for the general kernel.
+__device__ __forceinline__ void coarse_select_warp(const float* __restrict__ dist_row, int C, int Cs,
+                                                   const int32_t* __restrict__ list_len, int w, int k, int q,
+                                                   int32_t* __restrict__ probes, uint32_t* __restrict__ qflags,
+                                                   int force_exact, int lane) {
+  u64 mine = kKeyInf;
+  u64 thr = kKeyInf;
+  for (int c0 = 0; c0 < Cs; c0 += 128) {            // four independent loads in flight per lane
+    float dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int c = c0 + 32 * u + lane;
+      dv[u] = (c < C) ? dist_row[c] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int c = c0 + 32 * u + lane;
+      u64 key = (c < C) ? make_key(dv[u], (uint32_t)c) : kKeyInf;
+      unsigned mask = __ballot_sync(0xffffffffu, key < thr);
+      while (mask) {
+        int src = __ffs(mask) - 1;
+        u64 nk = shfl_u64(key, src);
+        warp_list_insert(mine, nk, lane);
+        thr = shfl_u64(mine, w);
+        mask &= mask - 1;
+        mask &= __ballot_sync(0xffffffffu, key < thr);
+      }
+    }
+  }
+  uint32_t flags = force_exact ? (kFlagExact | kWhyForced) : 0u;
+  u64 kw = shfl_u64(mine, w), kw1 = shfl_u64(mine, w - 1);
+  // a tie across the w-th place makes the kept set order dependent
+  if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact | kWhyCoarseTie;
+  // sentinel quirk of the reference: a selected distance >= 100 is undefined
+  if (key_dist(kw1) >= 100.0f) flags |= kFlagExact | kWhyCoarseFar;
+  int len = 0;
+  if (lane < w) {
+    int cid = (int)key_t(mine);
+    probes[(size_t)q * w + lane] = cid;
+    len = (list_len != nullptr) ? list_len[cid] : k;   // nullptr: quantisation only (fb_encode_*), no lists involved
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) len += __shfl_xor_sync(0xffffffffu, len, s);
+  if (len < k) flags |= kFlagExact | kWhyFewRows;  // re-probe loop (freddy.c:262) needed
+  if (lane == 0) qflags[q] = flags;
+}
+
 // ---------------------------------------------------------------------------
 // HOT(1) coarse quantizer: squared L2 of each query against all C centroids
 // (sequential 3-op chain per dimension, index_utils.c:500-508), then the w
@@ -163,39 +211,51 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
   for (int qq = warp; qq < QT; qq += kCoarseThreads / kWarp) {
     const int q = q0 + qq;
     if (q >= nq) continue;
-    u64 mine = kKeyInf;
-    u64 thr = kKeyInf;
-    for (int c0 = 0; c0 < Cs; c0 += 32) {
-      int c = c0 + lane;
-      u64 key = (c < C) ? make_key(dist[qq * Cs + c], (uint32_t)c) : kKeyInf;
-      unsigned mask = __ballot_sync(0xffffffffu, key < thr);
-      while (mask) {
-        int src = __ffs(mask) - 1;
-        u64 nk = shfl_u64(key, src);
-        warp_list_insert(mine, nk, lane);
-        thr = shfl_u64(mine, w);
-        mask &= mask - 1;
-        mask &= __ballot_sync(0xffffffffu, key < thr);
+    coarse_select_warp(dist + (size_t)qq * Cs, C, Cs, list_len, w, k, q, probes, qflags, force_exact, lane);
+  }
+}
+
+// Small batches (a single query is the reference's everyday call): one thread per (query, centroid) so that
+// the 300-step chain of one query spreads over 8 CTAs instead of one; distances go through global memory to a
+// second, one-warp-per-query selection kernel.
+constexpr int kCoarseSmallThreads = 128;
+__global__ void __launch_bounds__(kCoarseSmallThreads)
+coarse_dist_small_kernel(const float* __restrict__ queries, int d, const float* __restrict__ coarseT, int Cs,
+                         float* __restrict__ dist_out) {            // [nq][Cs]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qs = reinterpret_cast<float*>(smem_raw);                   // [d]
+  const int q = blockIdx.y, c = blockIdx.x * kCoarseSmallThreads + threadIdx.x;
+  for (int i = threadIdx.x; i < d; i += kCoarseSmallThreads) qs[i] = queries[(size_t)q * d + i];
+  __syncthreads();
+  if (c >= Cs) return;
+  const float* col = coarseT + c;
+  float acc = 0.0f;
+  constexpr int B = 10;                              // dimensions per batch; the next batch loads while this one computes
+  float cur[B], nxt[B];
+#pragma unroll
+  for (int u = 0; u < B; u++) cur[u] = (u < d) ? __ldg(col + (size_t)u * Cs) : 0.0f;
+  for (int i = 0; i < d; i += B) {
+#pragma unroll
+    for (int u = 0; u < B; u++) nxt[u] = (i + B + u < d) ? __ldg(col + (size_t)(i + B + u) * Cs) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+      if (i + u < d) {
+        const float t = xsub(qs[i + u], cur[u]);
+        acc = xadd(acc, xmul(t, t));
       }
     }
-    // lanes 0..w-1: the w nearest lists; lane w: the runner-up
-    uint32_t flags = force_exact ? (kFlagExact | kWhyForced) : 0u;
-    u64 kw = shfl_u64(mine, w), kw1 = shfl_u64(mine, w - 1);
-    // a tie across the w-th place makes the kept set order dependent
-    if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact | kWhyCoarseTie;
-    // sentinel quirk of the reference: a selected distance >= 100 is undefined
-    if (key_dist(kw1) >= 100.0f) flags |= kFlagExact | kWhyCoarseFar;
-    int len = 0;
-    if (lane < w) {
-      int cid = (int)key_t(mine);
-      probes[(size_t)q * w + lane] = cid;
-      len = (list_len != nullptr) ? list_len[cid] : k;   // nullptr: quantisation only (fb_encode_*), no lists involved
-    }
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) len += __shfl_xor_sync(0xffffffffu, len, s);
-    if (len < k) flags |= kFlagExact | kWhyFewRows;  // re-probe loop (freddy.c:262) needed
-    if (lane == 0) qflags[q] = flags;
+    for (int u = 0; u < B; u++) cur[u] = nxt[u];
   }
+  dist_out[(size_t)q * Cs + c] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+coarse_select_small_kernel(const float* __restrict__ dist, int nq, int C, int Cs, const int32_t* __restrict__ list_len,
+                           int w, int k, int32_t* __restrict__ probes, uint32_t* __restrict__ qflags, int force_exact) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  coarse_select_warp(dist + (size_t)q * Cs, C, Cs, list_len, w, k, q, probes, qflags, force_exact, threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------
@@ -453,14 +513,15 @@ adc_scan_kernel(CodeTableDev tab,
                 const int32_t* __restrict__ task_list,   // [ntasks] list per task, or nullptr (list = task % n_lists... see host)
                 int tasks_per_lut,                       // LUT index = task / tasks_per_lut
                 int lists_per_task_mod,                  // if task_list == nullptr: list = task % lists_per_task_mod
+                int segs,                                // CTAs per task: each scans 1/segs of the list's blocks
                 const float* __restrict__ lut, int K, int KK,
-                u64* __restrict__ partial) {             // [ntasks][kScanWarps][KK]
+                u64* __restrict__ partial) {             // [ntasks * segs][KK]: the CTA's KK smallest keys, ascending
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   float* slut = reinterpret_cast<float*>(smem_raw);
   const int m = (M > 0) ? M : tab.m;
   const int U = (M > 0) ? (M + 3) / 4 : tab.U;
-  const int task = blockIdx.x;
+  const int task = blockIdx.x / segs, seg = blockIdx.x % segs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lut_bytes = (uint32_t)((size_t)m * K * sizeof(float));
 
@@ -477,6 +538,7 @@ adc_scan_kernel(CodeTableDev tab,
   const int blk0 = tab.list_blk[list];
   const int len = tab.list_len[list];
   const int nblk = (len + 31) >> 5;
+  const int b_lo = (int)(((int64_t)nblk * seg) / segs), b_hi = (int)(((int64_t)nblk * (seg + 1)) / segs);
   mbar_wait(&bar, 0);
 
   u64 mine = kKeyInf;
@@ -484,7 +546,7 @@ adc_scan_kernel(CodeTableDev tab,
   const char* lut_bytes_base = reinterpret_cast<const char*>(slut);
   const uint32_t row_stride = (uint32_t)K * 4u;
 
-  for (int b = warp; b < nblk; b += kScanWarps) {
+  for (int b = b_lo + warp; b < b_hi; b += kScanWarps) {
     const uint2* up = tab.units + ((size_t)(blk0 + b) * U) * 32 + lane;
     const float acc = adc_block_row<M, 0>(up, lut_bytes_base, m, U, row_stride);
     const bool valid = (b * 32 + lane) < len;
@@ -503,7 +565,19 @@ adc_scan_kernel(CodeTableDev tab,
       thr_bits = key_dbits(shfl_u64(mine, KK - 1));
     }
   }
-  if (lane < KK) partial[((size_t)task * kScanWarps + warp) * KK + lane] = mine;
+  // merge the warps' lists inside the CTA (the LUT is no longer needed: reuse its shared memory)
+  __syncthreads();
+  u64* stage = reinterpret_cast<u64*>(smem_raw);
+  stage[warp * 32 + lane] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    for (int l = 1; l < kScanWarps; l++) {
+      const u64 other = stage[l * 32 + lane];
+      if (__ballot_sync(0xffffffffu, other <= (shfl_u64(mine, KK - 1) | 0xFFFFFFFFull)) == 0) continue;   // keeps distance ties
+      warp_list_merge(mine, other, lane);
+    }
+    if (lane < KK) partial[(size_t)blockIdx.x * KK + lane] = mine;
+  }
 }
 
 // same chain from units already in registers (software-pipelined scan, M > 0)
@@ -806,13 +880,36 @@ finalize_kernel(const u64* __restrict__ partial, int lists_per_query, int KK, in
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
+  // the query's lists_per_query * KK keys as one flat stream, 4 x 32 independent loads in flight; a key enters
+  // the warp's 32-key list if it is not larger than the current (k+2)-th distance (keeps distance ties)
   u64 mine = kKeyInf;
   const u64* base = partial + (size_t)q * lists_per_query * KK;
-  for (int l = 0; l < lists_per_query; l++) {
-    u64 other = (lane < KK) ? base[(size_t)l * KK + lane] : kKeyInf;
-    if (__ballot_sync(0xffffffffu, other <= (shfl_u64(mine, KK - 1) | 0xFFFFFFFFull)) == 0) continue;   // keeps distance ties
-    warp_list_merge(mine, other, lane);
+  const int n_keys = lists_per_query * KK;
+  u64 thr = kKeyInf;
+  for (int i0 = 0; i0 < n_keys; i0 += 128) {
+    u64 kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + 32 * u + lane;
+      kv[u] = (i < n_keys) ? base[i] : kKeyInf;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      unsigned mask = __ballot_sync(0xffffffffu, kv[u] != kKeyInf && kv[u] <= thr);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        const u64 nk = shfl_u64(kv[u], src);
+        if (nk <= thr) {                                   // thr may have dropped since the ballot
+          warp_list_insert(mine, nk, lane);
+          const u64 kth = shfl_u64(mine, KK - 1);
+          thr = (kth == kKeyInf) ? kKeyInf : (kth | 0xFFFFFFFFull);
+        }
+        mask &= mask - 1;
+      }
+    }
   }
+  // lanes >= KK may hold keys beyond the (k+2)-th distance group that other lists truncated: not part of the contract
+  if (lane >= KK) mine = kKeyInf;
   const uint32_t flags = has_input_flags ? qflags[q] : 0u;
   warp_emit_topk(mine, lane, q, q_base, k, flags, ids, sentinel, qflags, out_ids, out_dists, exact_list, exact_count,
                  exact_total, kth_key, KK);
