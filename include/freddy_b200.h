@@ -169,6 +169,16 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
 int fb_encode_ivfadc(fb_engine* e, const float* vectors, int64_t n, int32_t* out_coarse_ids, int16_t* out_codes);
 int fb_encode_pq(fb_engine* e, int kind, const float* vectors, int64_t n, int16_t* out_codes);
 
+/* ---- grouping_pq ---------------------------------------------------------------
+ * grouping_pq(int[] ids, int[] group_ids) (freddy.c:1178-1401): the rows of the flat pq table whose id is in
+ * `ids` (table order, each once), each assigned to the nearest group vector (word-vector rows of `group_ids`,
+ * taken in ascending id order) by ADC distance; strict `<` from 100, first minimum wins.
+ * out_ids / out_group_ids: [n_ids] caller-allocated, *n_out rows written.
+ * FB_ERR_INVALID "Group ids do not exist" as the SRF raises it (:1243-1245); FB_ERR_REFERENCE_UB where every
+ * distance is >= 100.  Needs fb_load_pq + fb_load_vectors.                                                */
+int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* group_ids, int n_groups,
+                   int32_t* out_ids, int32_t* out_group_ids, int* n_out);
+
 int fb_synchronize(fb_engine* e);
 /* Run all subsequent work on the caller's CUDA stream (a cudaStream_t passed as
  * void*; NULL restores the engine's own stream).  Lets a host runtime order the

@@ -808,3 +808,45 @@ int fo_encode(const float* vectors, int n, int d, const float* coarse, int C,
   free(res);
   return rc;
 }
+
+
+/* ref: freddy.c:1178-1401 grouping_pq */
+int fo_grouping_pq(const FoIndex* ix, const float* vectors, const int32_t* vec_ids, int n_vec,
+                   const int32_t* ids, int n_ids, const int32_t* group_ids, int n_groups,
+                   int32_t* out_ids, int32_t* out_group_ids) {
+  const int m = ix->m, K = ix->K, d = ix->d, sub = d / m;
+  int32_t* groups = malloc(sizeof(int32_t) * (size_t)(n_groups > 0 ? n_groups : 1));
+  memcpy(groups, group_ids, sizeof(int32_t) * (size_t)n_groups);
+  qsort(groups, (size_t)n_groups, sizeof(int32_t), cmp_i32);                  /* :1222 */
+  /* `SELECT id, vector ... WHERE id IN (groups) ORDER BY id ASC`: one row per distinct existing id (:1224-1246) */
+  float* luts = malloc(sizeof(float) * (size_t)(n_groups > 0 ? n_groups : 1) * m * K);
+  int found = 0;
+  for (int g = 0; g < n_groups; g++) {
+    if (g > 0 && groups[g] == groups[g - 1]) continue;
+    int lo = 0, hi = n_vec;
+    while (lo < hi) { int mid = (lo + hi) / 2; if (vec_ids[mid] < groups[g]) lo = mid + 1; else hi = mid; }
+    if (lo < n_vec && vec_ids[lo] == groups[g]) {
+      /* row `found` of the result pairs with groups[found] in the reference: only equal when nothing is missing */
+      fo_precomputed_distances(luts + (size_t)found * m * K, m, K, sub, vectors + (size_t)lo * d, ix->codebook);   /* :1291-1299 */
+      found++;
+    }
+  }
+  if (found != n_groups) { free(groups); free(luts); return -1; }             /* "Group ids do not exist" */
+  int32_t* rows = NULL;
+  const int n = select_target_rows(ix, ids, n_ids, &rows);                    /* :1303-1321 */
+  int rc = n;
+  for (int i = 0; i < n; i++) {
+    const int16_t* codes = ix->codes + (size_t)rows[i] * m;
+    float min_dist = 100;                                                     /* :1326 */
+    int nearest = -1;
+    for (int g = 0; g < n_groups; g++) {
+      float distance = fo_pq_distance_int16(luts + (size_t)g * m * K, codes, m, K);   /* :1341-1347 */
+      if (distance < min_dist) { min_dist = distance; nearest = g; }
+    }
+    if (nearest < 0) { rc = -2; nearest = 0; }
+    out_ids[i] = ix->ids[rows[i]];
+    out_group_ids[i] = n_groups > 0 ? groups[nearest] : -1;
+  }
+  free(rows); free(groups); free(luts);
+  return rc;
+}

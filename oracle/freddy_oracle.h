@@ -86,6 +86,16 @@ int fo_pq_search_in_batch(const FoIndex* ix, const float* queries, int nq, int k
 int fo_encode(const float* vectors, int n, int d, const float* coarse, int C,
               const float* codebook, int m, int K, int32_t* out_coarse_ids, int16_t* out_codes);
 
+/* ---- grouping_pq (freddy.c:1178-1401) ---- */
+/* ix: flat PQ index (codebook = pq codebook, codes = pq codes).  vectors/vec_ids: the normalized word-vector
+ * table (ids ascending).  Group vectors are taken in ascending group-id order; every selected pq row (table
+ * order, `WHERE id IN`) gets the first group with the smallest ADC distance below 100.
+ * Returns the number of rows written, -1 "Group ids do not exist" (:1243-1245), -2 where the reference reads
+ * an uninitialised assignment. */
+int fo_grouping_pq(const FoIndex* ix, const float* vectors, const int32_t* vec_ids, int n_vec,
+                   const int32_t* ids, int n_ids, const int32_t* group_ids, int n_groups,
+                   int32_t* out_ids, int32_t* out_group_ids);
+
 /* ---- vector UDFs (core_functions.c, cosine_similarity.c) ---- */
 double fo_cosine_similarity(const float* v1, const float* v2, int n);      /* cosine_similarity.c:12-37 */
 double fo_cosine_similarity_norm(const float* v1, const float* v2, int n); /* cosine_similarity.c:39-45 */

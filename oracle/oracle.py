@@ -72,6 +72,8 @@ def lib():
         L.fo_vec_minus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fo_vec_plus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.fo_vec_normalize.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.fo_grouping_pq.argtypes = [C.POINTER(FoIndex), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]
         L.fo_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.fo_analogy_3cosadd_many.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
@@ -288,6 +290,15 @@ class ReferenceSession:
             self._err("ivpq_search_in", n)
         return qo.reshape(nq, k), ids.reshape(nq, k), raw.reshape(nq, k)
 
+    def grouping_pq(self, ids, group_ids):
+        ii, gi = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(group_ids, np.int32)
+        oi, og = np.empty(max(1, len(ii)), np.int32), np.empty(max(1, len(ii)), np.int32)
+        self.R.ref_grouping_pq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        n = self.R.ref_grouping_pq(_p(ii), len(ii), _p(gi), len(gi), _p(oi), _p(og))
+        if n < 0:
+            self._err("grouping_pq", n)
+        return oi[:n].copy(), og[:n].copy()
+
     def ivfadc_search(self, queries, k):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
         ids = np.empty((len(q), k), np.int32)
@@ -388,6 +399,15 @@ class OracleIndex:
             lib().fo_pq_search(C.byref(self.ix), _p(q[i]), k, tk)
             ids[i], ds[i] = self._unpack(tk, 1, k)
         return ids, ds
+
+    def grouping_pq(self, vectors, vec_ids, ids, group_ids):
+        """oracle: (ids, group ids, rc) of grouping_pq (freddy.c:1178-1401); flat PQ index"""
+        v = np.ascontiguousarray(vectors, np.float32)
+        vi = np.ascontiguousarray(vec_ids, np.int32)
+        ii, gi = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(group_ids, np.int32)
+        oi, og = np.empty(max(1, len(ii)), np.int32), np.empty(max(1, len(ii)), np.int32)
+        n = lib().fo_grouping_pq(C.byref(self.ix), _p(v), _p(vi), len(vi), _p(ii), len(ii), _p(gi), len(gi), _p(oi), _p(og))
+        return (oi[:max(n, 0)].copy(), og[:max(n, 0)].copy(), n)
 
     def pq_search_in_batch(self, queries, k, targets, use_target_lists=False):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.ix.d)

@@ -555,3 +555,19 @@ static void bytea_binop(Datum (*fn)(FunctionCallInfo), const float* a, const flo
 void ref_vec_minus_bytea(const float* a, const float* b, int d, float* out) { bytea_binop(vec_minus_bytea, a, b, d, out); }
 void ref_vec_plus_bytea(const float* a, const float* b, int d, float* out) { bytea_binop(vec_plus_bytea, a, b, d, out); }
 void ref_vec_normalize_bytea(const float* a, int d, float* out) { bytea_binop(vec_normalize_bytea, a, NULL, d, out); }
+
+/* grouping_pq(int[] ids, int[] group_ids) -> rows (id, group id).  returns the number of rows or -1 (elog ERROR) */
+extern Datum grouping_pq(FunctionCallInfo fcinfo);
+int ref_grouping_pq(const int32* ids, int n, const int32* groups, int ng, int32* out_ids, int32* out_groups) {
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_int_array(ids, n));
+  fc.args[1] = PointerGetDatum(make_int_array(groups, ng));
+  char* text = malloc((size_t)(n > 0 ? n : 1) * 2 * 16 + 16);
+  int rows = run_srf(grouping_pq, &fc, 2, n, text, NULL);
+  for (int i = 0; i < rows && i < n; i++) {
+    out_ids[i] = atoi(text + (size_t)(i * 2) * 16);
+    out_groups[i] = atoi(text + (size_t)(i * 2 + 1) * 16);
+  }
+  free(text);
+  return rows;
+}

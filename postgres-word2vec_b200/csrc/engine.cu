@@ -23,6 +23,7 @@
 #include "knn_join_kernels.cuh"
 #include "pipeline_kernels.cuh"
 #include "rerank_kernels.cuh"
+#include "grouping_kernels.cuh"
 
 using namespace fb;
 
@@ -1220,38 +1221,10 @@ int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w, i
   return check_error_flag(e);
 }
 
-int fb_pq_search(fb_engine* e, const float* queries, int nq, int k, int32_t* out_ids, float* out_dists) {
-  if (!e) return FB_ERR_INVALID;
-  int rc = check_common(e, nq, k);
-  if (rc) return rc;
-  if ((rc = check_pq_ready(e))) return rc;
-  if (nq == 0) return FB_OK;
-  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
-  FB_CUDA(e, cudaSetDevice(e->device));
-  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
-  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
-  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
-  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  if ((rc = pq_dev(e, e->pq, e->q_stage.p, nq, k, 100.0f, e->id_stage.p, e->dist_stage.p))) return rc;  // freddy.c:90-92
-  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-  FB_CUDA(e, cudaStreamSynchronize(e->stream));
-  return FB_OK;
-}
-
-int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
-                          int use_target_lists, int32_t* out_ids, float* out_dists) {
-  (void)use_target_lists;  // loop-nest choice of the reference (freddy.c:600-631); results are identical
-  if (!e) return FB_ERR_INVALID;
-  int rc = check_common(e, nq, k);
-  if (rc) return rc;
-  if ((rc = check_pq_ready(e))) return rc;
-  if (n_targets < 0 || (n_targets > 0 && !targets)) return fail(e, FB_ERR_INVALID, "bad target array");
-  if (nq == 0) return FB_OK;
-  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
-  FB_CUDA(e, cudaSetDevice(e->device));
+static // Rows of the flat pq table selected by `WHERE id IN (targets)` in table order, each once (freddy.c:544-562,
+// :1286-1300), gathered into a temporary blocked table; `view` borrows its buffers (ids = the full pq table's).
+int build_pq_subset(fb_engine* e, const int32_t* targets, int n_targets, CodeTable& view, std::vector<int32_t>& rows) {
   // rows selected by `WHERE id IN (targets)` in table order (freddy.c:544-562)
-  std::vector<int32_t> rows;
   rows.reserve(n_targets);
   for (int i = 0; i < n_targets; i++) {
     if (e->pq_ids_sorted) {
@@ -1290,10 +1263,46 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, con
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   FB_CUDA(e, cudaStreamSynchronize(e->stream));  // host vectors go out of scope below
-  CodeTable view;  // borrow buffers; ids come from the full pq table (rowno = pq row)
+  // borrow buffers; ids come from the full pq table (rowno = pq row)
   view.units = tmp.units; view.rowno = tmp.rowno; view.list_blk = tmp.list_blk; view.list_len = tmp.list_len;
   view.ids = e->pq.ids; view.m = e->pq.m; view.U = U; view.n_lists = nl; view.N = n; view.n_blocks = n_blocks;
 
+  return FB_OK;
+}
+
+int fb_pq_search(fb_engine* e, const float* queries, int nq, int k, int32_t* out_ids, float* out_dists) {
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if ((rc = check_pq_ready(e))) return rc;
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if ((rc = pq_dev(e, e->pq, e->q_stage.p, nq, k, 100.0f, e->id_stage.p, e->dist_stage.p))) return rc;  // freddy.c:90-92
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
+int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
+                          int use_target_lists, int32_t* out_ids, float* out_dists) {
+  (void)use_target_lists;  // loop-nest choice of the reference (freddy.c:600-631); results are identical
+  if (!e) return FB_ERR_INVALID;
+  int rc = check_common(e, nq, k);
+  if (rc) return rc;
+  if ((rc = check_pq_ready(e))) return rc;
+  if (n_targets < 0 || (n_targets > 0 && !targets)) return fail(e, FB_ERR_INVALID, "bad target array");
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int32_t> rows;
+  CodeTable view;
+  if ((rc = build_pq_subset(e, targets, n_targets, view, rows))) return rc;
   FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
@@ -1998,6 +2007,81 @@ int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, in
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
   for (int i = 0; i < nq; i++) out_query_ids[i] = e->vec_ids_host[rows[i]];
   return check_error_flag(e);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// grouping_pq(int[] ids, int[] group_ids) (freddy.c:1178-1401)
+int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* group_ids, int n_groups,
+                   int32_t* out_ids, int32_t* out_group_ids, int* n_out) {
+  if (!e || n_ids < 0 || n_groups < 0 || !n_out) return fail(e, FB_ERR_INVALID, "fb_grouping_pq: bad arguments");
+  int rc = check_pq_ready(e);
+  if (rc) return rc;
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "grouping_pq reads the group vectors from the word-vector table: fb_load_vectors first");
+  if (e->vec_d != e->d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, pq index d=%d", e->vec_d, e->d);
+  *n_out = 0;
+  if ((n_ids > 0 && (!ids || !out_ids || !out_group_ids)) || (n_groups > 0 && !group_ids)) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  // group vectors: `WHERE id IN (group ids) ORDER BY id ASC`; every id must select its own row (freddy.c:1228-1246)
+  std::vector<int32_t> groups(group_ids, group_ids + n_groups);
+  std::sort(groups.begin(), groups.end());
+  std::vector<int32_t> grows(n_groups);
+  for (int g = 0; g < n_groups; g++) {
+    grows[g] = vec_row_of(e, groups[g]);
+    if (grows[g] < 0 || (g > 0 && groups[g] == groups[g - 1])) return fail(e, FB_ERR_INVALID, "Group ids do not exist");
+  }
+  if (n_ids == 0) return FB_OK;
+  std::vector<int32_t> rows;
+  CodeTable view;
+  if ((rc = build_pq_subset(e, ids, n_ids, view, rows))) return rc;
+  const int n = (int)rows.size();
+  *n_out = n;
+  if (n == 0) return FB_OK;
+  for (int i = 0; i < n; i++) out_ids[i] = e->pq_ids_host[rows[i]];
+  if (n_groups == 0) return fail(e, FB_ERR_REFERENCE_UB, "no groups: the reference reads an uninitialised assignment (freddy.c:1326-1352)");
+  const Codebook& cb = e->cb[FB_CB_PQ];
+  const int d = e->d, m = cb.m, K = cb.K;
+  const size_t lut_bytes = (size_t)m * K * sizeof(float);
+  if (2 * lut_bytes > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT too large for shared memory");
+  FB_CUDA(e, e->ana_rows.ensure((size_t)n_groups));
+  FB_CUDA(e, e->q_stage.ensure((size_t)n_groups * d));
+  FB_CUDA(e, e->lut.ensure((size_t)n_groups * m * K));
+  const int n_slots = (int)view.n_blocks * 32;
+  FB_CUDA(e, e->id_stage.ensure((size_t)n_slots));
+  FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, grows.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  gather_vec_rows_kernel<<<n_groups, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, n_groups, e->q_stage.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  if ((rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, n_groups, e->lut.p))) return rc;   // freddy.c:1291-1299
+  {
+    StageTimer t(e, ST_SCAN);
+    const int ctas = (int)((view.n_blocks + kGroupThreads / 32 - 1) / (kGroupThreads / 32));
+    auto kern = (m == 12) ? grouping_argmin_kernel<12> : grouping_argmin_kernel<0>;
+    FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * lut_bytes)));
+    kern<<<ctas, kGroupThreads, 2 * lut_bytes, e->stream>>>(view.dev(), (int)view.n_blocks, n, e->lut.p, n_groups, K,
+                                                           e->id_stage.p, e->small.p + 2);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  std::vector<int32_t> nearest((size_t)n_slots);
+  FB_CUDA(e, cudaMemcpyAsync(nearest.data(), e->id_stage.p, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  int32_t flag = 0;
+  FB_CUDA(e, cudaMemcpy(&flag, e->small.p + 2, sizeof flag, cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(e->small.p + 2, 0, sizeof(int32_t));
+    return fail(e, FB_ERR_REFERENCE_UB, "a row is >= 100 away from every group: the reference's assignment is uninitialised (freddy.c:1326-1352)");
+  }
+  // the temporary table is laid out in pseudo lists of 4096 rows, each padded to whole blocks: walk the slots
+  int i = 0;
+  for (int s_ = 0; s_ < n_slots && i < n; s_++)
+    if (nearest[s_] >= 0) out_group_ids[i++] = groups[nearest[s_]];
+  if (i != n) return fail(e, FB_ERR_CUDA, "grouping_pq: internal slot accounting (%d of %d rows)", i, n);
+  e->host_rows += (int64_t)n * n_groups;
+  e->bytes_per_row = 2 * m + 4;
+  return FB_OK;
 }
 
 }  // extern "C"

@@ -227,6 +227,15 @@ class Engine:
         self._check(self._lib.fb_encode_pq(self._h, kind, _ptr(v), n, _ptr(codes)))
         return codes
 
+    def grouping_pq(self, ids, group_ids):
+        """grouping_pq(int[], int[]) -> (ids, group ids) of the selected pq rows in table order   freddy.c:1178-1401"""
+        ids, gids = _i32(ids), _i32(group_ids)
+        out_i, out_g = np.empty(len(ids), np.int32), np.empty(len(ids), np.int32)
+        n = C.c_int(0)
+        self._check(self._lib.fb_grouping_pq(self._h, _ptr(ids), len(ids), _ptr(gids), len(gids), _ptr(out_i), _ptr(out_g),
+                                             C.byref(n)))
+        return out_i[:n.value].copy(), out_g[:n.value].copy()
+
     def synchronize(self):
         self._check(self._lib.fb_synchronize(self._h))
 

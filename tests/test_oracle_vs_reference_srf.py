@@ -177,3 +177,33 @@ def test_ivfadc_batch_search_equals_w1_search(ref, oracle_mod):
     assert rc == 0
     np.testing.assert_array_equal(oids, rids)
     _same(np.where(oids == -1, np.float32(100.0), od), rraw)
+
+
+def test_grouping_pq_against_the_real_srf():
+    """fo_grouping_pq vs the reference's own grouping_pq SRF (freddy.c:1178-1401) through the emulator:
+    ids in table order, group assignment incl. ties between groups (first group in ascending id order wins),
+    duplicate / unknown input ids, and the "Group ids do not exist" error"""
+    from helpers import small_index
+    from oracle import oracle
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    vectors = ix["vectors"].copy()
+    vectors[500] = vectors[100]                                   # groups 101 and 501 are the same vector: ties
+    rs = oracle.ReferenceSession()
+    rs.load_pq(ix)
+    rs.load_vectors_table(vectors, vec_ids)
+    oi = oracle.OracleIndex(ix, flat_pq=True)
+    rng = np.random.default_rng(2)
+    ids = rng.choice(np.arange(1, ix["N"] + 200), size=3000, replace=True).astype(np.int32)
+    for groups in ([501, 101, 7, 9000], [42], [19999, 3, 250, 251, 252, 17, 101]):
+        g = np.asarray(groups, np.int32)
+        want_i, want_g = rs.grouping_pq(ids, g)
+        got_i, got_g, rc = oi.grouping_pq(vectors, vec_ids, ids, g)
+        assert rc == len(want_i)
+        np.testing.assert_array_equal(got_i, want_i)
+        np.testing.assert_array_equal(got_g, want_g)
+    assert 501 not in set(oi.grouping_pq(vectors, vec_ids, ids, [501, 101])[1].tolist())
+    with pytest.raises(RuntimeError):
+        rs.grouping_pq(ids, np.asarray([5, 10 ** 8], np.int32))
+    assert oi.grouping_pq(vectors, vec_ids, ids, [5, 10 ** 8])[2] == -1
+    assert oi.grouping_pq(vectors, vec_ids, ids, [5, 5])[2] == -1
