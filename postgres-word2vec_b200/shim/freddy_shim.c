@@ -24,7 +24,7 @@
 #include "freddy_b200.h"
 
 static fb_engine* engine = NULL;
-static int pinned_d = 0;
+static int pinned_d = 0, vecs_d = 0;
 static bool pinned_ivfadc = false, pinned_pq = false, pinned_ivpq = false, pinned_vecs = false;
 
 static void fb_check(int rc) {
@@ -96,6 +96,7 @@ static void pin_vectors(void) {
   }
   SPI_finish();
   fb_check(fb_load_vectors(engine, ids, vecs, n, d));
+  vecs_d = d;
   pinned_vecs = true;
 }
 
@@ -379,4 +380,50 @@ void freddy_shim_reset(void) {
   engine = NULL;
   pinned_ivfadc = pinned_pq = pinned_ivpq = pinned_vecs = false;
   pinned_d = 0;
+}
+
+/* grouping_pq(int[] ids, int[] group_ids) -> SETOF (id int4, group id int4)   replaces freddy.c:1185-1371 */
+PG_FUNCTION_INFO_V1(grouping_pq);
+Datum grouping_pq(PG_FUNCTION_ARGS) {
+  FuncCallContext* funcctx;
+  UsrFctxGrouping* u;
+  if (SRF_IS_FIRSTCALL()) {
+    MemoryContext old;
+    TupleDesc desc;
+    int n = 0, ng = 0, n_out = 0;
+    int *ids, *groups;
+    int32 *out_ids, *out_groups;
+    funcctx = SRF_FIRSTCALL_INIT();
+    old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    ids = int_array(PG_GETARG_ARRAYTYPE_P(0), &n);
+    groups = int_array(PG_GETARG_ARRAYTYPE_P(1), &ng);
+    pin_vectors();                                   /* the group vectors come from the normalized table */
+    pin_pq(vecs_d);
+    out_ids = palloc(sizeof(int32) * (n ? n : 1));
+    out_groups = palloc(sizeof(int32) * (n ? n : 1));
+    fb_check(fb_grouping_pq(engine, ids, n, groups, ng, out_ids, out_groups, &n_out));
+    u = palloc(sizeof(UsrFctxGrouping));
+    u->ids = out_ids;
+    u->size = n_out;
+    u->nearestGroup = out_groups;                    /* already group ids, not indices */
+    u->groups = NULL;
+    u->iter = 0;
+    u->groupsSize = ng;
+    u->values = palloc(2 * sizeof(char*));
+    u->values[0] = palloc(18);
+    u->values[1] = palloc(18);
+    funcctx->user_fctx = u;
+    desc = CreateTemplateTupleDesc(2);
+    TupleDescInitEntry(desc, 1, "Ids", INT4OID, -1, 0);
+    TupleDescInitEntry(desc, 2, "GroupIds", INT4OID, -1, 0);
+    funcctx->attinmeta = TupleDescGetAttInMetadata(desc);
+    MemoryContextSwitchTo(old);
+  }
+  funcctx = SRF_PERCALL_SETUP();
+  u = (UsrFctxGrouping*)funcctx->user_fctx;
+  if (u->iter >= u->size) SRF_RETURN_DONE(funcctx);
+  snprintf(u->values[0], 18, "%d", u->ids[u->iter]);
+  snprintf(u->values[1], 18, "%d", u->nearestGroup[u->iter]);
+  u->iter++;
+  SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(BuildTupleFromCStrings(funcctx->attinmeta, u->values)));
 }

@@ -89,3 +89,22 @@ def test_shim_knn_join(shim, oracle_mod):
         np.testing.assert_array_equal(rq, np.repeat(qids[:, None], 5, 1))
         np.testing.assert_array_equal(ids, oids)
         _same(raw, od)
+
+
+def test_shim_grouping_pq(shim, oracle_mod):
+    """the seventh SRF behind the shim: grouping_pq(int[], int[]) through the fmgr / SRF protocol"""
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    s = shim()
+    s.load_pq(ix)
+    s.load_vectors_table(ix["vectors"], vec_ids)
+    rng = np.random.default_rng(5)
+    ids = rng.choice(np.arange(1, ix["N"] + 100), size=1500, replace=True).astype(np.int32)
+    groups = np.asarray([77, 5, 1234, 19000], np.int32)
+    got_i, got_g = s.grouping_pq(ids, groups)
+    want_i, want_g, rc = oracle_mod.OracleIndex(ix, flat_pq=True).grouping_pq(ix["vectors"], vec_ids, ids, groups)
+    assert rc == len(want_i)
+    np.testing.assert_array_equal(got_i, want_i)
+    np.testing.assert_array_equal(got_g, want_g)
+    with pytest.raises(RuntimeError):
+        s.grouping_pq(ids, np.asarray([5, 10 ** 8], np.int32))
