@@ -94,3 +94,30 @@ def test_pv_readme_shape_and_udf_mirror(eng, oracle_mod):
     rows = udf.k_nearest_neighbour(vec_to_bytea(q[1]), 4)
     e2, _ = oracle_mod.knn_exact(ix["vectors"], vec_ids, q[1:2], 4)
     assert [r[0] for r in rows] == [int(i) for i in e2[0]]
+
+
+def test_edge_cases(eng, oracle_mod):
+    from freddy_b200 import FreddyError, _lib
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    eng.load_ivfadc_index(ix)
+    eng.load_pq_index(ix)
+    eng.load_vectors(vec_ids, ix["vectors"])
+    empty = np.zeros((0, ix["d"]), np.float32)
+    assert eng.knn_exact(empty, 5)[0].shape == (0, 5)
+    assert eng.ivfadc_search_pv(empty, 5, 20, 3)[0].shape == (0, 5)
+    q = queries_from(ix, 3, seed=1)
+    with pytest.raises(FreddyError) as ei:
+        eng.knn_exact(q, 33)                                       # the exact scan keeps at most 32 keys per query
+    assert ei.value.code == _lib.FB_ERR_UNSUPPORTED
+    with pytest.raises(FreddyError) as ei:
+        eng.ivfadc_search_pv(q, 60, 20, 3)                         # pvf * k beyond the candidate buffer
+    assert ei.value.code == _lib.FB_ERR_UNSUPPORTED
+    with pytest.raises(FreddyError):
+        eng.ivfadc_search_pv(q, 5, 0, 3)
+    ids, s = eng.knn_exact(q, 4, np.asarray([10 ** 8], np.int32))  # no target row exists: nothing but padding
+    assert (ids == -1).all() and (s == 0).all()
+    cids, codes = eng.encode_ivfadc(empty)
+    assert cids.shape == (0,) and codes.shape == (0, 12)
+    gi, gg = eng.grouping_pq(np.zeros(0, np.int32), np.asarray([5], np.int32))
+    assert len(gi) == 0 and len(gg) == 0
