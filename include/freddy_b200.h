@@ -212,6 +212,9 @@ enum {
   FB_OPT_PIPE_RAMP = 14,       /* 1: the first and last pipeline chunks are shortened (quarter, half); default 0  */
   FB_OPT_CUDA_GRAPHS = 15,     /* 1 (default): host-buffer fb_ivfadc_search calls with <= 16 queries replay a
                                   captured CUDA graph of the whole call (upload, kernels, download)      */
+  FB_OPT_ZERO_COPY_UPLOAD = 16, /* 1 (default): fb_ivfadc_search batches whose query buffer is pinned (page-locked) host
+                                  memory are read by the coarse kernel directly (mapped pointer), which also writes
+                                  the device copy: the upload overlaps the coarse step; pageable buffers are copied */
   FB_OPT_PIPE_DEBUG = 11,      /* timing aid, results are NOT valid: 1 = producers only (no scan),
                                   2 = scan only (LUT scratch left as is)                           */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the

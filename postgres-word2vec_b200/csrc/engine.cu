@@ -159,6 +159,10 @@ struct fb_engine {
   std::vector<GraphEntry> graphs;
   uint64_t graph_epoch = 0;        // bumped by loads / option changes: kernel arguments are baked into a graph
   int use_graphs = 1;
+  // set by fb_ivfadc_search for large batches in pinned host memory: the coarse kernel reads the queries through
+  // this host-mapped pointer and writes the device copy (d_q) itself, so the upload overlaps the coarse step
+  const float* coarse_src = nullptr;
+  int zero_copy = 1;
   float* pin_q = nullptr; int32_t* pin_ids = nullptr; float* pin_d = nullptr; int32_t* pin_flag = nullptr;
   size_t pin_q_floats = 0;
   int pipe_shape = 0;
@@ -410,8 +414,9 @@ int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k, int64_
   auto kern = e->packed_fp32 ? coarse_select_kernel_t<QT, true> : coarse_select_kernel_t<QT, false>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(nq + QT - 1) / QT, kCoarseThreads, smem, e->stream>>>(
-      d_q + (size_t)q0 * e->d, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k, e->probes.p + (size_t)q0 * w,
-      e->qflags.p + q0, e->force_exact ? 1 : 0, e->one);
+      (e->coarse_src ? e->coarse_src : d_q) + (size_t)q0 * e->d, nq, e->d, e->coarseT.p, e->C, e->Cs, e->fine.list_len.p, w, k,
+      e->probes.p + (size_t)q0 * w, e->qflags.p + q0, e->force_exact ? 1 : 0, e->one,
+      e->coarse_src ? const_cast<float*>(d_q) + (size_t)q0 * e->d : nullptr);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
@@ -1213,8 +1218,20 @@ int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w, i
   FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
-  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  if ((rc = ivfadc_dev(e, e->q_stage.p, nq, k, w, e->id_stage.p, e->dist_stage.p))) return rc;
+  const float* mapped = nullptr;
+  if (e->zero_copy && nq > 32 && k <= 30 && w <= 31) {      // the batched coarse kernel will run (it does the staging)
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, queries) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
+      mapped = static_cast<const float*>(attr.devicePointer);
+    else
+      cudaGetLastError();
+  }
+  if (mapped == nullptr)
+    FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  e->coarse_src = mapped;
+  rc = ivfadc_dev(e, e->q_stage.p, nq, k, w, e->id_stage.p, e->dist_stage.p);
+  e->coarse_src = nullptr;
+  if (rc) return rc;
   FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1347,6 +1364,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_PIPE_SHAPE: e->pipe_shape = (int)value; return FB_OK;
     case FB_OPT_PIPE_RAMP: e->pipe_ramp = value != 0; return FB_OK;
     case FB_OPT_CUDA_GRAPHS: e->use_graphs = value != 0; return FB_OK;
+    case FB_OPT_ZERO_COPY_UPLOAD: e->zero_copy = value != 0; return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");

@@ -111,17 +111,26 @@ coarse_select_kernel_t(const float* __restrict__ queries, int nq, int d,
                      const int32_t* __restrict__ list_len, int w, int k,
                      int32_t* __restrict__ probes,      // [nq][w]
                      uint32_t* __restrict__ qflags,      // [nq]
-                     int force_exact, float one) {
+                     int force_exact, float one, float* __restrict__ q_copy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* qs = reinterpret_cast<float*>(smem_raw);     // [d][QT]
   float* dist = qs + (size_t)d * QT;           // [QT][Cs]
   const int q0 = blockIdx.x * QT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  // stage the tile's queries (coalesced rows -> [d][QT]).  `queries` may be pinned HOST memory mapped into the
+  // device address space: the upload then happens here, overlapped across CTAs with the distance work, and
+  // `q_copy` receives the device copy the later stages read (fb_ivfadc_search, large batches).
+#pragma unroll 1
   for (int idx = tid; idx < d * QT; idx += kCoarseThreads) {
-    int i = idx / QT, qq = idx % QT;
-    int q = q0 + qq;
-    qs[idx] = (q < nq) ? queries[(size_t)q * d + i] : 0.0f;
+    const int qq = idx / d, i = idx - qq * d;
+    const int q = q0 + qq;
+    float v = 0.0f;
+    if (q < nq) {
+      v = queries[(size_t)q * d + i];
+      if (q_copy != nullptr) q_copy[(size_t)q * d + i] = v;
+    }
+    qs[i * QT + qq] = v;
   }
   __syncthreads();
 

@@ -107,3 +107,10 @@ def test_host_buffer_call_matches_device_path(eng):
         eng.synchronize()
         np.testing.assert_array_equal(ids, oi.cpu().numpy())
         np.testing.assert_array_equal(d.view(np.uint32), od.cpu().numpy().view(np.uint32))
+        # pinned host buffers: the coarse kernel reads the queries through the mapped pointer (zero-copy upload)
+        hq = torch.from_numpy(q).pin_memory()
+        hi = torch.empty(len(q), 5, dtype=torch.int32).pin_memory()
+        hd = torch.empty(len(q), 5, dtype=torch.float32).pin_memory()
+        eng.ivfadc_search_ptr(hq.data_ptr(), len(q), 5, 10, hi.data_ptr(), hd.data_ptr())
+        np.testing.assert_array_equal(hi.numpy(), ids)
+        np.testing.assert_array_equal(hd.numpy().view(np.uint32), d.view(np.uint32))
