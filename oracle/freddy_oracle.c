@@ -637,6 +637,16 @@ static const float* ivpq_vector_of(const FoIvpqIndex* ix, int32_t id) {   /* INN
   return NULL;
 }
 
+/* computePQDistanceInt16 over getPrecomputedDistancesDouble's table (index_utils.c:457-475, :1126-1133) */
+static float pq_distance_pairs(const float* lut, const int16_t* codes, int m, int K) {
+  float distance = 0;
+  for (int l = 0; l < m / 2; l++) {
+    float pair = lut[(size_t)(2 * l) * K + codes[2 * l]] + lut[(size_t)(2 * l + 1) * K + codes[2 * l + 1]];
+    distance += pair;
+  }
+  return distance;
+}
+
 /* ref: ivpq_search_in.c:197-684 (first-call body).  The target-list mode only reorders the
  * loop nest (row-major collect, then query-major evaluate, :546-607) except for the
  * `targetCounts < k*alpha_original` skip (:553-557), which is kept. */
@@ -648,7 +658,12 @@ int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k
   const int d = ix->d, m = ix->m, K = ix->K, sub = d / m, cells = ix->Kc * ix->Kc;
   int alpha = alpha_original;
   if (pvf < 1) pvf = 1;                              /* :206-208 */
-  if ((method == 0 || method == 2) && alpha * k > double_threshold) return -10;   /* pair-LUT variant (:261-275) not restated */
+  /* pair-LUT variant (:261-275, index_utils.c:457-475): preDists[pair][c0 + K*c1] = d(pos 2l, c0) + d(pos 2l+1, c1),
+   * the row's distance = sum over the positions/2 pairs (a trailing odd position is never looked at).  The pair
+   * sums are formed on the fly here instead of materialising the K*K table; same fp32 additions in the same order.
+   * codes2[] is an int16 array (:417,:447-451): the pair code overflows it when K*K > 32768. */
+  const int double_codes = (method == 0 || method == 2) && alpha * k > double_threshold;
+  if (double_codes && (int64_t)K * K > 32768) return -10;
   const int kk = k * pvf;
   int64_t rounds = 0, pairs = 0;
 
@@ -703,7 +718,8 @@ int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k
         }
         float dist;
         if (method == 1) dist = fo_square_distance(queries + (size_t)q * d, vec, d);
-        else dist = fo_pq_distance_int16(luts + (size_t)q * m * K, codes, m, K);
+        else dist = double_codes ? pq_distance_pairs(luts + (size_t)q * m * K, codes, m, K)
+                                 : fo_pq_distance_int16(luts + (size_t)q * m * K, codes, m, K);
         if (dist < max_dists[q]) {
           if (method == 2) pv_append(pv + (size_t)q * (BATCH + kk), BATCH + kk, kk, &fill[q], &max_dists[q], ix->ids[r], dist, vec);
           else { fo_update_topk(topks + (size_t)q * k, dist, ix->ids[r], k); max_dists[q] = topks[(size_t)q * k + k - 1].distance; }
@@ -719,7 +735,8 @@ int fo_ivpq_search_in(const FoIvpqIndex* ix, const float* queries, int nq, int k
           const float* vec = (method != 0) ? ivpq_vector_of(ix, ix->ids[r]) : NULL;
           float dist;
           if (method == 1) dist = fo_square_distance(queries + (size_t)q * d, vec, d);
-          else dist = fo_pq_distance_int16(luts + (size_t)q * m * K, ix->codes + (size_t)r * m, m, K);
+          else dist = double_codes ? pq_distance_pairs(luts + (size_t)q * m * K, ix->codes + (size_t)r * m, m, K)
+                                   : fo_pq_distance_int16(luts + (size_t)q * m * K, ix->codes + (size_t)r * m, m, K);
           if (dist < max_dists[q]) {
             if (method == 2) pv_append(pv + (size_t)q * (BATCH + kk), BATCH + kk, kk, &fill[q], &max_dists[q], ix->ids[r], dist, vec);
             else { fo_update_topk(topks + (size_t)q * k, dist, ix->ids[r], k); max_dists[q] = topks[(size_t)q * k + k - 1].distance; }

@@ -1846,8 +1846,12 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
   const int d = e->ivpq_d, m = cb.m, K = cb.K, Kc = e->ivpq_Kc, cells = Kc * Kc;
   if (cb.m != e->ivpq.m || cb.m * cb.sub != d) return fail(e, FB_ERR_INVALID, "ivpq codebook / table shape mismatch");
   if (method != 0 && e->vec_d != d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, index d=%d", e->vec_d, d);
-  if (method != 1 && (int64_t)alpha * k > double_threshold)
-    return fail(e, FB_ERR_UNSUPPORTED, "alpha*k > double_threshold selects the pair-LUT variant (index_utils.c:457-475), not built");
+  // alpha*k > double_threshold selects the pair-LUT variant (ivpq_search_in.c:261-275); decided once from the
+  // alpha of the call, like the reference.  Its pair codes live in an int16 array (:417, :447-451).
+  const bool pair_sums = method != 1 && (int64_t)alpha * k > double_threshold;
+  if (pair_sums && (int64_t)e->cb[FB_CB_IVPQ].K * e->cb[FB_CB_IVPQ].K > 32768)
+    return fail(e, FB_ERR_REFERENCE_UB, "pair-LUT variant with K=%d: the reference's int16 pair codes overflow (ivpq_search_in.c:447-451)",
+                e->cb[FB_CB_IVPQ].K);
   if ((int64_t)k * pvf > kJoinMaxP) return fail(e, FB_ERR_UNSUPPORTED, "k*pvf=%lld > %d", (long long)k * pvf, kJoinMaxP);
   if (nq == 0) return FB_OK;
   if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
@@ -1928,6 +1932,7 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
   prm.d = d; prm.m = m; prm.K = K; prm.Kc = Kc; prm.k = k; prm.pvf = pvf; prm.method = method;
   prm.n_targets_sql = n_targets; prm.confidence = confidence; prm.stat_total = (int)e->ivpq_stats_host[cells];
   prm.skip_below = use_target_lists ? k * alpha : 0;
+  prm.pair_sums = pair_sums ? 1 : 0;
   while (n_active > 0) {                                                                        // :299
     prm.min_target = (int)std::min<int64_t>((int64_t)k * cur_alpha, 0x7fffffff);
     FB_CUDA(e, cudaMemcpyAsync(e->j_active.p, active.data(), (size_t)n_active * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));

@@ -35,7 +35,27 @@ struct JoinParams {
   int stat_total;                    // (int)statistics[cells]
   int skip_below;                    // target-list mode: k * alpha_original, else 0
   int last_iteration;                // every active query exhausted all cells
+  int pair_sums;                     // alpha*k > long_codes_threshold: distances as sums of pair sums (index_utils.c:457-475)
 };
+
+// Pair-LUT variant (getPrecomputedDistancesDouble, index_utils.c:457-475 + computePQDistanceInt16): the table entry
+// of a code pair is d(pos 2l, c0) + d(pos 2l+1, c1); the row distance is the sequential sum of the m/2 pair entries
+// (a trailing odd position is never looked at).  The pair sums are formed on the fly: same additions, same order.
+__device__ __forceinline__ float adc_row_pairs(const CodeTableDev& tab, int blk, int lane_in_blk,
+                                               const float* __restrict__ lut, int K) {
+  float acc = 0.0f;
+  const uint2* up = tab.units + ((size_t)blk * tab.U) * 32 + lane_in_blk;
+  const int pairs = tab.m / 2;
+  for (int u = 0; u < tab.U; u++) {
+    const uint2 v = up[u * 32];
+    const int p = 4 * u;
+    if (p / 2 < pairs)
+      acc = xadd(acc, xadd(lut[(size_t)(p + 0) * K + ((v.x & 0xFFFFu) >> 2)], lut[(size_t)(p + 1) * K + (v.x >> 18)]));
+    if (p / 2 + 1 < pairs)
+      acc = xadd(acc, xadd(lut[(size_t)(p + 2) * K + ((v.y & 0xFFFFu) >> 2)], lut[(size_t)(p + 3) * K + (v.y >> 18)]));
+  }
+  return acc;
+}
 
 // index_utils.c:673-682, float/double mix as written there
 __device__ __forceinline__ float confidence_hyp(int expect, int size, float p, int stat_size) {
@@ -388,7 +408,7 @@ ivpq_scan_kernel(const float* __restrict__ queries, const int32_t* __restrict__ 
         }
         dist = acc;
       } else {
-        dist = adc_row_global(ttab, t >> 5, t & 31, slut, K);
+        dist = prm.pair_sums ? adc_row_pairs(ttab, t >> 5, t & 31, slut, K) : adc_row_global(ttab, t >> 5, t & 31, slut, K);
       }
       keys[slot] = make_key(dist, (uint32_t)t);                                   // t = arrival order
     }

@@ -58,6 +58,18 @@ def test_knn_join_edge_cases(setup):
     ids, d = e.ivpq_search_in(q, 5, dup, 2, 2, 2, True, 0.6)
     eids, ed, rc, _ = oi.search_in(q, 5, dup, 2, 2, 2, True, 0.6)
     assert_same_topk(ids, d, eids, ed, "duplicate / unknown targets")
-    with pytest.raises(FreddyError) as ei:
-        e.ivpq_search_in(q, 5, targets, 3, 2, 0, False, 0.8, double_threshold=10)            # pair-LUT variant
-    assert ei.value.code == _lib.FB_ERR_UNSUPPORTED
+    assert FreddyError is not None and _lib is not None
+
+
+@pytest.mark.parametrize("method", [0, 2])
+@pytest.mark.parametrize("use_tl", [False, True])
+def test_knn_join_pair_lut_variant(setup, method, use_tl):
+    """alpha*k > double_threshold: distances are sums of pair sums (getPrecomputedDistancesDouble,
+    index_utils.c:457-475); the oracle's form is pinned to the real SRF in
+    test_oracle_vs_reference_srf.py::test_ivpq_search_in_pair_lut_variant"""
+    e, oi, targets, q = setup
+    for (k, alpha, pvf, conf) in ((5, 3, 4, 0.8), (3, 40, 20, 0.8), (5, 100, 20, 0.8)):
+        ids, d = e.ivpq_search_in(q, k, targets, alpha, pvf, method, use_tl, conf, double_threshold=0)
+        eids, ed, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf, 0)
+        assert rc == 0
+        assert_same_topk(ids, d, eids, ed, f"pair-LUT method={method} tl={use_tl} k={k} alpha={alpha}")

@@ -207,3 +207,26 @@ def test_grouping_pq_against_the_real_srf():
         rs.grouping_pq(ids, np.asarray([5, 10 ** 8], np.int32))
     assert oi.grouping_pq(vectors, vec_ids, ids, [5, 10 ** 8])[2] == -1
     assert oi.grouping_pq(vectors, vec_ids, ids, [5, 5])[2] == -1
+
+
+@pytest.mark.parametrize("method", [0, 2])
+@pytest.mark.parametrize("use_tl", [False, True])
+def test_ivpq_search_in_pair_lut_variant(ref, oracle_mod, method, use_tl):
+    """alpha*k > double_threshold: the reference switches to getPrecomputedDistancesDouble (index_utils.c:457-475),
+    whose distances are sums of PAIR sums — different fp32 roundings from the single-position chain"""
+    ivpq, vec, vec_ids, targets, q = _ivpq_setup(m=12, K=64)        # K*K = 4096 fits the reference's int16 pair codes
+    oi = oracle_mod.OracleIvpq(ivpq, vec, vec_ids)
+    qids = np.arange(500, 500 + len(q), dtype=np.int32)
+    differs = False
+    for (k, alpha, pvf, conf) in ((5, 3, 4, 0.8), (3, 40, 20, 0.8)):
+        s = ref()
+        s.load_ivpq(ivpq, vec, vec_ids)
+        rq, rids, rraw = s.ivpq_search_in(q, qids, k, targets, alpha, pvf, method, use_tl, conf, 0)
+        oids, od, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf, 0)
+        assert rc == 0
+        np.testing.assert_array_equal(oids, rids, err_msg=f"pair-LUT method={method} tl={use_tl} k={k} alpha={alpha}")
+        _same(od, rraw)
+        _, od1, _, _ = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf)
+        differs |= bool((od1.view(np.uint32) != od.view(np.uint32)).any())
+    if method == 0:
+        assert differs, "the pair-sum chain should round differently from the single-position chain somewhere"
