@@ -165,3 +165,47 @@ def test_encode_against_reference_update_codebook():
     assert rc == 0
     np.testing.assert_array_equal(got, want)
     assert (got[:40] == 3).all()
+
+
+def test_sql_level_oracles_are_built_from_pinned_pieces():
+    """k_nearest_neighbour / k_nearest_neighbour_ivfadc_pv are plpgsql in the reference; their oracle restatement
+    (oracle.knn_exact, oracle.ivfadc_search_pv) must equal the composition of the reference's OWN compiled pieces:
+    the real ivfadc_search SRF (candidates) and the real cosine_similarity_bytea (similarities), ordered by
+    (similarity desc, table row asc) and cut at k."""
+    from helpers import queries_from, small_index
+    from oracle import oracle
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built")
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    vectors = ix["vectors"]
+    q = queries_from(ix, 12, seed=31, noise=0.03)
+    rs = oracle.ReferenceSession()
+    R = rs.R
+
+    def ref_sim(a, b):
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        return np.float32(R.ref_cosine_similarity_bytea(a.ctypes.data, b.ctypes.data, len(a)))
+
+    # (1) the vectorised float4 chain == the reference's scalar loop, bit for bit
+    sims = oracle.cosine_similarity_bytea_many(q[0], vectors[:400])
+    want = np.array([ref_sim(q[0], v) for v in vectors[:400]], np.float32)
+    np.testing.assert_array_equal(sims.view(np.uint32), want.view(np.uint32))
+    # (2) post-verification: real SRF candidates + real similarities
+    k, pvf, w = 4, 5, 3
+    rs.load_ivfadc(ix, w)
+    cand, _, _ = rs.ivfadc_search(q, k * pvf)
+    got_ids, got_s = oracle.ivfadc_search_pv(oracle.OracleIndex(ix), vectors, vec_ids, q, k, pvf, w, threads=2)
+    row_of = {int(i): r for r, i in enumerate(vec_ids)}
+    for qi in range(len(q)):
+        rows = [row_of[int(c)] for c in cand[qi] if int(c) in row_of]
+        scored = sorted(((-float(ref_sim(q[qi], vectors[r])), r) for r in rows))[:k]
+        assert [int(vec_ids[r]) for _, r in scored] == [int(i) for i in got_ids[qi] if i >= 0]
+        np.testing.assert_array_equal(np.array([-s for s, _ in scored], np.float32).view(np.uint32),
+                                      got_s[qi][:len(scored)].view(np.uint32))
+    # (3) exact k-NN over a slice of the table
+    sub_ids = vec_ids[:600]
+    e_ids, e_s = oracle.knn_exact(vectors[:600], sub_ids, q[:3], 5)
+    for qi in range(3):
+        scored = sorted(((-float(ref_sim(q[qi], vectors[r])), r) for r in range(600)))[:5]
+        assert [int(sub_ids[r]) for _, r in scored] == e_ids[qi].tolist()
