@@ -102,5 +102,34 @@ def srf_golden():
     print("wrote srf_golden.npz")
 
 
+def srf_golden_ext():
+    """second fixture (tests/golden/srf_golden_ext.npz): the reference's own grouping_pq SRF and updateCodebook
+    assignments on the same tiny seeded index, plus the word-vector table they read"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "postgres-word2vec_b200"))
+    from freddy_b200.index_build import make_synthetic_index
+    ix = make_synthetic_index(3000, d=24, m=6, K=16, C=12, n_train=3000, n_clusters=8, sigma=0.5, kmeans_iters=4,
+                              seed=99, device="cpu", with_pq=True, keep_vectors=True)
+    vec = ix.pop("vectors_t").numpy().copy()
+    vec[700] = vec[40]                                           # two identical group vectors (ids 41 and 701)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    rng = np.random.default_rng(11)
+    S = oracle.ReferenceSession()
+    S.load_pq(ix)
+    S.load_vectors_table(vec, vec_ids)
+    in_ids = rng.choice(np.arange(1, 3100), size=900, replace=True).astype(np.int32)
+    groups = np.asarray([701, 41, 7, 2500, 1234], np.int32)
+    g_ids, g_groups = S.grouping_pq(in_ids, groups)
+    new_rows = (vec[rng.choice(len(vec), 200, replace=False)] +
+                0.02 * rng.standard_normal((200, vec.shape[1])).astype(np.float32)).astype(np.float32)
+    assign = oracle.reference_update_codebook_assignments(new_rows, ix["pq_codebook"])
+    np.savez_compressed(
+        os.path.join(HERE, "srf_golden_ext.npz"),
+        d=ix["d"], m=ix["m"], K=ix["K"], N=ix["N"], ids=ix["ids"], pq_codebook=ix["pq_codebook"], pq_codes=ix["pq_codes"],
+        vectors=vec, grouping_in_ids=in_ids, grouping_groups=groups, grouping_out_ids=g_ids, grouping_out_groups=g_groups,
+        encode_rows=new_rows, encode_pq_codes=assign)
+    print("wrote srf_golden_ext.npz")
+
+
 if __name__ == "__main__":
     main()
+    srf_golden_ext()

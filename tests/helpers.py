@@ -38,3 +38,10 @@ def srf_golden():
     ix = {k: (int(g[k]) if k in ("d", "m", "K", "C", "N") else g[k]) for k in
           ("d", "m", "K", "C", "N", "coarse", "residual_codebook", "ids", "coarse_ids", "codes", "pq_codebook", "pq_codes")}
     return ix, g
+
+
+def srf_golden_ext():
+    """grouping_pq / updateCodebook outputs of the reference's own code on the tiny seeded index
+    (tests/golden/make_golden.py::srf_golden_ext)"""
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srf_golden_ext.npz"))

@@ -42,3 +42,20 @@ def test_grouping_pq(eng, oracle_mod, shape):
     with pytest.raises(FreddyError) as ei:
         eng.grouping_pq(ids, np.asarray([5, 10 ** 8], np.int32))
     assert "Group ids do not exist" in str(ei.value)
+
+
+def test_against_reference_golden_ext(eng):
+    """the CUDA engine directly against committed outputs of the reference's own grouping_pq SRF and
+    updateCodebook (tests/golden/srf_golden_ext.npz)"""
+    from freddy_b200 import _lib
+    from helpers import srf_golden_ext
+    g = srf_golden_ext()
+    ix = {"d": int(g["d"]), "m": int(g["m"]), "K": int(g["K"]), "N": int(g["N"]), "ids": g["ids"],
+          "pq_codebook": g["pq_codebook"], "pq_codes": g["pq_codes"]}
+    eng.load_pq_index(ix)
+    eng.load_vectors(np.asarray(g["ids"], np.int32), g["vectors"])
+    ids, groups = eng.grouping_pq(g["grouping_in_ids"], g["grouping_groups"])
+    np.testing.assert_array_equal(ids, g["grouping_out_ids"])
+    np.testing.assert_array_equal(groups, g["grouping_out_groups"])
+    eng.load_codebook(_lib.FB_CB_PQ, g["pq_codebook"])
+    np.testing.assert_array_equal(eng.encode_pq(g["encode_rows"]), g["encode_pq_codes"])

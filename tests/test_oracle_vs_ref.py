@@ -209,3 +209,22 @@ def test_sql_level_oracles_are_built_from_pinned_pieces():
     for qi in range(3):
         scored = sorted(((-float(ref_sim(q[qi], vectors[r])), r) for r in range(600)))[:5]
         assert [int(sub_ids[r]) for _, r in scored] == e_ids[qi].tolist()
+
+
+def test_oracle_against_committed_extended_golden():
+    """no /root/reference needed: grouping_pq and the quantisation rule against outputs of the reference's own
+    code committed in tests/golden/srf_golden_ext.npz"""
+    from helpers import srf_golden_ext
+    from oracle import oracle
+    g = srf_golden_ext()
+    ix = {"d": int(g["d"]), "m": int(g["m"]), "K": int(g["K"]), "C": 0, "N": int(g["N"]), "ids": g["ids"],
+          "pq_codebook": g["pq_codebook"], "pq_codes": g["pq_codes"]}
+    oi = oracle.OracleIndex(ix, flat_pq=True)
+    ids, groups, rc = oi.grouping_pq(g["vectors"], g["ids"], g["grouping_in_ids"], g["grouping_groups"])
+    assert rc == len(g["grouping_out_ids"])
+    np.testing.assert_array_equal(ids, g["grouping_out_ids"])
+    np.testing.assert_array_equal(groups, g["grouping_out_groups"])
+    assert 701 not in set(groups.tolist()) and 41 in set(groups.tolist())      # identical vectors: the lower id wins
+    _, codes, rc = oracle.encode(g["encode_rows"], g["pq_codebook"])
+    assert rc == 0
+    np.testing.assert_array_equal(codes, g["encode_pq_codes"])
