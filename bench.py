@@ -184,7 +184,10 @@ class ReferencePool:
         import multiprocessing as mp
         import shutil
         import tempfile
-        self.dir = tempfile.mkdtemp(prefix="fb_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        need = sum(np.asarray(ix[k]).nbytes for k in ("coarse", "residual_codebook", "ids", "coarse_ids", "codes"))
+        shm = "/dev/shm"
+        use_shm = os.path.isdir(shm) and shutil.disk_usage(shm).free > 2 * need + (64 << 20)
+        self.dir = tempfile.mkdtemp(prefix="fb_ref_", dir=shm if use_shm else None)
         self._rm = shutil.rmtree
         for k in ("coarse", "residual_codebook", "ids", "coarse_ids", "codes"):
             np.save(os.path.join(self.dir, k + ".npy"), np.ascontiguousarray(ix[k]))
@@ -240,7 +243,13 @@ def main():
         del vec
         from oracle import oracle
         use_ref = os.path.exists(oracle.REF_SO)
-        pool = ReferencePool(a, ix) if use_ref else None
+        pool = None
+        if use_ref:
+            try:
+                pool = ReferencePool(a, ix)
+            except Exception as ex:
+                print(f"reference pool unavailable ({ex}); using the oracle port", file=sys.stderr)
+                use_ref = False
         vals = []
         budget = max(1.0, a.cpu_seconds / max(1, a.steps))
         for i in range(a.warmup + a.steps):
@@ -454,8 +463,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle
+        pool = None
         if os.path.exists(oracle.REF_SO):       # the reference's own SRF, one backend per core
-            pool = ReferencePool(a, ix)
+            try:
+                pool = ReferencePool(a, ix)
+            except Exception as ex:              # e.g. no room for the table copies: fall back to the oracle port
+                print(f"reference pool unavailable ({ex}); using the oracle port", file=sys.stderr)
+                pool = None
+        if pool is not None:
             cpu = reference_arm(a, ix, h_q.numpy(), a.cpu_seconds, pool)
             pool.close()
             n_chk = min(len(cpu["ids"]), 256)    # and our result for the same queries must be its result
