@@ -148,7 +148,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
 
   // Register re-balancing between the roles (warpgroup-wide setmaxnreg): the CTA is launched with
   // Cfg::kLaunchRegs registers per thread; the scan-side warpgroups give theirs back down to kScanRegs,
-  // the producer warpgroups take them (e.g. 768 * 56 + 256 * 88 = 64 K), so the LUT build can keep its
+  // the producer warpgroups take them (12 + 14 warps: 512 * 64 + 384 * 80 <= 896 * 72), so the LUT build can keep its
   // operands for several dimensions in flight while the scan warps only need a few dozen registers.
   if (warp >= kPipeWarps - kPipeProdWarps) {
     if constexpr (kPipeProdRegs > Cfg::kLaunchRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeProdRegs));
@@ -157,12 +157,12 @@ ivfadc_pipe_kernel(const PipeArgs a) {
   }
 
   // ============================================================ producers
-  // 8 warps = 2 job halves x 4 warps; a thread owns 4 adjacent codes (two packed pairs) x 8 jobs of the
-  // 16-job group: per dimension one 16-byte read of its codes and two broadcast 16-byte reads of
-  // residuals feed 48 packed operations (shared-memory wavefronts per operation: 0.17).
+  // PW warps = PW/4 job splits x 4 warps (128 code threads); a thread owns 4 adjacent codes (two packed pairs)
+  // x JT jobs of the group: per dimension one 16-byte read of its codes and JT/4 broadcast 16-byte reads of
+  // residuals feed 6*JT packed operations (JT = 8: shared-memory wavefronts per operation 0.17).
   if (warp >= kPipeWarps - kPipeProdWarps) {
     const int pt = (warp - (kPipeWarps - kPipeProdWarps)) * kWarp + lane;   // 0..255
-    const int half = pt >> 7, ct = pt & 127;            // job split (8 jobs each), code thread
+    const int half = pt >> 7, ct = pt & 127;            // job split index (JT jobs each), code thread
     const int slice = blockIdx.x % a.n_slices, group = blockIdx.x / a.n_slices;
     if (a.lut_njobs <= 0 || group >= a.n_groups) return;
     const int pos = slice / a.tiles, tile = slice % a.tiles;
