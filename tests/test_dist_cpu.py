@@ -66,3 +66,42 @@ def test_two_rank_gather_matches_single(oracle_mod):
         assert p.exitcode == 0
     np.testing.assert_array_equal(gi, eids)
     np.testing.assert_array_equal(gd.view(np.uint32), ed.view(np.uint32))
+
+
+def _worker_vocab(rank, world, port, vectors, vec_ids, q, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from freddy_b200.dist import allgather_merge_topk_desc, shard_range
+    from oracle import oracle
+    b, e = shard_range(len(vectors), rank, world)                  # this rank's rows of the word-vector table
+    ids, s = oracle.knn_exact(vectors[b:e], vec_ids[b:e], q, k)
+    gi, gs = allgather_merge_topk_desc(torch.from_numpy(ids), torch.from_numpy(s))
+    if rank == 1:
+        out.put((gi.numpy(), gs.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_vocabulary_sharded_exact_knn(oracle_mod):
+    """exact k-NN with the vocabulary split over two ranks + one all-gather == the single-rank scan, incl. duplicated
+    vectors whose equal similarities straddle the shard boundary (global row order must survive the merge)"""
+    ix = small_index()
+    vectors = ix["vectors"][:3001].copy()
+    vec_ids = np.asarray(ix["ids"][:3001], np.int32)
+    vectors[2000:2010] = vectors[100:110]                          # duplicates in the other shard
+    q = np.ascontiguousarray(vectors[[100, 105, 2500, 7]], np.float32)
+    k = 6
+    eids, es = oracle_mod.knn_exact(vectors, vec_ids, q, k)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_vocab, args=(r, 2, port, vectors, vec_ids, q, k, out)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    gi, gs = out.get(timeout=120)
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    np.testing.assert_array_equal(gi, eids)
+    np.testing.assert_array_equal(gs.view(np.uint32), es.view(np.uint32))
