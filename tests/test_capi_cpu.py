@@ -43,3 +43,52 @@ def test_round_through_text(lib, oracle_mod):
     L = oracle_mod.lib()
     for v in (0.0, 0.1234567, 1.9999996, 1000.0, 3.4e-7):
         assert lib.fb_round_through_text(v) == L.fo_round_through_text(v)
+
+
+def test_option_and_status_constants_match_the_header():
+    """the ctypes mirror must use the header's numbers (FB_OPT_*, FB_ERR_*, FB_CB_*) and the counters struct must
+    have the header's fields in the header's order"""
+    from freddy_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "freddy_b200.h")).read()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(FB_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    assert len(consts) > 15
+    checked = 0
+    for name, val in consts.items():
+        if hasattr(_lib, name):
+            assert getattr(_lib, name) == val, f"{name}: header {val}, _lib.py {getattr(_lib, name)}"
+            checked += 1
+    assert checked >= 15, checked
+    body = re.search(r"typedef struct \{(.*?)\} fb_counters;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            fields += [f.strip() for f in decl.split(None, 1)[1].split(",")]
+    assert fields == [n for n, _ in _lib.Counters._fields_], (fields, [n for n, _ in _lib.Counters._fields_])
+
+
+def test_bench_reference_pool_smoke(oracle_mod):
+    """bench.py's CPU arm: the reference's own SRF in spawned single-threaded backends over memory-mapped tables
+    gives the oracle port's bits (tiny index; skipped when oracle/_ref is not built)"""
+    import argparse
+    import sys
+    if not os.path.exists(oracle_mod.REF_SO):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, ROOT)
+    import bench
+    from helpers import queries_from, small_index
+    ix = small_index()
+    a = argparse.Namespace(k=5, w=4, d=ix["d"])
+    pool = bench.ReferencePool(a, ix)
+    try:
+        pool.procs = min(pool.procs, 4)
+        q = queries_from(ix, 37, seed=3)
+        ids, raw, dt = pool.run(q)
+    finally:
+        pool.close()
+    eids, ed, rc, _ = oracle_mod.OracleIndex(ix).ivfadc_search(q, 5, 4)
+    assert rc == 0 and dt > 0
+    import numpy as np
+    np.testing.assert_array_equal(ids, eids)
+    np.testing.assert_array_equal(raw.view(np.uint32), ed.view(np.uint32))
