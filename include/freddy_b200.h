@@ -152,6 +152,9 @@ int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids
  * knn_in_exact(bytea, k, int[]) (:1026-1038): similarity = cosine_similarity_bytea (core_functions.c:67-81,
  * sequential float4 dot), ORDER BY similarity DESC FETCH FIRST k.  Equal similarities are ordered by table
  * row (SQL leaves that order to the executor).  Fewer than k rows: id -1, similarity 0.  k <= 32.
+ * The whole-table form (and the analogy scans above) runs as a tensor-core pre-filter (bf16 tcgen05.mma over the
+ * TMA-staged table, error bound proven in csrc/prefilter_kernels.cuh) followed by the fp32 chain on the
+ * candidates: same ids, same similarity bits as the plain fp32 scan (FB_OPT_PREFILTER = 0).
  * fb_ivfadc_search_pv: k_nearest_neighbour_ivfadc_pv(bytea, k) (:574-591) with pvf = get_pvf(), w = get_w():
  * ivfadc_search(v, pvf*k) INNER JOIN vectors ON idx = id, re-ranked by cosine_similarity_bytea.          */
 int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
@@ -217,6 +220,9 @@ enum {
                                   the device copy: the upload overlaps the coarse step; pageable buffers are copied */
   FB_OPT_PIPE_DEBUG = 11,      /* timing aid, results are NOT valid: 1 = producers only (no scan),
                                   2 = scan only (LUT scratch left as is)                           */
+  FB_OPT_PREFILTER = 17,       /* 1 (default): fb_knn_exact (whole table) and the analogy scans select candidates with a bf16
+                                  tcgen05 GEMM whose error is bounded, then decide with the reference's fp32 chain
+                                  (identical results); 0: the fp32 scan kernels do all the work                    */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */
@@ -235,6 +241,9 @@ typedef struct {
   int64_t exact_coarse_tie, exact_coarse_far, exact_few_rows, exact_scan_tie, exact_forced;
   double ms_pipe;           /* pipeline-kernel launches (LUT build + scan in one) */
   int64_t n_pipe_launches;
+  /* tensor-core pre-filter of the exact scans: queries it answered, queries handed back to the fp32 scan
+   * (candidate buffer overflow), candidates emitted (counted under FB_OPT_PROFILE only) */
+  int64_t prefilter_queries, prefilter_overflow_queries, prefilter_candidates;
 } fb_counters;
 int fb_get_counters(fb_engine* e, fb_counters* out);  /* synchronizes the stream */
 int fb_reset_counters(fb_engine* e);

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <atomic>
@@ -24,6 +25,8 @@
 #include "pipeline_kernels.cuh"
 #include "rerank_kernels.cuh"
 #include "grouping_kernels.cuh"
+#include "subset_kernels.cuh"
+#include "prefilter_kernels.cuh"
 
 using namespace fb;
 
@@ -38,6 +41,10 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }          // fb_destroy selects the device before the engine (and its buffers) goes away
   cudaError_t ensure(size_t count) {
     if (count <= n && p) return cudaSuccess;
     g_alloc_generation++;
@@ -59,6 +66,7 @@ struct DevBuf {
 struct CodeTable {
   DevBuf<uint2> units;
   DevBuf<int32_t> rowno, list_blk, list_len, ids;
+  DevBuf<int32_t> sorted_ids, sorted_rows;   // (id, row) pairs ordered by id, rows ascending inside an id: `WHERE id IN (...)` on the device
   int m = 0, U = 0, n_lists = 0;
   int64_t N = 0, n_blocks = 0;
   bool loaded = false;
@@ -69,7 +77,10 @@ struct CodeTable {
     t.ids = ids.p; t.m = m; t.U = U; t.n_lists = n_lists;
     return t;
   }
-  void release() { units.release(); rowno.release(); list_blk.release(); list_len.release(); ids.release(); loaded = false; }
+  void release() {
+    units.release(); rowno.release(); list_blk.release(); list_len.release(); ids.release();
+    sorted_ids.release(); sorted_rows.release(); loaded = false;
+  }
 };
 
 struct Codebook {
@@ -95,7 +106,9 @@ struct fb_engine {
   int C = 0, Cs = 0, d = 0;
   bool coarse_loaded = false;
   Codebook cb[FB_CB_KINDS];
-  CodeTable fine, pq, tmp;  // tmp: per-call target subset of pq
+  CodeTable fine, pq, tmp;  // tmp: per-call target subset of pq (units / rowno only; compact, one list)
+  DevBuf<uint32_t> sel_bitmap;          // `WHERE id IN (...)` on the device (subset_kernels.cuh)
+  DevBuf<int32_t> sel_word_base, sel_total, sel_wanted, zero_i32;
   std::vector<int32_t> pq_ids_host;
   bool pq_ids_sorted = true;
   std::unordered_map<int32_t, int32_t> pq_id_to_row;
@@ -127,6 +140,21 @@ struct fb_engine {
   bool vec_loaded = false;
   DevBuf<float> va, vb, vo;
   DevBuf<double> vdo;
+  // tensor-core pre-filter of the exact scans (prefilter_kernels.cuh): bf16 image of the table [N_pad][kpa], its TMA map,
+  // the largest row norm, and per-call scratch
+  DevBuf<__nv_bfloat16> vec_bf16, pf_qb;
+  CUtensorMap pf_tm_v;
+  bool pf_ready = false;
+  int pf_kpa = 0;
+  int64_t pf_N_pad = 0;
+  float pf_vmax = 0.0f;
+  int prefilter = 1;          // FB_OPT_PREFILTER
+  DevBuf<float> pf_eps2;
+  DevBuf<uint32_t> pf_gbest, pf_norm;
+  DevBuf<int32_t> pf_cnt, pf_ovf, pf_rows_out, pf_ex;
+  DevBuf<int2> pf_cand;
+  DevBuf<PfUnit> pf_units;
+  int64_t pf_queries = 0, pf_overflow_queries = 0, pf_candidates = 0;
   DevBuf<int32_t> ana_rows;
   DevBuf<u64> ana_partial;
 
@@ -182,6 +210,10 @@ struct fb_engine {
   int bytes_per_row = 0;
   int64_t host_rows = 0;
 };
+
+static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int kk, const int32_t* d_exclude,
+                             int32_t* d_out_ids, float* d_out_sims, int32_t* d_out_rows, std::vector<int32_t>& overflow);
+static bool pf_usable(const fb_engine* e, int kk);
 
 namespace {
 
@@ -469,7 +501,7 @@ int launch_lut_cfg(fb_engine* e, const Codebook& cb, const float* d_q, const flo
   auto kern = lut_build_kernel<W, TKS, PACKED>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // e->one: run-time 1.0f (common.cuh: keeps ptxas from contracting the packed chain)
-  kern<<<grid, TK, smem, e->stream>>>(d_q, e->d, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, cb.m, cb.K, cb.sub,
+  kern<<<grid, TK, smem, e->stream>>>(d_q, cb.m * cb.sub, d_coarse, d_probes, jobs_per_query, njobs, cb.cbT.p, cb.m, cb.K, cb.sub,
                                       TK, d_lut, e->one);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -526,38 +558,38 @@ int launch_lut(fb_engine* e, const Codebook& cb, const float* d_q, const float* 
 }
 
 template <int M>
-int launch_scan_m(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
-                  int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial) {
+int launch_scan_m(fb_engine* e, const CodeTableDev& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
+                  int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial, float sentinel) {
   size_t smem = std::max<size_t>((size_t)tab.m * K * sizeof(float), (size_t)kScanWarps * 32 * sizeof(u64));
   if (smem > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT (%zu bytes) exceeds shared memory", smem);
   auto kern = adc_scan_kernel<M>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ntasks * segs, kScanThreads, smem, e->stream>>>(tab.dev(), d_task_list, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
+  kern<<<ntasks * segs, kScanThreads, smem, e->stream>>>(tab, d_task_list, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial, sentinel);
   e->launches++;
   e->n_scan_launches++;
   FB_CUDA(e, cudaGetLastError());
   return FB_OK;
 }
 
-int launch_scan(fb_engine* e, const CodeTable& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
-                int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial) {
+int launch_scan(fb_engine* e, const CodeTableDev& tab, const int32_t* d_task_list, int ntasks, int tasks_per_lut,
+                int list_mod, int segs, const float* d_lut, int K, int KK, u64* d_partial, float sentinel) {
   StageTimer t(e, ST_SCAN);
   switch (tab.m) {
-    case 8: return launch_scan_m<8>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
-    case 12: return launch_scan_m<12>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
-    case 16: return launch_scan_m<16>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
-    default: return launch_scan_m<0>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial);
+    case 8: return launch_scan_m<8>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial, sentinel);
+    case 12: return launch_scan_m<12>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial, sentinel);
+    case 16: return launch_scan_m<16>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial, sentinel);
+    default: return launch_scan_m<0>(e, tab, d_task_list, ntasks, tasks_per_lut, list_mod, segs, d_lut, K, KK, d_partial, sentinel);
   }
 }
 
 template <int M, int KC>
-int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
+int launch_qscan_mk(fb_engine* e, const CodeTableDev& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
                     float sentinel, int32_t* d_out_ids, float* d_out_dists) {
   size_t smem = std::max<size_t>(2 * (size_t)tab.m * K * sizeof(float), kQScanWarps * 32 * sizeof(u64));
   if (smem > e->smem_optin - 1024) return FB_ERR_UNSUPPORTED;  // caller falls back to one list per CTA
   auto kern = adc_scan_query_kernel<M, KC>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab.dev(), e->probes.p + (size_t)q0 * w, w, d_lut, K, KK, k, sentinel,
+  kern<<<nq, kQScanThreads, smem, e->stream>>>(tab, e->probes.p + (size_t)q0 * w, w, d_lut, K, KK, k, sentinel,
                                                e->qflags.p + q0, d_out_ids, d_out_dists, e->exact_list.p,
                                                e->small.p + 0, e->counters64.p + 1, e->kth.p + q0, q0);
   e->launches++;
@@ -567,7 +599,7 @@ int launch_qscan_mk(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, c
 }
 
 // throughput form: one CTA per query, finalize fused
-int launch_qscan(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
+int launch_qscan(fb_engine* e, const CodeTableDev& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
                  float sentinel, int32_t* oi, float* od) {
   StageTimer t(e, ST_SCAN);
 #define FB_QS(M_, K_) return launch_qscan_mk<M_, K_>(e, tab, q0, nq, w, d_lut, K, KK, k, sentinel, oi, od)
@@ -582,6 +614,19 @@ int launch_qscan(fb_engine* e, const CodeTable& tab, int q0, int nq, int w, cons
   }
   FB_QS(0, 0);
 #undef FB_QS
+}
+
+// ivfadc_batch_search: queries whose k-th slot is still empty after the first round and that are not flagged yet
+__global__ void batch_unfilled_kernel(const int32_t* __restrict__ out_ids, int nq, int k, uint32_t* __restrict__ qflags,
+                                      int32_t* __restrict__ exact_list, int32_t* __restrict__ exact_count, u64* __restrict__ exact_total) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const uint32_t f = qflags[q];
+  if ((f & kFlagExact) || out_ids[(size_t)q * k + k - 1] != -1) return;
+  qflags[q] = f | kFlagExact | kWhyFewRows;
+  exact_list[atomicAdd(exact_count, 1)] = q;
+  atomicAdd(exact_total, 1ull);
+  atomicAdd(exact_total + 3, 1ull);
 }
 
 __global__ void collect_flagged_kernel(const uint32_t* __restrict__ qflags, int n, int q_base, int32_t* __restrict__ exact_list,
@@ -619,12 +664,12 @@ int launch_scan_keys(fb_engine* e, const CodeTable& tab, const int32_t* d_probes
   return launch_scan_keys_mk<0, 0>(e, tab, d_probes, nq, w, d_lut, K, d_keys, stride, d_nkeys);
 }
 
-int launch_finalize(fb_engine* e, const CodeTable& tab, int q0, int lists_per_query, int KK, int k, int nq, float sentinel,
+int launch_finalize(fb_engine* e, const CodeTableDev& tab, int q0, int lists_per_query, int KK, int k, int nq, float sentinel,
                     bool has_input_flags, int32_t* d_out_ids, float* d_out_dists) {
   StageTimer t(e, ST_FINALIZE);
   const int warps = 8;
   finalize_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, e->stream>>>(
-      e->partial.p, lists_per_query, KK, k, nq, tab.ids.p, sentinel, e->qflags.p + q0, has_input_flags ? 1 : 0, d_out_ids,
+      e->partial.p, lists_per_query, KK, k, nq, tab.ids, sentinel, e->qflags.p + q0, has_input_flags ? 1 : 0, d_out_ids,
       d_out_dists, e->exact_list.p, e->small.p + 0, e->counters64.p + 1, e->kth.p + q0, q0);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
@@ -752,8 +797,9 @@ int run_pipeline(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int
 }
 
 // ---- the IVFADC pipeline on device pointers --------------------------------
+// batch_mode: ivfadc_batch_search's loop (one list per round, sentinel 100.0, rounds until k rows were ADMITTED)
 int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists,
-               float sentinel = 1000.0f) {
+               float sentinel = 1000.0f, bool batch_mode = false) {
   int rc = check_common(e, nq, k);
   if (rc) return rc;
   if (!e->coarse_loaded || !e->cb[FB_CB_RESIDUAL].loaded || !e->fine.loaded)
@@ -841,14 +887,14 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
       }
       if (rc) { e->stream = main_stream; return rc; }
       // HOT(3)+(4): one CTA per query when the chunk fills the GPU, else one CTA per (query, list)
-      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine, (int)q0, n, w, lutbuf, K, KK, k, sentinel, oi, od)
+      rc = (n >= e->qscan_min_queries) ? launch_qscan(e, e->fine.dev(), (int)q0, n, w, lutbuf, K, KK, k, sentinel, oi, od)
                                        : FB_ERR_UNSUPPORTED;
       if (rc == FB_ERR_UNSUPPORTED) {
         // few (query, list) tasks: split every list over `segs` CTAs so that the launch still fills the GPU
         const int segs = std::max(1, std::min(16, (2 * e->num_sms) / std::max(1, n * w)));
         rc = e->partial.ensure((size_t)chunk * w * 16 * KK) == cudaSuccess ? FB_OK : FB_ERR_CUDA;
-        if (!rc) rc = launch_scan(e, e->fine, pr, n * w, 1, 1, segs, lutbuf, K, KK, e->partial.p);
-        if (!rc) rc = launch_finalize(e, e->fine, (int)q0, w * segs, KK, k, n, sentinel, true, oi, od);
+        if (!rc) rc = launch_scan(e, e->fine.dev(), pr, n * w, 1, 1, segs, lutbuf, K, KK, e->partial.p, sentinel);
+        if (!rc) rc = launch_finalize(e, e->fine.dev(), (int)q0, w * segs, KK, k, n, sentinel, true, oi, od);
       }
       if (overlap) cudaEventRecord(e->ev_scan_done[c & 1], e->s_scan);
       e->stream = main_stream;
@@ -882,6 +928,12 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     FB_CUDA(e, cudaMemcpyAsync(e->small.p, &cnt, sizeof cnt, cudaMemcpyHostToDevice, e->stream));
     e->launches++;
   }
+  if (batch_mode && (fast || large_k)) {
+    // ivfadc_batch_search goes on probing while a query's top-k has an empty slot (admissions, not rows, are counted)
+    batch_unfilled_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>(d_out_ids, nq, k, e->qflags.p, e->exact_list.p, e->small.p + 0,
+                                                                   e->counters64.p + 1);
+    e->launches++;
+  }
   {
     // flagged queries (boundary ties, re-probe loop, large k/w): the literal kernel, once per call
     StageTimer t(e, ST_EXACT);
@@ -889,7 +941,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
         d_q, e->d, e->coarse.p, e->coarseT.p, e->C, e->Cs, cb.cbT.p, K, cb.sub, e->fine.dev(), w, k,
         e->exact_list.p, e->small.p + 0, e->small.p + 1, e->exact_lut.p,
         fast ? e->qflags.p : nullptr, e->probes.p, e->kth.p, d_out_ids, d_out_dists, e->small.p + 2, ex_stage, sentinel,
-        (fast || large_k) ? nullptr : e->counters64.p + 0);
+        (fast || large_k) ? nullptr : e->counters64.p + 0, batch_mode ? 1 : 0);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
   }
@@ -996,25 +1048,35 @@ int ivfadc_search_graph(fb_engine* e, const float* queries, int nq, int k, int w
   return FB_OK;
 }
 
-// ---- flat PQ pipeline over `tab` (the pq table or a per-call subset) --------
-int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, float sentinel,
+// ---- flat PQ pipeline over a one-list table (the pq table or a per-call subset) --------
+// freddy.c:74-134 (pq_search), :514-631 (pq_search_in_batch), :1070-1143 (pq_search_in): one LUT per query on the
+// raw query, every row of the table scanned by every query.  Throughput form: one CTA per query keeps its LUT
+// resident in shared memory and walks the whole table (codes come from L2: 100k targets = 2.4 MB), top-k and
+// the reference's tie order fused (adc_scan_query_kernel, w = 1).  Few queries: the table is cut into `segs`
+// segments per query so that the launch still fills the GPU (adc_scan_kernel + finalize_kernel).
+// rows_upper: host-side upper bound of the table's row count (the exact count of a subset lives on the device).
+int pq_dev(fb_engine* e, const CodeTableDev& tab, int64_t rows_upper, const float* d_q, int nq, int k, float sentinel,
            int32_t* d_out_ids, float* d_out_dists) {
   const Codebook& cb = e->cb[FB_CB_PQ];
-  const int m = cb.m, K = cb.K;
+  const int m = cb.m, K = cb.K, d = cb.m * cb.sub;
   const bool fast = (k <= 30);
   const int KK = k + 2;
-  const int nl = tab.n_lists;
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->query_chunk, nq));
-  // bound the per-warp partial lists (chunk * nl * 8 * KK keys)
-  while (chunk > 1 && (size_t)chunk * nl * KK * sizeof(u64) > ((size_t)1 << 30)) chunk /= 2;
+  const int64_t blocks_upper = std::max<int64_t>(1, (rows_upper + 31) / 32);
+  auto segs_for = [&](int n) {
+    if (n >= 2 * e->num_sms) return 1;
+    return (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(4 * e->num_sms + n - 1) / n, blocks_upper / 8, (int64_t)1024}));
+  };
+  const int segs_max = segs_for((int)std::min<int64_t>(chunk, nq));
   FB_CUDA(e, e->lut.ensure((size_t)chunk * m * K));
   FB_CUDA(e, e->qflags.ensure((size_t)chunk));
   FB_CUDA(e, e->exact_list.ensure((size_t)chunk));
   FB_CUDA(e, e->kth.ensure((size_t)chunk));
-  FB_CUDA(e, e->iota_lists.ensure((size_t)nl));
-  if (fast) FB_CUDA(e, e->partial.ensure((size_t)chunk * nl * KK));
-  iota_kernel<<<(nl + 255) / 256, 256, 0, e->stream>>>(e->iota_lists.p, nl);
-  e->launches++;
+  FB_CUDA(e, e->probes.ensure((size_t)chunk));
+  FB_CUDA(e, e->zero_i32.ensure(4));
+  FB_CUDA(e, cudaMemsetAsync(e->zero_i32.p, 0, 4 * sizeof(int32_t), e->stream));
+  FB_CUDA(e, cudaMemsetAsync(e->probes.p, 0, (size_t)chunk * sizeof(int32_t), e->stream));   // every query "probes" list 0
+  if (fast && segs_max > 1) FB_CUDA(e, e->partial.ensure((size_t)chunk * segs_max * KK));
   size_t ex_smem = kExactFixedSmem;
   int ex_stage = 0;
   if (ex_smem + (size_t)m * K * sizeof(float) <= e->smem_optin) { ex_stage = m * K; ex_smem += (size_t)m * K * sizeof(float); }
@@ -1022,14 +1084,23 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
   int rc;
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
     const int n = (int)std::min<int64_t>(chunk, nq - q0);
-    const float* dq = d_q + (size_t)q0 * e->d;
+    const float* dq = d_q + (size_t)q0 * d;
     int32_t* oi = d_out_ids + (size_t)q0 * k;
     float* od = d_out_dists + (size_t)q0 * k;
     FB_CUDA(e, cudaMemsetAsync(e->small.p, 0, 2 * sizeof(int32_t), e->stream));
+    FB_CUDA(e, cudaMemsetAsync(e->qflags.p, 0, (size_t)n * sizeof(uint32_t), e->stream));
     if ((rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, n, e->lut.p))) return rc;   // freddy.c:519-525
     if (fast && !e->force_exact) {
-      if ((rc = launch_scan(e, tab, nullptr, n * nl, nl, nl, 1, e->lut.p, K, KK, e->partial.p))) return rc;
-      if ((rc = launch_finalize(e, tab, 0, nl, KK, k, n, sentinel, false, oi, od))) return rc;
+      const int segs = segs_for(n);
+      rc = (segs == 1) ? launch_qscan(e, tab, 0, n, 1, e->lut.p, K, KK, k, sentinel, oi, od) : FB_ERR_UNSUPPORTED;
+      if (rc == FB_ERR_UNSUPPORTED) {
+        const int sg = std::max(segs, 1);
+        if (e->partial.ensure((size_t)chunk * sg * KK) != cudaSuccess) return fail(e, FB_ERR_CUDA, "out of device memory");
+        if ((rc = launch_scan(e, tab, e->probes.p, n, 1, 1, sg, e->lut.p, K, KK, e->partial.p, sentinel))) return rc;
+        if ((rc = launch_finalize(e, tab, 0, sg, KK, k, n, sentinel, false, oi, od))) return rc;
+      } else if (rc) {
+        return rc;
+      }
     } else {
       iota_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->exact_list.p, n);
       int32_t cnt = n;
@@ -1039,12 +1110,11 @@ int pq_dev(fb_engine* e, const CodeTable& tab, const float* d_q, int nq, int k, 
     {
       StageTimer t(e, ST_EXACT);
       pq_exact_kernel<<<2 * e->num_sms, kExactThreads, ex_smem, e->stream>>>(
-          tab.dev(), e->iota_lists.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1,
+          tab, e->zero_i32.p, e->lut.p, K, k, sentinel, e->exact_list.p, e->small.p + 0, e->small.p + 1,
           (fast && !e->force_exact) ? e->kth.p : nullptr, oi, od, ex_stage);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }
-    e->host_rows += (int64_t)n * tab.N;  // every query sees every row of the table
   }
   e->queries_done += nq;
   e->bytes_per_row = 2 * m + 4;
@@ -1055,7 +1125,60 @@ int check_pq_ready(fb_engine* e) {
   if (!e->cb[FB_CB_PQ].loaded || !e->pq.loaded) return fail(e, FB_ERR_INVALID, "flat PQ index not loaded (pq codebook / pq table)");
   const Codebook& cb = e->cb[FB_CB_PQ];
   if (cb.m != e->pq.m) return fail(e, FB_ERR_INVALID, "pq codebook m=%d but pq table m=%d", cb.m, e->pq.m);
-  e->d = cb.m * cb.sub;
+  return FB_OK;
+}
+int pq_dim(const fb_engine* e) { return e->cb[FB_CB_PQ].m * e->cb[FB_CB_PQ].sub; }
+
+// sorted (id, row) image of a table's id column on the device: the `WHERE id IN (...)` index
+int build_id_index(fb_engine* e, CodeTable& tab, const int32_t* ids, int64_t N) {
+  std::vector<int32_t> order((size_t)N), sid((size_t)N);
+  for (int64_t r = 0; r < N; r++) order[r] = (int32_t)r;
+  if (!std::is_sorted(ids, ids + N))
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ids[a] < ids[b]; });
+  for (int64_t r = 0; r < N; r++) sid[r] = ids[order[r]];
+  FB_CUDA(e, tab.sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
+  FB_CUDA(e, tab.sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
+  if (N > 0) {
+    FB_CUDA(e, cudaMemcpy(tab.sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    FB_CUDA(e, cudaMemcpy(tab.sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  return FB_OK;
+}
+
+// Rows of `src` selected by `WHERE id IN (wanted)` in table order, every matching row once (freddy.c:544-562,
+// :1286-1300), gathered on the device into the compact one-list table e->tmp.  Nothing comes back to the host:
+// the row count stays in e->sel_total[0] (= the list length the scan kernels read).  `view` describes the
+// subset for the kernels; rows_upper bounds its row count.
+int build_subset(fb_engine* e, const CodeTable& src, const int32_t* wanted, int n_wanted, CodeTableDev& view, int64_t& rows_upper) {
+  const int64_t N = src.N;
+  const int n_words = (int)std::max<int64_t>(1, (N + 31) / 32);
+  rows_upper = std::min<int64_t>(N, n_wanted);
+  const int n_slots = (int)std::max<int64_t>(32, (rows_upper + 31) / 32 * 32);
+  CodeTable& tmp = e->tmp;
+  FB_CUDA(e, tmp.units.ensure((size_t)n_slots * src.U));
+  FB_CUDA(e, tmp.rowno.ensure((size_t)n_slots));
+  FB_CUDA(e, e->sel_rows.ensure((size_t)n_slots));
+  FB_CUDA(e, e->sel_bitmap.ensure((size_t)n_words));
+  FB_CUDA(e, e->sel_word_base.ensure((size_t)n_words));
+  FB_CUDA(e, e->sel_total.ensure(4));
+  FB_CUDA(e, e->sel_wanted.ensure((size_t)std::max(1, n_wanted)));
+  FB_CUDA(e, e->zero_i32.ensure(4));
+  FB_CUDA(e, cudaMemsetAsync(e->zero_i32.p, 0, 4 * sizeof(int32_t), e->stream));
+  FB_CUDA(e, cudaMemsetAsync(e->sel_bitmap.p, 0, (size_t)n_words * sizeof(uint32_t), e->stream));
+  if (n_wanted > 0) {
+    FB_CUDA(e, cudaMemcpyAsync(e->sel_wanted.p, wanted, (size_t)n_wanted * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    subset_mark_kernel<<<(n_wanted + 255) / 256, 256, 0, e->stream>>>(src.sorted_ids.p, src.sorted_rows.p, (int)N, e->sel_wanted.p,
+                                                                      n_wanted, e->sel_bitmap.p);
+    e->launches++;
+  }
+  subset_scan_kernel<<<1, 1024, 0, e->stream>>>(e->sel_bitmap.p, n_words, e->sel_word_base.p, e->sel_total.p, nullptr);
+  subset_compact_kernel<<<(n_words + 255) / 256, 256, 0, e->stream>>>(e->sel_bitmap.p, n_words, e->sel_word_base.p, e->sel_rows.p);
+  subset_gather_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(src.units.p, src.U, e->sel_rows.p, e->sel_total.p, tmp.units.p,
+                                                                     tmp.rowno.p, n_slots);
+  e->launches += 3;
+  FB_CUDA(e, cudaGetLastError());
+  view.units = tmp.units.p; view.rowno = tmp.rowno.p; view.list_blk = e->zero_i32.p; view.list_len = e->sel_total.p;
+  view.ids = src.ids.p; view.m = src.m; view.U = src.U; view.n_lists = 1;
   return FB_OK;
 }
 
@@ -1186,14 +1309,11 @@ int fb_load_pq(fb_engine* e, const int32_t* ids, const int16_t* codes, int64_t N
   if (!e || (N > 0 && (!ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_load_pq: bad arguments");
   if (!e->cb[FB_CB_PQ].loaded) return fail(e, FB_ERR_INVALID, "fb_load_pq: load the pq codebook first");
   FB_CUDA(e, cudaSetDevice(e->device));
-  int rc = build_table(e, e->pq, ids, nullptr, 0, 8192, codes, N, m, e->cb[FB_CB_PQ].K);
+  // one list holding the whole table in table order
+  int rc = build_table(e, e->pq, ids, nullptr, 0, 0x7fffffff, codes, N, m, e->cb[FB_CB_PQ].K);
   if (rc) return rc;
   e->pq_ids_host.assign(ids, ids + N);
-  e->pq_ids_sorted = std::is_sorted(e->pq_ids_host.begin(), e->pq_ids_host.end());
-  e->pq_id_to_row.clear();
-  if (!e->pq_ids_sorted)
-    for (int64_t r = 0; r < N; r++) e->pq_id_to_row.emplace(ids[r], (int32_t)r);  // first row wins
-  return FB_OK;
+  return build_id_index(e, e->pq, ids, N);
 }
 
 int fb_ivfadc_search_dev(fb_engine* e, const float* d_queries, int nq, int k, int w, int32_t* d_out_ids, float* d_out_dists) {
@@ -1238,55 +1358,6 @@ int fb_ivfadc_search(fb_engine* e, const float* queries, int nq, int k, int w, i
   return check_error_flag(e);
 }
 
-static // Rows of the flat pq table selected by `WHERE id IN (targets)` in table order, each once (freddy.c:544-562,
-// :1286-1300), gathered into a temporary blocked table; `view` borrows its buffers (ids = the full pq table's).
-int build_pq_subset(fb_engine* e, const int32_t* targets, int n_targets, CodeTable& view, std::vector<int32_t>& rows) {
-  // rows selected by `WHERE id IN (targets)` in table order (freddy.c:544-562)
-  rows.reserve(n_targets);
-  for (int i = 0; i < n_targets; i++) {
-    if (e->pq_ids_sorted) {
-      auto it = std::lower_bound(e->pq_ids_host.begin(), e->pq_ids_host.end(), targets[i]);
-      if (it != e->pq_ids_host.end() && *it == targets[i]) rows.push_back((int32_t)(it - e->pq_ids_host.begin()));
-    } else {
-      auto it = e->pq_id_to_row.find(targets[i]);
-      if (it != e->pq_id_to_row.end()) rows.push_back(it->second);
-    }
-  }
-  std::sort(rows.begin(), rows.end());
-  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-  const int n = (int)rows.size();
-  // temporary blocked table over the selected rows
-  CodeTable& tmp = e->tmp;
-  const int per_list = 4096;
-  const int nl = std::max(1, (n + per_list - 1) / per_list);
-  std::vector<int32_t> len(nl, 0), blk(nl, 0);
-  int64_t n_blocks = 0;
-  for (int c = 0; c < nl; c++) {
-    len[c] = std::max(0, std::min(per_list, n - c * per_list));
-    blk[c] = (int32_t)n_blocks;
-    n_blocks += (len[c] + 31) / 32;
-  }
-  const int U = e->pq.U;
-  const int n_slots = (int)std::max<int64_t>(1, n_blocks) * 32;
-  FB_CUDA(e, tmp.units.ensure((size_t)n_slots * U));
-  FB_CUDA(e, tmp.rowno.ensure((size_t)n_slots));
-  FB_CUDA(e, tmp.list_blk.ensure(nl));
-  FB_CUDA(e, tmp.list_len.ensure(nl));
-  FB_CUDA(e, e->sel_rows.ensure((size_t)std::max(1, n)));
-  FB_CUDA(e, cudaMemcpyAsync(tmp.list_blk.p, blk.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  FB_CUDA(e, cudaMemcpyAsync(tmp.list_len.p, len.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  if (n > 0) FB_CUDA(e, cudaMemcpyAsync(e->sel_rows.p, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  gather_rows_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->pq.units.p, U, e->sel_rows.p, n, tmp.units.p, tmp.rowno.p, n_slots);
-  e->launches++;
-  FB_CUDA(e, cudaGetLastError());
-  FB_CUDA(e, cudaStreamSynchronize(e->stream));  // host vectors go out of scope below
-  // borrow buffers; ids come from the full pq table (rowno = pq row)
-  view.units = tmp.units; view.rowno = tmp.rowno; view.list_blk = tmp.list_blk; view.list_len = tmp.list_len;
-  view.ids = e->pq.ids; view.m = e->pq.m; view.U = U; view.n_lists = nl; view.N = n; view.n_blocks = n_blocks;
-
-  return FB_OK;
-}
-
 int fb_pq_search(fb_engine* e, const float* queries, int nq, int k, int32_t* out_ids, float* out_dists) {
   if (!e) return FB_ERR_INVALID;
   int rc = check_common(e, nq, k);
@@ -1295,11 +1366,13 @@ int fb_pq_search(fb_engine* e, const float* queries, int nq, int k, int32_t* out
   if (nq == 0) return FB_OK;
   if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
-  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  const int d = pq_dim(e);
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
-  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  if ((rc = pq_dev(e, e->pq, e->q_stage.p, nq, k, 100.0f, e->id_stage.p, e->dist_stage.p))) return rc;  // freddy.c:90-92
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if ((rc = pq_dev(e, e->pq.dev(), e->pq.N, e->q_stage.p, nq, k, 100.0f, e->id_stage.p, e->dist_stage.p))) return rc;  // freddy.c:90-92
+  e->host_rows += (int64_t)nq * e->pq.N;   // every query sees every row of the table
   FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1317,18 +1390,22 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, con
   if (nq == 0) return FB_OK;
   if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
-  std::vector<int32_t> rows;
-  CodeTable view;
-  if ((rc = build_pq_subset(e, targets, n_targets, view, rows))) return rc;
-  FB_CUDA(e, e->q_stage.ensure((size_t)nq * e->d));
+  const int d = pq_dim(e);
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
-  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  rc = pq_dev(e, view, e->q_stage.p, nq, k, 1000.0f, e->id_stage.p, e->dist_stage.p);  // freddy.c:415
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CodeTableDev view;
+  int64_t rows_upper = 0;
+  if ((rc = build_subset(e, e->pq, targets, n_targets, view, rows_upper))) return rc;
+  rc = pq_dev(e, view, rows_upper, e->q_stage.p, nq, k, 1000.0f, e->id_stage.p, e->dist_stage.p);  // freddy.c:415
   if (rc) return rc;
+  int32_t n_sel = 0;
+  FB_CUDA(e, cudaMemcpyAsync(&n_sel, e->sel_total.p, sizeof n_sel, cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->host_rows += (int64_t)nq * n_sel;     // every query sees every selected row
   return FB_OK;
 }
 
@@ -1365,6 +1442,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_PIPE_RAMP: e->pipe_ramp = value != 0; return FB_OK;
     case FB_OPT_CUDA_GRAPHS: e->use_graphs = value != 0; return FB_OK;
     case FB_OPT_ZERO_COPY_UPLOAD: e->zero_copy = value != 0; return FB_OK;
+    case FB_OPT_PREFILTER: e->prefilter = value != 0; return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");
@@ -1401,6 +1479,9 @@ int fb_get_counters(fb_engine* e, fb_counters* out) {
   out->n_scan_launches = e->n_scan_launches;
   out->ms_pipe = e->ms[ST_PIPE];
   out->n_pipe_launches = e->n_pipe_launches;
+  out->prefilter_queries = e->pf_queries;
+  out->prefilter_overflow_queries = e->pf_overflow_queries;
+  out->prefilter_candidates = e->pf_candidates;
   return FB_OK;
 }
 
@@ -1412,6 +1493,7 @@ int fb_reset_counters(fb_engine* e) {
   FB_CUDA(e, cudaMemset(e->counters64.p, 0, 8 * sizeof(u64)));
   for (double& v : e->ms) v = 0;
   e->launches = 0; e->queries_done = 0; e->n_scan_launches = 0; e->n_pipe_launches = 0; e->host_rows = 0;
+  e->pf_queries = 0; e->pf_overflow_queries = 0; e->pf_candidates = 0;
   return FB_OK;
 }
 
@@ -1447,8 +1529,8 @@ int vec_row_of(const fb_engine* e, int32_t id) {
 }
 
 // d_q: device [nq][d] query vectors; h_rows: host [nq][3] excluded table rows
-int analogy_scan_dev(fb_engine* e, const float* d_q, const std::vector<int32_t>& h_rows, int nq, int32_t* d_out_ids,
-                     float* d_out_scores) {
+int analogy_scan_fp32(fb_engine* e, const float* d_q, const std::vector<int32_t>& h_rows, int nq, int32_t* d_out_ids,
+                      float* d_out_scores) {
   const int d = e->vec_d;
   const int64_t N = e->vec_N;
   const int tiles = (nq + kAnaQT - 1) / kAnaQT, nq_pad = tiles * kAnaQT;
@@ -1478,6 +1560,34 @@ int analogy_scan_dev(fb_engine* e, const float* d_q, const std::vector<int32_t>&
   e->bytes_per_row = d * 4;
   return FB_OK;
 }
+
+// arg-max with exclusions: the tensor-core pre-filter with k' = 1 + 3 (the three excluded rows may occupy the top
+// places), the fp32 scan for whatever it hands back
+int analogy_scan_dev(fb_engine* e, const float* d_q, const std::vector<int32_t>& h_rows, int nq, int32_t* d_out_ids,
+                     float* d_out_scores) {
+  if (!pf_usable(e, 4)) return analogy_scan_fp32(e, d_q, h_rows, nq, d_out_ids, d_out_scores);
+  const int d = e->vec_d;
+  FB_CUDA(e, e->pf_ex.ensure((size_t)nq * 3));
+  FB_CUDA(e, cudaMemcpyAsync(e->pf_ex.p, h_rows.data(), (size_t)nq * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  std::vector<int32_t> ovf;
+  int rc = knn_prefilter_dev(e, d_q, nq, 1, 4, e->pf_ex.p, d_out_ids, d_out_scores, nullptr, ovf);   // synchronises: h_rows may go away
+  if (rc || ovf.empty()) return rc;
+  const int no = (int)ovf.size();
+  std::vector<int32_t> sub_rows((size_t)no * 3);
+  FB_CUDA(e, e->vb.ensure((size_t)no * d));
+  FB_CUDA(e, e->pv_cand.ensure((size_t)no));
+  FB_CUDA(e, e->sub_vT.ensure((size_t)no));
+  for (int i = 0; i < no; i++) {
+    for (int j = 0; j < 3; j++) sub_rows[(size_t)i * 3 + j] = h_rows[(size_t)ovf[i] * 3 + j];
+    FB_CUDA(e, cudaMemcpyAsync(e->vb.p + (size_t)i * d, d_q + (size_t)ovf[i] * d, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  if ((rc = analogy_scan_fp32(e, e->vb.p, sub_rows, no, e->pv_cand.p, e->sub_vT.p))) return rc;
+  for (int i = 0; i < no; i++) {
+    FB_CUDA(e, cudaMemcpyAsync(d_out_ids + ovf[i], e->pv_cand.p + i, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    FB_CUDA(e, cudaMemcpyAsync(d_out_scores + ovf[i], e->sub_vT.p + i, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  return FB_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1493,14 +1603,39 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   const int64_t slice_rows = 32 * 8192;
   DevBuf<float> stage;
   FB_CUDA(e, stage.ensure((size_t)std::min<int64_t>(std::max<int64_t>(N, 1), slice_rows) * d));
+  // bf16 image for the tensor-core pre-filter of the exact scans (d <= 320): [N_pad][kpa], zero padded
+  e->pf_ready = false;
+  const int kch = (d + kPfBK - 1) / kPfBK;
+  const bool want_pf = kch <= kPfMaxKch && N > 0 && pf_encode_fn() != nullptr;
+  if (want_pf) {
+    e->pf_kpa = kch * kPfBK;
+    e->pf_N_pad = (N + kPfBN - 1) / kPfBN * kPfBN;
+    FB_CUDA(e, e->vec_bf16.ensure((size_t)e->pf_N_pad * e->pf_kpa));
+    FB_CUDA(e, e->pf_norm.ensure(1));
+    FB_CUDA(e, cudaMemsetAsync(e->vec_bf16.p, 0, (size_t)e->pf_N_pad * e->pf_kpa * sizeof(__nv_bfloat16), e->stream));
+    FB_CUDA(e, cudaMemsetAsync(e->pf_norm.p, 0, sizeof(uint32_t), e->stream));
+  }
   for (int64_t r0 = 0; r0 < N; r0 += slice_rows) {
     const int64_t n = std::min(slice_rows, N - r0);
     FB_CUDA(e, cudaMemcpyAsync(stage.p, vectors + (size_t)r0 * d, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     transpose_rows_kernel<<<(unsigned)((n + 31) / 32), 256, 0, e->stream>>>(stage.p, n, d, e->vecT.p + (size_t)(r0 / 32) * d * 32);
+    if (want_pf)
+      pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(stage.p, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)r0 * e->pf_kpa,
+                                                                            e->pf_norm.p);
     FB_CUDA(e, cudaGetLastError());
     FB_CUDA(e, cudaStreamSynchronize(e->stream));
   }
   stage.release();
+  if (want_pf) {
+    uint32_t nb = 0;
+    FB_CUDA(e, cudaMemcpy(&nb, e->pf_norm.p, sizeof nb, cudaMemcpyDeviceToHost));
+    float n2;
+    memcpy(&n2, &nb, sizeof n2);
+    e->pf_vmax = sqrtf(n2) * 1.000001f;
+    // a non-finite row (or an all-zero table) leaves the exact scans on the fp32 kernels
+    e->pf_ready = std::isfinite(e->pf_vmax) && e->pf_vmax > 0.0f &&
+                  pf_make_tensor_map(&e->pf_tm_v, e->vec_bf16.p, e->pf_N_pad, e->pf_kpa, kPfBN);
+  }
   if (N > 0) FB_CUDA(e, cudaMemcpy(e->vec_ids.p, ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
   e->vec_ids_host.assign(ids, ids + N);
   e->vec_ids_sorted = std::is_sorted(e->vec_ids_host.begin(), e->vec_ids_host.end());
@@ -1645,6 +1780,83 @@ static int knn_exact_dev(fb_engine* e, const float* vT, int64_t N, const int32_t
   return FB_OK;
 }
 
+}  // extern "C"
+
+// Exact top-k over the WHOLE word-vector table through the tensor-core pre-filter (prefilter_kernels.cuh):
+// bf16 tcgen05 scores select candidates, the reference's fp32 chain decides.  d_q: device [nq][d]; d_exclude:
+// device [nq][3] table rows that never win (analogy) or nullptr; kk = k + excluded rows.  Queries whose candidate
+// buffer overflowed come back in `overflow` (query indices): the caller re-does them with the fp32 scan.
+static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int kk, const int32_t* d_exclude,
+                             int32_t* d_out_ids, float* d_out_sims, int32_t* d_out_rows, std::vector<int32_t>& overflow) {
+  const int d = e->vec_d, kpa = e->pf_kpa, kch = kpa / kPfBK;
+  const int64_t N = e->vec_N;
+  const int n_vt = (int)(e->pf_N_pad / kPfBN);
+  const int q_batch = 8192;                                   // bounds the candidate buffers (8192 x 4096 x 8 B = 256 MB)
+  const int nb_max = std::min(nq, q_batch), nb_pad = (nb_max + kPfBM - 1) / kPfBM * kPfBM;
+  FB_CUDA(e, e->pf_qb.ensure((size_t)nb_pad * kpa));
+  FB_CUDA(e, e->pf_eps2.ensure((size_t)nb_pad));
+  FB_CUDA(e, e->pf_gbest.ensure((size_t)nb_pad * kPfMaxK));
+  FB_CUDA(e, e->pf_cnt.ensure((size_t)nb_pad));
+  FB_CUDA(e, e->pf_cand.ensure((size_t)nb_pad * kPfCandCap));
+  FB_CUDA(e, e->pf_ovf.ensure((size_t)nb_pad + 1));
+  FB_CUDA(e, e->pf_units.ensure((size_t)pf_max_units(nb_pad / kPfBM, e->num_sms)));
+  FB_CUDA(e, cudaFuncSetAttribute(prefilter_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PfSmem::total));
+  std::vector<PfUnit> units((size_t)pf_max_units(nb_pad / kPfBM, e->num_sms));
+  std::vector<int32_t> h_ovf((size_t)nb_pad + 1), h_cnt;
+  for (int q0 = 0; q0 < nq; q0 += q_batch) {
+    const int n = std::min(q_batch, nq - q0), n_pad = (n + kPfBM - 1) / kPfBM * kPfBM, QT = n_pad / kPfBM;
+    int n_units = 0;
+    pf_make_units(QT, n_vt, e->num_sms, units.data(), &n_units);
+    CUtensorMap tm_q;
+    if (!pf_make_tensor_map(&tm_q, e->pf_qb.p, n_pad, kpa, kPfBM)) return fail(e, FB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    FB_CUDA(e, cudaMemcpyAsync(e->pf_units.p, units.data(), (size_t)n_units * sizeof(PfUnit), cudaMemcpyHostToDevice, e->stream));
+    FB_CUDA(e, cudaMemsetAsync(e->pf_ovf.p, 0, sizeof(int32_t), e->stream));
+    pf_queries_prepare_kernel<<<(n_pad + 7) / 8, 256, 0, e->stream>>>(d_q + (size_t)q0 * d, n, n_pad, d, kpa, e->pf_vmax, e->pf_qb.p,
+                                                                     e->pf_eps2.p, e->pf_gbest.p, e->pf_cnt.p);
+    e->launches++;
+    PfArgs a;
+    memset(&a, 0, sizeof a);
+    a.units = e->pf_units.p; a.n_units = n_units; a.kch = kch; a.ksteps = (d + 15) / 16; a.N = N; a.nq = n; a.kk = kk;
+    a.eps2 = e->pf_eps2.p; a.gbest = e->pf_gbest.p; a.cand_cnt = e->pf_cnt.p; a.cand = e->pf_cand.p; a.cap = kPfCandCap;
+    {
+      StageTimer t(e, ST_SCAN);
+      prefilter_gemm_kernel<<<std::min(e->num_sms, n_units), kPfThreads, PfSmem::total, e->stream>>>(tm_q, e->pf_tm_v, a);
+      e->launches++;
+      e->n_scan_launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
+    {
+      StageTimer t(e, ST_FINALIZE);
+      const size_t smem = (size_t)kPfCandCap * sizeof(u64) + (size_t)d * sizeof(float);
+      pf_rescore_kernel<<<n, kPfRescoreThreads, smem, e->stream>>>(
+          d_q + (size_t)q0 * d, d, e->vecT.p, e->pf_cnt.p, e->pf_cand.p, kPfCandCap, kk, e->pf_eps2.p,
+          d_exclude ? d_exclude + (size_t)q0 * 3 : nullptr, k, e->vec_ids.p, d_out_ids + (size_t)q0 * k, d_out_sims + (size_t)q0 * k,
+          d_out_rows ? d_out_rows + (size_t)q0 * k : nullptr, e->pf_ovf.p + 1, e->pf_ovf.p, nullptr);
+      e->launches++;
+      FB_CUDA(e, cudaGetLastError());
+    }
+    FB_CUDA(e, cudaMemcpyAsync(h_ovf.data(), e->pf_ovf.p, ((size_t)n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (e->profile) {
+      h_cnt.resize((size_t)n);
+      FB_CUDA(e, cudaMemcpyAsync(h_cnt.data(), e->pf_cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    }
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < h_ovf[0]; i++) overflow.push_back(q0 + h_ovf[1 + i]);
+    if (e->profile) for (int i = 0; i < n; i++) e->pf_candidates += h_cnt[i];
+  }
+  e->pf_queries += nq;
+  e->pf_overflow_queries += (int64_t)overflow.size();
+  e->host_rows += (int64_t)nq * N;
+  e->bytes_per_row = d * 4;
+  return FB_OK;
+}
+
+static bool pf_usable(const fb_engine* e, int kk) {
+  return e->prefilter && e->pf_ready && kk <= kPfMaxK;
+}
+
+extern "C" {
+
 int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
                  int32_t* out_ids, float* out_sims) {
   if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_knn_exact: bad arguments");
@@ -1660,7 +1872,24 @@ int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
   FB_CUDA(e, cudaMemcpyAsync(e->va.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   int rc;
-  if (targets == nullptr) {
+  if (targets == nullptr && pf_usable(e, k)) {
+    std::vector<int32_t> ovf;
+    rc = knn_prefilter_dev(e, e->va.p, nq, k, k, nullptr, e->id_stage.p, e->dist_stage.p, nullptr, ovf);
+    if (rc == FB_OK && !ovf.empty()) {
+      // overflowed queries (heavy duplication around the k-th place): the fp32 scan answers them
+      const int no = (int)ovf.size();
+      FB_CUDA(e, e->vb.ensure((size_t)no * d));
+      FB_CUDA(e, e->pv_cand.ensure((size_t)no * k));
+      FB_CUDA(e, e->vo.ensure((size_t)no * k));
+      for (int i = 0; i < no; i++)
+        FB_CUDA(e, cudaMemcpyAsync(e->vb.p + (size_t)i * d, e->va.p + (size_t)ovf[i] * d, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+      rc = knn_exact_dev(e, e->vecT.p, e->vec_N, nullptr, e->vb.p, no, k, e->pv_cand.p, e->vo.p);
+      for (int i = 0; i < no && rc == FB_OK; i++) {
+        FB_CUDA(e, cudaMemcpyAsync(e->id_stage.p + (size_t)ovf[i] * k, e->pv_cand.p + (size_t)i * k, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+        FB_CUDA(e, cudaMemcpyAsync(e->dist_stage.p + (size_t)ovf[i] * k, e->vo.p + (size_t)i * k, (size_t)k * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+      }
+    }
+  } else if (targets == nullptr) {
     rc = knn_exact_dev(e, e->vecT.p, e->vec_N, nullptr, e->va.p, nq, k, e->id_stage.p, e->dist_stage.p);
   } else {
     // WHERE id = ANY(targets): the matching rows in table order, each once (freddy--0.0.1.sql:1026-1038)
@@ -2024,7 +2253,7 @@ int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, in
   FB_CUDA(e, cudaStreamSynchronize(e->stream));   // rows is a local
   // one list per round, argmin with the first minimum winning (freddy.c:846-866) == the w = 1 case of
   // ivfadc_search's selection; rounds continue until k rows were seen; sentinel 100.0 (:823-827)
-  if ((rc = ivfadc_dev(e, e->q_stage.p, nq, k, 1, e->id_stage.p, e->dist_stage.p, 100.0f))) return rc;
+  if ((rc = ivfadc_dev(e, e->q_stage.p, nq, k, 1, e->id_stage.p, e->dist_stage.p, 100.0f, true))) return rc;
   FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaMemcpyAsync(out_dists, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -2042,8 +2271,9 @@ int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* g
   if (!e || n_ids < 0 || n_groups < 0 || !n_out) return fail(e, FB_ERR_INVALID, "fb_grouping_pq: bad arguments");
   int rc = check_pq_ready(e);
   if (rc) return rc;
+  const int d = pq_dim(e);
   if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "grouping_pq reads the group vectors from the word-vector table: fb_load_vectors first");
-  if (e->vec_d != e->d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, pq index d=%d", e->vec_d, e->d);
+  if (e->vec_d != d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, pq index d=%d", e->vec_d, d);
   *n_out = 0;
   if ((n_ids > 0 && (!ids || !out_ids || !out_group_ids)) || (n_groups > 0 && !group_ids)) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
@@ -2056,22 +2286,26 @@ int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* g
     if (grows[g] < 0 || (g > 0 && groups[g] == groups[g - 1])) return fail(e, FB_ERR_INVALID, "Group ids do not exist");
   }
   if (n_ids == 0) return FB_OK;
-  std::vector<int32_t> rows;
-  CodeTable view;
-  if ((rc = build_pq_subset(e, ids, n_ids, view, rows))) return rc;
-  const int n = (int)rows.size();
+  CodeTableDev view;
+  int64_t rows_upper = 0;
+  if ((rc = build_subset(e, e->pq, ids, n_ids, view, rows_upper))) return rc;
+  int32_t n = 0;
+  FB_CUDA(e, cudaMemcpyAsync(&n, e->sel_total.p, sizeof n, cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
   *n_out = n;
   if (n == 0) return FB_OK;
+  std::vector<int32_t> rows((size_t)n);
+  FB_CUDA(e, cudaMemcpy(rows.data(), e->sel_rows.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) out_ids[i] = e->pq_ids_host[rows[i]];
   if (n_groups == 0) return fail(e, FB_ERR_REFERENCE_UB, "no groups: the reference reads an uninitialised assignment (freddy.c:1326-1352)");
   const Codebook& cb = e->cb[FB_CB_PQ];
-  const int d = e->d, m = cb.m, K = cb.K;
+  const int m = cb.m, K = cb.K;
   const size_t lut_bytes = (size_t)m * K * sizeof(float);
   if (2 * lut_bytes > e->smem_optin - 1024) return fail(e, FB_ERR_UNSUPPORTED, "LUT too large for shared memory");
+  const int n_blocks = (n + 31) / 32, n_slots = n_blocks * 32;
   FB_CUDA(e, e->ana_rows.ensure((size_t)n_groups));
   FB_CUDA(e, e->q_stage.ensure((size_t)n_groups * d));
   FB_CUDA(e, e->lut.ensure((size_t)n_groups * m * K));
-  const int n_slots = (int)view.n_blocks * 32;
   FB_CUDA(e, e->id_stage.ensure((size_t)n_slots));
   FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, grows.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
   gather_vec_rows_kernel<<<n_groups, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, n_groups, e->q_stage.p);
@@ -2080,11 +2314,10 @@ int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* g
   if ((rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, n_groups, e->lut.p))) return rc;   // freddy.c:1291-1299
   {
     StageTimer t(e, ST_SCAN);
-    const int ctas = (int)((view.n_blocks + kGroupThreads / 32 - 1) / (kGroupThreads / 32));
+    const int ctas = (n_blocks + kGroupThreads / 32 - 1) / (kGroupThreads / 32);
     auto kern = (m == 12) ? grouping_argmin_kernel<12> : grouping_argmin_kernel<0>;
     FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * lut_bytes)));
-    kern<<<ctas, kGroupThreads, 2 * lut_bytes, e->stream>>>(view.dev(), (int)view.n_blocks, n, e->lut.p, n_groups, K,
-                                                           e->id_stage.p, e->small.p + 2);
+    kern<<<ctas, kGroupThreads, 2 * lut_bytes, e->stream>>>(view, n_blocks, n, e->lut.p, n_groups, K, e->id_stage.p, e->small.p + 2);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
   }
@@ -2097,11 +2330,10 @@ int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* g
     cudaMemset(e->small.p + 2, 0, sizeof(int32_t));
     return fail(e, FB_ERR_REFERENCE_UB, "a row is >= 100 away from every group: the reference's assignment is uninitialised (freddy.c:1326-1352)");
   }
-  // the temporary table is laid out in pseudo lists of 4096 rows, each padded to whole blocks: walk the slots
-  int i = 0;
-  for (int s_ = 0; s_ < n_slots && i < n; s_++)
-    if (nearest[s_] >= 0) out_group_ids[i++] = groups[nearest[s_]];
-  if (i != n) return fail(e, FB_ERR_CUDA, "grouping_pq: internal slot accounting (%d of %d rows)", i, n);
+  for (int i = 0; i < n; i++) {            // the subset is one compact list: slot i = i-th selected row
+    if (nearest[i] < 0) return fail(e, FB_ERR_CUDA, "grouping_pq: internal slot accounting (slot %d of %d)", i, n);
+    out_group_ids[i] = groups[nearest[i]];
+  }
   e->host_rows += (int64_t)n * n_groups;
   e->bytes_per_row = 2 * m + 4;
   return FB_OK;

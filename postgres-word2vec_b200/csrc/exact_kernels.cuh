@@ -289,7 +289,8 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
                     int32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                     int32_t* __restrict__ error_flag, int lut_stage_floats,
                     float sentinel,                      // 1000.0 (freddy.c:184) / 100.0 (freddy.c:823-827)
-                    u64* __restrict__ rows_counter) {    // statistics (rows whose ADC distance was computed), or nullptr
+                    u64* __restrict__ rows_counter,      // statistics (rows whose ADC distance was computed), or nullptr
+                    int batch_mode) {                    // ivfadc_batch_search's loop (freddy.c:838-981), see below
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ExactShared sh = exact_carve(smem_raw, k, lut_stage_floats);
   unsigned char* p = smem_raw + kExactFixedSmem + sizeof(float) * (size_t)lut_stage_floats;
@@ -347,8 +348,12 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
     long long found = 0;
     int n_black = 0;
     bool failed = false;
-    while (found < k) {                                  // freddy.c:262
-      if (C - n_black < w) { failed = true; break; }     // reference would index cq[-1]
+    // ivfadc_search counts the rows it fetched (freddy.c:377).  ivfadc_batch_search counts ADMISSIONS
+    // (`foundInstances++` inside `if (distance < maxDist)`, freddy.c:966-972) and probes on while a query has
+    // fewer than k of them, i.e. exactly while its top-k still has an empty slot (every admission fills one
+    // until the array is full); its per-round list is the plain arg-min below 1000 (freddy.c:854-866).
+    while (batch_mode ? (sh.tk_t[k - 1] == kNoRow) : (found < k)) {   // freddy.c:262 / :977-981
+      if (C - n_black < w) { failed = true; break; }     // reference would index cq[-1] / reuse a stale list
       for (int c = tid; c < C; c += kExactThreads) {     // freddy.c:272-278
         float acc = 0.0f;
         for (int i = 0; i < d; i++) {
@@ -365,6 +370,10 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
         for (int i = 0; i < C; i++) {
           if (black[i]) continue;
           float dist = cdist[i];
+          if (batch_mode) {                               // freddy.c:854-866: first minimum below 1000
+            if (dist < min_dist) { min_dist = dist; sel[0] = i; sel_d[0] = dist; }
+            continue;
+          }
           if (dist < min_dist) {
             if (!(dist < 100.0f)) { bad = 1; break; }     // reference would write sel[w]
             int slot = w;
@@ -375,6 +384,7 @@ ivfadc_exact_kernel(const float* __restrict__ queries, int d,
             min_dist = sel_d[w - 1];
           }
         }
+        if (batch_mode && sel[0] < 0) bad = 1;           // nothing below 1000 left: the reference re-reads a stale list
         if (!bad) for (int j = 0; j < w; j++) black[sel[j]] = 1;   // freddy.c:289-293
         sh.misc[4] = bad;
       }

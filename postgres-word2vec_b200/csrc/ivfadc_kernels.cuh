@@ -524,7 +524,8 @@ adc_scan_kernel(CodeTableDev tab,
                 int lists_per_task_mod,                  // if task_list == nullptr: list = task % lists_per_task_mod
                 int segs,                                // CTAs per task: each scans 1/segs of the list's blocks
                 const float* __restrict__ lut, int K, int KK,
-                u64* __restrict__ partial) {             // [ntasks * segs][KK]: the CTA's KK smallest keys, ascending
+                u64* __restrict__ partial,               // [ntasks * segs][KK]: the CTA's KK smallest keys, ascending
+                float sentinel) {                        // rows with distance >= sentinel are never admitted (freddy.c:369)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   float* slut = reinterpret_cast<float*>(smem_raw);
@@ -551,7 +552,10 @@ adc_scan_kernel(CodeTableDev tab,
   mbar_wait(&bar, 0);
 
   u64 mine = kKeyInf;
-  uint32_t thr_bits = 0xFFFFFFFFu;
+  // the reference admits with `distance < maxDist`, maxDist starting at the sentinel: the largest admissible
+  // distance is the float just below it (distances are >= +0, so bit patterns order like the values)
+  const uint32_t thr0 = __float_as_uint(sentinel) - 1u;
+  uint32_t thr_bits = thr0;
   const char* lut_bytes_base = reinterpret_cast<const char*>(slut);
   const uint32_t row_stride = (uint32_t)K * 4u;
 
@@ -571,7 +575,7 @@ adc_scan_kernel(CodeTableDev tab,
         warp_list_insert(mine, nk, lane);
         mask &= mask - 1;
       }
-      thr_bits = key_dbits(shfl_u64(mine, KK - 1));
+      thr_bits = min(thr0, key_dbits(shfl_u64(mine, KK - 1)));
     }
   }
   // merge the warps' lists inside the CTA (the LUT is no longer needed: reuse its shared memory)
@@ -727,7 +731,7 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     mbar_fence_init();
-    s_thr = 0xFFFFFFFFu;
+    s_thr = __float_as_uint(sentinel) - 1u;   // strict admission below the sentinel (freddy.c:369)
   }
   __syncthreads();
   if (tid == 0) {
@@ -740,7 +744,8 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
   }
 
   u64 mine = kKeyInf;
-  uint32_t my_thr = 0xFFFFFFFFu;
+  const uint32_t thr0 = __float_as_uint(sentinel) - 1u;
+  uint32_t my_thr = thr0;
   const uint32_t row_stride = (uint32_t)Kc * 4u;
 
   for (int j = 0; j < w; j++) {
@@ -786,7 +791,7 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
           warp_list_insert(mine, shfl_u64(key, src), lane);
           mask &= mask - 1;
         }
-        my_thr = key_dbits(shfl_u64(mine, KK - 1));
+        my_thr = min(thr0, key_dbits(shfl_u64(mine, KK - 1)));
         if (lane == 0 && my_thr < thr) atomicMin(&s_thr, my_thr);
       }
     }

@@ -284,6 +284,7 @@ __device__ void block_reference_topk(const u64* __restrict__ keys, int n, int k,
     const int n_out = min(n_s, k);
     for (int i = tid; i < n_out; i += kJoinThreads) {
       const uint32_t db = key_dbits(sbuf[i]);
+      if (!(__uint_as_float(db) < sentinel)) continue;     // strict admission below the sentinel: the slot stays (-1, sentinel)
       int s0 = i, e0 = i;
       while (s0 > 0 && key_dbits(sbuf[s0 - 1]) == db) s0--;
       while (e0 + 1 < n_out && key_dbits(sbuf[e0 + 1]) == db) e0++;
@@ -473,6 +474,7 @@ ivpq_scan_kernel(const float* __restrict__ queries, const int32_t* __restrict__ 
       const int n_s = block_select_smallest(keys, n_cand, P, false, 0, sbuf, s_hist, s_misc);
       __syncthreads();
       for (int j = tid; j < n_s; j += kJoinThreads) {
+        if (!(key_dist(sbuf[j]) < MAX_DIST)) { pv_d[j] = MAX_DIST; continue; }   // never entered the PV buffer (ivpq_search_in.c:505)
         const int t = (int)key_t(sbuf[j]);
         const int vr = t_vrow[t];
         const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);

@@ -138,7 +138,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
     for (int p = 0; p < 2; p++) {
       mbar_init(&ctl->stg_full[p], kPipeScanWarps);
       mbar_init(&ctl->stg_empty[p], 1);
-      ctl->thr[p] = 0xFFFFFFFFu;
+      ctl->thr[p] = __float_as_uint(a.sentinel) - 1u;   // strict admission below the sentinel (freddy.c:369)
       ctl->stage_q[p] = -1;
     }
     mbar_init(&ctl->cb_bar, 1);
@@ -297,7 +297,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
       }
       warp_emit_topk(mine, lane, q, a.q_base, a.k, a.qflags[q], a.tab.ids, a.sentinel, a.qflags, a.out_ids, a.out_dists,
                      a.exact_list, a.exact_count, a.exact_total, a.kth_key, 32);
-      if (lane == 0) ctl->thr[p] = 0xFFFFFFFFu;
+      if (lane == 0) ctl->thr[p] = __float_as_uint(a.sentinel) - 1u;
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->stg_empty[p]);
     }
@@ -309,7 +309,8 @@ ivfadc_pipe_kernel(const PipeArgs a) {
     constexpr int UU = (M + 3) / 4;
     const uint32_t smem_base = smem_u32(smem_raw);
     u64 mine = kKeyInf;
-    uint32_t my_thr = 0xFFFFFFFFu;
+    const uint32_t thr0 = __float_as_uint(a.sentinel) - 1u;
+    uint32_t my_thr = thr0;
     int nq_seen = 0, p = 0;
     for (int t = 0;; t++) {
       const int b = t % kPipeBufs;
@@ -319,7 +320,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
         p = nq_seen & 1;
         if (nq_seen >= 2) mbar_wait(&ctl->stg_empty[p], (uint32_t)(((nq_seen >> 1) - 1) & 1));
         mine = kKeyInf;
-        my_thr = 0xFFFFFFFFu;
+        my_thr = thr0;
       }
       if (ds.z < 0) {
         if (warp == 0 && lane == 0) ctl->stage_q[p] = -1;
@@ -365,7 +366,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
             warp_list_insert(mine, shfl_u64(key, src), lane);
             mask &= mask - 1;
           }
-          my_thr = key_dbits(shfl_u64(mine, a.KK - 1));
+          my_thr = min(thr0, key_dbits(shfl_u64(mine, a.KK - 1)));
           if (lane == 0 && my_thr < thr) atomicMin(&ctl->thr[p], my_thr);
         }
       };

@@ -17,6 +17,7 @@ FB_OPT_LUT_TILE = 6
 FB_OPT_LUT_CTAS_PER_SM, FB_OPT_OVERLAP = 7, 8
 FB_OPT_PIPELINE, FB_OPT_PIPE_CHUNK, FB_OPT_PIPE_DEBUG, FB_OPT_PLACEMENT_WINDOW = 9, 10, 11, 12
 FB_OPT_PIPE_SHAPE, FB_OPT_PIPE_RAMP, FB_OPT_CUDA_GRAPHS, FB_OPT_ZERO_COPY_UPLOAD = 13, 14, 15, 16
+FB_OPT_PREFILTER = 17
 
 
 class Counters(C.Structure):
@@ -28,6 +29,7 @@ class Counters(C.Structure):
         ("exact_coarse_tie", C.c_int64), ("exact_coarse_far", C.c_int64), ("exact_few_rows", C.c_int64),
         ("exact_scan_tie", C.c_int64), ("exact_forced", C.c_int64),
         ("ms_pipe", C.c_double), ("n_pipe_launches", C.c_int64),
+        ("prefilter_queries", C.c_int64), ("prefilter_overflow_queries", C.c_int64), ("prefilter_candidates", C.c_int64),
     ]
 
 

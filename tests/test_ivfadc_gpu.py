@@ -163,6 +163,36 @@ def test_flat_pq(eng, oracle_mod):
     assert_same_topk(ids, d, eids, ed, "fewer targets than k")
 
 
+def test_flat_pq_in_batch_shapes(eng, oracle_mod):
+    """pq_search_in_batch: the target subset is built on the device (id -> rows, bitmap, scan, gather); unsorted and
+    repeated ids in the table (every matching row is a candidate, once, in table order), many queries (one CTA per
+    query, resident LUT) and few queries (the table cut into segments), empty and unknown target lists"""
+    ix = dict(small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True))
+    rng = np.random.default_rng(4)
+    ids = rng.permutation(np.arange(1, ix["N"] + 1)).astype(np.int32)
+    ids[100:140] = ids[5000:5040]                       # repeated ids: both rows are selected by `id IN (...)`
+    ix["ids"] = ids
+    eng.load_pq_index(ix)
+    oi = oracle_mod.OracleIndex(ix, flat_pq=True)
+    targets = np.concatenate([ids[90:150], ids[4990:5050], rng.choice(ids, 4000), [10 ** 8, -5]]).astype(np.int32)
+    for nq in (1, 7, 400):
+        q = queries_from(ix, nq, seed=nq)
+        got = eng.pq_search_in_batch(q, 5, targets)
+        exp = oi.pq_search_in_batch(q, 5, targets)
+        assert_same_topk(got[0], got[1], exp[0], exp[1], f"pq_search_in_batch nq={nq}")
+    q = queries_from(ix, 9, seed=2)
+    for t in (np.zeros(0, np.int32), np.asarray([10 ** 8], np.int32)):
+        got = eng.pq_search_in_batch(q, 4, t)
+        assert (got[0] == -1).all() and (got[1] == np.float32(1000.0)).all()
+    got = eng.pq_search(q, 12)                          # the whole table, few queries: segmented scan + finalize
+    exp = oi.pq_search(q, 12)
+    assert_same_topk(got[0], got[1], exp[0], exp[1], "pq_search few queries")
+    q = queries_from(ix, 700, seed=3)
+    got = eng.pq_search(q, 3)                           # the whole table, one CTA per query
+    exp = oi.pq_search(q, 3)
+    assert_same_topk(got[0], got[1], exp[0], exp[1], "pq_search many queries")
+
+
 def test_against_reference_srf_golden(eng):
     """the CUDA engine directly against committed outputs of the reference's own SRFs
     (freddy.c run through the emulator, tests/golden/make_golden.py)"""
