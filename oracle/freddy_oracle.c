@@ -262,22 +262,40 @@ static int cmp_i32(const void* a, const void* b) {
   return (x > y) - (x < y);
 }
 
-/* Rows selected by `WHERE id IN (targets)` in table order: ids are ascending,
- * duplicates and unknown ids in the IN-list select nothing extra. */
+/* Rows selected by `WHERE id IN (targets)` in TABLE order, every matching row once (duplicates and unknown ids
+ * in the IN-list select nothing extra; an id carried by several rows selects them all).  Strictly ascending id
+ * columns (the bulk-loaded tables) take the fast path: one binary search per listed id. */
 static int select_target_rows(const FoIndex* ix, const int32_t* targets, int n_targets, int32_t** rows_out) {
   int32_t* sorted = malloc(sizeof(int32_t) * (size_t)(n_targets > 0 ? n_targets : 1));
-  int32_t* rows = malloc(sizeof(int32_t) * (size_t)(n_targets > 0 ? n_targets : 1));
   memcpy(sorted, targets, sizeof(int32_t) * (size_t)n_targets);
   qsort(sorted, (size_t)n_targets, sizeof(int32_t), cmp_i32);
+  int ascending = 1;
+  for (int64_t r = 1; r < ix->N && ascending; r++) ascending = ix->ids[r - 1] < ix->ids[r];
+  int32_t* rows;
   int n = 0;
-  for (int i = 0; i < n_targets; i++) {
-    if (i > 0 && sorted[i] == sorted[i - 1]) continue;
-    int lo = 0, hi = ix->N - 1;
-    while (lo <= hi) {
-      int mid = lo + (hi - lo) / 2;
-      if (ix->ids[mid] < sorted[i]) lo = mid + 1;
-      else if (ix->ids[mid] > sorted[i]) hi = mid - 1;
-      else { rows[n++] = mid; break; }
+  if (ascending) {
+    rows = malloc(sizeof(int32_t) * (size_t)(n_targets > 0 ? n_targets : 1));
+    for (int i = 0; i < n_targets; i++) {
+      if (i > 0 && sorted[i] == sorted[i - 1]) continue;
+      int lo = 0, hi = ix->N - 1;
+      while (lo <= hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (ix->ids[mid] < sorted[i]) lo = mid + 1;
+        else if (ix->ids[mid] > sorted[i]) hi = mid - 1;
+        else { rows[n++] = mid; break; }
+      }
+    }
+  } else {
+    rows = malloc(sizeof(int32_t) * (size_t)(ix->N > 0 ? ix->N : 1));
+    for (int64_t r = 0; r < ix->N; r++) {
+      int lo = 0, hi = n_targets - 1, hit = 0;
+      while (lo <= hi && !hit) {
+        int mid = lo + (hi - lo) / 2;
+        if (sorted[mid] < ix->ids[r]) lo = mid + 1;
+        else if (sorted[mid] > ix->ids[r]) hi = mid - 1;
+        else hit = 1;
+      }
+      if (hit) rows[n++] = (int32_t)r;
     }
   }
   free(sorted);

@@ -123,9 +123,12 @@ struct fb_engine {
   std::unordered_map<int32_t, int32_t> ivpq_id_to_row;
   int ivpq_Kc = 0, ivpq_d = 0;
   bool ivpq_loaded = false;
-  DevBuf<int32_t> j_cell, j_vrow, j_id, j_active, j_ncells, j_filled, j_tcounts;
+  DevBuf<int32_t> j_cell, j_vrow, j_id, j_active, j_active2, j_ncells, j_filled, j_tcounts;
+  DevBuf<int32_t> j_counts, j_cell_start, j_perm, j_state;
+  DevBuf<uint16_t> j_sel_cells;
   DevBuf<uint32_t> j_bitmaps;
   DevBuf<u64> j_keys;
+  int64_t join_rounds = 0, join_pairs = 0;
   // word-vector table (analogy / exact rerank)
   DevBuf<float> vecT;
   DevBuf<int32_t> vec_ids, vec_sorted_ids, vec_sorted_rows;   // sorted (id, row) pairs: id -> row on the device
@@ -2040,25 +2043,24 @@ int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const i
   const int cells = Kc * Kc;
   for (int64_t r = 0; r < N; r++)
     if (coarse_ids[r] < 0 || coarse_ids[r] >= cells) return fail(e, FB_ERR_INVALID, "row %lld: coarse_id %d out of range", (long long)r, coarse_ids[r]);
-  int rc = build_table(e, e->ivpq, ids, nullptr, 0, 8192, codes, N, m, e->cb[FB_CB_IVPQ].K);
+  int rc = build_table(e, e->ivpq, ids, nullptr, 0, 0x7fffffff, codes, N, m, e->cb[FB_CB_IVPQ].K);   // one list, table order
   if (rc) return rc;
+  if ((rc = build_id_index(e, e->ivpq, ids, N))) return rc;
   FB_CUDA(e, e->coarse_multi.ensure((size_t)2 * Kc * (d / 2)));
   FB_CUDA(e, e->ivpq_stats.ensure((size_t)cells + 1));
   FB_CUDA(e, e->ivpq_cells.ensure((size_t)std::max<int64_t>(1, N)));
   FB_CUDA(e, cudaMemcpy(e->coarse_multi.p, coarse_multi, (size_t)2 * Kc * (d / 2) * sizeof(float), cudaMemcpyHostToDevice));
   FB_CUDA(e, cudaMemcpy(e->ivpq_stats.p, stats, ((size_t)cells + 1) * sizeof(float), cudaMemcpyHostToDevice));
   if (N > 0) FB_CUDA(e, cudaMemcpy(e->ivpq_cells.p, coarse_ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-  e->ivpq_ids_host.assign(ids, ids + N);
-  e->ivpq_cells_host.assign(coarse_ids, coarse_ids + N);
   e->ivpq_stats_host.assign(stats, stats + cells + 1);
-  e->ivpq_ids_sorted = std::is_sorted(e->ivpq_ids_host.begin(), e->ivpq_ids_host.end());
-  e->ivpq_id_to_row.clear();
-  if (!e->ivpq_ids_sorted)
-    for (int64_t r = 0; r < N; r++) e->ivpq_id_to_row.emplace(ids[r], (int32_t)r);
   e->ivpq_Kc = Kc; e->ivpq_d = d; e->ivpq_loaded = true;
   return FB_OK;
 }
 
+// ivpq_search_in (ivpq_search_in.c:61-721).  Per call: the target set becomes a compact CELL-MAJOR table on the
+// device (`id IN (targets)` -> rows -> stable counting sort by multi-index cell); per round of the reference's
+// retry loop: cell selection per active query, then a scan that touches only the rows of the selected cells.
+// The active list is compacted on the device; the host reads back two integers per round.
 int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets, int alpha,
                       int pvf, int method, int use_target_lists, float confidence, int double_threshold,
                       int32_t* out_ids, float* out_dists) {
@@ -2078,128 +2080,107 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
   // alpha*k > double_threshold selects the pair-LUT variant (ivpq_search_in.c:261-275); decided once from the
   // alpha of the call, like the reference.  Its pair codes live in an int16 array (:417, :447-451).
   const bool pair_sums = method != 1 && (int64_t)alpha * k > double_threshold;
-  if (pair_sums && (int64_t)e->cb[FB_CB_IVPQ].K * e->cb[FB_CB_IVPQ].K > 32768)
-    return fail(e, FB_ERR_REFERENCE_UB, "pair-LUT variant with K=%d: the reference's int16 pair codes overflow (ivpq_search_in.c:447-451)",
-                e->cb[FB_CB_IVPQ].K);
+  if (pair_sums && (int64_t)K * K > 32768)
+    return fail(e, FB_ERR_REFERENCE_UB, "pair-LUT variant with K=%d: the reference's int16 pair codes overflow (ivpq_search_in.c:447-451)", K);
   if ((int64_t)k * pvf > kJoinMaxP) return fail(e, FB_ERR_UNSUPPORTED, "k*pvf=%lld > %d", (long long)k * pvf, kJoinMaxP);
   if (nq == 0) return FB_OK;
   if (!queries || !out_ids || !out_dists) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
-  e->d = d;
 
-  // rows selected by `fq.id IN (targets)` in table order (ivpq_search_in.c:352-401)
-  std::vector<int32_t> rows;
-  rows.reserve(n_targets);
-  for (int i = 0; i < n_targets; i++) {
-    if (e->ivpq_ids_sorted) {
-      auto it = std::lower_bound(e->ivpq_ids_host.begin(), e->ivpq_ids_host.end(), targets[i]);
-      if (it != e->ivpq_ids_host.end() && *it == targets[i]) rows.push_back((int32_t)(it - e->ivpq_ids_host.begin()));
-    } else {
-      auto it = e->ivpq_id_to_row.find(targets[i]);
-      if (it != e->ivpq_id_to_row.end()) rows.push_back(it->second);
-    }
-  }
-  std::sort(rows.begin(), rows.end());
-  rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-  const int nt = (int)rows.size();
-  std::vector<int32_t> h_cell(std::max(1, nt)), h_vrow(std::max(1, nt)), h_id(std::max(1, nt));
-  for (int t = 0; t < nt; t++) {
-    h_cell[t] = e->ivpq_cells_host[rows[t]];
-    h_id[t] = e->ivpq_ids_host[rows[t]];
-    h_vrow[t] = (method != 0) ? vec_row_of(e, h_id[t]) : -1;
-  }
-  // temporary blocked table over the target rows (arrival order = slot order)
-  CodeTable& tmp = e->jtmp;
-  const int U = e->ivpq.U;
-  const int n_slots = std::max(1, (nt + 31) / 32) * 32;
-  FB_CUDA(e, tmp.units.ensure((size_t)n_slots * U));
-  FB_CUDA(e, tmp.rowno.ensure((size_t)n_slots));
-  FB_CUDA(e, e->sel_rows.ensure((size_t)std::max(1, nt)));
-  FB_CUDA(e, e->j_cell.ensure(h_cell.size()));
-  FB_CUDA(e, e->j_vrow.ensure(h_vrow.size()));
-  FB_CUDA(e, e->j_id.ensure(h_id.size()));
-  if (nt > 0) {
-    FB_CUDA(e, cudaMemcpyAsync(e->sel_rows.p, rows.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    FB_CUDA(e, cudaMemcpyAsync(e->j_cell.p, h_cell.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    FB_CUDA(e, cudaMemcpyAsync(e->j_vrow.p, h_vrow.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    FB_CUDA(e, cudaMemcpyAsync(e->j_id.p, h_id.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  }
-  gather_rows_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(e->ivpq.units.p, U, e->sel_rows.p, nt, tmp.units.p, tmp.rowno.p, n_slots);
-  e->launches++;
-  FB_CUDA(e, cudaGetLastError());
-  CodeTableDev ttab;
-  ttab.units = tmp.units.p; ttab.rowno = tmp.rowno.p; ttab.list_blk = nullptr; ttab.list_len = nullptr;
-  ttab.ids = nullptr; ttab.m = m; ttab.U = U; ttab.n_lists = 1;
-
+  // ---- the target set: rows selected by `fq.id IN (targets)` in table order (ivpq_search_in.c:352-401) ----
   FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CodeTableDev sub;
+  int64_t rows_upper = 0;
+  if ((rc = build_subset(e, e->ivpq, targets, n_targets, sub, rows_upper))) return rc;   // only sel_rows / sel_total are used
+  const int nt_up = (int)std::max<int64_t>(1, rows_upper);
+  const int n_chunks = (nt_up + kJoinChunk - 1) / kJoinChunk;
+  const int U = e->ivpq.U;
+  const int n_slots = (nt_up + 31) / 32 * 32;
+  FB_CUDA(e, e->j_cell.ensure((size_t)nt_up));
+  FB_CUDA(e, e->j_vrow.ensure((size_t)nt_up));
+  FB_CUDA(e, e->j_id.ensure((size_t)nt_up));
+  FB_CUDA(e, e->j_perm.ensure((size_t)nt_up));
+  FB_CUDA(e, e->j_counts.ensure((size_t)n_chunks * kJoinCells));
+  FB_CUDA(e, e->j_cell_start.ensure((size_t)kJoinCells + 1));
+  FB_CUDA(e, e->jtmp.units.ensure((size_t)n_slots * U));
+  FB_CUDA(e, e->j_state.ensure(4));
+  join_rows_kernel<<<(nt_up + 255) / 256, 256, 0, e->stream>>>(e->sel_rows.p, e->sel_total.p, e->ivpq_cells.p, e->ivpq.ids.p,
+                                                               e->vec_sorted_ids.p, e->vec_sorted_rows.p, (int)e->vec_N,
+                                                               method != 0 ? 1 : 0, e->j_cell.p, e->j_id.p, e->j_vrow.p);
+  join_cell_count_kernel<<<n_chunks, 32, 0, e->stream>>>(e->j_cell.p, e->sel_total.p, e->j_counts.p);
+  join_cell_scan_kernel<<<1, kJoinCells, 0, e->stream>>>(e->j_counts.p, n_chunks, e->j_cell_start.p);
+  join_cell_scatter_kernel<<<n_chunks, 32, 0, e->stream>>>(e->j_cell.p, e->sel_total.p, e->j_counts.p, e->sel_rows.p, e->ivpq.units.p, U,
+                                                           e->j_perm.p, e->jtmp.units.p);
+  e->launches += 4;
+  FB_CUDA(e, cudaGetLastError());
+  CodeTableDev ctab;
+  ctab.units = e->jtmp.units.p; ctab.rowno = nullptr; ctab.list_blk = nullptr; ctab.list_len = nullptr;
+  ctab.ids = nullptr; ctab.m = m; ctab.U = U; ctab.n_lists = 1;
+
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->j_active.ensure((size_t)nq));
+  FB_CUDA(e, e->j_active2.ensure((size_t)nq));
   FB_CUDA(e, e->j_ncells.ensure((size_t)nq));
   FB_CUDA(e, e->j_filled.ensure((size_t)nq));
   FB_CUDA(e, e->j_tcounts.ensure((size_t)nq));
-  FB_CUDA(e, e->j_bitmaps.ensure((size_t)nq * 32));
-  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  FB_CUDA(e, e->j_sel_cells.ensure((size_t)nq * 1024));
   FB_CUDA(e, cudaMemsetAsync(e->j_tcounts.p, 0, (size_t)nq * sizeof(int32_t), e->stream));
+  iota_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>(e->j_active.p, nq);
+  e->launches++;
   if (method != 1) {   // LUT per query on the raw query (ivpq_search_in.c:279-290)
     FB_CUDA(e, e->lut.ensure((size_t)nq * m * K));
     if ((rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, nq, e->lut.p))) return rc;
   }
-  const size_t smem = sizeof(u64) * kJoinSortN + (sizeof(float) * 2 + sizeof(int32_t)) * kJoinMaxP +
+  const size_t smem = sizeof(u64) * 2 * kJoinSortN + (sizeof(float) * 2 + sizeof(int32_t)) * kJoinMaxP +
                       (method != 1 ? (size_t)m * K * sizeof(float) : 0);
   if (smem > e->smem_optin - 4096) return fail(e, FB_ERR_UNSUPPORTED, "LUT too large for the join kernel");
-  FB_CUDA(e, cudaFuncSetAttribute(ivpq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t key_budget = (size_t)512 << 20;
-  const int q_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, key_budget / (sizeof(u64) * (size_t)std::max(1, nt))));
-  FB_CUDA(e, e->j_keys.ensure((size_t)q_chunk * std::max(1, nt)));
+  FB_CUDA(e, cudaFuncSetAttribute(ivpq_scan_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent scan CTAs; each owns a slice of global key scratch for queries with more than kJoinSortN candidate rows
+  int scan_ctas = std::max(1, std::min(nq, 2 * e->num_sms));
+  while (scan_ctas > 1 && (size_t)scan_ctas * nt_up * sizeof(u64) > ((size_t)256 << 20)) scan_ctas /= 2;
+  FB_CUDA(e, e->j_keys.ensure((size_t)scan_ctas * nt_up));
 
-  std::vector<int32_t> active(nq), n_cells(nq), filled(nq);
-  for (int i = 0; i < nq; i++) active[i] = i;
   int n_active = nq;
   int64_t cur_alpha = alpha;
+  int32_t* act = e->j_active.p;
+  int32_t* act_next = e->j_active2.p;
   JoinParams prm;
   prm.d = d; prm.m = m; prm.K = K; prm.Kc = Kc; prm.k = k; prm.pvf = pvf; prm.method = method;
   prm.n_targets_sql = n_targets; prm.confidence = confidence; prm.stat_total = (int)e->ivpq_stats_host[cells];
   prm.skip_below = use_target_lists ? k * alpha : 0;
   prm.pair_sums = pair_sums ? 1 : 0;
+  prm.last_iteration = 0;
   while (n_active > 0) {                                                                        // :299
     prm.min_target = (int)std::min<int64_t>((int64_t)k * cur_alpha, 0x7fffffff);
-    FB_CUDA(e, cudaMemcpyAsync(e->j_active.p, active.data(), (size_t)n_active * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    const int32_t st0[4] = {1, 0, 0, 0};      // [0] all active queries exhausted every cell (AND), [1] next active count, [2] work counter
+    FB_CUDA(e, cudaMemcpyAsync(e->j_state.p, st0, sizeof st0, cudaMemcpyHostToDevice, e->stream));
     {
       StageTimer t(e, ST_COARSE);
-      ivpq_select_kernel<<<n_active, 1024, 0, e->stream>>>(e->q_stage.p, e->j_active.p, d, Kc, e->coarse_multi.p,
-                                                           e->ivpq_stats.p, prm, e->j_bitmaps.p, e->j_ncells.p);
+      ivpq_select_kernel<<<n_active, 1024, 0, e->stream>>>(e->q_stage.p, act, d, Kc, e->coarse_multi.p, e->ivpq_stats.p, prm,
+                                                           e->j_sel_cells.p, e->j_ncells.p, e->j_state.p);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
     }
-    FB_CUDA(e, cudaMemcpyAsync(n_cells.data(), e->j_ncells.p, (size_t)n_active * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    FB_CUDA(e, cudaStreamSynchronize(e->stream));
-    bool last = true;                                                                           // index_utils.c:404-406
-    for (int i = 0; i < n_active; i++) last = last && (n_cells[i] >= cells);
-    prm.last_iteration = last ? 1 : 0;
     {
       StageTimer t(e, ST_SCAN);
-      for (int c0 = 0; c0 < n_active; c0 += q_chunk) {
-        const int nc = std::min(q_chunk, n_active - c0);
-        ivpq_scan_kernel<<<nc, kJoinThreads, smem, e->stream>>>(
-            e->q_stage.p, e->j_active.p + c0, prm, ttab, nt, e->j_cell.p, e->j_vrow.p, e->j_id.p, e->vecT.p, e->lut.p,
-            e->j_bitmaps.p + (size_t)c0 * 32, e->j_tcounts.p, e->j_keys.p, e->id_stage.p, e->dist_stage.p,
-            e->j_filled.p + c0);
-        e->launches++;
-        e->n_scan_launches++;
-        FB_CUDA(e, cudaGetLastError());
-      }
+      ivpq_scan_cells_kernel<<<std::min(scan_ctas, n_active), kJoinThreads, smem, e->stream>>>(
+          e->q_stage.p, act, n_active, prm, ctab, e->j_cell_start.p, e->j_perm.p, e->j_vrow.p, e->j_id.p, e->vecT.p, e->lut.p,
+          e->j_sel_cells.p, e->j_ncells.p, e->j_state.p, e->j_tcounts.p, e->j_keys.p, (size_t)nt_up, e->id_stage.p, e->dist_stage.p,
+          e->j_filled.p, e->j_state.p + 2, e->counters64.p + 7);
+      e->launches++;
+      e->n_scan_launches++;
+      FB_CUDA(e, cudaGetLastError());
     }
-    FB_CUDA(e, cudaMemcpyAsync(filled.data(), e->j_filled.p, (size_t)n_active * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    join_next_active_kernel<<<(n_active + 255) / 256, 256, 0, e->stream>>>(act, e->j_filled.p, n_active, act_next, e->j_state.p);
+    e->launches++;
+    int32_t st[2] = {0, 0};
+    FB_CUDA(e, cudaMemcpyAsync(st, e->j_state.p, sizeof st, cudaMemcpyDeviceToHost, e->stream));
     FB_CUDA(e, cudaStreamSynchronize(e->stream));
-    if (!last) {                                                                                // :639-666
-      int n_new = 0;
-      for (int i = 0; i < n_active; i++)
-        if (!filled[i]) active[n_new++] = active[i];
-      n_active = n_new;
-    } else {
-      n_active = 0;
-    }
+    e->join_rounds++;
+    n_active = st[0] ? 0 : st[1];                                                                // :639-666 (lastIteration ends the loop)
+    std::swap(act, act_next);
     cur_alpha += cur_alpha;                                                                     // :680
   }
   FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));

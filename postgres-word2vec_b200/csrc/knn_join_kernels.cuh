@@ -7,9 +7,9 @@
 //                        in ascending sum order, cumulative cell frequency, and the first prefix
 //                        whose getConfidenceHyp reaches `confidence` (the
 //                        reference's priority-queue traversal visits exactly that prefix)
-//   ivpq_scan_kernel     per active query: the target rows whose cell was selected, in table
-//                        order (= the reference's candidate arrival order) -> PQ / exact
-//                        distances -> the reference's selection:
+//   ivpq_scan_cells_kernel  per active query: the target rows of its selected cells (the per-call target
+//                        set is laid out cell-major; keys carry the rows' table order = the reference's
+//                        candidate arrival order) -> PQ / exact distances -> the reference's selection:
 //                          method 0/1  strict-admission top-k replayed literally over the
 //                                      rows that can matter (fact B, tests/test_topk_semantics.py)
 //                          method 2    the k*pvf smallest PQ distances (what the (200 + k*pvf)
@@ -74,8 +74,9 @@ ivpq_select_kernel(const float* __restrict__ queries, const int32_t* __restrict_
                    const float* __restrict__ coarse_multi,    // [2][Kc][d/2]
                    const float* __restrict__ stats,           // [Kc*Kc + 1]
                    JoinParams prm,
-                   uint32_t* __restrict__ bitmaps,            // [n_active][32]
-                   int32_t* __restrict__ n_cells) {           // [n_active]
+                   uint16_t* __restrict__ sel_cells,          // [n_active][1024] selected cells, ascending cell sum
+                   int32_t* __restrict__ n_cells,             // [n_active]
+                   int32_t* __restrict__ round_state) {       // [0]: AND over the active queries of "all cells selected"
   __shared__ float sd[64];
   __shared__ u64 keys[1024];
   __shared__ float prob[1025];
@@ -122,13 +123,11 @@ ivpq_select_kernel(const float* __restrict__ queries, const int32_t* __restrict_
       atomicMin(&first_ok, n);
   __syncthreads();
   const int n_sel = first_ok;
-  if (tid < 32) bitmaps[(size_t)x * 32 + tid] = 0u;
-  __syncthreads();
-  if (tid < n_sel) {
-    const uint32_t cell = key_t(keys[tid]);
-    atomicOr(&bitmaps[(size_t)x * 32 + (cell >> 5)], 1u << (cell & 31));
+  if (tid < n_sel) sel_cells[(size_t)x * 1024 + tid] = (uint16_t)key_t(keys[tid]);
+  if (tid == 0) {
+    n_cells[x] = n_sel;
+    if (n_sel < cells) atomicAnd(round_state, 0);                                 // index_utils.c:404-406 (lastIteration)
   }
-  if (tid == 0) n_cells[x] = n_sel;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -342,174 +341,295 @@ topk_from_keys_kernel(const u64* __restrict__ key_base, size_t stride, const int
   }
 }
 
+// =======================================================================================
+// Second draft of the join's data path: the per-call target set as a CELL-MAJOR compact table.
+//   join_rows_kernel        per selected target row t (table order = arrival order): cell, id, word-vector row
+//   join_cell_count/scan/scatter   stable counting sort of the rows by cell (arrival order kept inside a
+//                           cell), gathering the code units into a compact blocked table in that order
+//   ivpq_scan_cells_kernel  per active query: only the rows of ITS selected cells are touched
+// The selection that follows is key based ((distance, arrival t)), so the order in which a query's
+// candidates are generated does not matter.
+// =======================================================================================
+constexpr int kJoinChunk = 512;      // rows per counting-sort chunk (one warp walks a chunk in arrival order)
+constexpr int kJoinCells = 1024;
+
+__global__ void join_rows_kernel(const int32_t* __restrict__ sel_rows, const int32_t* __restrict__ n_sel,
+                                 const int32_t* __restrict__ cells, const int32_t* __restrict__ ids,
+                                 const int32_t* __restrict__ vec_sorted_ids, const int32_t* __restrict__ vec_sorted_rows, int n_vec,
+                                 int need_vec, int32_t* __restrict__ t_cell, int32_t* __restrict__ t_id, int32_t* __restrict__ t_vrow) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *n_sel) return;
+  const int row = sel_rows[t];
+  const int id = ids[row];
+  t_cell[t] = cells[row];
+  t_id[t] = id;
+  int vr = -1;
+  if (need_vec && id >= 0) {                                        // `INNER JOIN vecs ON fq.id = vecs.id`: first row carrying the id
+    int lo = 0, hi = n_vec;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (vec_sorted_ids[mid] < id) lo = mid + 1; else hi = mid; }
+    if (lo < n_vec && vec_sorted_ids[lo] == id) vr = vec_sorted_rows[lo];
+  }
+  t_vrow[t] = vr;
+}
+
+// counts[chunk][cell]: one warp per chunk, shared-memory histogram
+__global__ void __launch_bounds__(32)
+join_cell_count_kernel(const int32_t* __restrict__ t_cell, const int32_t* __restrict__ n_sel, int32_t* __restrict__ counts) {
+  __shared__ int hist[kJoinCells];
+  const int chunk = blockIdx.x, lane = threadIdx.x;
+  const int n = *n_sel;
+  for (int c = lane; c < kJoinCells; c += 32) hist[c] = 0;
+  __syncwarp();
+  const int t0 = chunk * kJoinChunk, t1 = min(n, t0 + kJoinChunk);
+  for (int t = t0 + lane; t < t1; t += 32) atomicAdd(&hist[t_cell[t]], 1);
+  __syncwarp();
+  for (int c = lane; c < kJoinCells; c += 32) counts[(size_t)chunk * kJoinCells + c] = hist[c];
+}
+
+// cell_start[c] (exclusive scan over cells of the per-cell totals, cell_start[1024] = n) and, in place,
+// counts[chunk][c] -> first slot of that chunk's rows inside cell c.  One CTA, thread = cell.
+__global__ void __launch_bounds__(kJoinCells)
+join_cell_scan_kernel(int32_t* __restrict__ counts, int n_chunks, int32_t* __restrict__ cell_start) {
+  __shared__ int s_part[kJoinCells];
+  const int c = threadIdx.x;
+  int tot = 0;
+  for (int ch = 0; ch < n_chunks; ch++) tot += counts[(size_t)ch * kJoinCells + c];
+  s_part[c] = tot;
+  __syncthreads();
+  for (int off = 1; off < kJoinCells; off <<= 1) {
+    const int v = (c >= off) ? s_part[c - off] : 0;
+    __syncthreads();
+    s_part[c] += v;
+    __syncthreads();
+  }
+  int base = s_part[c] - tot;
+  cell_start[c] = base;
+  if (c == kJoinCells - 1) cell_start[kJoinCells] = s_part[c];
+  for (int ch = 0; ch < n_chunks; ch++) {
+    const int v = counts[(size_t)ch * kJoinCells + c];
+    counts[(size_t)ch * kJoinCells + c] = base;
+    base += v;
+  }
+}
+
+// stable scatter: row t goes to slot pos = (first slot of its chunk in its cell) + (rows of the same cell earlier in
+// the chunk); perm[pos] = t and the row's code units are gathered from the pinned table into the compact one
+__global__ void __launch_bounds__(32)
+join_cell_scatter_kernel(const int32_t* __restrict__ t_cell, const int32_t* __restrict__ n_sel, const int32_t* __restrict__ chunk_base,
+                         const int32_t* __restrict__ sel_rows, const uint2* __restrict__ src_units, int U,
+                         int32_t* __restrict__ perm, uint2* __restrict__ dst_units) {
+  __shared__ int cursor[kJoinCells];
+  const int chunk = blockIdx.x, lane = threadIdx.x;
+  const int n = *n_sel;
+  for (int c = lane; c < kJoinCells; c += 32) cursor[c] = chunk_base[(size_t)chunk * kJoinCells + c];
+  __syncwarp();
+  const int t0 = chunk * kJoinChunk, t1 = min(n, t0 + kJoinChunk);
+  for (int tb = t0; tb < t1; tb += 32) {
+    const int t = tb + lane;
+    const bool live = t < t1;
+    const int cell = live ? t_cell[t] : -1 - lane;                  // dead lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int pos = -1;
+    if (live) pos = cursor[cell] + rank;
+    __syncwarp();
+    if (live && rank == 0) cursor[cell] += __popc(peers);
+    __syncwarp();
+    if (live) {
+      perm[pos] = t;
+      const int r = sel_rows[t];
+      const int sb = r >> 5, sl = r & 31, db = pos >> 5, dl = pos & 31;
+      for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = src_units[((size_t)sb * U + u) * 32 + sl];
+    }
+  }
+}
+
+// next round's active list: the queries of this round whose k-th slot stayed empty (ivpq_search_in.c:639-666)
+__global__ void join_next_active_kernel(const int32_t* __restrict__ active, const int32_t* __restrict__ filled, int n_active,
+                                        int32_t* __restrict__ next_active, int32_t* __restrict__ round_state) {   // [1]: count
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_active) return;
+  if (!filled[x]) next_active[atomicAdd(round_state + 1, 1)] = active[x];
+}
+
 // ---------------------------------------------------------------------------------------
-// candidate scan + selection: one CTA per active query
+// candidate scan + selection over the cell-major target table: persistent CTAs, one active query at a time
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kJoinThreads)
-ivpq_scan_kernel(const float* __restrict__ queries, const int32_t* __restrict__ active, JoinParams prm,
-                 // target rows of this call (table order): blocked codes, cell, word-vector row (-1 = none), id
-                 CodeTableDev ttab, int n_trows, const int32_t* __restrict__ t_cell, const int32_t* __restrict__ t_vrow,
-                 const int32_t* __restrict__ t_id,
-                 const float* __restrict__ vT,                 // word vectors, dimension-major 32-row blocks
-                 const float* __restrict__ luts,               // [nq][m][K] indexed by query (methods 0, 2)
-                 const uint32_t* __restrict__ bitmaps, int32_t* __restrict__ target_counts,   // [nq] accumulated, as the reference
-                 u64* __restrict__ key_scratch,                // [gridDim.x][n_trows]
-                 int32_t* __restrict__ out_ids, float* __restrict__ out_dists,                // [nq][k]
-                 int32_t* __restrict__ filled) {               // [n_active] 1 if the k-th slot is filled
+ivpq_scan_cells_kernel(const float* __restrict__ queries, const int32_t* __restrict__ active, int n_active, JoinParams prm,
+                       CodeTableDev ctab,                     // compact cell-major code table (slot = position in perm)
+                       const int32_t* __restrict__ cell_start, const int32_t* __restrict__ perm,
+                       const int32_t* __restrict__ t_vrow, const int32_t* __restrict__ t_id,
+                       const float* __restrict__ vT, const float* __restrict__ luts,
+                       const uint16_t* __restrict__ sel_cells, const int32_t* __restrict__ n_cells,
+                       const int32_t* __restrict__ round_state,   // [0] = last iteration (set by the select kernel of this round)
+                       int32_t* __restrict__ target_counts,
+                       u64* __restrict__ key_scratch, size_t scratch_stride,   // [gridDim.x][scratch_stride] for queries beyond the shared buffer
+                       int32_t* __restrict__ out_ids, float* __restrict__ out_dists, int32_t* __restrict__ filled,
+                       int32_t* __restrict__ work_counter, u64* __restrict__ pair_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_bits[32];
-  __shared__ int s_warp_cnt[kJoinThreads / 32];
-  __shared__ int s_base;
   __shared__ unsigned s_hist[256];
   __shared__ int s_misc[8];
+  __shared__ int s_x, s_n;
   u64* sbuf = reinterpret_cast<u64*>(smem_raw);                                   // [kJoinSortN]
-  float* tk_d = reinterpret_cast<float*>(sbuf + kJoinSortN);                      // [k]
+  u64* kbuf = sbuf + kJoinSortN;                                                  // [kJoinSortN] candidate keys of small queries
+  float* tk_d = reinterpret_cast<float*>(kbuf + kJoinSortN);                      // [k]
   int32_t* tk_id = reinterpret_cast<int32_t*>(tk_d + kJoinMaxP);                  // [k]
   float* pv_d = reinterpret_cast<float*>(tk_id + kJoinMaxP);                      // [P] exact distances (method 2)
   float* slut = pv_d + kJoinMaxP;                                                 // [m*K] (methods 0, 2)
-  const int x = blockIdx.x, q = active[x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = prm.d, m = prm.m, K = prm.K, k = prm.k;
   const float MAX_DIST = 1000.0f;
-  const float* qv = queries + (size_t)q * d;
-  u64* keys = key_scratch + (size_t)x * n_trows;
+  const int last_iteration = round_state[0];
 
-  if (tid < 32) s_bits[tid] = bitmaps[(size_t)x * 32 + tid];
-  if (tid == 0) s_base = 0;
-  if (prm.method != 1) {
-    const float4* src = reinterpret_cast<const float4*>(luts + (size_t)q * m * K);
-    for (int i = tid; i < m * K / 4; i += kJoinThreads) reinterpret_cast<float4*>(slut)[i] = src[i];
-  }
-  __syncthreads();
-
-  // ---- candidates in arrival order: target rows whose cell is selected (and, for methods 1/2,
-  //      that join to a word vector) ----
-  for (int t0 = 0; t0 < n_trows; t0 += kJoinThreads) {
-    const int t = t0 + tid;
-    bool cand = false;
-    if (t < n_trows) {
-      const int cell = t_cell[t];
-      cand = (s_bits[cell >> 5] >> (cell & 31)) & 1u;
-      if (cand && prm.method != 0 && t_vrow[t] < 0) cand = false;                 // INNER JOIN vecs
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, cand);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+  for (;;) {
     __syncthreads();
-    int off = s_base;
-    for (int wv = 0; wv < warp; wv++) off += s_warp_cnt[wv];
-    if (cand) {
-      const int slot = off + __popc(bal & ((1u << lane) - 1u));
-      float dist;
-      if (prm.method == 1) {
-        const int vr = t_vrow[t];
-        const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
-        float acc = 0.0f;
-        for (int i = 0; i < d; i++) {
-          const float tt = xsub(qv[i], vp[(size_t)i * 32]);
-          acc = xadd(acc, xmul(tt, tt));
+    if (tid == 0) { s_x = atomicAdd(work_counter, 1); s_n = 0; }
+    __syncthreads();
+    const int x = s_x;
+    if (x >= n_active) break;
+    const int q = active[x];
+    const float* qv = queries + (size_t)q * d;
+    const int nc = n_cells[x];
+    const uint16_t* cl = sel_cells + (size_t)x * 1024;
+    if (prm.method != 1) {
+      const float4* src = reinterpret_cast<const float4*>(luts + (size_t)q * m * K);
+      for (int i = tid; i < m * K / 4; i += kJoinThreads) reinterpret_cast<float4*>(slut)[i] = src[i];
+    }
+    // rows this query will look at (an upper bound of its candidates): decides where the keys live
+    int cap_rows = 0;
+    for (int ci = tid; ci < nc; ci += kJoinThreads) { const int c = cl[ci]; cap_rows += cell_start[c + 1] - cell_start[c]; }
+    for (int o = 16; o >= 1; o >>= 1) cap_rows += __shfl_xor_sync(0xffffffffu, cap_rows, o);
+    if (lane == 0 && cap_rows) atomicAdd(&s_n, cap_rows);
+    __syncthreads();
+    const int rows_upper = s_n;
+    __syncthreads();
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    u64* keys = (rows_upper <= kJoinSortN) ? kbuf : key_scratch + (size_t)blockIdx.x * scratch_stride;
+
+    // ---- candidates: the rows of the selected cells (and, for methods 1/2, that join to a word vector) ----
+    for (int ci = warp; ci < nc; ci += kJoinThreads / 32) {
+      const int c = cl[ci];
+      const int s0 = cell_start[c], s1 = cell_start[c + 1];
+      for (int pb = s0; pb < s1; pb += 32) {
+        const int pos = pb + lane;
+        bool cand = pos < s1;
+        int t = 0;
+        if (cand) {
+          t = perm[pos];
+          if (prm.method != 0 && t_vrow[t] < 0) cand = false;                     // INNER JOIN vecs
         }
-        dist = acc;
-      } else {
-        dist = prm.pair_sums ? adc_row_pairs(ttab, t >> 5, t & 31, slut, K) : adc_row_global(ttab, t >> 5, t & 31, slut, K);
+        float dist = 0.0f;
+        if (cand) {
+          if (prm.method == 1) {
+            const int vr = t_vrow[t];
+            const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
+            float acc = 0.0f;
+            for (int i = 0; i < d; i++) {
+              const float tt = xsub(qv[i], vp[(size_t)i * 32]);
+              acc = xadd(acc, xmul(tt, tt));
+            }
+            dist = acc;
+          } else {
+            dist = prm.pair_sums ? adc_row_pairs(ctab, pos >> 5, pos & 31, slut, K) : adc_row_global(ctab, pos >> 5, pos & 31, slut, K);
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) keys[base + __popc(bal & ((1u << lane) - 1u))] = make_key(dist, (uint32_t)t);   // t = arrival order
       }
-      keys[slot] = make_key(dist, (uint32_t)t);                                   // t = arrival order
     }
+    __threadfence_block();
     __syncthreads();
+    const int n_cand = s_n;
+
+    // ---- the reference's bookkeeping around the round ----
     if (tid == 0) {
-      int tot = 0;
-      for (int wv = 0; wv < kJoinThreads / 32; wv++) tot += s_warp_cnt[wv];
-      s_base += tot;
+      const int tc = target_counts[q] + n_cand;                                   // ivpq_search_in.c:461
+      if (prm.skip_below > 0 && tc < prm.skip_below && !last_iteration) { target_counts[q] = 0; s_misc[7] = 1; }   // :553-557
+      else { target_counts[q] = tc; s_misc[7] = 0; }
+      if (pair_counter) atomicAdd(pair_counter, (u64)n_cand);
+    }
+    for (int i = tid; i < k; i += kJoinThreads) { tk_d[i] = MAX_DIST; tk_id[i] = -1; }
+    __syncthreads();
+    const bool skipped = s_misc[7] != 0;
+
+    if (!skipped && n_cand > 0) {
+      if (prm.method != 2) {
+        // strict-admission top-k over the stream in arrival order: only rows with d <= v (v = k-th
+        // smallest) matter, of the ties at v only the k earliest; replay them literally.
+        const int n_s = block_select_smallest(keys, n_cand, k, true, k, sbuf, s_hist, s_misc);
+        __syncthreads();
+        int n_pad = 32;
+        while (n_pad < n_s) n_pad <<= 1;
+        for (int i = tid; i < n_pad; i += kJoinThreads) {
+          const u64 e = sbuf[i];
+          sbuf[i] = (i < n_s) ? (((u64)key_t(e) << 32) | key_dbits(e)) : kKeyInf;
+        }
+        __syncthreads();
+        block_bitonic_sort(sbuf, n_pad);
+        if (tid == 0) {
+          float max_dist = MAX_DIST;
+          for (int i = 0; i < n_s; i++) {
+            const float dist = __uint_as_float((uint32_t)sbuf[i]);
+            if (dist < max_dist) {                                                // :523-530 / :531-541
+              int slot = k;
+              while (slot > 0 && !(tk_d[slot - 1] < dist)) slot--;
+              if (slot < k) {
+                for (int j = k - 1; j > slot; j--) { tk_d[j] = tk_d[j - 1]; tk_id[j] = tk_id[j - 1]; }
+                tk_d[slot] = dist;
+                tk_id[slot] = t_id[(uint32_t)(sbuf[i] >> 32)];
+              }
+              max_dist = tk_d[k - 1];
+            }
+          }
+        }
+      } else {
+        // PQ + post verification: the k*pvf smallest PQ distances survive the buffer (ties by arrival),
+        // exact distances on them in that order, literal top-k (postverify, index_utils.c:477-498)
+        const int P = k * prm.pvf;
+        const int n_s = block_select_smallest(keys, n_cand, P, false, 0, sbuf, s_hist, s_misc);
+        __syncthreads();
+        for (int j = tid; j < n_s; j += kJoinThreads) {
+          if (!(key_dist(sbuf[j]) < MAX_DIST)) { pv_d[j] = MAX_DIST; continue; }   // never entered the PV buffer (:505)
+          const int vr = t_vrow[key_t(sbuf[j])];
+          const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
+          float acc = 0.0f;
+          for (int i = 0; i < d; i++) {
+            const float tt = xsub(qv[i], vp[(size_t)i * 32]);
+            acc = xadd(acc, xmul(tt, tt));
+          }
+          pv_d[j] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          float max_dist = MAX_DIST;
+          for (int j = 0; j < n_s; j++) {
+            const float dist = pv_d[j];
+            if (dist < max_dist) {
+              int slot = k;
+              while (slot > 0 && !(tk_d[slot - 1] < dist)) slot--;
+              if (slot < k) {
+                for (int jj = k - 1; jj > slot; jj--) { tk_d[jj] = tk_d[jj - 1]; tk_id[jj] = tk_id[jj - 1]; }
+                tk_d[slot] = dist;
+                tk_id[slot] = t_id[key_t(sbuf[j])];
+              }
+              max_dist = tk_d[k - 1];
+            }
+          }
+        }
+      }
     }
     __syncthreads();
-  }
-  const int n_cand = s_base;
-  __threadfence_block();
-  __syncthreads();
-
-  // ---- the reference's bookkeeping around the round ----
-  bool skipped = false;
-  if (tid == 0) {
-    const int tc = target_counts[q] + n_cand;                                     // ivpq_search_in.c:461
-    if (prm.skip_below > 0 && tc < prm.skip_below && !prm.last_iteration) { target_counts[q] = 0; s_misc[7] = 1; }   // :553-557
-    else { target_counts[q] = tc; s_misc[7] = 0; }
-  }
-  for (int i = tid; i < k; i += kJoinThreads) { tk_d[i] = MAX_DIST; tk_id[i] = -1; }
-  __syncthreads();
-  skipped = s_misc[7] != 0;
-
-  if (!skipped && n_cand > 0) {
-    if (prm.method != 2) {
-      // strict-admission top-k over the stream in arrival order: only rows with d <= v (v = k-th
-      // smallest) matter, of the ties at v only the k earliest; replay them literally.
-      const int n_s = block_select_smallest(keys, n_cand, k, true, k, sbuf, s_hist, s_misc);
-      __syncthreads();
-      // re-key by arrival and sort
-      int n_pad = 32;
-      while (n_pad < n_s) n_pad <<= 1;
-      for (int i = tid; i < n_pad; i += kJoinThreads) {
-        const u64 e = sbuf[i];
-        sbuf[i] = (i < n_s) ? (((u64)key_t(e) << 32) | key_dbits(e)) : kKeyInf;
-      }
-      __syncthreads();
-      block_bitonic_sort(sbuf, n_pad);
-      if (tid == 0) {
-        float max_dist = MAX_DIST;
-        for (int i = 0; i < n_s; i++) {
-          const float dist = __uint_as_float((uint32_t)sbuf[i]);
-          if (dist < max_dist) {                                                  // :523-530 / :531-541
-            int slot = k;
-            while (slot > 0 && !(tk_d[slot - 1] < dist)) slot--;
-            if (slot < k) {
-              for (int j = k - 1; j > slot; j--) { tk_d[j] = tk_d[j - 1]; tk_id[j] = tk_id[j - 1]; }
-              tk_d[slot] = dist;
-              tk_id[slot] = t_id[(uint32_t)(sbuf[i] >> 32)];
-            }
-            max_dist = tk_d[k - 1];
-          }
-        }
-      }
-    } else {
-      // PQ + post verification: the k*pvf smallest PQ distances survive the buffer (ties by arrival),
-      // exact distances on them in that order, literal top-k (postverify, index_utils.c:477-498)
-      const int P = k * prm.pvf;
-      const int n_s = block_select_smallest(keys, n_cand, P, false, 0, sbuf, s_hist, s_misc);
-      __syncthreads();
-      for (int j = tid; j < n_s; j += kJoinThreads) {
-        if (!(key_dist(sbuf[j]) < MAX_DIST)) { pv_d[j] = MAX_DIST; continue; }   // never entered the PV buffer (ivpq_search_in.c:505)
-        const int t = (int)key_t(sbuf[j]);
-        const int vr = t_vrow[t];
-        const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
-        float acc = 0.0f;
-        for (int i = 0; i < d; i++) {
-          const float tt = xsub(qv[i], vp[(size_t)i * 32]);
-          acc = xadd(acc, xmul(tt, tt));
-        }
-        pv_d[j] = acc;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        float max_dist = MAX_DIST;
-        for (int j = 0; j < n_s; j++) {
-          const float dist = pv_d[j];
-          if (dist < max_dist) {
-            int slot = k;
-            while (slot > 0 && !(tk_d[slot - 1] < dist)) slot--;
-            if (slot < k) {
-              for (int jj = k - 1; jj > slot; jj--) { tk_d[jj] = tk_d[jj - 1]; tk_id[jj] = tk_id[jj - 1]; }
-              tk_d[slot] = dist;
-              tk_id[slot] = t_id[key_t(sbuf[j])];
-            }
-            max_dist = tk_d[k - 1];
-          }
-        }
-      }
+    for (int i = tid; i < k; i += kJoinThreads) {
+      out_ids[(size_t)q * k + i] = tk_id[i];
+      out_dists[(size_t)q * k + i] = tk_d[i];
     }
+    if (tid == 0) filled[x] = (tk_d[k - 1] != MAX_DIST) ? 1 : 0;                   // :643
   }
-  __syncthreads();
-  for (int i = tid; i < k; i += kJoinThreads) {
-    out_ids[(size_t)q * k + i] = tk_id[i];
-    out_dists[(size_t)q * k + i] = tk_d[i];
-  }
-  if (tid == 0) filled[x] = (tk_d[k - 1] != MAX_DIST) ? 1 : 0;                    // :643
 }
 
 }  // namespace fb

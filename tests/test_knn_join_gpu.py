@@ -73,3 +73,34 @@ def test_knn_join_pair_lut_variant(setup, method, use_tl):
         eids, ed, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, conf, 0)
         assert rc == 0
         assert_same_topk(ids, d, eids, ed, f"pair-LUT method={method} tl={use_tl} k={k} alpha={alpha}")
+
+
+@pytest.mark.parametrize("m,K", [(12, 1024), (30, 32)])
+def test_knn_join_d300_multi_index_32x32(oracle_mod, m, K):
+    """the shapes of index_creation/config/ivpq_config.json (m=30, K=32) and of BASELINE config 4 (m=12, K=1024):
+    d=300, 2 x 32 multi-index, alpha=100, pvf=20, method 2 (PQ + post verification) and the other two methods"""
+    import torch
+    from freddy_b200 import Engine
+    from freddy_b200.index_build import make_ivpq_index
+    from helpers import small_index
+    ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)
+    vec = np.ascontiguousarray(ix["vectors"])
+    N = len(vec)
+    rng = np.random.default_rng(8)
+    trows = np.sort(rng.choice(N, 20000, replace=False))
+    ivpq = make_ivpq_index(torch.from_numpy(vec), m=m, K=K, Kc=32, n_train=N, kmeans_iters=3, seed=3, target_rows=trows)
+    vec_ids = np.asarray(ivpq["ids"], np.int32)
+    targets = (trows + 1).astype(np.int32)
+    q = np.ascontiguousarray(vec[rng.choice(N, 160, replace=False)] + 0.01 * rng.standard_normal((160, 300)).astype(np.float32))
+    e = Engine(0)
+    try:
+        e.load_ivpq_index(ivpq)
+        e.load_vectors(vec_ids, vec)
+        oi = oracle_mod.OracleIvpq(ivpq, vec, vec_ids)
+        for method, use_tl, k, alpha, pvf in ((2, True, 5, 100, 20), (2, False, 5, 100, 20), (0, True, 5, 10, 1), (1, False, 3, 4, 1)):
+            ids, d = e.ivpq_search_in(q, k, targets, alpha, pvf, method, use_tl, 0.8)
+            eids, ed, rc, st = oi.search_in(q, k, targets, alpha, pvf, method, use_tl, 0.8)
+            assert rc == 0
+            assert_same_topk(ids, d, eids, ed, f"d=300 m={m} K={K} method={method} tl={use_tl}")
+    finally:
+        e.close()

@@ -89,6 +89,26 @@ def test_flat_pq_drivers(ref, oracle_mod):
     _same(od, rraw)
 
 
+def test_pq_search_in_batch_unsorted_and_repeated_ids(oracle_mod, ref):
+    """`WHERE id IN (...)` on a table whose id column is neither ascending nor unique: rows come in TABLE order and
+    every row carrying a listed id is a candidate — the oracle's general row selection against the real SRF"""
+    ix = dict(small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True))
+    rng = np.random.default_rng(4)
+    ids = rng.permutation(np.arange(1, ix["N"] + 1)).astype(np.int32)
+    ids[100:140] = ids[5000:5040]
+    ix["ids"] = ids
+    s = ref()
+    s.load_pq(ix)
+    oi = oracle_mod.OracleIndex(ix, flat_pq=True)
+    targets = np.concatenate([ids[90:150], ids[4990:5050], rng.choice(ids, 1500), [10 ** 8, -5]]).astype(np.int32)
+    q = queries_from(ix, 9, seed=2)
+    qids = np.arange(len(q), dtype=np.int32)
+    rq, rids, rraw = s.pq_search_in_batch(q, qids, 5, targets, False)
+    oids, od = oi.pq_search_in_batch(q, 5, targets)
+    np.testing.assert_array_equal(oids, rids)
+    _same(od, rraw)
+
+
 def _ivpq_setup(N=12000, d=48, m=12, K=64, Kc=8, nt=3000, seed=5):
     import torch
     from freddy_b200.index_build import make_ivpq_index
