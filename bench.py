@@ -69,7 +69,21 @@ def parse():
     ap.add_argument("--pipe-shape", type=int, default=None, help="role split of the pipeline CTA (FB_OPT_PIPE_SHAPE)")
     ap.add_argument("--pipe-ramp", type=int, default=None, help="0: uniform pipeline chunks")
     ap.add_argument("--pipe-debug", type=int, default=None, help="timing aid (invalid results): 1 producers only, 2 scan only")
+    ap.add_argument("--secondary", default=None,
+                    help="comma list of secondary workloads reported in config.secondary: 3,4,5 (BASELINE configs), sigma03, nominal; "
+                         "'none' skips them.  Default: all five on one GPU, 4 and 5 (the sharded ones) on several")
+    ap.add_argument("--secondary-sample", type=int, default=256, help="queries of each secondary workload checked against the reference")
     return ap.parse_args()
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def workload_name(a):
@@ -139,9 +153,12 @@ def build_index(a, device):
 
 def cpu_arm(a, ix, queries, seconds):
     """times the oracle (plain-C restatement of freddy.c:247-378) on all host threads"""
+    return cpu_arm_threads(a, ix, queries, seconds, os.cpu_count() or 1)
+
+
+def cpu_arm_threads(a, ix, queries, seconds, threads):
     from oracle import oracle
     oi = oracle.OracleIndex(ix)
-    threads = os.cpu_count() or 1
     # calibrate on a small sample, then size one run to ~`seconds`
     n0 = min(len(queries), 4 * threads)
     t = time.time()
@@ -299,9 +316,10 @@ def main():
         g = torch.Generator(); g.manual_seed(4321)
         sel = torch.randperm(a.n, generator=g)[:a.batch * world]
         all_q = vec[sel.to(dev)].contiguous()
+        vec_t = vec                              # kept for the secondary workloads (3.6 GB of the 180)
         del vec
     else:
-        ix, t_build, all_q = {"d": a.d, "m": a.m, "K": a.K, "C": a.C, "N": a.n}, 0.0, None
+        ix, t_build, all_q, vec_t = {"d": a.d, "m": a.m, "K": a.K, "C": a.C, "N": a.n}, 0.0, None, None
     if world > 1:
         shapes = {"coarse": ((a.C, a.d), torch.float32), "residual_codebook": ((a.m, a.K, a.d // a.m), torch.float32),
                   "coarse_ids": ((a.n,), torch.int32), "codes": ((a.n, a.m), torch.int16)}
@@ -390,11 +408,12 @@ def main():
                 wall.append((time.perf_counter() - t) * 1e3)
         barrier()
         ms = sum(s.elapsed_time(e) for s, e in evs) if use_events else sum(wall)
+        ms_local = ms
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, ms_local
 
     clocks = ClockSampler(local_rank)   # samples through warm-up + timed region (same load in both)
     clocks.start()
@@ -404,7 +423,7 @@ def main():
     if a.pipe_debug is not None:    # after the warm-up: the LUT scratch then holds valid LUTs for the scan-only mode
         eng.set_option(_lib.FB_OPT_PIPE_DEBUG, a.pipe_debug)
     eng.reset_counters()
-    ms_total = timed(step_dev, a.steps, True)
+    ms_total, ms_rank = timed(step_dev, a.steps, True)
     clk = clocks.stop()
     c = eng.counters()
     value = world * nq * a.steps / (ms_total / 1e3)
@@ -443,7 +462,7 @@ def main():
     # end to end through the host-buffer C-ABI call
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, a.steps, False)
+    ms_e2e, ms_e2e_rank = timed(step_e2e, a.steps, False)
     e2e_value = world * nq * a.steps / (ms_e2e / 1e3)
 
     # single-query latency through the same host-buffer call (the form config[1] names)
@@ -485,6 +504,37 @@ def main():
             cpu = cpu_arm(a, ix, h_q.numpy(), a.cpu_seconds)
             cpu = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
 
+    # what each rank saw (the max over ranks hid which rank / stage was slow)
+    mine = {"rank": rank, "gpu": local_rank, "ms_per_step_device": ms_rank / a.steps, "ms_per_step_e2e": ms_e2e_rank / a.steps,
+            "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]), "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons"),
+            "stage_ms_per_step": {s_: c["ms_" + s_] / a.steps for s_ in ("coarse", "pipe", "lut", "scan", "exact")},
+            "exact_path_queries_per_step": exact_q / a.steps}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+
+    secondary = []
+    which = a.secondary if a.secondary is not None else ("3,4,5,sigma03,nominal" if world == 1 else "4,5")
+    if which != "none" and a.pipe_debug is None:
+        import bench_secondary
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        eng.close()                              # the headline engine's scratch (2 x 0.98 GB of LUTs) is not needed any more
+        try:
+            secondary = bench_secondary.run(a, lambda: Engine(local_rank), dev, rank, world, dist, vec_t,
+                                            (peak, float(pk.get("bf16_tflops", 1590.0))), set(which.split(",")), a.secondary_sample)
+        except Exception as ex:                  # a secondary workload must never take the headline line down with it
+            import traceback
+            traceback.print_exc()
+            secondary = [{"name": "secondary workloads", "error": repr(ex)}]
+
+    if rank == 0 and cpu is not None and not a.no_cpu_baseline:
+        # (i) the SPI-free port on ONE thread next to the all-cores numbers, and the CPU it ran on
+        one = cpu_arm_threads(a, ix, h_q.numpy(), 3.0, 1)
+        cpu["oracle_port_single_thread_queries_per_s"] = one["value"]
+        cpu["cpu_model"] = cpu_model()
+        cpu["host_cores"] = os.cpu_count()
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -495,7 +545,8 @@ def main():
                           "single_query_latency_us": lat_us,
                           "exact_path_queries_per_step": exact_q / a.steps,
                           "exact_path_reasons_per_step": {r: c["exact_" + r] / a.steps for r in
-                                                          ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")}},
+                                                          ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")},
+                          "per_rank": per_rank, "secondary": secondary},
                "clocks": clk, "gpu_launches": launches,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * a.d * 4 * world,
                        "d2h_bytes_per_step": nq * k * 8 * world, "ms_per_step": ms_e2e / a.steps},

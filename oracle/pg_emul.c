@@ -46,6 +46,13 @@ typedef struct EmTable {
   int vec_bytes;        /* bytes per row             */
   const float* freq;    /* stat: coarse_freq         */
   bytea** cache;        /* lazily built varlenas     */
+  /* what the real tables have: a btree on coarse_id (index_creation/ivfadc.py:209-210, ivpq.py) and one on id.
+   * Built lazily; a statement with `coarse_id IN (...)` / `id IN (...)` then touches only the matching rows and
+   * returns them in heap (table) order, as a bitmap heap scan does. */
+  int64* by_a_start;    /* [max_a + 2] CSR over column a     */
+  int32* by_a_rows;     /* [nrows] rows grouped by a, ascending inside a group */
+  int32 max_a;
+  int ids_ascending;    /* -1 unknown, 0 no, 1 strictly ascending id column */
 } EmTable;
 
 typedef struct { char key[64]; char val[64]; } EmConfig;
@@ -61,6 +68,8 @@ void ref_reset(void) {
       for (int64 r = 0; r < g_tables[t].nrows; r++) free(g_tables[t].cache[r]);
       free(g_tables[t].cache);
     }
+    free(g_tables[t].by_a_start);
+    free(g_tables[t].by_a_rows);
   }
   g_ntables = 0;
   g_nconfig = 0;
@@ -82,6 +91,7 @@ int ref_register_table(const char* name, int kind, int64 nrows, const int32* id,
   memset(t, 0, sizeof *t);
   snprintf(t->name, 64, "%s", name);
   t->kind = kind; t->nrows = nrows; t->id = id; t->a = a; t->b = b; t->vec = vec; t->vec_bytes = vec_bytes; t->freq = freq;
+  t->ids_ascending = -1;
   return 0;
 }
 
@@ -159,6 +169,46 @@ static int64 find_id_row(const EmTable* t, int32 id) {
   }
   for (int64 r = 0; r < t->nrows; r++) if (t->id[r] == id) return r;
   return -1;
+}
+
+static void build_a_index(EmTable* t) {
+  if (t->by_a_start || !t->a) return;
+  int32 mx = -1;
+  for (int64 r = 0; r < t->nrows; r++) if (t->a[r] > mx) mx = t->a[r];
+  t->max_a = mx;
+  t->by_a_start = calloc((size_t)mx + 3, sizeof(int64));
+  t->by_a_rows = malloc(sizeof(int32) * (size_t)(t->nrows ? t->nrows : 1));
+  for (int64 r = 0; r < t->nrows; r++) if (t->a[r] >= 0) t->by_a_start[t->a[r] + 1]++;
+  for (int32 c = 0; c <= mx; c++) t->by_a_start[c + 1] += t->by_a_start[c];
+  int64* cur = malloc(sizeof(int64) * ((size_t)mx + 2));
+  memcpy(cur, t->by_a_start, sizeof(int64) * ((size_t)mx + 2));
+  for (int64 r = 0; r < t->nrows; r++) if (t->a[r] >= 0) t->by_a_rows[cur[t->a[r]]++] = (int32)r;
+  free(cur);
+}
+
+static int ids_ascending(EmTable* t) {
+  if (t->ids_ascending < 0) {
+    int asc = 1;
+    for (int64 r = 1; r < t->nrows && asc; r++) asc = t->id[r - 1] < t->id[r];
+    t->ids_ascending = asc;
+  }
+  return t->ids_ascending;
+}
+
+/* Results of table statements are freed a few statements later (Postgres frees them at SPI_finish; the reference
+ * never looks at a tuptable after issuing four more statements): a ring of the last kKeep results. */
+enum { kKeep = 4 };
+static struct { HeapTuple* rows; HeapTupleData* block; SPITupleTable* tt; } g_ring[kKeep];
+static int g_ring_pos = 0;
+
+static void remember_result(HeapTuple* rows, HeapTupleData* block, SPITupleTable* tt) {
+  free(g_ring[g_ring_pos].rows);
+  free(g_ring[g_ring_pos].block);
+  free(g_ring[g_ring_pos].tt);
+  g_ring[g_ring_pos].rows = rows;
+  g_ring[g_ring_pos].block = block;
+  g_ring[g_ring_pos].tt = tt;
+  g_ring_pos = (g_ring_pos + 1) % kKeep;
 }
 
 static void set_result(HeapTuple* rows, int64 n) {
@@ -267,17 +317,44 @@ int SPI_exec(const char* src, long tcount) {
   }
   const bool order_by_pos = strstr(src, "ORDER BY pos") != NULL;
 
-  HeapTuple* rows = malloc(sizeof(HeapTuple) * (size_t)(t->nrows ? t->nrows : 1));
+  /* candidate rows in table order: through the coarse_id / id indexes when the statement has such a predicate */
+  int64 n_cand = 0;
+  int32* cand = NULL;           /* NULL: every row */
+  if (cids && t->a) {
+    build_a_index(t);
+    int64 tot = 0;
+    for (int i = 0; i < n_cids; i++)
+      if (cids[i] >= 0 && cids[i] <= t->max_a) tot += t->by_a_start[cids[i] + 1] - t->by_a_start[cids[i]];
+    cand = malloc(sizeof(int32) * (size_t)(tot ? tot : 1));
+    for (int i = 0; i < n_cids; i++)
+      if (cids[i] >= 0 && cids[i] <= t->max_a)
+        for (int64 x = t->by_a_start[cids[i]]; x < t->by_a_start[cids[i] + 1]; x++) cand[n_cand++] = t->by_a_rows[x];
+    if (n_cids > 1) qsort(cand, (size_t)n_cand, sizeof(int32), cmp_i32);   /* heap order across the lists */
+  } else if (ids && ids_ascending(t)) {
+    cand = malloc(sizeof(int32) * (size_t)(n_ids ? n_ids : 1));
+    for (int i = 0; i < n_ids; i++) {                                      /* ids[] sorted unique, id column ascending */
+      int64 lo = 0, hi = t->nrows - 1;
+      while (lo <= hi) {
+        int64 mid = (lo + hi) / 2;
+        if (t->id[mid] < ids[i]) lo = mid + 1; else if (t->id[mid] > ids[i]) hi = mid - 1; else { cand[n_cand++] = (int32)mid; break; }
+      }
+    }
+  }
+  const int64 n_scan = cand ? n_cand : t->nrows;
+  HeapTuple* rows = malloc(sizeof(HeapTuple) * (size_t)(n_scan ? n_scan : 1));
+  HeapTupleData* block = calloc((size_t)(n_scan ? n_scan : 1), sizeof(HeapTupleData));
   int64 n = 0;
-  for (int64 r = 0; r < t->nrows; r++) {
+  for (int64 x = 0; x < n_scan; x++) {
+    const int64 r = cand ? cand[x] : x;
     if (cids && !in_sorted(cids, n_cids, t->a[r])) continue;
     if (ids && !in_sorted(ids, n_ids, t->id[r])) continue;
     int64 r2 = -1;
     if (t2) { r2 = find_id_row(t2, t->id[r]); if (r2 < 0) continue; }
-    HeapTuple h = calloc(1, sizeof(HeapTupleData));
+    HeapTuple h = &block[n];
     h->table = t; h->row = r; h->table2 = t2; h->row2 = r2; h->proj = proj; h->nproj = nproj;
     rows[n++] = h;
   }
+  free(cand);
   if (order_by_pos && t->kind == T_CODEBOOK) {       /* stable sort by pos */
     HeapTuple* sorted = malloc(sizeof(HeapTuple) * (size_t)(n ? n : 1));
     int maxpos = 0;
@@ -290,6 +367,7 @@ int SPI_exec(const char* src, long tcount) {
   }
   free(cids); free(ids);
   set_result(rows, n);
+  remember_result(rows, block, SPI_tuptable);
   return 1;
 }
 
