@@ -260,10 +260,11 @@ def run(a, eng_factory, dev, rank, world, dist, vec_t, peaks, which, sample, rep
     vec = None
 
     # ------------------------------------------------------------------ generator variants of the headline shape (rank 0 only)
-    def ivfadc_variant(name, sigma, zipf, kmeans_iters, n_train, note):
+    def ivfadc_variant(name, sigma, zipf, kmeans_iters, n_train, note, from_centres=False):
         t0 = time.time()
         ix = make_synthetic_index(N, d=d, m=m, K=K, C=a.C, n_train=min(n_train, N), n_clusters=1000, sigma=sigma, zipf=zipf,
-                                  kmeans_iters=kmeans_iters, seed=1234, device=dev, keep_vectors=True)
+                                  kmeans_iters=kmeans_iters, seed=1234, device=dev, keep_vectors=True,
+                                  coarse_from_centres=from_centres)
         vt = ix.pop("vectors_t")
         gq = torch.Generator(); gq.manual_seed(4321)
         sel = torch.randperm(N, generator=gq)[:a.batch]
@@ -312,7 +313,8 @@ def run(a, eng_factory, dev, rank, world, dist, vec_t, peaks, which, sample, rep
             ivfadc_variant("sigma03: headline shape on SURVEY 8(d)'s generator", 0.3, 0.7, 10, 100_000,
                            "sigma = 0.3 collapses clusters onto few distinct code vectors: many exact-distance ties across the k-th place")
         if "nominal" in which:
-            ivfadc_variant("nominal: headline shape, probed lists near N*w/C rows", a.sigma, 0.0, 25, 300_000,
-                           "equal cluster sizes and a longer k-means: the size-biased list length approaches the nominal 3000 rows")
+            ivfadc_variant("nominal: headline shape, probed lists near N*w/C rows", a.sigma, 0.0, 10, 100_000,
+                           "equal cluster sizes, coarse k-means started from the generating centres: one list per cluster, "
+                           "about the nominal N/C = 3000 rows each", from_centres=True)
     eng.close()
     return out

@@ -299,6 +299,74 @@ class ReferenceSession:
             self._err("grouping_pq", n)
         return oi[:n].copy(), og[:n].copy()
 
+    # ---- insert_batch (both libraries) and the SRFs only the shim has -----------------------------------
+    def load_insert_tables(self, index, ivpq, vectors, vec_ids, w=3):
+        """everything insert_batch touches: pq / residual / ivpq codebooks and row tables, coarse tables, both
+        word-vector tables (original = normalized here)"""
+        self.load_ivfadc(index, w)
+        self.load_pq(index)
+        self.load_ivpq(ivpq, vectors, vec_ids)
+        self._table("google_vecs", self.T_VECS, len(vec_ids), ids=np.asarray(vec_ids, np.int32), vec=np.asarray(vectors, np.float32))
+        self.set_config("get_vecs_name_original()", "google_vecs")
+        self.set_config("get_vecs_name()", "google_vecs_norm")
+
+    def insert_batch(self, terms, tokens, norm_vectors, raw_vectors):
+        """terms: what the caller passes; tokens / vectors: the rows the SQL-side tokenisation returns for the new
+        terms (the emulator answers the tokenize() statement with them).  Returns the DML statements issued."""
+        nv = np.ascontiguousarray(norm_vectors, np.float32)
+        rv = np.ascontiguousarray(raw_vectors, np.float32)
+        toks = (C.c_char_p * len(tokens))(*[t.encode() for t in tokens])
+        self.R.ref_set_tokenization.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_int]
+        self.R.ref_set_tokenization(len(tokens), toks, _p(nv), _p(rv), nv.shape[1])
+        self.R.ref_statement_log.restype = C.c_char_p
+        self.R.ref_clear_statement_log()
+        tt = (C.c_char_p * len(terms))(*[t.encode() for t in terms])
+        self.R.ref_insert_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        r = self.R.ref_insert_batch(len(terms), tt)
+        if r != 0:
+            self._err("insert_batch", r)
+        return self.R.ref_statement_log().decode().splitlines()
+
+    def knn_exact_search(self, query, k, targets=None):
+        q = np.ascontiguousarray(query, np.float32).ravel()
+        t = None if targets is None else np.ascontiguousarray(targets, np.int32)
+        ids, sims = np.full(k, -1, np.int32), np.zeros(k, np.float32)
+        self.R.ref_knn_exact_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        n = self.R.ref_knn_exact_search(_p(q), len(q), k, None if t is None else _p(t), 0 if t is None else len(t), _p(ids), _p(sims))
+        if n < 0:
+            self._err("knn_exact_search", n)
+        return ids[:n], sims[:n]
+
+    def ivfadc_search_pv(self, query, k):
+        q = np.ascontiguousarray(query, np.float32).ravel()
+        ids, sims = np.full(k, -1, np.int32), np.zeros(k, np.float32)
+        self.R.ref_ivfadc_search_pv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        n = self.R.ref_ivfadc_search_pv(_p(q), len(q), k, _p(ids), _p(sims))
+        if n < 0:
+            self._err("ivfadc_search_pv", n)
+        return ids[:n], sims[:n]
+
+    def analogy_3cosadd_batch(self, ids_abc):
+        t = np.ascontiguousarray(ids_abc, np.int32).reshape(-1, 3)
+        ids, sc = np.empty(len(t), np.int32), np.empty(len(t), np.float32)
+        self.R.ref_analogy_3cosadd_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        n = self.R.ref_analogy_3cosadd_batch(_p(t), len(t), _p(ids), _p(sc))
+        if n != len(t):
+            self._err("analogy_3cosadd_batch", n)
+        return ids, sc
+
+    def cosine_similarity_batch(self, a, b, variant):
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        out = np.empty(len(a), np.float64)
+        self.R.ref_cosine_similarity_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        n = self.R.ref_cosine_similarity_batch(_p(a), _p(b), len(a), a.shape[1], variant, _p(out))
+        if n != len(a):
+            self._err("cosine_similarity_batch", n)
+        return out
+
+    def repin(self):
+        return self.R.ref_freddy_repin()
+
     def ivfadc_search(self, queries, k):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
         ids = np.empty((len(q), k), np.int32)

@@ -228,10 +228,83 @@ static void next_word(const char** pp, char* out, int cap) {
   *pp = p;
 }
 
+/* ---- what insert_batch needs: its tokenisation statement answered from registered rows, DML recorded ---- */
+static struct { int n; char** tokens; bytea** norm; bytea** raw; } g_tok;
+static char* g_log = NULL;
+static size_t g_log_len = 0, g_log_cap = 0;
+
+static bytea* make_bytea0(const void* data, size_t bytes) {
+  bytea* b = malloc(VARHDRSZ + bytes);
+  SET_VARSIZE(b, VARHDRSZ + bytes);
+  memcpy(VARDATA(b), data, bytes);
+  return b;
+}
+
+/* rows `SELECT replace(term...) AS token, tokenize(term), tokenize_raw(term) FROM unnest(...)` returns */
+void ref_set_tokenization(int n, const char** tokens, const float* norm, const float* raw, int d) {
+  g_tok.n = n;
+  g_tok.tokens = malloc(sizeof(char*) * (size_t)(n ? n : 1));
+  g_tok.norm = malloc(sizeof(bytea*) * (size_t)(n ? n : 1));
+  g_tok.raw = malloc(sizeof(bytea*) * (size_t)(n ? n : 1));
+  for (int i = 0; i < n; i++) {
+    g_tok.tokens[i] = strdup(tokens[i]);
+    g_tok.norm[i] = make_bytea0(norm + (size_t)i * d, sizeof(float) * (size_t)d);
+    g_tok.raw[i] = make_bytea0(raw + (size_t)i * d, sizeof(float) * (size_t)d);
+  }
+}
+const char* ref_statement_log(void) { return g_log ? g_log : ""; }
+void ref_clear_statement_log(void) { g_log_len = 0; if (g_log) g_log[0] = 0; }
+static void log_statement(const char* src) {
+  const size_t n = strlen(src);
+  if (g_log_len + n + 2 > g_log_cap) { g_log_cap = (g_log_len + n + 2) * 2; g_log = realloc(g_log, g_log_cap); }
+  memcpy(g_log + g_log_len, src, n);
+  g_log_len += n;
+  g_log[g_log_len++] = '\n';
+  g_log[g_log_len] = 0;
+}
+
 int SPI_exec(const char* src, long tcount) {
   (void)tcount;
   SPI_processed = 0;
   SPI_tuptable = NULL;
+  if (!strncmp(src, "INSERT ", 7) || !strncmp(src, "UPDATE ", 7)) {   /* recorded, not applied (tables are read-only images) */
+    log_statement(src);
+    SPI_processed = 1;
+    return 1;
+  }
+  if (strstr(src, "tokenize(") != NULL) {
+    HeapTuple* rows = malloc(sizeof(HeapTuple) * (size_t)(g_tok.n ? g_tok.n : 1));
+    for (int i = 0; i < g_tok.n; i++) {
+      rows[i] = calloc(1, sizeof(HeapTupleData));
+      rows[i]->natts = 3;
+      rows[i]->values = malloc(sizeof(char*) * 3);
+      rows[i]->values[0] = g_tok.tokens[i];
+      rows[i]->values[1] = rows[i]->values[2] = NULL;
+      rows[i]->bins = malloc(sizeof(Datum) * 3);
+      rows[i]->bins[0] = PointerGetDatum(g_tok.tokens[i]);
+      rows[i]->bins[1] = PointerGetDatum(g_tok.norm[i]);
+      rows[i]->bins[2] = PointerGetDatum(g_tok.raw[i]);
+    }
+    set_result(rows, g_tok.n);
+    return 1;
+  }
+  if (!strncmp(src, "SELECT max(id) FROM ", 20)) {                    /* the shim's cheap "did the table grow" probe */
+    char tn[64];
+    const char* pp = src + 20;
+    next_word(&pp, tn, sizeof tn);
+    EmTable* mt = find_table(tn);
+    if (!mt) { elog(ERROR, "pg_emul: unknown table %s", tn); }
+    int32 mx = 0;
+    for (int64 r = 0; r < mt->nrows; r++) if (r == 0 || mt->id[r] > mx) mx = mt->id[r];
+    HeapTuple* rows = malloc(sizeof(HeapTuple));
+    rows[0] = calloc(1, sizeof(HeapTupleData));
+    rows[0]->natts = 1;
+    rows[0]->values = malloc(sizeof(char*));
+    rows[0]->values[0] = malloc(16);
+    snprintf(rows[0]->values[0], 16, "%d", mx);
+    set_result(rows, 1);
+    return 1;
+  }
   const char* from = strstr(src, " FROM ");
   if (strncmp(src, "SELECT ", 7) != 0 || !from) { elog(ERROR, "pg_emul: unsupported statement: %.80s", src); }
   const char* p = from + 6;
@@ -376,6 +449,7 @@ int SPI_execute(const char* src, bool read_only, long tcount) { (void)read_only;
 Datum SPI_getbinval(HeapTuple h, TupleDesc desc, int fnumber, bool* isnull) {
   (void)desc;
   if (isnull) *isnull = false;
+  if (h->table == NULL && h->bins != NULL) return h->bins[fnumber - 1];         /* ad-hoc row with binary columns */
   if (h->table == NULL) return Int32GetDatum(atoi(h->values[fnumber - 1]));  /* config row */
   EmTable* t = (EmTable*)h->table;
   if (fnumber < 1 || fnumber > h->nproj) { elog(ERROR, "pg_emul: column %d out of range", fnumber); }
@@ -383,7 +457,7 @@ Datum SPI_getbinval(HeapTuple h, TupleDesc desc, int fnumber, bool* isnull) {
     case COL_ID: return Int32GetDatum(t->id[h->row]);
     case COL_COARSE: case COL_POS: return Int32GetDatum(t->a[h->row]);
     case COL_CODE: return Int32GetDatum(t->b[h->row]);
-    case COL_COUNT: return Int32GetDatum(0);
+    case COL_COUNT: return Int32GetDatum(100);   /* codebook `count` column (insert_batch's running means) */
     case COL_VEC: return PointerGetDatum(row_bytea(t, h->row));
     case COL_VEC2: return PointerGetDatum(row_bytea((EmTable*)h->table2, h->row2));
     case COL_FREQ: return Float4GetDatum(t->freq[h->row]);
@@ -648,4 +722,110 @@ int ref_grouping_pq(const int32* ids, int n, const int32* groups, int ng, int32*
   }
   free(text);
   return rows;
+}
+
+/* ---- insert_batch(varchar[]) through fmgr: the reference's (freddy.c:1403-1658) or the shim's.  DML statements
+ * land in the statement log (ref_statement_log).  returns 0 or -1 (elog ERROR) ---- */
+extern Datum insert_batch(PG_FUNCTION_ARGS);
+int ref_insert_batch(int n, const char** terms) {
+  FunctionCallInfoData fc = {0};
+  ArrayType* a = calloc(1, sizeof *a);
+  a->ndim = 1; a->elemtype = 1043 /* VARCHAROID */; a->nelems = n;
+  a->elems = malloc(sizeof(Datum) * (size_t)(n ? n : 1));
+  for (int i = 0; i < n; i++) a->elems[i] = PointerGetDatum(make_bytea(terms[i], strlen(terms[i])));
+  fc.args[0] = PointerGetDatum(a);
+  fc.nargs = 1;
+  jmp_buf env;
+  FmgrInfo fl = {0};
+  fc.flinfo = &fl;
+  fb_emul_error_jmp = &env;
+  if (setjmp(env)) { fb_emul_error_jmp = NULL; return -1; }
+  insert_batch(&fc);
+  fb_emul_error_jmp = NULL;
+  return 0;
+}
+
+/* ---- SRFs that exist only in the shim (GPU paths the reference reaches through plpgsql + per-row UDF calls) ---- */
+extern Datum knn_exact_search(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum knn_in_exact_search(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum ivfadc_search_pv(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum analogy_3cosadd_batch(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum cosine_similarity_batch(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum freddy_repin(PG_FUNCTION_ARGS) __attribute__((weak));
+
+static int collect_single_f32(int n, int k, const char* text, int32* ids, float* vals) {
+  for (int i = 0; i < n && i < k; i++) {
+    ids[i] = atoi(text + (size_t)(i * 2) * 16);
+    vals[i] = strtof(text + (size_t)(i * 2 + 1) * 16, NULL);
+  }
+  return n;
+}
+/* targets == NULL: k_nearest_neighbour(bytea, k); else knn_in_exact(bytea, k, int[]) */
+int ref_knn_exact_search(const float* q, int d, int k, const int32* targets, int nt, int32* ids, float* sims) {
+  if (!knn_exact_search || !knn_in_exact_search) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_bytea(q, sizeof(float) * (size_t)d));
+  fc.args[1] = Int32GetDatum(k);
+  if (targets) fc.args[2] = PointerGetDatum(make_int_array(targets, nt));
+  char* text = malloc((size_t)k * 2 * 16 + 16);
+  int n = run_srf(targets ? knn_in_exact_search : knn_exact_search, &fc, 2, k, text, NULL);
+  if (n > 0) collect_single_f32(n, k, text, ids, sims);
+  free(text);
+  return n;
+}
+int ref_ivfadc_search_pv(const float* q, int d, int k, int32* ids, float* sims) {
+  if (!ivfadc_search_pv) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_bytea(q, sizeof(float) * (size_t)d));
+  fc.args[1] = Int32GetDatum(k);
+  char* text = malloc((size_t)k * 2 * 16 + 16);
+  int n = run_srf(ivfadc_search_pv, &fc, 2, k, text, NULL);
+  if (n > 0) collect_single_f32(n, k, text, ids, sims);
+  free(text);
+  return n;
+}
+/* ids_abc: [n][3] word ids; rows (query index, winner id, score) */
+int ref_analogy_3cosadd_batch(const int32* ids_abc, int n, int32* out_ids, float* out_scores) {
+  if (!analogy_3cosadd_batch) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_int_array(ids_abc, 3 * n));
+  char* text = malloc((size_t)(n ? n : 1) * 3 * 16 + 16);
+  int rows = run_srf(analogy_3cosadd_batch, &fc, 3, n, text, NULL);
+  for (int i = 0; i < rows && i < n; i++) {
+    if (atoi(text + (size_t)(i * 3) * 16) != i) { rows = -2; break; }
+    out_ids[i] = atoi(text + (size_t)(i * 3 + 1) * 16);
+    out_scores[i] = strtof(text + (size_t)(i * 3 + 2) * 16, NULL);
+  }
+  free(text);
+  return rows;
+}
+/* variant 0: cosine_similarity, 1: cosine_similarity_norm, 2: cosine_similarity_bytea; rows (index, similarity as %.17g) */
+int ref_cosine_similarity_batch(const float* a, const float* b, int n, int d, int variant, double* out) {
+  if (!cosine_similarity_batch) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_bytea_array(a, n, d));
+  fc.args[1] = PointerGetDatum(make_bytea_array(b, n, d));
+  fc.args[2] = Int32GetDatum(variant);
+  jmp_buf env;
+  FmgrInfo fl = {0};
+  fc.flinfo = &fl;
+  int rows = 0;
+  fb_emul_error_jmp = &env;
+  if (setjmp(env)) { fb_emul_error_jmp = NULL; return -1; }
+  for (;;) {
+    fc.srf_state = 0;
+    Datum r = cosine_similarity_batch(&fc);
+    if (fc.srf_state != 1) break;
+    HeapTuple h = (HeapTuple)DatumGetPointer(r);
+    if (rows < n) out[rows] = strtod(h->values[1], NULL);
+    rows++;
+  }
+  fb_emul_error_jmp = NULL;
+  return rows;
+}
+int ref_freddy_repin(void) {
+  if (!freddy_repin) return -3;
+  FunctionCallInfoData fc = {0};
+  call_plain(freddy_repin, &fc);
+  return 0;
 }

@@ -4,5 +4,6 @@
 #define INT2OID 21
 #define INT4OID 23
 #define FLOAT4OID 700
+#define FLOAT8OID 701
 #define BYTEAOID 17
 #endif

@@ -11,6 +11,7 @@ typedef struct AttInMetadata { TupleDesc tupdesc; } AttInMetadata;
 typedef struct HeapTupleData {
   int natts; char** values;
   const void* table; int64 row; const void* table2; int64 row2; const int* proj; int nproj;
+  Datum* bins;            /* ad-hoc result rows (no table): binary values per column, or NULL */
 } HeapTupleData;
 typedef HeapTupleData* HeapTuple;
 typedef struct FuncCallContext {

@@ -631,14 +631,22 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_
   // k-th smallest distance, rows with d > v can neither enter nor rearrange the entries <= v (fact B,
   // tests/test_topk_semantics.py), so the literal loop over S = {rows with d <= v} in arrival order gives
   // the reference's result.  S is complete in this list iff some lane < n_valid holds a key with d > v (or none):
-  // then the warp replays it here (fact D).  Tie groups too long for that go to the general kernel.
+  // then the warp replays it here (fact D).  S need not even be complete (fact E): the first k rows of S in
+  // arrival order are all admitted (the array is not yet full of entries <= v), after that every row tied at v
+  // is rejected (strict `<`) and every later row with d < v evicts the EARLIEST surviving tie (equal entries are
+  // inserted in front of each other, so the earliest sits last).  Hence only the rows with d < v and the k
+  // earliest rows tied at v matter; further ties replay as rejections.  Keys order ties by arrival, so the list
+  // holds the earliest ones: the replay below is exact as soon as the list shows k ties (or all of S).
+  // What remains for the general kernel: a list saturated with rows <= v that shows fewer than k ties
+  // (needs more than 32 - k rows below v, or the k+2-key lists of the segmented scan).
   const u64 kk = shfl_u64(mine, k), kk1 = shfl_u64(mine, k - 1);
   bool replayed = false;
   if (kk != kKeyInf && key_dbits(kk) == key_dbits(kk1)) {
     const uint32_t v = key_dbits(kk1);
     const bool member = lane < n_valid && (mine != kKeyInf) && key_dbits(mine) <= v;
     const unsigned members = __ballot_sync(0xffffffffu, member);
-    if (members == (n_valid >= 32 ? 0xffffffffu : ((1u << n_valid) - 1u))) {
+    const int n_ties = __popc(__ballot_sync(0xffffffffu, member && key_dbits(mine) == v));
+    if (members == (n_valid >= 32 ? 0xffffffffu : ((1u << n_valid) - 1u)) && n_ties < k) {
       flags |= kFlagExact | kWhyScanTie;
     } else {
       // S by arrival: (arrival << 32 | distance bits), non-members last

@@ -17,11 +17,12 @@ import numpy as np
 import torch
 
 
-def _kmeans(x, k, iters, gen):
-    """Lloyd k-means on rows of x (float32 tensor); empty clusters keep their centroid."""
+def _kmeans(x, k, iters, gen, init=None):
+    """Lloyd k-means on rows of x (float32 tensor); empty clusters keep their centroid.
+    init: optional [k][d] starting centroids (default: k random rows)."""
     n = x.shape[0]
     perm = torch.randperm(n, generator=gen, device=x.device)[:k]
-    cent = x[perm].clone()
+    cent = x[perm].clone() if init is None else init.clone()
     if k > n:  # tiny inputs: pad with jittered copies
         extra = x[torch.randint(0, n, (k - n,), generator=gen, device=x.device)]
         cent = torch.cat([cent, extra + 1e-3 * torch.randn(extra.shape, generator=gen, device=x.device)])
@@ -47,8 +48,10 @@ def _nearest(x, cent, chunk=65536):
 
 def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clusters=1000,
                          sigma=0.3, kmeans_iters=10, seed=1234, device=None, with_pq=False,
-                         keep_vectors=False, zipf=0.7):
-    """Returns a dict of numpy arrays (plus 'vectors_t': the torch tensor, if keep_vectors)."""
+                         keep_vectors=False, zipf=0.7, coarse_from_centres=False):
+    """Returns a dict of numpy arrays (plus 'vectors_t': the torch tensor, if keep_vectors).
+    coarse_from_centres: start the coarse k-means from the (normalised) generating centres (needs C == n_clusters):
+    one centroid per true cluster, i.e. inverted lists of the nominal N / C rows."""
     assert d % m == 0, "d must be divisible by m"
     sub = d // m
     dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
@@ -70,7 +73,10 @@ def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clus
     train = vecs[:ntr]
 
     # --- coarse quantizer
-    coarse = _kmeans(train, C, kmeans_iters, gen)
+    init = None
+    if coarse_from_centres and C == n_clusters:
+        init = centres / centres.norm(dim=1, keepdim=True) / (1.0 + sigma * sigma) ** 0.5   # E[v | cluster] of the normalised rows
+    coarse = _kmeans(train, C, kmeans_iters, gen, init=init)
     coarse_ids = _nearest(vecs, coarse)
 
     # --- residual PQ codebook (trained on the residuals of the training prefix)

@@ -1,8 +1,14 @@
-/* freddy_shim.c — the PostgreSQL side of the drop-in: the six search SRFs of the FREDDY
- * extension (freddy--0.0.1.sql:370-392) with their first-call bodies replaced by calls into
- * libfreddy_b200.so (include/freddy_b200.h).  Built with PGXS next to the reference's
- * index_utils.c / output_utils.c / core_functions.c (table-name and parameter lookup, bytea
- * converters, loaders and the non-search UDFs stay the reference's own code).
+/* freddy_shim.c — the PostgreSQL side of the drop-in.  It takes the place of freddy.c and ivpq_search_in.c in
+ * the extension's OBJS and defines EVERY symbol freddy--0.0.1.sql binds to them:
+ *   the seven search SRFs (pq_search, ivfadc_search, pq_search_in, pq_search_in_batch, ivfadc_batch_search,
+ *   ivpq_search_in, grouping_pq; freddy--0.0.1.sql:370-397) with their first-call bodies replaced by calls into
+ *   libfreddy_b200.so (include/freddy_b200.h);
+ *   insert_batch (quantisation on the GPU, table mutation through the reference's own helpers);
+ *   the converters read_bytea / read_bytea_int16 / read_bytea_float / vec_to_bytea;
+ * plus SRFs for the GPU paths SQL reaches through plpgsql today (exact k-NN, post verification, analogy, batched
+ * cosine) and freddy_repin().  Built with PGXS next to the reference's index_utils.c / output_utils.c /
+ * core_functions.c / cosine_similarity.c (table-name and parameter lookup, bytea converters, the scalar UDFs stay
+ * the reference's own code).
  *
  * One engine per backend process, created on first use (a CUDA context cannot cross fork());
  * each index is read through SPI ONCE per session and pinned in HBM — the reference re-reads
@@ -25,7 +31,47 @@
 
 static fb_engine* engine = NULL;
 static int pinned_d = 0, vecs_d = 0;
-static bool pinned_ivfadc = false, pinned_pq = false, pinned_ivpq = false, pinned_vecs = false;
+
+/* What a pin was made from.  The reference re-reads its tables on every call; a pinned copy has to notice when
+ * they changed: (1) the configured table names (the set_... / init functions, freddy--0.0.1.sql:5-148) are resolved on
+ * every call anyway (one `SELECT * FROM get_..()` each) and compared; (2) `SELECT max(id)` of the row table is
+ * one btree probe and catches appended rows, also from other backends; (3) insert_batch and the SQL-callable
+ * freddy_repin() bump a generation for everything else (UPDATEs of codebooks, bulk reloads). */
+typedef struct Pin {
+  bool valid;
+  char names[3][100];
+  int max_id;
+  long generation;
+} Pin;
+static Pin pin_ivfadc_state, pin_pq_state, pin_ivpq_state, pin_vecs_state;
+static long pin_generation = 0;
+
+static int table_max_id(const char* table) {
+  char command[200];
+  int v = 0;
+  bool isnull;
+  snprintf(command, sizeof command, "SELECT max(id) FROM %s", table);
+  SPI_connect();
+  if (SPI_exec(command, 0) > 0 && SPI_tuptable != NULL && SPI_processed == 1)
+    v = DatumGetInt32(SPI_getbinval(SPI_tuptable->vals[0], SPI_tuptable->tupdesc, 1, &isnull));
+  SPI_finish();
+  return v;
+}
+
+/* true: the pin is still what the tables say; false: (re)pin and call pin_record */
+static bool pin_current(const Pin* p, const char* n0, const char* n1, const char* n2, const char* row_table) {
+  if (!p->valid || p->generation != pin_generation) return false;
+  if (strcmp(p->names[0], n0 ? n0 : "") || strcmp(p->names[1], n1 ? n1 : "") || strcmp(p->names[2], n2 ? n2 : "")) return false;
+  return row_table == NULL || table_max_id(row_table) == p->max_id;
+}
+static void pin_record(Pin* p, const char* n0, const char* n1, const char* n2, const char* row_table) {
+  snprintf(p->names[0], 100, "%s", n0 ? n0 : "");
+  snprintf(p->names[1], 100, "%s", n1 ? n1 : "");
+  snprintf(p->names[2], 100, "%s", n2 ? n2 : "");
+  p->max_id = row_table ? table_max_id(row_table) : 0;
+  p->generation = pin_generation;
+  p->valid = true;
+}
 
 static void fb_check(int rc) {
   if (rc != FB_OK) elog(ERROR, "freddy_b200: %s", fb_last_error(engine));
@@ -78,9 +124,9 @@ static void pin_vectors(void) {
   int n, d = 0;
   int32* ids;
   float* vecs = NULL;
-  if (pinned_vecs) return;
-  ensure_engine();
   getTableName(NORMALIZED, name, 100);
+  if (pin_current(&pin_vecs_state, name, NULL, NULL, name)) return;
+  ensure_engine();
   snprintf(command, sizeof command, "SELECT id, vector FROM %s", name);
   SPI_connect();
   if (SPI_exec(command, 0) <= 0 || SPI_tuptable == NULL) elog(ERROR, "cannot read %s", name);
@@ -97,7 +143,7 @@ static void pin_vectors(void) {
   SPI_finish();
   fb_check(fb_load_vectors(engine, ids, vecs, n, d));
   vecs_d = d;
-  pinned_vecs = true;
+  pin_record(&pin_vecs_state, name, NULL, NULL, name);
 }
 
 static void pin_ivfadc(int d) {
@@ -108,10 +154,12 @@ static void pin_ivfadc(int d) {
   int32 *ids, *cids;
   int16* codes;
   float* coarse;
-  if (pinned_ivfadc && pinned_d == d) return;
-  ensure_engine();
+  char cqname[100];
   getTableName(RESIDUAL_CODEBOOK, cbname, 100);
   getTableName(RESIDUAL_QUANTIZATION, finename, 100);
+  getTableName(COARSE_QUANTIZATION, cqname, 100);
+  if (pinned_d == d && pin_current(&pin_ivfadc_state, cbname, finename, cqname, finename)) return;
+  ensure_engine();
   cb = getCodebook(cbname);                                   /* index_utils.c:577-630 */
   cq = getCoarseQuantizer(&C);                                /* index_utils.c:531-575 */
   coarse = palloc(sizeof(float) * (size_t)C * d);
@@ -121,7 +169,7 @@ static void pin_ivfadc(int d) {
                             d / cb.positions));
   n = fetch_code_table(finename, true, &ids, &cids, &codes, &m);
   fb_check(fb_load_fine(engine, ids, cids, codes, n, m));
-  pinned_ivfadc = true;
+  pin_record(&pin_ivfadc_state, cbname, finename, cqname, finename);
   pinned_d = d;
 }
 
@@ -131,15 +179,15 @@ static void pin_pq(int d) {
   int n, m;
   int32* ids;
   int16* codes;
-  if (pinned_pq) return;
-  ensure_engine();
   getTableName(CODEBOOK, cbname, 100);
   getTableName(PQ_QUANTIZATION, tname, 100);
+  if (pin_current(&pin_pq_state, cbname, tname, NULL, tname)) return;
+  ensure_engine();
   cb = getCodebook(cbname);
   fb_check(fb_load_codebook(engine, FB_CB_PQ, flatten_codebook(cb, d / cb.positions), cb.positions, cb.codeSize, d / cb.positions));
   n = fetch_code_table(tname, false, &ids, NULL, &codes, &m);
   fb_check(fb_load_pq(engine, ids, codes, n, m));
-  pinned_pq = true;
+  pin_record(&pin_pq_state, cbname, tname, NULL, tname);
 }
 
 static void pin_ivpq(int d) {
@@ -149,11 +197,11 @@ static void pin_ivpq(int d) {
   int n, m;
   int32 *ids, *cids;
   int16* codes;
-  if (pinned_ivpq) return;
-  ensure_engine();
   getTableName(IVPQ_CODEBOOK, cbname, 100);
   getTableName(IVPQ_QUANTIZATION, tname, 100);
   getTableName(COARSE_QUANTIZATION_MULTI, cqname, 100);
+  if (pin_current(&pin_ivpq_state, cbname, tname, cqname, tname)) return;
+  ensure_engine();
   cb = getCodebook(cbname);                                   /* ivpq_search_in.c:216-218 */
   cqm = getCodebook(cqname);                                  /* ivpq_search_in.c:222-224 */
   stats = getStatistics();                                    /* ivpq_search_in.c:232 */
@@ -161,7 +209,7 @@ static void pin_ivpq(int d) {
   fb_check(fb_load_codebook(engine, FB_CB_IVPQ, flatten_codebook(cb, d / cb.positions), cb.positions, cb.codeSize, d / cb.positions));
   n = fetch_code_table(tname, true, &ids, &cids, &codes, &m);
   fb_check(fb_load_ivpq(engine, flatten_codebook(cqm, d / 2), cqm.codeSize, d, ids, cids, codes, n, m, stats));
-  pinned_ivpq = true;
+  pin_record(&pin_ivpq_state, cbname, tname, cqname, tname);
 }
 
 /* ---- SRF plumbing: the value-per-call emission every search SRF shares (freddy.c:394-409) ---- */
@@ -331,19 +379,7 @@ Datum ivfadc_batch_search(PG_FUNCTION_ARGS) {
     int32* ids = palloc(sizeof(int32) * (size_t)(n ? n : 1) * k);
     float* dist = palloc(sizeof(float) * (size_t)(n ? n : 1) * k);
     pin_vectors();                                                    /* the query vectors live in the normalized table */
-    {
-      /* d of the index = d of the vectors table: pin with the first vector's length */
-      char name[100], command[200];
-      bool isnull;
-      int d;
-      getTableName(NORMALIZED, name, 100);
-      snprintf(command, sizeof command, "SELECT id, vector FROM %s", name);
-      SPI_connect();
-      SPI_exec(command, 0);
-      d = SPI_processed ? (VARSIZE(DatumGetByteaP(SPI_getbinval(SPI_tuptable->vals[0], SPI_tuptable->tupdesc, 2, &isnull))) - VARHDRSZ) / (int)sizeof(float4) : 0;
-      SPI_finish();
-      pin_ivfadc(d);
-    }
+    pin_ivfadc(vecs_d);                                               /* d of the index = d of the vectors table */
     fb_check(fb_ivfadc_batch_search(engine, qids, n, k, out_q, ids, dist, &nq));   /* replaces freddy.c:757-982 */
     finish_batch(funcctx, out_q, nq, ids, dist, k);
     MemoryContextSwitchTo(old);
@@ -378,8 +414,16 @@ Datum ivpq_search_in(PG_FUNCTION_ARGS) {
 void freddy_shim_reset(void) {
   if (engine) fb_destroy(engine);
   engine = NULL;
-  pinned_ivfadc = pinned_pq = pinned_ivpq = pinned_vecs = false;
+  pin_ivfadc_state.valid = pin_pq_state.valid = pin_ivpq_state.valid = pin_vecs_state.valid = false;
   pinned_d = 0;
+}
+
+/* freddy_repin(): forget every pinned table; the next call of each search function reads its tables again.
+ * CREATE FUNCTION freddy_repin() RETURNS integer AS '$libdir/freddy', 'freddy_repin' LANGUAGE C; */
+PG_FUNCTION_INFO_V1(freddy_repin);
+Datum freddy_repin(PG_FUNCTION_ARGS) {
+  pin_generation++;
+  PG_RETURN_INT32((int32)pin_generation);
 }
 
 /* grouping_pq(int[] ids, int[] group_ids) -> SETOF (id int4, group id int4)   replaces freddy.c:1185-1371 */
@@ -426,4 +470,413 @@ Datum grouping_pq(PG_FUNCTION_ARGS) {
   snprintf(u->values[1], 18, "%d", u->nearestGroup[u->iter]);
   u->iter++;
   SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(BuildTupleFromCStrings(funcctx->attinmeta, u->values)));
+}
+
+/* ===========================================================================================
+ * GPU paths SQL reaches through plpgsql + one UDF call per row today.  Each SRF below is what the
+ * plpgsql bodies in freddy--0.0.1.sql would call instead (INTEGRATION.md shows the edited bodies).
+ * Similarities are float4 / float8 values printed so that float4in / float8in read back the exact
+ * bits ("%.9g" / "%.17g"); the reference's distance SRFs keep their lossy "%f".
+ * =========================================================================================== */
+static Datum emit_single_exact(FunctionCallInfo fcinfo) {
+  FuncCallContext* funcctx = SRF_PERCALL_SETUP();
+  UsrFctx* u = (UsrFctx*)funcctx->user_fctx;
+  if (u->iter >= u->k) SRF_RETURN_DONE(funcctx);
+  snprintf(u->values[0], 16, "%d", u->tk[u->iter].id);
+  snprintf(u->values[1], 16, "%.9g", u->tk[u->iter].distance);
+  u->iter++;
+  SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(BuildTupleFromCStrings(funcctx->attinmeta, u->values)));
+}
+
+/* rows that joined nothing are not returned (INNER JOIN / fewer than k rows in the table): id -1 is dropped */
+static int drop_unfilled(int32* ids, float* vals, int k) {
+  int n = 0;
+  for (int i = 0; i < k; i++)
+    if (ids[i] >= 0) { ids[n] = ids[i]; vals[n] = vals[i]; n++; }
+  return n;
+}
+
+/* knn_exact_search(bytea, int) -> SETOF (id int4, similarity float4): the body of k_nearest_neighbour(bytea, int)
+ * (freddy--0.0.1.sql:426-439: ORDER BY cosine_similarity_bytea(v, vector) DESC FETCH FIRST k over the whole table) */
+PG_FUNCTION_INFO_V1(knn_exact_search);
+Datum knn_exact_search(PG_FUNCTION_ARGS) {
+  if (SRF_IS_FIRSTCALL()) {
+    FuncCallContext* funcctx = SRF_FIRSTCALL_INIT();
+    MemoryContext old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    int k = PG_GETARG_INT32(1), n = 0;
+    float4* q;
+    int32* ids = palloc(sizeof(int32) * (k > 0 ? k : 1));
+    float* sims = palloc(sizeof(float) * (k > 0 ? k : 1));
+    convert_bytea_float4(PG_GETARG_BYTEA_P(0), &q, &n);
+    pin_vectors();
+    if (n != vecs_d) elog(ERROR, "query vector has %d dimensions, the table %d", n, vecs_d);
+    fb_check(fb_knn_exact(engine, q, 1, k, NULL, 0, ids, sims));
+    finish_single(funcctx, ids, sims, drop_unfilled(ids, sims, k));
+    MemoryContextSwitchTo(old);
+  }
+  return emit_single_exact(fcinfo);
+}
+
+/* knn_in_exact_search(bytea, int, int[]): the body of knn_in_exact (freddy--0.0.1.sql:1026-1038, WHERE id = ANY(ids)) */
+PG_FUNCTION_INFO_V1(knn_in_exact_search);
+Datum knn_in_exact_search(PG_FUNCTION_ARGS) {
+  if (SRF_IS_FIRSTCALL()) {
+    FuncCallContext* funcctx = SRF_FIRSTCALL_INIT();
+    MemoryContext old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    int k = PG_GETARG_INT32(1), n = 0, nt = 0;
+    float4* q;
+    int* targets = int_array(PG_GETARG_ARRAYTYPE_P(2), &nt);
+    int32* ids = palloc(sizeof(int32) * (k > 0 ? k : 1));
+    float* sims = palloc(sizeof(float) * (k > 0 ? k : 1));
+    int32 none = -1;
+    convert_bytea_float4(PG_GETARG_BYTEA_P(0), &q, &n);
+    pin_vectors();
+    if (n != vecs_d) elog(ERROR, "query vector has %d dimensions, the table %d", n, vecs_d);
+    fb_check(fb_knn_exact(engine, q, 1, k, nt > 0 ? targets : &none, nt > 0 ? nt : 1, ids, sims));
+    finish_single(funcctx, ids, sims, drop_unfilled(ids, sims, k));
+    MemoryContextSwitchTo(old);
+  }
+  return emit_single_exact(fcinfo);
+}
+
+/* ivfadc_search_pv(bytea, int): the body of k_nearest_neighbour_ivfadc_pv (freddy--0.0.1.sql:574-591):
+ * ivfadc_search(v, get_pvf() * k) JOIN vectors, re-ranked by cosine_similarity_bytea, first k */
+PG_FUNCTION_INFO_V1(ivfadc_search_pv);
+Datum ivfadc_search_pv(PG_FUNCTION_ARGS) {
+  if (SRF_IS_FIRSTCALL()) {
+    FuncCallContext* funcctx = SRF_FIRSTCALL_INIT();
+    MemoryContext old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    int k = PG_GETARG_INT32(1), n = 0, w, pvf;
+    float4* q;
+    int32* ids = palloc(sizeof(int32) * (k > 0 ? k : 1));
+    float* sims = palloc(sizeof(float) * (k > 0 ? k : 1));
+    getParameter(PARAM_W, &w);
+    getParameter(PARAM_PVF, &pvf);
+    convert_bytea_float4(PG_GETARG_BYTEA_P(0), &q, &n);
+    pin_ivfadc(n);
+    pin_vectors();
+    fb_check(fb_ivfadc_search_pv(engine, q, 1, k, pvf, w, ids, sims));
+    finish_single(funcctx, ids, sims, drop_unfilled(ids, sims, k));
+    MemoryContextSwitchTo(old);
+  }
+  return emit_single_exact(fcinfo);
+}
+
+/* analogy_3cosadd_batch(int[] ids) -> SETOF (query int4, id int4, score float4): ids = flattened (a, b, c) word-id
+ * triples; per triple the row analogy_3cosadd returns (freddy--0.0.1.sql:1270-1288).  One call answers a batch. */
+PG_FUNCTION_INFO_V1(analogy_3cosadd_batch);
+Datum analogy_3cosadd_batch(PG_FUNCTION_ARGS) {
+  if (SRF_IS_FIRSTCALL()) {
+    FuncCallContext* funcctx = SRF_FIRSTCALL_INIT();
+    MemoryContext old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    int n3 = 0, nq;
+    int* abc = int_array(PG_GETARG_ARRAYTYPE_P(0), &n3);
+    int32 *ids, *qidx;
+    float* scores;
+    if (n3 % 3 != 0) elog(ERROR, "analogy_3cosadd_batch expects (a, b, c) id triples, got %d ids", n3);
+    nq = n3 / 3;
+    ids = palloc(sizeof(int32) * (nq ? nq : 1));
+    scores = palloc(sizeof(float) * (nq ? nq : 1));
+    qidx = palloc(sizeof(int32) * (nq ? nq : 1));
+    for (int i = 0; i < nq; i++) qidx[i] = i;
+    pin_vectors();
+    fb_check(fb_analogy_3cosadd(engine, abc, nq, ids, scores));
+    finish_batch(funcctx, qidx, nq, ids, scores, 1);
+    MemoryContextSwitchTo(old);
+  }
+  {
+    FuncCallContext* funcctx = SRF_PERCALL_SETUP();
+    UsrFctxBatch* u = (UsrFctxBatch*)funcctx->user_fctx;
+    if (u->iter >= u->queryIdsSize) SRF_RETURN_DONE(funcctx);
+    snprintf(u->values[0], 16, "%d", u->queryIds[u->iter]);
+    snprintf(u->values[1], 16, "%d", u->tk[u->iter][0].id);
+    snprintf(u->values[2], 16, "%.9g", u->tk[u->iter][0].distance);
+    u->iter++;
+    SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(BuildTupleFromCStrings(funcctx->attinmeta, u->values)));
+  }
+}
+
+/* cosine_similarity_batch(bytea[] a, bytea[] b, int variant) -> SETOF (idx int4, similarity float8): n independent
+ * pairs in one call; variant 0 cosine_similarity, 1 cosine_similarity_norm, 2 cosine_similarity_bytea
+ * (core_functions.c:23-81, cosine_similarity.c:12-45) */
+typedef struct CosBatchCtx { int n, iter; double* out; char* values[2]; char buf0[16], buf1[32]; } CosBatchCtx;
+PG_FUNCTION_INFO_V1(cosine_similarity_batch);
+Datum cosine_similarity_batch(PG_FUNCTION_ARGS) {
+  FuncCallContext* funcctx;
+  CosBatchCtx* u;
+  if (SRF_IS_FIRSTCALL()) {
+    MemoryContext old;
+    TupleDesc desc;
+    int na = 0, nb = 0, da = 0, db = 0;
+    float *a, *b;
+    funcctx = SRF_FIRSTCALL_INIT();
+    old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    a = bytea_array_to_matrix(PG_GETARG_ARRAYTYPE_P(0), &na, &da);
+    b = bytea_array_to_matrix(PG_GETARG_ARRAYTYPE_P(1), &nb, &db);
+    if (na != nb || da != db) elog(ERROR, "cosine_similarity_batch: %d x %d against %d x %d", na, da, nb, db);
+    u = palloc(sizeof(CosBatchCtx));
+    u->n = na;
+    u->iter = 0;
+    u->out = palloc(sizeof(double) * (na ? na : 1));
+    u->values[0] = u->buf0;
+    u->values[1] = u->buf1;
+    ensure_engine();
+    fb_check(fb_cosine_similarity(engine, PG_GETARG_INT32(2), a, b, na, da, u->out));
+    funcctx->user_fctx = u;
+    desc = CreateTemplateTupleDesc(2);
+    TupleDescInitEntry(desc, 1, "Idx", INT4OID, -1, 0);
+    TupleDescInitEntry(desc, 2, "Similarity", FLOAT8OID, -1, 0);
+    funcctx->attinmeta = TupleDescGetAttInMetadata(desc);
+    MemoryContextSwitchTo(old);
+  }
+  funcctx = SRF_PERCALL_SETUP();
+  u = (CosBatchCtx*)funcctx->user_fctx;
+  if (u->iter >= u->n) SRF_RETURN_DONE(funcctx);
+  snprintf(u->values[0], 16, "%d", u->iter);
+  snprintf(u->values[1], 32, "%.17g", u->out[u->iter]);
+  u->iter++;
+  SRF_RETURN_NEXT(funcctx, HeapTupleGetDatum(BuildTupleFromCStrings(funcctx->attinmeta, u->values)));
+}
+
+/* ===========================================================================================
+ * The rest of what freddy--0.0.1.sql binds to freddy.c (:399-424): bytea <-> array converters and insert_batch.
+ * =========================================================================================== */
+static ArrayType* make_array(Datum* values, int n, Oid type) {
+  int dims[1], lbs[1];
+  int16 len;
+  bool byval;
+  char align;
+  dims[0] = n;
+  lbs[0] = 1;
+  get_typlenbyvalalign(type, &len, &byval, &align);
+  return construct_md_array(values, NULL, 1, dims, lbs, type, len, byval, align);
+}
+
+PG_FUNCTION_INFO_V1(read_bytea);          /* bytea -> int4[]   (freddy.c:1660-1698) */
+Datum read_bytea(PG_FUNCTION_ARGS) {
+  int32* v;
+  int n = 0;
+  Datum* d;
+  convert_bytea_int32(PG_GETARG_BYTEA_P(0), &v, &n);
+  d = palloc(sizeof(Datum) * (n ? n : 1));
+  for (int i = 0; i < n; i++) d[i] = Int32GetDatum(v[i]);
+  PG_RETURN_ARRAYTYPE_P(make_array(d, n, INT4OID));
+}
+
+PG_FUNCTION_INFO_V1(read_bytea_int16);    /* bytea -> int2[]   (freddy.c:1700-1738) */
+Datum read_bytea_int16(PG_FUNCTION_ARGS) {
+  int16* v;
+  int n = 0;
+  Datum* d;
+  convert_bytea_int16(PG_GETARG_BYTEA_P(0), &v, &n);
+  d = palloc(sizeof(Datum) * (n ? n : 1));
+  for (int i = 0; i < n; i++) d[i] = Int16GetDatum(v[i]);
+  PG_RETURN_ARRAYTYPE_P(make_array(d, n, INT2OID));
+}
+
+PG_FUNCTION_INFO_V1(read_bytea_float);    /* bytea -> float4[] (freddy.c:1740-1778) */
+Datum read_bytea_float(PG_FUNCTION_ARGS) {
+  float4* v;
+  int n = 0;
+  Datum* d;
+  convert_bytea_float4(PG_GETARG_BYTEA_P(0), &v, &n);
+  d = palloc(sizeof(Datum) * (n ? n : 1));
+  for (int i = 0; i < n; i++) d[i] = Float4GetDatum(v[i]);
+  PG_RETURN_ARRAYTYPE_P(make_array(d, n, FLOAT4OID));
+}
+
+PG_FUNCTION_INFO_V1(vec_to_bytea);        /* float4[] / int4[] / int2[] -> bytea (freddy.c:1780-1826) */
+Datum vec_to_bytea(PG_FUNCTION_ARGS) {
+  ArrayType* arr = PG_GETARG_ARRAYTYPE_P(0);
+  Datum* data;
+  int n = 0;
+  bytea* out = NULL;
+  getArray(arr, &data, &n);
+  if (ARR_ELEMTYPE(arr) == FLOAT4OID) {
+    float4* v = palloc(sizeof(float4) * (n ? n : 1));
+    for (int i = 0; i < n; i++) v[i] = DatumGetFloat4(data[i]);
+    convert_float4_bytea(v, &out, n);
+  } else if (ARR_ELEMTYPE(arr) == INT4OID) {
+    int32* v = palloc(sizeof(int32) * (n ? n : 1));
+    for (int i = 0; i < n; i++) v[i] = DatumGetInt32(data[i]);
+    convert_int32_bytea(v, &out, n);
+  } else if (ARR_ELEMTYPE(arr) == INT2OID) {
+    int16* v = palloc(sizeof(int16) * (n ? n : 1));
+    for (int i = 0; i < n; i++) v[i] = DatumGetInt16(data[i]);
+    convert_int16_bytea(v, &out, n);
+  } else {
+    elog(ERROR, "Unknown element type: %d", (int)ARR_ELEMTYPE(arr));
+  }
+  PG_RETURN_BYTEA_P(out);
+}
+
+/* insert_batch(varchar[] terms) (freddy.c:1403-1658): tokenise the new terms, quantise their vectors for the three
+ * indexes, update the codebooks' running means, INSERT the rows.  Here the quantisation — coarse assignment,
+ * residuals, nearest codeword per sub-vector for the pq, residual and ivpq codebooks — runs on the GPU
+ * (fb_encode_ivfadc / fb_encode_pq: the reference's strict `<`-from-100 first-minimum rule, index_utils.c:923-939,
+ * freddy.c:1567-1582); the codebook drift and every INSERT / UPDATE statement are the reference's own helpers
+ * (updateCodebook, update*Relation in index_utils.c), fed with the GPU's codes.  The pinned tables are
+ * invalidated at the end: the next search re-reads them. */
+static int** codes_to_rows(const int16* codes, int n, int m) {
+  int** rows = palloc(sizeof(int*) * (n ? n : 1));
+  for (int i = 0; i < n; i++) {
+    rows[i] = palloc(sizeof(int) * m);
+    for (int j = 0; j < m; j++) rows[i][j] = codes[(size_t)i * m + j];
+  }
+  return rows;
+}
+
+static void load_codebook_only(int kind, tableType which, int d) {
+  char name[100];
+  CodebookCompound cb;
+  getTableName(which, name, 100);
+  cb = getCodebook(name);
+  fb_check(fb_load_codebook(engine, kind, flatten_codebook(cb, d / cb.positions), cb.positions, cb.codeSize, d / cb.positions));
+}
+
+PG_FUNCTION_INFO_V1(insert_batch);
+Datum insert_batch(PG_FUNCTION_ARGS) {
+  char nameNorm[100], nameOrig[100], namePqCb[100], namePq[100], nameResCb[100], nameFine[100], nameIvCb[100], nameIv[100],
+      nameCqMulti[100];
+  Datum* termsData;
+  int nTerms = 0, planeSize = 0, nNew = 0, d = 0, C = 0;
+  char **terms, **tokens;
+  char *command, *cur;
+  float4 **vecNorm, **vecRaw;
+  float *flat, *coarse;
+  CodebookWithCounts cbPq, cbRes, cbIv;
+  CodebookCompound cqMulti;
+  CoarseQuantizer cq;
+  int pqPos = 0, pqCodes = 0, resPos = 0, resCodes = 0, ivPos = 0, ivCodes = 0;
+  int32* cids;
+  int16 *codesPq, *codesRes, *codesIv;
+  int *cidsInt, *cqMultiIds, *incPq, *incRes, *incIv;
+  int **rowsPq, **rowsRes, **rowsIv, **scratch;
+  float** residuals;
+
+  getTableName(CODEBOOK, namePqCb, 100);
+  getTableName(PQ_QUANTIZATION, namePq, 100);
+  getTableName(RESIDUAL_CODEBOOK, nameResCb, 100);
+  getTableName(RESIDUAL_QUANTIZATION, nameFine, 100);
+  getTableName(NORMALIZED, nameNorm, 100);
+  getTableName(ORIGINAL, nameOrig, 100);
+  getTableName(IVPQ_QUANTIZATION, nameIv, 100);
+  getTableName(IVPQ_CODEBOOK, nameIvCb, 100);
+  getTableName(COARSE_QUANTIZATION_MULTI, nameCqMulti, 100);
+
+  /* the terms that are not in the vocabulary yet, tokenised by the SQL side (freddy.c:1483-1552) */
+  getArray(PG_GETARG_ARRAYTYPE_P(0), &termsData, &nTerms);
+  terms = palloc(sizeof(char*) * (nTerms ? nTerms : 1));
+  for (int j = 0; j < nTerms; j++) {
+    int len = VARSIZE(termsData[j]) - VARHDRSZ;
+    terms[j] = palloc(len + 1);
+    memcpy(terms[j], VARDATA(termsData[j]), len);
+    terms[j][len] = 0;
+    planeSize += len;
+  }
+  command = palloc(planeSize + 2 * nTerms + 400);
+  cur = command;
+  cur += sprintf(cur, "SELECT replace(term, ' ', '_') AS token, tokenize(term), tokenize_raw(term) FROM unnest('{");
+  for (int i = 0; i < nTerms; i++) cur += sprintf(cur, i < nTerms - 1 ? "%s, " : "%s", terms[i]);
+  cur += sprintf(cur, "}'::varchar(100)[]) AS term WHERE NOT replace(term, ' ', '_') IN (SELECT word FROM %s)", nameNorm);
+  SPI_connect();
+  if (SPI_exec(command, 0) <= 0 || SPI_tuptable == NULL) elog(ERROR, "insert_batch: tokenisation failed");
+  nNew = (int)SPI_processed;
+  tokens = SPI_palloc(sizeof(char*) * (nNew ? nNew : 1));
+  vecNorm = SPI_palloc(sizeof(float4*) * (nNew ? nNew : 1));
+  vecRaw = SPI_palloc(sizeof(float4*) * (nNew ? nNew : 1));
+  for (int i = 0; i < nNew; i++) {
+    bool isnull;
+    HeapTuple t = SPI_tuptable->vals[i];
+    char* tok = SPI_getvalue(t, SPI_tuptable->tupdesc, 1);
+    bytea* vn = DatumGetByteaP(SPI_getbinval(t, SPI_tuptable->tupdesc, 2, &isnull));
+    bytea* vr = DatumGetByteaP(SPI_getbinval(t, SPI_tuptable->tupdesc, 3, &isnull));
+    d = (VARSIZE(vn) - VARHDRSZ) / sizeof(float4);
+    tokens[i] = SPI_palloc(strlen(tok) + 1);
+    strcpy(tokens[i], tok);
+    vecNorm[i] = SPI_palloc(sizeof(float4) * d);
+    vecRaw[i] = SPI_palloc(sizeof(float4) * d);
+    memcpy(vecNorm[i], VARDATA(vn), sizeof(float4) * d);
+    memcpy(vecRaw[i], VARDATA(vr), sizeof(float4) * d);
+  }
+  SPI_finish();
+  if (nNew == 0) PG_RETURN_INT32(0);
+
+  /* ---- quantisation on the GPU ---- */
+  ensure_engine();
+  cq = getCoarseQuantizer(&C);
+  coarse = palloc(sizeof(float) * (size_t)C * d);
+  for (int i = 0; i < C; i++) memcpy(coarse + (size_t)i * d, cq[i].vector, sizeof(float) * d);
+  fb_check(fb_load_coarse(engine, coarse, C, d));
+  load_codebook_only(FB_CB_PQ, CODEBOOK, d);
+  load_codebook_only(FB_CB_RESIDUAL, RESIDUAL_CODEBOOK, d);
+  load_codebook_only(FB_CB_IVPQ, IVPQ_CODEBOOK, d);
+  cbPq = getCodebookWithCounts(&pqPos, &pqCodes, namePqCb);
+  cbRes = getCodebookWithCounts(&resPos, &resCodes, nameResCb);
+  cbIv = getCodebookWithCounts(&ivPos, &ivCodes, nameIvCb);
+  flat = palloc(sizeof(float) * (size_t)nNew * d);
+  for (int i = 0; i < nNew; i++) memcpy(flat + (size_t)i * d, vecNorm[i], sizeof(float) * d);
+  cids = palloc(sizeof(int32) * nNew);
+  codesPq = palloc(sizeof(int16) * (size_t)nNew * pqPos);
+  codesRes = palloc(sizeof(int16) * (size_t)nNew * resPos);
+  codesIv = palloc(sizeof(int16) * (size_t)nNew * ivPos);
+  fb_check(fb_encode_pq(engine, FB_CB_PQ, flat, nNew, codesPq));                 /* updateCodebook's assignment, pq codebook */
+  fb_check(fb_encode_ivfadc(engine, flat, nNew, cids, codesRes));                /* freddy.c:1567-1582 + residual codebook */
+  fb_check(fb_encode_pq(engine, FB_CB_IVPQ, flat, nNew, codesIv));               /* ivpq codebook (raw vectors) */
+  rowsPq = codes_to_rows(codesPq, nNew, pqPos);
+  rowsRes = codes_to_rows(codesRes, nNew, resPos);
+  rowsIv = codes_to_rows(codesIv, nNew, ivPos);
+  cidsInt = palloc(sizeof(int) * nNew);
+  residuals = palloc(sizeof(float*) * nNew);
+  for (int i = 0; i < nNew; i++) {
+    cidsInt[i] = cq[cids[i]].id;
+    residuals[i] = palloc(sizeof(float) * d);
+    for (int j = 0; j < d; j++) residuals[i][j] = vecNorm[i][j] - cq[cids[i]].vector[j];
+  }
+  /* multi-index cell of the ivpq index (freddy.c:1584-1605): 2 x Kc sub-distances per row, bookkeeping-sized */
+  cqMulti = getCodebook(nameCqMulti);
+  cqMultiIds = palloc(sizeof(int) * nNew);
+  for (int i = 0; i < nNew; i++) {
+    int factor = 1;
+    cqMultiIds[i] = 0;
+    for (int pos = 0; pos < cqMulti.positions; pos++) {
+      int sub = d / cqMulti.positions, best = 0;
+      float minDist = 1000.0;
+      for (int j = 0; j < cqMulti.codeSize; j++) {
+        float dist = squareDistance(vecNorm[i] + pos * sub, cqMulti.codebook[j + pos * cqMulti.codeSize].vector, sub);
+        if (dist < minDist) { best = j; minDist = dist; }
+      }
+      cqMultiIds[i] += factor * best;
+      factor *= cqMulti.positions;
+    }
+  }
+
+  /* ---- codebook drift: the reference's own running-mean update (index_utils.c:908-957); its assignments are
+   *      recomputed there on the CPU and must be the GPU's ---- */
+  scratch = palloc(sizeof(int*) * nNew);
+  incPq = palloc(sizeof(int) * pqPos * pqCodes);
+  updateCodebook(vecNorm, nNew, d / pqPos, cbPq, pqPos, pqCodes, scratch, incPq);
+  for (int i = 0; i < nNew; i++)
+    for (int j = 0; j < pqPos; j++)
+      if (scratch[i][j] != rowsPq[i][j]) elog(ERROR, "insert_batch: GPU and reference pq codes differ (row %d pos %d)", i, j);
+  incRes = palloc(sizeof(int) * resPos * resCodes);
+  updateCodebook(residuals, nNew, d / resPos, cbRes, resPos, resCodes, scratch, incRes);
+  for (int i = 0; i < nNew; i++)
+    for (int j = 0; j < resPos; j++)
+      if (scratch[i][j] != rowsRes[i][j]) elog(ERROR, "insert_batch: GPU and reference residual codes differ (row %d pos %d)", i, j);
+  incIv = palloc(sizeof(int) * ivPos * ivCodes);
+  updateCodebook(vecNorm, nNew, d / ivPos, cbIv, ivPos, ivCodes, scratch, incIv);
+
+  /* ---- the rows and the codebooks, through the reference's statements (index_utils.c:959-1074) ---- */
+  updateProductQuantizationRelation(rowsPq, tokens, pqPos, cbPq, namePq, nNew, NULL);
+  updateProductQuantizationRelation(rowsRes, tokens, resPos, cbRes, nameFine, nNew, cidsInt);
+  updateProductQuantizationRelation(rowsIv, NULL, ivPos, cbIv, nameIv, nNew, cqMultiIds);
+  updateCodebookRelation(cbPq, pqPos, pqCodes, namePqCb, incPq, d / pqPos);
+  updateCodebookRelation(cbRes, resPos, resCodes, nameResCb, incRes, d / resPos);
+  updateCodebookRelation(cbIv, ivPos, ivCodes, nameIvCb, incIv, d / ivPos);
+  updateWordVectorsRelation(nameNorm, tokens, vecNorm, nNew, d);
+  updateWordVectorsRelation(nameOrig, tokens, vecRaw, nNew, d);
+
+  pin_generation++;            /* codebooks moved, rows were appended: every pinned table is stale */
+  PG_RETURN_INT32(0);
 }

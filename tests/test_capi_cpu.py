@@ -92,3 +92,28 @@ def test_bench_reference_pool_smoke(oracle_mod):
     import numpy as np
     np.testing.assert_array_equal(ids, eids)
     np.testing.assert_array_equal(raw.view(np.uint32), ed.view(np.uint32))
+
+
+def test_shim_defines_every_symbol_the_sql_script_binds(oracle_mod):
+    """CREATE EXTENSION resolves every `AS '$libdir/freddy', '<symbol>'` of freddy--0.0.1.sql in ONE library.  The
+    deployment drops freddy.c / ivpq_search_in.c for the shim, so the shim (+ the reference files that stay:
+    index_utils.c, core_functions.c, cosine_similarity.c, output_utils.c) must define all 23 of them.
+    tests/golden/sql_symbols.json is the list parsed from the reference's SQL script; when /root/reference is present
+    the list is re-derived and must match."""
+    import json
+    import subprocess
+    if not os.path.exists(oracle_mod.SHIM_SO):
+        pytest.skip("oracle/_ref/libfreddy_shim_emul.so not built")
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "sql_symbols.json")))["symbols"]
+    sql = "/root/reference/freddy_extension/freddy--0.0.1.sql"
+    if os.path.exists(sql):
+        live = sorted(set(re.findall(r"AS '\$libdir/freddy', '([a-z0-9_]+)'", open(sql).read())))
+        assert live == want
+    assert len(want) == 23
+    out = subprocess.run(["nm", "-D", "--defined-only", oracle_mod.SHIM_SO], capture_output=True, text=True, check=True).stdout
+    defined = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = [s for s in want if s not in defined]
+    assert not missing, f"symbols the SQL script binds but the shim library lacks: {missing}"
+    for extra in ("knn_exact_search", "knn_in_exact_search", "ivfadc_search_pv", "analogy_3cosadd_batch",
+                  "cosine_similarity_batch", "freddy_repin"):
+        assert extra in defined, extra
