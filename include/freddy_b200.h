@@ -211,7 +211,8 @@ enum {
                                   far as possible (arrival order travels with each row, results do
                                   not change); value = candidate rows examined per slot (default 256,
                                   0/1 = keep arrival order).  Applies to the next fb_load_fine.      */
-  FB_OPT_PIPE_SHAPE = 13,      /* role split of the pipeline CTA (producer warps, scan warps): 0 = (12,14), 1 = (8,18), 2 = (8,14) with a 4x16 producer tile */
+  FB_OPT_PIPE_SHAPE = 13,      /* role split of the pipeline CTA (producer warps, scan warps): 0 = (12,14), 1 = (8,18), 2 = (8,14) with a 4x16 producer tile,
+                                  3 = (16,10) for LUT-bound indexes (short probed lists) */
   FB_OPT_PIPE_RAMP = 14,       /* 1: the first and last pipeline chunks are shortened (quarter, half); default 0  */
   FB_OPT_CUDA_GRAPHS = 15,     /* 1 (default): host-buffer fb_ivfadc_search calls with <= 16 queries replay a
                                   captured CUDA graph of the whole call (upload, kernels, download)      */
@@ -223,6 +224,11 @@ enum {
   FB_OPT_PREFILTER = 17,       /* 1 (default): fb_knn_exact (whole table) and the analogy scans select candidates with a bf16
                                   tcgen05 GEMM whose error is bounded, then decide with the reference's fp32 chain
                                   (identical results); 0: the fp32 scan kernels do all the work                    */
+  FB_OPT_PREFILTER_LOCKSTEP = 19, /* table tiles a pre-filter CTA may run ahead of the slowest CTA that streams the same
+                                  slab for another query tile (default 8; 0 = free running): keeps shared tiles in L2  */
+  FB_OPT_BYTE_CODES = 18,      /* 1 (default): tables with K <= 256 and m <= 16 also keep a true uint8 image of their codes
+                                  (16 bytes per row, one 16-byte load per row in the scan kernels: the layout the
+                                  reference's index_creation/config/*.json, k = 256, call for); 0: 16-bit units only      */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

@@ -65,6 +65,8 @@ struct DevBuf {
 
 struct CodeTable {
   DevBuf<uint2> units;
+  DevBuf<uint4> units8;                      // byte-code image (K <= 256, m <= 16): 16 bytes per row, same slots as `units`
+  bool has8 = false;
   DevBuf<int32_t> rowno, list_blk, list_len, ids;
   DevBuf<int32_t> sorted_ids, sorted_rows;   // (id, row) pairs ordered by id, rows ascending inside an id: `WHERE id IN (...)` on the device
   int m = 0, U = 0, n_lists = 0;
@@ -73,13 +75,14 @@ struct CodeTable {
   std::vector<int32_t> h_list_len;
   CodeTableDev dev() const {
     CodeTableDev t;
+    t.units8 = has8 ? units8.p : nullptr;
     t.units = units.p; t.rowno = rowno.p; t.list_blk = list_blk.p; t.list_len = list_len.p;
     t.ids = ids.p; t.m = m; t.U = U; t.n_lists = n_lists;
     return t;
   }
   void release() {
-    units.release(); rowno.release(); list_blk.release(); list_len.release(); ids.release();
-    sorted_ids.release(); sorted_rows.release(); loaded = false;
+    units.release(); units8.release(); rowno.release(); list_blk.release(); list_len.release(); ids.release();
+    sorted_ids.release(); sorted_rows.release(); loaded = false; has8 = false;
   }
 };
 
@@ -152,11 +155,15 @@ struct fb_engine {
   int64_t pf_N_pad = 0;
   float pf_vmax = 0.0f;
   int prefilter = 1;          // FB_OPT_PREFILTER
+  int byte_codes = 1;         // FB_OPT_BYTE_CODES
+  bool used8 = false;         // the last scan read the byte image (accounting of algorithmic bytes)
   DevBuf<float> pf_eps2;
   DevBuf<uint32_t> pf_gbest, pf_norm;
   DevBuf<int32_t> pf_cnt, pf_ovf, pf_rows_out, pf_ex;
   DevBuf<int2> pf_cand;
   DevBuf<PfUnit> pf_units;
+  DevBuf<int32_t> pf_progress;
+  int pf_lockstep = 8;        // FB_OPT_PREFILTER_LOCKSTEP
   int64_t pf_queries = 0, pf_overflow_queries = 0, pf_candidates = 0;
   DevBuf<int32_t> ana_rows;
   DevBuf<u64> ana_partial;
@@ -343,6 +350,8 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
   int64_t n_blocks = 0;
   for (int c = 0; c < n_lists; c++) { blk[c] = (int32_t)n_blocks; n_blocks += (len[c] + 31) / 32; }
   std::vector<uint2> units((size_t)std::max<int64_t>(1, n_blocks) * U * 32, make_uint2(0, 0));
+  const bool want8 = K <= 256 && m <= 16;   // true uint8 code table: what index_creation/config/*_config.json (k = 256) produce
+  std::vector<uint4> units8(want8 ? (size_t)std::max<int64_t>(1, n_blocks) * 32 : 0, make_uint4(0, 0, 0, 0));
   std::vector<int32_t> rowno((size_t)std::max<int64_t>(1, n_blocks) * 32, -1);
   for (int64_t r = 0; r < N; r++)
     for (int p = 0; p < m; p++) {
@@ -393,6 +402,11 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
       }
       units[((size_t)b * U + u) * 32 + L] = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
     }
+    if (want8) {
+      uint32_t wds[4] = {0, 0, 0, 0};
+      for (int p2 = 0; p2 < m; p2++) wds[p2 >> 2] |= (uint32_t)(uint8_t)cr[p2] << (8 * (p2 & 3));
+      units8[(size_t)b * 32 + L] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    }
     rowno[(size_t)b * 32 + L] = (int32_t)r;
   }
   FB_CUDA(e, tab.units.ensure(units.size()));
@@ -401,6 +415,11 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
   FB_CUDA(e, tab.list_len.ensure(n_lists));
   FB_CUDA(e, tab.ids.ensure((size_t)std::max<int64_t>(1, N)));
   FB_CUDA(e, cudaMemcpy(tab.units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  tab.has8 = want8;
+  if (want8) {
+    FB_CUDA(e, tab.units8.ensure(units8.size()));
+    FB_CUDA(e, cudaMemcpy(tab.units8.p, units8.data(), units8.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+  }
   FB_CUDA(e, cudaMemcpy(tab.rowno.p, rowno.data(), rowno.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   FB_CUDA(e, cudaMemcpy(tab.list_blk.p, blk.data(), n_lists * sizeof(int32_t), cudaMemcpyHostToDevice));
   FB_CUDA(e, cudaMemcpy(tab.list_len.p, len.data(), n_lists * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -585,12 +604,12 @@ int launch_scan(fb_engine* e, const CodeTableDev& tab, const int32_t* d_task_lis
   }
 }
 
-template <int M, int KC>
+template <int M, int KC, bool C8 = false>
 int launch_qscan_mk(fb_engine* e, const CodeTableDev& tab, int q0, int nq, int w, const float* d_lut, int K, int KK, int k,
                     float sentinel, int32_t* d_out_ids, float* d_out_dists) {
   size_t smem = std::max<size_t>(2 * (size_t)tab.m * K * sizeof(float), kQScanWarps * 32 * sizeof(u64));
   if (smem > e->smem_optin - 1024) return FB_ERR_UNSUPPORTED;  // caller falls back to one list per CTA
-  auto kern = adc_scan_query_kernel<M, KC>;
+  auto kern = adc_scan_query_kernel<M, KC, C8>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nq, kQScanThreads, smem, e->stream>>>(tab, e->probes.p + (size_t)q0 * w, w, d_lut, K, KK, k, sentinel,
                                                e->qflags.p + q0, d_out_ids, d_out_dists, e->exact_list.p,
@@ -611,6 +630,10 @@ int launch_qscan(fb_engine* e, const CodeTableDev& tab, int q0, int nq, int w, c
     if (tab.m == 8) FB_QS(8, 1024);
     if (tab.m == 16) FB_QS(16, 1024);
   } else if (K == 256) {
+    if (tab.m == 12 && tab.units8 != nullptr && e->byte_codes) {
+      e->used8 = true;
+      return launch_qscan_mk<12, 256, true>(e, tab, q0, nq, w, d_lut, K, KK, k, sentinel, oi, od);
+    }
     if (tab.m == 12) FB_QS(12, 256);
     if (tab.m == 8) FB_QS(8, 256);
     if (tab.m == 16) FB_QS(16, 256);
@@ -694,11 +717,11 @@ size_t exact_smem_bytes(const fb_engine* e, int w) {
 // ---- throughput form: warp-specialised pipeline (pipeline_kernels.cuh) ------
 // Beat c (= one launch) builds the LUTs of chunk c+1 and scans chunk c; two LUT
 // buffers alternate.  nchunks + 1 launches on the engine stream.
-template <int M, int KC, int SUB, class Cfg>
+template <int M, int KC, int SUB, class Cfg, bool C8 = false>
 int run_pipeline_t(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int k, int w, int KK, float sentinel,
                    int32_t* d_out_ids, float* d_out_dists, int64_t chunk) {
   using L = PipeSmem<M, KC, SUB, Cfg>;
-  auto kern = ivfadc_pipe_kernel<M, KC, SUB, Cfg>;
+  auto kern = ivfadc_pipe_kernel<M, KC, SUB, Cfg, C8>;
   FB_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
   // Chunk boundaries.  The first launch only builds LUTs and the last one only scans, so the chunks ramp
   // up at the start and down at the end (quarter, half, full ... half, quarter of `chunk`): the two
@@ -791,10 +814,18 @@ int run_pipeline(fb_engine* e, const Codebook& cb, const float* d_q, int nq, int
     switch (e->pipe_shape) {   // (producer warps, scan warps[, jobs per producer thread]): tuning knob, FB_OPT_PIPE_SHAPE
       case 1: FB_PIPE_GO(1024, 8, 18);
       case 2: FB_PIPE_GO(1024, 8, 14, 16);
+      case 3: FB_PIPE_GO(1024, 16, 10);      // LUT-bound indexes (probed lists near the nominal N*w/C rows): more producers
       default: FB_PIPE_GO(1024, 12, 14);
     }
   }
-  if (cb.K == 256) FB_PIPE_GO(256, 12, 14);
+  if (cb.K == 256) {
+    if (e->fine.has8 && e->byte_codes) {
+      if (PipeSmem<12, 256, 25, PipeCfg<12, 14>>::total > e->smem_optin) return FB_ERR_UNSUPPORTED;
+      e->used8 = true;
+      return run_pipeline_t<12, 256, 25, PipeCfg<12, 14>, true>(e, cb, d_q, nq, k, w, KK, sentinel, d_out_ids, d_out_dists, chunk);
+    }
+    FB_PIPE_GO(256, 12, 14);
+  }
 #undef FB_PIPE_GO
   return FB_ERR_UNSUPPORTED;
 }
@@ -814,6 +845,7 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
   if (w > e->C) return fail(e, FB_ERR_REFERENCE_UB, "w=%d > %d coarse centroids: the reference indexes cq[-1] (freddy.c:296-302)", w, e->C);
   if (nq == 0) return FB_OK;
   const int m = cb.m, K = cb.K;
+  e->used8 = false;
   const bool fast = (k <= 30 && w <= 31);
   const bool large_k = (!fast && w <= 31);   // k in 31..1024: materialised-key path (scan -> keys -> reference top-k)
   const int KK = k + 2;   // k + 2 keys: enough to settle a boundary tie in the merge (warp_emit_topk)
@@ -949,7 +981,8 @@ int ivfadc_dev(fb_engine* e, const float* d_q, int nq, int k, int w, int32_t* d_
     FB_CUDA(e, cudaGetLastError());
   }
   e->queries_done += nq;
-  e->bytes_per_row = 2 * m + 4;
+  // algorithmic bytes per scanned row: int2 codes + int4 id, or one byte per code when the byte image is read
+  e->bytes_per_row = e->used8 ? m + 4 : 2 * m + 4;
   return FB_OK;
 }
 
@@ -1180,6 +1213,7 @@ int build_subset(fb_engine* e, const CodeTable& src, const int32_t* wanted, int 
                                                                      tmp.rowno.p, n_slots);
   e->launches += 3;
   FB_CUDA(e, cudaGetLastError());
+  view.units8 = nullptr;
   view.units = tmp.units.p; view.rowno = tmp.rowno.p; view.list_blk = e->zero_i32.p; view.list_len = e->sel_total.p;
   view.ids = src.ids.p; view.m = src.m; view.U = src.U; view.n_lists = 1;
   return FB_OK;
@@ -1446,6 +1480,8 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_CUDA_GRAPHS: e->use_graphs = value != 0; return FB_OK;
     case FB_OPT_ZERO_COPY_UPLOAD: e->zero_copy = value != 0; return FB_OK;
     case FB_OPT_PREFILTER: e->prefilter = value != 0; return FB_OK;
+    case FB_OPT_BYTE_CODES: e->byte_codes = value != 0; return FB_OK;
+    case FB_OPT_PREFILTER_LOCKSTEP: e->pf_lockstep = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");
@@ -1803,6 +1839,7 @@ static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int 
   FB_CUDA(e, e->pf_cand.ensure((size_t)nb_pad * kPfCandCap));
   FB_CUDA(e, e->pf_ovf.ensure((size_t)nb_pad + 1));
   FB_CUDA(e, e->pf_units.ensure((size_t)pf_max_units(nb_pad / kPfBM, e->num_sms)));
+  FB_CUDA(e, e->pf_progress.ensure((size_t)pf_max_units(nb_pad / kPfBM, e->num_sms)));
   FB_CUDA(e, cudaFuncSetAttribute(prefilter_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PfSmem::total));
   std::vector<PfUnit> units((size_t)pf_max_units(nb_pad / kPfBM, e->num_sms));
   std::vector<int32_t> h_ovf((size_t)nb_pad + 1), h_cnt;
@@ -1814,6 +1851,7 @@ static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int 
     if (!pf_make_tensor_map(&tm_q, e->pf_qb.p, n_pad, kpa, kPfBM)) return fail(e, FB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     FB_CUDA(e, cudaMemcpyAsync(e->pf_units.p, units.data(), (size_t)n_units * sizeof(PfUnit), cudaMemcpyHostToDevice, e->stream));
     FB_CUDA(e, cudaMemsetAsync(e->pf_ovf.p, 0, sizeof(int32_t), e->stream));
+    FB_CUDA(e, cudaMemsetAsync(e->pf_progress.p, 0, (size_t)n_units * sizeof(int32_t), e->stream));
     pf_queries_prepare_kernel<<<(n_pad + 7) / 8, 256, 0, e->stream>>>(d_q + (size_t)q0 * d, n, n_pad, d, kpa, e->pf_vmax, e->pf_qb.p,
                                                                      e->pf_eps2.p, e->pf_gbest.p, e->pf_cnt.p);
     e->launches++;
@@ -1821,6 +1859,8 @@ static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int 
     memset(&a, 0, sizeof a);
     a.units = e->pf_units.p; a.n_units = n_units; a.kch = kch; a.ksteps = (d + 15) / 16; a.N = N; a.nq = n; a.kk = kk;
     a.eps2 = e->pf_eps2.p; a.gbest = e->pf_gbest.p; a.cand_cnt = e->pf_cnt.p; a.cand = e->pf_cand.p; a.cap = kPfCandCap;
+    a.progress = e->pf_progress.p; a.n_qt = QT;
+    a.lockstep = (n_units <= e->num_sms && QT > 1) ? e->pf_lockstep : 0;   // only when every unit has its own resident CTA
     {
       StageTimer t(e, ST_SCAN);
       prefilter_gemm_kernel<<<std::min(e->num_sms, n_units), kPfThreads, PfSmem::total, e->stream>>>(tm_q, e->pf_tm_v, a);
@@ -2115,6 +2155,7 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
   e->launches += 4;
   FB_CUDA(e, cudaGetLastError());
   CodeTableDev ctab;
+  ctab.units8 = nullptr;
   ctab.units = e->jtmp.units.p; ctab.rowno = nullptr; ctab.list_blk = nullptr; ctab.list_len = nullptr;
   ctab.ids = nullptr; ctab.m = m; ctab.U = U; ctab.n_lists = 1;
 

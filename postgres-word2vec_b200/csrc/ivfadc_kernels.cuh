@@ -28,6 +28,8 @@ namespace fb {
 // the reference's loop), -1 for padding.  Algorithmic bytes per row: 2*m + 4.
 // ---------------------------------------------------------------------------
 struct CodeTableDev {
+  const uint4* units8;      // [n_blocks][32] one byte per code, 16 bytes per row (tables with K <= 256, m <= 16), or nullptr:
+                            // a warp reads a 32-row block with ONE coalesced 512-byte load; algorithmic bytes per row m + 4
   const uint2* units;       // [n_blocks][U][32]
   const int32_t* rowno;     // [n_blocks][32]
   const int32_t* list_blk;  // [n_lists] first block of each list
@@ -715,7 +717,20 @@ __device__ __forceinline__ void warp_emit_topk(u64 mine, int lane, int q, int q_
 constexpr int kQScanThreads = 512;
 constexpr int kQScanWarps = kQScanThreads / kWarp;
 
+// ADC distance from a row of byte codes (uint4 = 16 codes), LUT in shared memory, M and KC compile-time
 template <int M, int KC>
+__device__ __forceinline__ float adc_bytes(const uint4& v, const char* lut_base) {
+  const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+  float acc = 0.0f;
+#pragma unroll
+  for (int p = 0; p < M; p++) {
+    const uint32_t code = (wds[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+    acc = xadd(acc, *reinterpret_cast<const float*>(lut_base + (size_t)p * KC * 4 + code * 4u));
+  }
+  return acc;
+}
+
+template <int M, int KC, bool C8 = false>
 __global__ void __launch_bounds__(kQScanThreads, 2)
 adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int w,
                       const float* __restrict__ lut, int K, int KK, int k, float sentinel,
@@ -765,14 +780,22 @@ adc_scan_query_kernel(CodeTableDev tab, const int32_t* __restrict__ probes, int 
     const char* lut_base = reinterpret_cast<const char*>(smem_raw) + (size_t)(j & 1) * lut_bytes;
     constexpr int UU = (M > 0) ? (M + 3) / 4 : 1;
     uint2 cur[UU], nxt[UU];
-    if (M > 0 && warp < nblk) {
+    uint4 cur8 = make_uint4(0, 0, 0, 0), nxt8 = make_uint4(0, 0, 0, 0);
+    if (C8) {
+      if (warp < nblk) cur8 = __ldg(tab.units8 + (size_t)(blk0 + warp) * 32 + lane);
+    } else if (M > 0 && warp < nblk) {
       const uint2* up0 = tab.units + ((size_t)(blk0 + warp) * U) * 32 + lane;
 #pragma unroll
       for (int u = 0; u < UU; u++) cur[u] = __ldg(up0 + u * 32);
     }
     for (int b = warp; b < nblk; b += kQScanWarps) {
       float acc;
-      if (M > 0) {
+      if (C8) {
+        const int bn = b + kQScanWarps;
+        if (bn < nblk) nxt8 = __ldg(tab.units8 + (size_t)(blk0 + bn) * 32 + lane);
+        acc = adc_bytes<(M > 0 ? M : 1), (KC > 0 ? KC : 1)>(cur8, lut_base);
+        cur8 = nxt8;
+      } else if (M > 0) {
         // the next block's codes are requested before this block's gathers: their latency hides behind them
         const int bn = b + kQScanWarps;
         if (bn < nblk) {

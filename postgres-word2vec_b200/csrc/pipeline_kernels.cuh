@@ -40,7 +40,8 @@ struct PipeCfg {
   static constexpr int kGroup = JT * kSplits;        // jobs per producer group
   static constexpr int kLaunchRegs = ((65536 / kThreads) & ~7) > 255 ? 248 : ((65536 / kThreads) & ~7);
   static constexpr int kScanRegs = 64;               // 56 left a loop bound of the scan warps in local memory (LDL in the hot loop)
-  static constexpr int kProdRegsRaw = ((kLaunchRegs * kThreads - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
+  // the SM's 64 K registers minus what the scan side keeps, shared out among the producer threads
+  static constexpr int kProdRegsRaw = ((65536 - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
   static constexpr int kProdRegs = kProdRegsRaw > 232 ? 232 : kProdRegsRaw;
   static_assert(PW % 4 == 0 && (SW + 2) % 4 == 0, "roles must be whole warpgroups");
   static_assert(kThreads <= 1024, "CTA too large");
@@ -117,7 +118,8 @@ struct PipeCtl {
 };
 static_assert(sizeof(PipeCtl) <= 256, "control block");
 
-template <int M, int KC, int SUB, class Cfg>
+// C8: the scan warps read the byte-code image of the table (CodeTableDev::units8, K <= 256): one 16-byte load per row
+template <int M, int KC, int SUB, class Cfg, bool C8 = false>
 __global__ void __launch_bounds__(Cfg::kThreads, 1)
 ivfadc_pipe_kernel(const PipeArgs a) {
   using L = PipeSmem<M, KC, SUB, Cfg>;
@@ -343,16 +345,8 @@ ivfadc_pipe_kernel(const PipeArgs a) {
 #pragma unroll
         for (int u = 0; u < UU; u++) v[u] = __ldg(up + u * 32);
       };
-      auto process = [&](const uint2 (&v)[UU], int i) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int u = 0; u < UU; u++) {
-          const uint32_t wlo = v[u].x, whi = v[u].y;
-          if (4 * u + 0 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 0) * KC * 4) + lut_s + (wlo & 0xFFFFu)));
-          if (4 * u + 1 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 1) * KC * 4) + lut_s + (wlo >> 16)));
-          if (4 * u + 2 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 2) * KC * 4) + lut_s + (whi & 0xFFFFu)));
-          if (4 * u + 3 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 3) * KC * 4) + lut_s + (whi >> 16)));
-        }
+      // a row's ADC distance is done: admission against the CTA-wide threshold, insertion into the warp's key list
+      auto consider = [&](float acc, int i) {
         const uint32_t thr = min(my_thr, lds_u32(thr_s));
         const uint32_t dbits = __float_as_uint(acc);
         const int blk = warp + i * kPipeScanWarps;
@@ -370,6 +364,47 @@ ivfadc_pipe_kernel(const PipeArgs a) {
           if (lane == 0 && my_thr < thr) atomicMin(&ctl->thr[p], my_thr);
         }
       };
+      auto process = [&](const uint2 (&v)[UU], int i) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int u = 0; u < UU; u++) {
+          const uint32_t wlo = v[u].x, whi = v[u].y;
+          if (4 * u + 0 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 0) * KC * 4) + lut_s + (wlo & 0xFFFFu)));
+          if (4 * u + 1 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 1) * KC * 4) + lut_s + (wlo >> 16)));
+          if (4 * u + 2 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 2) * KC * 4) + lut_s + (whi & 0xFFFFu)));
+          if (4 * u + 3 < M) acc = xadd(acc, lds_f32((uint32_t)((4 * u + 3) * KC * 4) + lut_s + (whi >> 16)));
+        }
+        consider(acc, i);
+      };
+      if constexpr (C8) {
+        // byte codes: one 16-byte load per row, three blocks in flight like the 16-bit path
+        const uint4* ubase8 = a.tab.units8 + (size_t)(blk0 + warp) * 32 + lane;
+        constexpr size_t ustep8 = (size_t)kPipeScanWarps * 32;
+        uint4 ta = make_uint4(0, 0, 0, 0), tb = ta, tc = ta;
+        auto load8 = [&](uint4& v, int i) { v = __ldg(ubase8 + (size_t)i * ustep8); };
+        auto process8 = [&](const uint4& v, int i) {
+          const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+          float acc = 0.0f;
+#pragma unroll
+          for (int pp = 0; pp < M; pp++) {
+            const uint32_t code4 = ((wds[pp >> 2] >> (8 * (pp & 3))) & 0xFFu) << 2;
+            acc = xadd(acc, lds_f32((uint32_t)(pp * KC * 4) + lut_s + code4));
+          }
+          consider(acc, i);
+        };
+        if (n_mine > 0) load8(ta, 0);
+        if (n_mine > 1) load8(tb, 1);
+        for (int i = 0; i < n_mine; i += 3) {
+          if (i + 2 < n_mine) load8(tc, i + 2);
+          process8(ta, i);
+          if (i + 1 >= n_mine) break;
+          if (i + 3 < n_mine) load8(ta, i + 3);
+          process8(tb, i + 1);
+          if (i + 2 >= n_mine) break;
+          if (i + 4 < n_mine) load8(tb, i + 4);
+          process8(tc, i + 2);
+        }
+      } else {
       if (n_mine > 0) load(sa, 0);
       if (n_mine > 1) load(sb, 1);
       for (int i = 0; i < n_mine; i += 3) {
@@ -381,6 +416,7 @@ ivfadc_pipe_kernel(const PipeArgs a) {
         if (i + 2 >= n_mine) break;
         if (i + 4 < n_mine) load(sb, i + 4);
         process(sc, i + 2);
+      }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->empty[b]);   // this warp is done with ring slot b

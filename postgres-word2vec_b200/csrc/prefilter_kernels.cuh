@@ -63,6 +63,12 @@ struct PfArgs {
   int cap;
   float* dump;             // debugging / tests: [nq_pad][dump_ld] every approximate score, or nullptr
   long long dump_ld;
+  // lock-step of the CTAs that stream the same slab (one per query tile): progress[u] = table tiles unit u has
+  // requested; a CTA does not run more than `lockstep` tiles ahead of the slowest sibling, so a tile fetched from
+  // HBM by the first CTA is still in L2 when the others ask for it.  0 = off (units are not all co-resident).
+  int* progress;
+  int n_qt;
+  int lockstep;
 };
 
 // shared-memory plan of prefilter_gemm_kernel (dynamic, base aligned to 1024 bytes by the kernel)
@@ -210,7 +216,24 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (iter > 0) mbar_wait_u32(bar_q_empty, (uint32_t)((iter - 1) & 1));   // MMAs of the previous unit are done with Q
         mbar_expect_tx_u32(bar_q_full, (uint32_t)a.kch * kPfQChunkBytes);
         for (int kc = 0; kc < a.kch; kc++) tma_load_2d(q_smem + kc * kPfQChunkBytes, &tm_q, kc * kPfBK, un.qt * kPfBM, bar_q_full);
+        const int sib0 = (u / a.n_qt) * a.n_qt;                      // units sib0 .. sib0 + n_qt - 1 stream this slab
         for (int vt = un.v_begin; vt < un.v_end; vt++) {
+          if (a.lockstep > 0) {
+            const int t = vt - un.v_begin;
+            if (t >= a.lockstep) {
+              for (;;) {
+                int slowest = 0x7fffffff;
+                for (int j = 0; j < a.n_qt; j++) {
+                  int pj;
+                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(pj) : "l"(a.progress + sib0 + j) : "memory");
+                  slowest = pj < slowest ? pj : slowest;
+                }
+                if (slowest >= t - a.lockstep) break;
+                __nanosleep(200);
+              }
+            }
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + u), "r"(t + 1) : "memory");
+          }
           for (int kc = 0; kc < a.kch; kc++) {
             mbar_wait_u32(bar_empty(stage), phase ^ 1u);
             mbar_expect_tx_u32(bar_full(stage), kPfVStageBytes);

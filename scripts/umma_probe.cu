@@ -153,6 +153,11 @@ int main(int argc, char** argv) {
   a.units = d_units; a.n_units = n_units; a.kch = kch; a.ksteps = ksteps; a.N = N; a.nq = nq; a.kk = kk;
   a.eps2 = d_eps2; a.gbest = d_gthr; a.cand_cnt = d_cnt; a.cand = d_cand; a.cap = kPfCandCap;
   a.dump = d_dump; a.dump_ld = N_pad;
+  int* d_progress;
+  CK(cudaMalloc(&d_progress, n_units * sizeof(int)));
+  const int lockstep = getenv("PF_LOCKSTEP") ? atoi(getenv("PF_LOCKSTEP")) : 8;
+  a.progress = d_progress; a.n_qt = QT; a.lockstep = (n_units <= sms && QT > 1) ? lockstep : 0;
+  printf("lockstep window %d tiles\n", a.lockstep);
   CK(cudaFuncSetAttribute(prefilter_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PfSmem::total));
   const size_t rs_smem = (size_t)kPfCandCap * 8 + (size_t)d * 4;
   const int grid = std::min(sms, n_units);
@@ -163,6 +168,7 @@ int main(int argc, char** argv) {
   for (int rep = 0; rep < reps; rep++) {
     pf_queries_prepare_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(d_q, nq, nq_pad, d, kpa, vmax, d_qb, d_eps2, d_gthr, d_cnt);
     CK(cudaMemsetAsync(d_ovf_cnt, 0, 4, st));
+    CK(cudaMemsetAsync(d_progress, 0, n_units * sizeof(int), st));
     CK(cudaEventRecord(e0, st));
     prefilter_gemm_kernel<<<grid, kPfThreads, PfSmem::total, st>>>(tm_q, tm_v, a);
     CK(cudaGetLastError());

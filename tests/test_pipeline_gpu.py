@@ -114,3 +114,29 @@ def test_host_buffer_call_matches_device_path(eng):
         eng.ivfadc_search_ptr(hq.data_ptr(), len(q), 5, 10, hi.data_ptr(), hd.data_ptr())
         np.testing.assert_array_equal(hi.numpy(), ids)
         np.testing.assert_array_equal(hd.numpy().view(np.uint32), d.view(np.uint32))
+
+
+def test_byte_code_table_k256(eng, oracle_mod):
+    """K = 256 (index_creation/config/ivfadc_config.json): the scan kernels read the true uint8 image of the codes
+    (16 bytes per row); results equal the 16-bit path and the oracle, scan bytes are accounted at m + 4 per row"""
+    from freddy_b200 import _lib
+    ix = small_index(N=60000, d=300, m=12, K=256, C=100, seed=1, n_clusters=100)
+    eng.load_ivfadc_index(ix)
+    oi = oracle_mod.OracleIndex(ix)
+    for nq, k, w in ((1300, 5, 10), (200, 7, 4), (3, 5, 6)):     # pipeline kernel / one CTA per query / one CTA per (query, list)
+        q = queries_from(ix, nq, seed=nq, noise=0.02)
+        eids, ed, rc, rows = oi.ivfadc_search(q, k, w, threads=8)
+        assert rc == 0
+        eng.set_option(_lib.FB_OPT_BYTE_CODES, 1)
+        ids, d, c = _search(eng, q, k, w, 1)
+        assert_same_topk(ids, d, eids, ed, f"byte codes nq={nq}")
+        assert c["rows_scanned"] == rows
+        if nq >= 64:
+            assert c["scan_bytes"] == rows * (12 + 4)
+        eng.set_option(_lib.FB_OPT_BYTE_CODES, 0)
+        try:
+            ids2, d2, c2 = _search(eng, q, k, w, 1)
+        finally:
+            eng.set_option(_lib.FB_OPT_BYTE_CODES, 1)
+        assert_same_topk(ids2, d2, eids, ed, f"16-bit units nq={nq}")
+        assert c2["scan_bytes"] == rows * (2 * 12 + 4)
