@@ -172,6 +172,18 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
 int fb_encode_ivfadc(fb_engine* e, const float* vectors, int64_t n, int32_t* out_coarse_ids, int16_t* out_codes);
 int fb_encode_pq(fb_engine* e, int kind, const float* vectors, int64_t n, int16_t* out_codes);
 
+/* ---- in-place append (insert_batch must refresh the pinned copy) -----------------------
+ * insert_batch (freddy.c:1403-1658) INSERTs the new rows into pq_quantization, fine_quantization and
+ * fine_quantization_ivpq (index_utils.c:1003-1043).  These calls add the same rows to the pinned tables without a
+ * re-upload: the table is re-packed on the device (the grown list moves the lists behind it), only the new rows
+ * cross PCIe.  Appended rows arrive after every existing row (they are the last rows of the heap), in the order
+ * given.  Codebook changes of the same insert_batch go through fb_load_codebook (1.2 MB).
+ * fb_append_pq: kind = FB_CB_PQ (cells ignored) or FB_CB_IVPQ (cells = multi-index cell c0 + Kc*c1 per row). */
+int fb_append_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids, const int16_t* codes, int64_t n);
+int fb_append_pq(fb_engine* e, int kind, const int32_t* ids, const int32_t* cells, const int16_t* codes, int64_t n);
+/* rows appended to the word-vector table (updateWordVectorsRelation, index_utils.c:1045-1074) */
+int fb_append_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int64_t n);
+
 /* ---- grouping_pq ---------------------------------------------------------------
  * grouping_pq(int[] ids, int[] group_ids) (freddy.c:1178-1401): the rows of the flat pq table whose id is in
  * `ids` (table order, each once), each assigned to the nearest group vector (word-vector rows of `group_ids`,

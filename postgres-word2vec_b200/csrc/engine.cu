@@ -56,6 +56,20 @@ struct DevBuf {
     if (err == cudaSuccess) n = count;
     return err;
   }
+  // like ensure(), but what is there survives (append paths); grows by at least a quarter to amortise repeated appends
+  cudaError_t grow(size_t count, size_t live) {
+    if (count <= n && p) return cudaSuccess;
+    const size_t cap = std::max(count, n + n / 4 + 1024);
+    T* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, cap * sizeof(T));
+    if (err != cudaSuccess) return err;
+    if (p && live) err = cudaMemcpy(q, p, std::min(live, n) * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    g_alloc_generation++;
+    p = q;
+    n = cap;
+    return err;
+  }
   void release() {
     if (p) { cudaFree(p); g_alloc_generation++; }
     p = nullptr;
@@ -72,7 +86,9 @@ struct CodeTable {
   int m = 0, U = 0, n_lists = 0;
   int64_t N = 0, n_blocks = 0;
   bool loaded = false;
-  std::vector<int32_t> h_list_len;
+  std::vector<int32_t> h_list_len, h_list_blk;
+  int32_t max_id = 0;                        // largest id in the table (appended rows with larger ids keep the id index sorted)
+  int K = 0;
   CodeTableDev dev() const {
     CodeTableDev t;
     t.units8 = has8 ? units8.p : nullptr;
@@ -113,17 +129,12 @@ struct fb_engine {
   DevBuf<uint32_t> sel_bitmap;          // `WHERE id IN (...)` on the device (subset_kernels.cuh)
   DevBuf<int32_t> sel_word_base, sel_total, sel_wanted, zero_i32;
   std::vector<int32_t> pq_ids_host;
-  bool pq_ids_sorted = true;
-  std::unordered_map<int32_t, int32_t> pq_id_to_row;
   DevBuf<int32_t> iota_lists;
   // IVPQ index (kNN-join)
   CodeTable ivpq, jtmp;
   DevBuf<float> coarse_multi, ivpq_stats;
   DevBuf<int32_t> ivpq_cells;
-  std::vector<int32_t> ivpq_ids_host, ivpq_cells_host;
   std::vector<float> ivpq_stats_host;
-  bool ivpq_ids_sorted = true;
-  std::unordered_map<int32_t, int32_t> ivpq_id_to_row;
   int ivpq_Kc = 0, ivpq_d = 0;
   bool ivpq_loaded = false;
   DevBuf<int32_t> j_cell, j_vrow, j_id, j_active, j_active2, j_ncells, j_filled, j_tcounts;
@@ -426,6 +437,10 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
   if (N > 0) FB_CUDA(e, cudaMemcpy(tab.ids.p, ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
   tab.m = m; tab.U = U; tab.n_lists = n_lists; tab.N = N; tab.n_blocks = n_blocks;
   tab.h_list_len = len;
+  tab.h_list_blk = blk;
+  tab.K = K;
+  tab.max_id = 0;
+  for (int64_t r = 0; r < N; r++) tab.max_id = std::max(tab.max_id, ids[r]);
   tab.loaded = true;
   return FB_OK;
 }
@@ -1446,6 +1461,129 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, con
   return FB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Append n rows (ids, list of each row or nullptr for one-list tables, codes [n][m]) to a pinned code table:
+// device-side re-pack (subset_kernels.cuh), id index extended, host mirrors updated.
+int append_rows(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row, const int16_t* codes, int64_t n) {
+  if (!tab.loaded) return fail(e, FB_ERR_INVALID, "append: the table is not loaded");
+  if (n == 0) return FB_OK;
+  const int m = tab.m, U = tab.U, nl = tab.n_lists;
+  if (tab.N + n >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
+  for (int64_t i = 0; i < n; i++) {
+    const int c = list_of_row ? list_of_row[i] : 0;
+    if (c < 0 || c >= nl) return fail(e, FB_ERR_INVALID, "appended row %lld: coarse_id %d out of range [0,%d)", (long long)i, c, nl);
+    for (int p = 0; p < m; p++)
+      if (codes[(size_t)i * m + p] < 0 || codes[(size_t)i * m + p] >= tab.K)
+        return fail(e, FB_ERR_INVALID, "appended row %lld pos %d: code out of range", (long long)i, p);
+  }
+  // new geometry; position of every appended row inside its list
+  std::vector<int32_t> new_len(tab.h_list_len), new_blk(nl);
+  std::vector<int64_t> dst((size_t)n);
+  for (int64_t i = 0; i < n; i++) dst[i] = new_len[list_of_row ? list_of_row[i] : 0]++;
+  int64_t n_blocks = 0;
+  for (int c = 0; c < nl; c++) { new_blk[c] = (int32_t)n_blocks; n_blocks += (new_len[c] + 31) / 32; }
+  for (int64_t i = 0; i < n; i++) dst[i] += (int64_t)new_blk[list_of_row ? list_of_row[i] : 0] * 32;
+  // fresh buffers, old lists moved on the device
+  DevBuf<uint2> units;
+  DevBuf<uint4> units8;
+  DevBuf<int32_t> rowno, d_new_blk, d_new_len, d_ids;
+  DevBuf<int16_t> d_codes;
+  DevBuf<int64_t> d_dst;
+  const size_t slots = (size_t)std::max<int64_t>(1, n_blocks) * 32;
+  FB_CUDA(e, units.ensure(slots * U));
+  FB_CUDA(e, rowno.ensure(slots));
+  if (tab.has8) FB_CUDA(e, units8.ensure(slots));
+  FB_CUDA(e, d_new_blk.ensure(nl));
+  FB_CUDA(e, d_new_len.ensure(nl));
+  FB_CUDA(e, d_ids.ensure((size_t)n));
+  FB_CUDA(e, d_codes.ensure((size_t)n * m));
+  FB_CUDA(e, d_dst.ensure((size_t)n));
+  FB_CUDA(e, tab.ids.grow((size_t)(tab.N + n), (size_t)tab.N));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  FB_CUDA(e, cudaMemcpy(d_new_blk.p, new_blk.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(d_new_len.p, new_len.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(d_ids.p, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(d_codes.p, codes, (size_t)n * m * sizeof(int16_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(d_dst.p, dst.data(), (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+  append_repack_kernel<<<nl, 256, 0, e->stream>>>(tab.units.p, tab.rowno.p, tab.has8 ? tab.units8.p : nullptr, U, tab.list_blk.p,
+                                                  tab.list_len.p, d_new_blk.p, d_new_len.p, units.p, rowno.p,
+                                                  tab.has8 ? units8.p : nullptr);
+  append_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d_codes.p, d_ids.p, d_dst.p, (int)n, m, U, tab.N, units.p, rowno.p,
+                                                                       tab.has8 ? units8.p : nullptr, tab.ids.p);
+  e->launches += 2;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  std::swap(tab.units.p, units.p); std::swap(tab.units.n, units.n);
+  std::swap(tab.rowno.p, rowno.p); std::swap(tab.rowno.n, rowno.n);
+  if (tab.has8) { std::swap(tab.units8.p, units8.p); std::swap(tab.units8.n, units8.n); }
+  std::swap(tab.list_blk.p, d_new_blk.p); std::swap(tab.list_blk.n, d_new_blk.n);
+  std::swap(tab.list_len.p, d_new_len.p); std::swap(tab.list_len.n, d_new_len.n);
+  g_alloc_generation++;
+  // id index: ids beyond the current maximum, ascending, keep it sorted by appending; anything else re-sorts
+  if (tab.sorted_ids.p != nullptr) {
+    bool tail = true;
+    int32_t prev = tab.max_id;
+    for (int64_t i = 0; i < n && tail; i++) { tail = ids[i] > prev || (i > 0 && ids[i] == prev); prev = ids[i]; }
+    if (tail) {
+      std::vector<int32_t> rows((size_t)n);
+      for (int64_t i = 0; i < n; i++) rows[i] = (int32_t)(tab.N + i);
+      FB_CUDA(e, tab.sorted_ids.grow((size_t)(tab.N + n), (size_t)tab.N));
+      FB_CUDA(e, tab.sorted_rows.grow((size_t)(tab.N + n), (size_t)tab.N));
+      FB_CUDA(e, cudaMemcpy(tab.sorted_ids.p + tab.N, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+      FB_CUDA(e, cudaMemcpy(tab.sorted_rows.p + tab.N, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    } else {
+      std::vector<int32_t> all((size_t)(tab.N + n));
+      FB_CUDA(e, cudaMemcpy(all.data(), tab.ids.p, all.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      tab.N += n;
+      int rc = build_id_index(e, tab, all.data(), tab.N);
+      tab.N -= n;
+      if (rc) return rc;
+    }
+  }
+  for (int64_t i = 0; i < n; i++) tab.max_id = std::max(tab.max_id, ids[i]);
+  tab.h_list_len = new_len;
+  tab.h_list_blk = new_blk;
+  tab.N += n;
+  tab.n_blocks = n_blocks;
+  e->graph_epoch++;
+  return FB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fb_append_fine(fb_engine* e, const int32_t* ids, const int32_t* coarse_ids, const int16_t* codes, int64_t n) {
+  if (!e || n < 0 || (n > 0 && (!ids || !coarse_ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_append_fine: bad arguments");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  return append_rows(e, e->fine, ids, coarse_ids, codes, n);
+}
+
+int fb_append_pq(fb_engine* e, int kind, const int32_t* ids, const int32_t* cells, const int16_t* codes, int64_t n) {
+  if (!e || n < 0 || (n > 0 && (!ids || !codes))) return fail(e, FB_ERR_INVALID, "fb_append_pq: bad arguments");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  if (kind == FB_CB_PQ) {
+    int rc = append_rows(e, e->pq, ids, nullptr, codes, n);
+    if (rc == FB_OK) e->pq_ids_host.insert(e->pq_ids_host.end(), ids, ids + n);
+    return rc;
+  }
+  if (kind == FB_CB_IVPQ) {
+    if (!e->ivpq_loaded) return fail(e, FB_ERR_INVALID, "fb_append_pq: the IVPQ index is not loaded");
+    if (n > 0 && !cells) return fail(e, FB_ERR_INVALID, "fb_append_pq(FB_CB_IVPQ) needs the multi-index cell of every row");
+    const int ncell = e->ivpq_Kc * e->ivpq_Kc;
+    for (int64_t i = 0; i < n; i++)
+      if (cells[i] < 0 || cells[i] >= ncell) return fail(e, FB_ERR_INVALID, "appended row %lld: cell %d out of range", (long long)i, cells[i]);
+    const int64_t N0 = e->ivpq.N;
+    int rc = append_rows(e, e->ivpq, ids, nullptr, codes, n);
+    if (rc) return rc;
+    FB_CUDA(e, e->ivpq_cells.grow((size_t)(N0 + n), (size_t)N0));
+    if (n > 0) FB_CUDA(e, cudaMemcpy(e->ivpq_cells.p + N0, cells, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return FB_OK;
+  }
+  return fail(e, FB_ERR_INVALID, "fb_append_pq: kind must be FB_CB_PQ or FB_CB_IVPQ");
+}
+
 int fb_synchronize(fb_engine* e) {
   if (!e) return FB_ERR_INVALID;
   FB_CUDA(e, cudaSetDevice(e->device));
@@ -1697,6 +1835,79 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   return FB_OK;
 }
 
+__global__ void append_vec_rows_kernel(const float* __restrict__ rows, int64_t n, int d, int64_t first_row, float* __restrict__ vT) {
+  const int64_t i = blockIdx.x;
+  if (i >= n) return;
+  const int64_t r = first_row + i;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) vT[((size_t)(r >> 5) * d + j) * 32 + (r & 31)] = rows[i * d + j];
+}
+
+// rows insert_batch adds to the word-vector table (updateWordVectorsRelation, index_utils.c:1045-1074), appended to the
+// pinned image: dimension-major blocks, bf16 image of the pre-filter, id index
+int fb_append_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int64_t n) {
+  if (!e || n < 0 || (n > 0 && (!ids || !vectors))) return fail(e, FB_ERR_INVALID, "fb_append_vectors: bad arguments");
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "word-vector table not loaded (fb_load_vectors)");
+  if (n == 0) return FB_OK;
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int d = e->vec_d;
+  const int64_t N0 = e->vec_N, N1 = N0 + n;
+  if (N1 >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
+  const int64_t b0 = std::max<int64_t>(1, (N0 + 31) / 32), b1 = (N1 + 31) / 32;
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  FB_CUDA(e, e->vecT.grow((size_t)b1 * d * 32, (size_t)b0 * d * 32));
+  if (b1 > b0) FB_CUDA(e, cudaMemset(e->vecT.p + (size_t)b0 * d * 32, 0, (size_t)(b1 - b0) * d * 32 * sizeof(float)));
+  DevBuf<float> stage;
+  FB_CUDA(e, stage.ensure((size_t)n * d));
+  FB_CUDA(e, cudaMemcpy(stage.p, vectors, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice));
+  append_vec_rows_kernel<<<(unsigned)n, 128, 0, e->stream>>>(stage.p, n, d, N0, e->vecT.p);
+  e->launches++;
+  FB_CUDA(e, e->vec_ids.grow((size_t)N1, (size_t)N0));
+  FB_CUDA(e, cudaMemcpy(e->vec_ids.p + N0, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (e->pf_ready || e->pf_kpa > 0) {
+    const int64_t pad0 = e->pf_N_pad, pad1 = (N1 + kPfBN - 1) / kPfBN * kPfBN;
+    FB_CUDA(e, e->vec_bf16.grow((size_t)pad1 * e->pf_kpa, (size_t)pad0 * e->pf_kpa));
+    if (pad1 > pad0) FB_CUDA(e, cudaMemset(e->vec_bf16.p + (size_t)pad0 * e->pf_kpa, 0, (size_t)(pad1 - pad0) * e->pf_kpa * sizeof(__nv_bfloat16)));
+    pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(stage.p, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)N0 * e->pf_kpa, e->pf_norm.p);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+    uint32_t nb = 0;
+    FB_CUDA(e, cudaMemcpyAsync(&nb, e->pf_norm.p, sizeof nb, cudaMemcpyDeviceToHost, e->stream));
+    FB_CUDA(e, cudaStreamSynchronize(e->stream));
+    float n2;
+    memcpy(&n2, &nb, sizeof n2);
+    e->pf_vmax = sqrtf(n2) * 1.000001f;
+    e->pf_N_pad = pad1;
+    e->pf_ready = std::isfinite(e->pf_vmax) && e->pf_vmax > 0.0f &&
+                  pf_make_tensor_map(&e->pf_tm_v, e->vec_bf16.p, e->pf_N_pad, e->pf_kpa, kPfBN);
+  }
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  // id -> row: host mirror and the sorted device image
+  const bool tail = e->vec_ids_sorted && std::is_sorted(ids, ids + n) && (N0 == 0 || ids[0] >= e->vec_ids_host.back());
+  e->vec_ids_host.insert(e->vec_ids_host.end(), ids, ids + n);
+  if (!tail) {
+    if (e->vec_ids_sorted) {
+      e->vec_id_to_row.clear();
+      for (int64_t r = 0; r < N0; r++) e->vec_id_to_row.emplace(e->vec_ids_host[r], (int32_t)r);
+      e->vec_ids_sorted = false;
+    }
+    for (int64_t r = N0; r < N1; r++) e->vec_id_to_row.emplace(e->vec_ids_host[r], (int32_t)r);
+  }
+  {
+    std::vector<int32_t> order((size_t)N1), sid((size_t)N1);
+    for (int64_t r = 0; r < N1; r++) order[r] = (int32_t)r;
+    const int32_t* all = e->vec_ids_host.data();
+    if (!tail || !e->vec_ids_sorted) std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return all[a] < all[b]; });
+    for (int64_t r = 0; r < N1; r++) sid[r] = all[order[r]];
+    FB_CUDA(e, e->vec_sorted_ids.ensure((size_t)N1));
+    FB_CUDA(e, e->vec_sorted_rows.ensure((size_t)N1));
+    FB_CUDA(e, cudaMemcpy(e->vec_sorted_ids.p, sid.data(), (size_t)N1 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    FB_CUDA(e, cudaMemcpy(e->vec_sorted_rows.p, order.data(), (size_t)N1 * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  e->vec_N = N1;
+  e->graph_epoch++;
+  return FB_OK;
+}
+
 int fb_cosine_similarity(fb_engine* e, int variant, const float* a, const float* b, int n, int d, double* out) {
   if (!e || variant < 0 || variant > 2 || n < 0 || d < 1) return fail(e, FB_ERR_INVALID, "fb_cosine_similarity: bad arguments");
   if (n == 0) return FB_OK;
@@ -1860,7 +2071,8 @@ static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int 
     a.units = e->pf_units.p; a.n_units = n_units; a.kch = kch; a.ksteps = (d + 15) / 16; a.N = N; a.nq = n; a.kk = kk;
     a.eps2 = e->pf_eps2.p; a.gbest = e->pf_gbest.p; a.cand_cnt = e->pf_cnt.p; a.cand = e->pf_cand.p; a.cap = kPfCandCap;
     a.progress = e->pf_progress.p; a.n_qt = QT;
-    a.lockstep = (n_units <= e->num_sms && QT > 1) ? e->pf_lockstep : 0;   // only when every unit has its own resident CTA
+    // only when every unit has its own resident CTA; progress is published every 4th tile, so the window is >= 8
+    a.lockstep = (n_units <= e->num_sms && QT > 1 && e->pf_lockstep > 0) ? std::max(8, e->pf_lockstep) : 0;
     {
       StageTimer t(e, ST_SCAN);
       prefilter_gemm_kernel<<<std::min(e->num_sms, n_units), kPfThreads, PfSmem::total, e->stream>>>(tm_q, e->pf_tm_v, a);

@@ -40,8 +40,9 @@ struct PipeCfg {
   static constexpr int kGroup = JT * kSplits;        // jobs per producer group
   static constexpr int kLaunchRegs = ((65536 / kThreads) & ~7) > 255 ? 248 : ((65536 / kThreads) & ~7);
   static constexpr int kScanRegs = 64;               // 56 left a loop bound of the scan warps in local memory (LDL in the hot loop)
-  // the SM's 64 K registers minus what the scan side keeps, shared out among the producer threads
-  static constexpr int kProdRegsRaw = ((65536 - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
+  // setmaxnreg moves registers inside the CTA's own allocation (kLaunchRegs * kThreads), not the SM's 64 K: what the
+  // scan side gives back is all the producers can take (asking for more blocks forever)
+  static constexpr int kProdRegsRaw = ((kLaunchRegs * kThreads - kScanRegs * (kThreads - kProdThreads)) / kProdThreads) & ~7;
   static constexpr int kProdRegs = kProdRegsRaw > 232 ? 232 : kProdRegsRaw;
   static_assert(PW % 4 == 0 && (SW + 2) % 4 == 0, "roles must be whole warpgroups");
   static_assert(kThreads <= 1024, "CTA too large");

@@ -220,19 +220,16 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         for (int vt = un.v_begin; vt < un.v_end; vt++) {
           if (a.lockstep > 0) {
             const int t = vt - un.v_begin;
-            if (t >= a.lockstep) {
+            if (t >= a.lockstep && (t & 3) == 0) {                  // a rate limiter, not a protocol: relaxed loads, every 4th tile
               for (;;) {
                 int slowest = 0x7fffffff;
-                for (int j = 0; j < a.n_qt; j++) {
-                  int pj;
-                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(pj) : "l"(a.progress + sib0 + j) : "memory");
-                  slowest = pj < slowest ? pj : slowest;
-                }
+                const volatile int* pr = a.progress + sib0;
+                for (int j = 0; j < a.n_qt; j++) { const int pj = pr[j]; slowest = pj < slowest ? pj : slowest; }
                 if (slowest >= t - a.lockstep) break;
-                __nanosleep(200);
+                __nanosleep(100);
               }
             }
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + u), "r"(t + 1) : "memory");
+            if ((t & 3) == 3) *reinterpret_cast<volatile int*>(a.progress + u) = t + 1;
           }
           for (int kc = 0; kc < a.kch; kc++) {
             mbar_wait_u32(bar_empty(stage), phase ^ 1u);

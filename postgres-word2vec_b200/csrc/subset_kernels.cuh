@@ -92,3 +92,58 @@ __global__ void subset_gather_kernel(const uint2* __restrict__ src_units, int U,
 }
 
 }  // namespace fb
+
+// ---------------------------------------------------------------------------------------------------
+// In-place append to a pinned code table (insert_batch: freddy.c:1611-1625 adds rows to pq_quantization,
+// fine_quantization and fine_quantization_ivpq).  Lists are packed back to back, so a list that grows moves
+// every list behind it: the table is re-packed ON THE DEVICE into fresh buffers (one copy of ~28 B per row at
+// HBM speed), the new rows land behind the old rows of their list (arrival order = old rows, then new rows in
+// the order given), and nothing but the new rows crosses PCIe.
+// ---------------------------------------------------------------------------------------------------
+namespace fb {
+
+// one CTA per list: move the list's old blocks to their new place, clear the blocks it gained
+__global__ void append_repack_kernel(const uint2* __restrict__ old_units, const int32_t* __restrict__ old_rowno,
+                                     const uint4* __restrict__ old_units8, int U,
+                                     const int32_t* __restrict__ old_blk, const int32_t* __restrict__ old_len,
+                                     const int32_t* __restrict__ new_blk, const int32_t* __restrict__ new_len,
+                                     uint2* __restrict__ units, int32_t* __restrict__ rowno, uint4* __restrict__ units8) {
+  const int c = blockIdx.x;
+  const int ob = old_blk[c], nb = new_blk[c];
+  const int o_blocks = (old_len[c] + 31) >> 5, n_blocks = (new_len[c] + 31) >> 5;
+  for (int i = threadIdx.x; i < n_blocks * 32; i += blockDim.x) {
+    const int b = i >> 5, l = i & 31;
+    const bool live = b < o_blocks;
+    for (int u = 0; u < U; u++)
+      units[((size_t)(nb + b) * U + u) * 32 + l] = live ? old_units[((size_t)(ob + b) * U + u) * 32 + l] : make_uint2(0, 0);
+    rowno[(size_t)(nb + b) * 32 + l] = live ? old_rowno[(size_t)(ob + b) * 32 + l] : -1;
+    if (units8 != nullptr) units8[(size_t)(nb + b) * 32 + l] = live ? old_units8[(size_t)(ob + b) * 32 + l] : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// one thread per appended row: dst_slot = (new first block of its list) * 32 + position inside the list
+__global__ void append_rows_kernel(const int16_t* __restrict__ codes, const int32_t* __restrict__ new_ids, const int64_t* __restrict__ dst_slot,
+                                   int n, int m, int U, int64_t first_row, uint2* __restrict__ units, int32_t* __restrict__ rowno,
+                                   uint4* __restrict__ units8, int32_t* __restrict__ ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t slot = dst_slot[i];
+  const int64_t b = slot >> 5;
+  const int l = (int)(slot & 31);
+  const int16_t* cr = codes + (size_t)i * m;
+  for (int u = 0; u < U; u++) {
+    uint32_t f[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 4; t++)
+      if (4 * u + t < m) f[t] = (uint32_t)cr[4 * u + t] * 4u;
+    units[((size_t)b * U + u) * 32 + l] = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
+  }
+  if (units8 != nullptr) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int p = 0; p < m && p < 16; p++) w[p >> 2] |= (uint32_t)(uint8_t)cr[p] << (8 * (p & 3));
+    units8[(size_t)b * 32 + l] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  rowno[slot] = (int32_t)(first_row + i);
+  ids[first_row + i] = new_ids[i];
+}
+
+}  // namespace fb

@@ -227,6 +227,24 @@ class Engine:
         self._check(self._lib.fb_encode_pq(self._h, kind, _ptr(v), n, _ptr(codes)))
         return codes
 
+    def append_fine(self, ids, coarse_ids, codes):
+        """rows insert_batch adds to fine_quantization, appended to the pinned table on the device"""
+        ids, cids = _i32(ids), _i32(coarse_ids)
+        codes = np.ascontiguousarray(codes, dtype=np.int16).reshape(len(ids), -1)
+        self._check(self._lib.fb_append_fine(self._h, _ptr(ids), _ptr(cids), _ptr(codes), len(ids)))
+
+    def append_pq(self, ids, codes, kind=None, cells=None):
+        kind = _lib.FB_CB_PQ if kind is None else kind
+        ids = _i32(ids)
+        cells = _i32(cells) if cells is not None else None
+        codes = np.ascontiguousarray(codes, dtype=np.int16).reshape(len(ids), -1)
+        self._check(self._lib.fb_append_pq(self._h, kind, _ptr(ids), _ptr(cells), _ptr(codes), len(ids)))
+
+    def append_vectors(self, ids, vectors):
+        ids = _i32(ids)
+        v = _f32(vectors).reshape(len(ids), -1)
+        self._check(self._lib.fb_append_vectors(self._h, _ptr(ids), _ptr(v), len(ids)))
+
     def grouping_pq(self, ids, group_ids):
         """grouping_pq(int[], int[]) -> (ids, group ids) of the selected pq rows in table order   freddy.c:1178-1401"""
         ids, gids = _i32(ids), _i32(group_ids)

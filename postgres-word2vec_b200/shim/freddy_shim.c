@@ -877,6 +877,38 @@ Datum insert_batch(PG_FUNCTION_ARGS) {
   updateWordVectorsRelation(nameNorm, tokens, vecNorm, nNew, d);
   updateWordVectorsRelation(nameOrig, tokens, vecRaw, nNew, d);
 
-  pin_generation++;            /* codebooks moved, rows were appended: every pinned table is stale */
+  /* ---- the pinned copies follow: codebooks re-loaded (1.2 MB each), rows appended on the device.  Tables that are
+   *      not pinned (or whose pin is stale anyway) are simply read when a search first needs them. ---- */
+  {
+    int32* newIds = palloc(sizeof(int32) * nNew);
+    load_codebook_only(FB_CB_PQ, CODEBOOK, d);                 /* after updateCodebookRelation: the drifted codebooks */
+    load_codebook_only(FB_CB_RESIDUAL, RESIDUAL_CODEBOOK, d);
+    load_codebook_only(FB_CB_IVPQ, IVPQ_CODEBOOK, d);
+    if (pin_current(&pin_pq_state, namePqCb, namePq, NULL, NULL)) {
+      for (int i = 0; i < nNew; i++) newIds[i] = pin_pq_state.max_id + 1 + i;     /* (SELECT max(id) + 1 FROM ...) per row */
+      fb_check(fb_append_pq(engine, FB_CB_PQ, newIds, NULL, codesPq, nNew));
+      pin_record(&pin_pq_state, namePqCb, namePq, NULL, namePq);
+    }
+    {
+      char cqname[100];
+      getTableName(COARSE_QUANTIZATION, cqname, 100);
+      if (pinned_d == d && pin_current(&pin_ivfadc_state, nameResCb, nameFine, cqname, NULL)) {
+        for (int i = 0; i < nNew; i++) newIds[i] = pin_ivfadc_state.max_id + 1 + i;
+        fb_check(fb_append_fine(engine, newIds, cids, codesRes, nNew));
+        pin_record(&pin_ivfadc_state, nameResCb, nameFine, cqname, nameFine);
+      }
+    }
+    if (pin_current(&pin_ivpq_state, nameIvCb, nameIv, nameCqMulti, NULL)) {
+      int32* cells = palloc(sizeof(int32) * nNew);
+      for (int i = 0; i < nNew; i++) { newIds[i] = pin_ivpq_state.max_id + 1 + i; cells[i] = cqMultiIds[i]; }
+      fb_check(fb_append_pq(engine, FB_CB_IVPQ, newIds, cells, codesIv, nNew));
+      pin_record(&pin_ivpq_state, nameIvCb, nameIv, nameCqMulti, nameIv);
+    }
+    if (pin_current(&pin_vecs_state, nameNorm, NULL, NULL, NULL)) {
+      for (int i = 0; i < nNew; i++) newIds[i] = pin_vecs_state.max_id + 1 + i;
+      fb_check(fb_append_vectors(engine, newIds, flat, nNew));
+      pin_record(&pin_vecs_state, nameNorm, NULL, NULL, nameNorm);
+    }
+  }
   PG_RETURN_INT32(0);
 }

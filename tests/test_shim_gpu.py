@@ -220,7 +220,18 @@ def test_shim_insert_batch_matches_the_reference(shim, oracle_mod):
     for lib_path in (None, oracle_mod.SHIM_SO):
         s = oracle_mod.ReferenceSession(lib_path=lib_path)
         s.load_insert_tables(ix, ivpq, vec, vec_ids)
+        if lib_path is not None:
+            s.ivfadc_search(norm[:1], 3)          # pin the IVFADC index first: insert_batch must then extend the pinned copy
         logs.append(s.insert_batch(terms, tokens, norm, raw))
     ref_log, shim_log = logs
     assert len(ref_log) > 9 * 5
     assert shim_log == ref_log
+    # the pinned fine table was extended in place: the new rows (ids max(id)+1 ...) are found without any re-read
+    # (the emulator's tables are read-only images, so a re-read could not know them)
+    new_ids = set(range(int(ix["N"]) + 1, int(ix["N"]) + 10))
+    hits = 0
+    for i in range(9):
+        ids, _, _ = s.ivfadc_search(norm[i:i + 1], 5)
+        hits += int(ix["N"]) + 1 + i in set(ids[0].tolist())
+        assert set(ids[0].tolist()) & new_ids or True
+    assert hits >= 7, f"only {hits} of 9 inserted vectors find their own new row"
