@@ -37,7 +37,8 @@ constexpr int kPfBN = 256;          // table rows per tile = TMEM columns of one
 constexpr int kPfBK = 64;           // bf16 elements per K chunk = 128 bytes = one swizzle-atom row
 constexpr int kPfStages = 4;        // table-tile ring depth
 constexpr int kPfMaxKch = 5;        // K chunks held for the query tile (d <= 320)
-constexpr int kPfThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int kPfEpiWarps = 8;      // two warps per TMEM lane quarter, each draining half of an accumulator's columns
+constexpr int kPfThreads = 64 + 32 * kPfEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, then the epilogue warps
 constexpr int kPfCandCap = 4096;    // candidates buffered per query while the bound is still rising (S slabs start cold:
                                     // about S * k * ln(rows per slab / k) emissions); more = overflow -> fp32 scan
 constexpr int kPfMaxK = 40;         // k' (k + excluded rows) the epilogue tracks
@@ -69,6 +70,7 @@ struct PfArgs {
   int* progress;
   int n_qt;
   int lockstep;
+  int dbg;                 // timing experiments only (results invalid): 1 = epilogue drains nothing, 2 = no MMAs issued, 4 = no TMA loads
 };
 
 // shared-memory plan of prefilter_gemm_kernel (dynamic, base aligned to 1024 bytes by the kernel)
@@ -101,6 +103,50 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Warp-converged issue: the whole warp runs the role's loops with warp-uniform values (the compiler keeps descriptors,
+// barrier addresses and counters in uniform registers), and the one-thread instructions are predicated on elect.sync
+// INSIDE the asm, so there is no divergent branch around them.  (With `if (lane == 0)` around the loops the issue of
+// one UTCHMMA took ~250 cycles of dependent R2UR / uniform-ALU work against the 128 cycles the MMA runs: ncu r2.)
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint32_t tx_bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %5;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar), "r"(tx_bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect_noexpect(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, both operands K-major
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -190,7 +236,7 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     for (int s = 0; s < kPfStages; s++) { mbar_init_u32(bar_full(s), 1); mbar_init_u32(bar_empty(s), 1); }
     mbar_init_u32(bar_q_full, 1);
     mbar_init_u32(bar_q_empty, 1);
-    for (int s = 0; s < 2; s++) { mbar_init_u32(bar_t_full(s), 1); mbar_init_u32(bar_t_empty(s), 4); }
+    for (int s = 0; s < 2; s++) { mbar_init_u32(bar_t_full(s), 1); mbar_init_u32(bar_t_empty(s), kPfEpiWarps); }
     mbar_fence_init();
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_v);
@@ -206,74 +252,72 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // =========================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, iter++) {
-        const PfUnit un = a.units[u];
-        if (iter > 0) mbar_wait_u32(bar_q_empty, (uint32_t)((iter - 1) & 1));   // MMAs of the previous unit are done with Q
-        mbar_expect_tx_u32(bar_q_full, (uint32_t)a.kch * kPfQChunkBytes);
-        for (int kc = 0; kc < a.kch; kc++) tma_load_2d(q_smem + kc * kPfQChunkBytes, &tm_q, kc * kPfBK, un.qt * kPfBM, bar_q_full);
-        const int sib0 = (u / a.n_qt) * a.n_qt;                      // units sib0 .. sib0 + n_qt - 1 stream this slab
-        for (int vt = un.v_begin; vt < un.v_end; vt++) {
-          if (a.lockstep > 0) {
-            const int t = vt - un.v_begin;
-            if (t >= a.lockstep && (t & 3) == 0) {                  // a rate limiter, not a protocol: relaxed loads, every 4th tile
-              for (;;) {
-                int slowest = 0x7fffffff;
-                const volatile int* pr = a.progress + sib0;
-                for (int j = 0; j < a.n_qt; j++) { const int pj = pr[j]; slowest = pj < slowest ? pj : slowest; }
-                if (slowest >= t - a.lockstep) break;
-                __nanosleep(100);
-              }
+    // =========================================================== TMA producer (whole warp, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, iter++) {
+      const PfUnit un = a.units[u];
+      if (iter > 0) mbar_wait_u32(bar_q_empty, (uint32_t)((iter - 1) & 1));   // MMAs of the previous unit are done with Q
+      mbar_expect_tx_elect(bar_q_full, (uint32_t)a.kch * kPfQChunkBytes);
+      for (int kc = 0; kc < a.kch; kc++)
+        tma_load_2d_elect_noexpect(q_smem + kc * kPfQChunkBytes, &tm_q, kc * kPfBK, un.qt * kPfBM, bar_q_full);
+      const int sib0 = (u / a.n_qt) * a.n_qt;                      // units sib0 .. sib0 + n_qt - 1 stream this slab
+      for (int vt = un.v_begin; vt < un.v_end; vt++) {
+        if (a.lockstep > 0) {
+          const int t = vt - un.v_begin;
+          if (t >= a.lockstep && (t & 3) == 0) {                  // a rate limiter, not a protocol: relaxed loads, every 4th tile
+            for (;;) {
+              int slowest = 0x7fffffff;
+              const volatile int* pr = a.progress + sib0;
+              for (int j = 0; j < a.n_qt; j++) { const int pj = pr[j]; slowest = pj < slowest ? pj : slowest; }
+              if (slowest >= t - a.lockstep) break;
+              __nanosleep(100);
             }
-            if ((t & 3) == 3) *reinterpret_cast<volatile int*>(a.progress + u) = t + 1;
           }
-          for (int kc = 0; kc < a.kch; kc++) {
-            mbar_wait_u32(bar_empty(stage), phase ^ 1u);
-            mbar_expect_tx_u32(bar_full(stage), kPfVStageBytes);
-            tma_load_2d(v_smem + stage * kPfVStageBytes, &tm_v, kc * kPfBK, vt * kPfBN, bar_full(stage));
-            if (++stage == kPfStages) { stage = 0; phase ^= 1u; }
-          }
+          if ((t & 3) == 3 && lane == 0) *reinterpret_cast<volatile int*>(a.progress + u) = t + 1;
+        }
+        for (int kc = 0; kc < a.kch; kc++) {
+          mbar_wait_u32(bar_empty(stage), phase ^ 1u);
+          if (a.dbg & 4) { if (lane == 0) mbar_arrive_u32(bar_full(stage)); }
+          else tma_load_2d_elect(v_smem + stage * kPfVStageBytes, &tm_v, kc * kPfBK, vt * kPfBN, bar_full(stage), kPfVStageBytes);
+          if (++stage == kPfStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = kPfIdesc;
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      int iter = 0;
-      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, iter++) {
-        const PfUnit un = a.units[u];
-        mbar_wait_u32(bar_q_full, (uint32_t)(iter & 1));
+    // =========================================================== MMA issuer (whole warp, one elected lane issues)
+    constexpr uint32_t idesc = kPfIdesc;
+    const uint64_t a_desc0 = umma_desc_sw128(q_smem), b_desc0 = umma_desc_sw128(v_smem);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    int iter = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, iter++) {
+      const PfUnit un = a.units[u];
+      mbar_wait_u32(bar_q_full, (uint32_t)(iter & 1));
+      tc_fence_after();
+      for (int vt = un.v_begin; vt < un.v_end; vt++) {
+        mbar_wait_u32(bar_t_empty(acc), acc_phase ^ 1u);   // the epilogue drained this accumulator
         tc_fence_after();
-        for (int vt = un.v_begin; vt < un.v_end; vt++) {
-          mbar_wait_u32(bar_t_empty(acc), acc_phase ^ 1u);   // the epilogue drained this accumulator
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kPfBN;
+        int ks_left = a.ksteps;
+        for (int kc = 0; kc < a.kch; kc++) {
+          mbar_wait_u32(bar_full(stage), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kPfBN;
-          int ks_left = a.ksteps;
-          for (int kc = 0; kc < a.kch; kc++) {
-            mbar_wait_u32(bar_full(stage), phase);
-            tc_fence_after();
-            const int nk = ks_left < 4 ? ks_left : 4;
-            for (int k = 0; k < nk; k++) {
-              const uint64_t ad = umma_desc_sw128(q_smem + kc * kPfQChunkBytes + k * 32);
-              const uint64_t bd = umma_desc_sw128(v_smem + stage * kPfVStageBytes + k * 32);
-              tc_mma_bf16(d_tmem, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
-            }
-            ks_left -= nk;
-            tc_commit(bar_empty(stage));          // the ring slot is free once these MMAs have read it
-            if (++stage == kPfStages) { stage = 0; phase ^= 1u; }
-          }
-          tc_commit(bar_t_full(acc));             // accumulator complete
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          // descriptors differ from the base ones only in the start-address field (bytes >> 4, no carry out of it)
+          const uint64_t ad = a_desc0 + (uint64_t)((kc * kPfQChunkBytes) >> 4);
+          const uint64_t bd = b_desc0 + (uint64_t)((stage * kPfVStageBytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (k < ks_left && !(a.dbg & 2)) tc_mma_bf16_elect(d_tmem, ad + 2u * k, bd + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          ks_left -= 4;
+          tc_commit_elect(bar_empty(stage));          // the ring slot is free once these MMAs have read it
+          if (++stage == kPfStages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(bar_q_empty);
+        tc_commit_elect(bar_t_full(acc));             // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      tc_commit_elect(bar_q_empty);
     }
   } else {
     // =========================================================== epilogue warps (thread = query)
@@ -281,7 +325,11 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // that works on query q (all slabs).  A row better than that minimum replaces it (compare-and-swap on the
     // slot), so the bound follows the kk-th best of ALL rows seen so far and the number of emissions per query
     // stays near kk * ln(N / kk) however many slabs there are.
+    // (ncu, 4 epilogue warps: the MMA thread waited for a drained accumulator 20 % of the time and the tensor pipe
+    // was busy 37 %: the drain, not TMA, set the pace.  Hence 8 warps, a max tree, and a bound refreshed every 4th tile.)
     const int quarter = warp & 3;                                  // TMEM lanes this warp may read
+    const int chalf = (warp - 2) >> 2;                             // which half of the accumulator's columns it drains
+    constexpr int kChunks = kPfBN / 32 / (kPfEpiWarps / 4);
     const int qlane = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int acc = 0;
@@ -301,30 +349,41 @@ prefilter_gemm_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
         return make_uint2(mv, (uint32_t)mi);
       };
+      uint32_t gmin = 0u;
       for (int vt = un.v_begin; vt < un.v_end; vt++) {
-        uint32_t gmin = live ? bound().x : 0xFFFFFFFFu;            // issued before the wait: overlaps the MMA of this tile
+        // the shared bound only rises: a stale copy just emits a few more candidates, so it is re-read every 4th tile
+        if (((vt - un.v_begin) & 3) == 0) gmin = live ? bound().x : 0xFFFFFFFFu;
         mbar_wait_u32(bar_t_full(acc), acc_phase);
         tc_fence_after();
         float thr_emit = !live ? INFINITY : (gmin == 0u ? -INFINITY : unordered_f32(gmin) - eps2);
         const long long row0 = (long long)vt * kPfBN;
 #pragma unroll 1
-        for (int c = 0; c < kPfBN / 32; c++) {
+        for (int c = chalf * kChunks; c < (chalf + 1) * kChunks && !(a.dbg & 1); c++) {
           float v[32];
           tmem_ld32(t_lane + (uint32_t)acc * kPfBN + (uint32_t)(c * 32), v);
-          if (a.dump != nullptr && live) {
+          float m8[8];                                             // max tree: 4 levels instead of a 31-deep chain
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const long long row = row0 + c * 32 + j;
-              if (row < a.N) a.dump[(long long)q * a.dump_ld + row] = v[j];
+          for (int j = 0; j < 8; j++) m8[j] = fmaxf(fmaxf(v[4 * j], v[4 * j + 1]), fmaxf(v[4 * j + 2], v[4 * j + 3]));
+          const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          if (mx >= thr_emit || a.dump != nullptr) {
+            // Rare path, kept SMALL on purpose: a 32-times unrolled body (13 k SASS lines) thrashed the instruction cache
+            // and cost as much as the whole GEMM.  The 32 scores go to a local array, a bit mask names the ones to look at.
+            float vv[32];
+            uint32_t todo = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) { vv[j] = v[j]; todo |= (v[j] >= thr_emit ? 1u : 0u) << j; }
+            if (a.dump != nullptr && live) {
+#pragma unroll 1
+              for (int j = 0; j < 32; j++) {
+                const long long row = row0 + c * 32 + j;
+                if (row < a.N) a.dump[(long long)q * a.dump_ld + row] = vv[j];
+              }
             }
-          }
-          float mx = v[0];
-#pragma unroll
-          for (int j = 1; j < 32; j++) mx = fmaxf(mx, v[j]);
-          if (mx >= thr_emit) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const float s = v[j];
+#pragma unroll 1
+            while (todo) {
+              const int j = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const float s = vv[j];
               const long long row = row0 + c * 32 + j;
               if (s >= thr_emit && row < a.N) {
                 const int slot = atomicAdd(a.cand_cnt + q, 1);

@@ -40,6 +40,7 @@ class Engine:
         self.device = device
         self.d = None
         self._cb_m = {}
+        self._cb_d = {}
 
     def close(self):
         if getattr(self, "_h", None):
@@ -69,6 +70,7 @@ class Engine:
             self.d = m * sub
         self._check(self._lib.fb_load_codebook(self._h, kind, _ptr(cb), m, K, sub))
         self._cb_m[kind] = m
+        self._cb_d[kind] = m * sub          # every index kind has its own dimension (a session may pin several)
 
     def load_fine(self, ids, coarse_ids, codes):
         ids, coarse_ids = _i32(ids), _i32(coarse_ids)
@@ -117,14 +119,14 @@ class Engine:
         return oq[:nout.value], ids[:nout.value], dists[:nout.value]
 
     def pq_search(self, queries, k):
-        q = _f32(queries).reshape(-1, self.d)
+        q = _f32(queries).reshape(-1, self._cb_d[_lib.FB_CB_PQ])
         nq = q.shape[0]
         ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
         self._check(self._lib.fb_pq_search(self._h, _ptr(q), nq, k, _ptr(ids), _ptr(dists)))
         return ids, dists
 
     def pq_search_in_batch(self, queries, k, targets, use_target_lists=False):
-        q = _f32(queries).reshape(-1, self.d)
+        q = _f32(queries).reshape(-1, self._cb_d[_lib.FB_CB_PQ])
         nq = q.shape[0]
         t = _i32(targets)
         ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)
@@ -150,7 +152,7 @@ class Engine:
 
     def ivpq_search_in(self, queries, k, targets, alpha, pvf, method, use_target_lists, confidence,
                        double_threshold=10_000_000):
-        q = _f32(queries).reshape(-1, self.d)
+        q = _f32(queries).reshape(-1, self._cb_d[_lib.FB_CB_IVPQ])
         nq = q.shape[0]
         t = _i32(targets)
         ids, dists = np.empty((nq, k), np.int32), np.empty((nq, k), np.float32)

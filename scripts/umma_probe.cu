@@ -157,7 +157,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&d_progress, n_units * sizeof(int)));
   const int lockstep = getenv("PF_LOCKSTEP") ? atoi(getenv("PF_LOCKSTEP")) : 8;
   a.progress = d_progress; a.n_qt = QT; a.lockstep = (n_units <= sms && QT > 1 && lockstep > 0) ? (lockstep < 8 ? 8 : lockstep) : 0;
-  printf("lockstep window %d tiles\n", a.lockstep);
+  a.dbg = getenv("PF_DBG") ? atoi(getenv("PF_DBG")) : 0;
+  printf("lockstep window %d tiles, dbg %d\n", a.lockstep, a.dbg);
   CK(cudaFuncSetAttribute(prefilter_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PfSmem::total));
   const size_t rs_smem = (size_t)kPfCandCap * 8 + (size_t)d * 4;
   const int grid = std::min(sms, n_units);
