@@ -237,7 +237,7 @@ enum {
                                   tcgen05 GEMM whose error is bounded, then decide with the reference's fp32 chain
                                   (identical results); 0: the fp32 scan kernels do all the work                    */
   FB_OPT_PREFILTER_LOCKSTEP = 19, /* table tiles a pre-filter CTA may run ahead of the slowest CTA that streams the same
-                                  slab for another query tile (default 8; 0 = free running): keeps shared tiles in L2  */
+                                  slab for another query tile (default 0 = free running; >= 8 throttles): keeps shared tiles in L2 */
   FB_OPT_BYTE_CODES = 18,      /* 1 (default): tables with K <= 256 and m <= 16 also keep a true uint8 image of their codes
                                   (16 bytes per row, one 16-byte load per row in the scan kernels: the layout the
                                   reference's index_creation/config/*.json, k = 256, call for); 0: 16-bit units only      */
