@@ -144,10 +144,19 @@ class ClockSampler:
 
 
 def build_index(a, device):
+    """coarse / codebook training in torch (index construction is outside the parity boundary); the assignment
+    and encoding of all N rows by the engine (fb_encode_ivfadc_dev: the reference's rule, freddy.c:1567-1582)"""
     from freddy_b200.index_build import make_synthetic_index
     t0 = time.time()
+    enc = None
+    if str(device).startswith("cuda") and a.impl == "ours":      # the reference arm stays free of this repo's library
+        from freddy_b200 import Engine
+        import torch
+        enc = Engine(torch.device(device).index or 0)
     ix = make_synthetic_index(a.n, d=a.d, m=a.m, K=a.K, C=a.C, n_train=min(100_000, a.n), n_clusters=1000,
-                              sigma=a.sigma, zipf=a.zipf, kmeans_iters=10, seed=1234, device=device, keep_vectors=True)
+                              sigma=a.sigma, zipf=a.zipf, kmeans_iters=10, seed=1234, device=device, keep_vectors=True, encoder=enc)
+    if enc is not None:
+        enc.close()
     return ix, time.time() - t0
 
 
@@ -541,6 +550,8 @@ def main():
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": workload_name(a), "parallelism": f"replicated index, queries sharded x{world}",
                           "l2": "flushed (256 MiB write) between timed steps", "index_build_s": round(t_build, 1), "index_upload_s": round(t_load, 1),
+                          "index_encode": ({"by": "fb_encode_ivfadc_dev (reference rule: freddy.c:1567-1582, index_utils.c:923-939)",
+                                            **ix["encode_report"]} if "encode_report" in ix else "float shortcut (torch)"),
                           "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]),
                           "single_query_latency_us": lat_us,
                           "exact_path_queries_per_step": exact_q / a.steps,

@@ -171,6 +171,10 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
  * then reads an uninitialised assignment).  The codebook drift update of insert_batch is not done here. */
 int fb_encode_ivfadc(fb_engine* e, const float* vectors, int64_t n, int32_t* out_coarse_ids, int16_t* out_codes);
 int fb_encode_pq(fb_engine* e, int kind, const float* vectors, int64_t n, int16_t* out_codes);
+/* the same with DEVICE pointers (index build: index_creation/ivfadc.py:36-96, ivpq.py:100-193 quantise the whole
+ * table; the rows are in HBM already) */
+int fb_encode_ivfadc_dev(fb_engine* e, const float* d_vectors, int64_t n, int32_t* d_out_coarse_ids, int16_t* d_out_codes);
+int fb_encode_pq_dev(fb_engine* e, int kind, const float* d_vectors, int64_t n, int16_t* d_out_codes);
 
 /* ---- in-place append (insert_batch must refresh the pinned copy) -----------------------
  * insert_batch (freddy.c:1403-1658) INSERTs the new rows into pq_quantization, fine_quantization and

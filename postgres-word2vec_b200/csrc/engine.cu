@@ -2215,8 +2215,14 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
 
 // quantisation of new rows as insert_batch assigns them (freddy.c:1567-1582, index_utils.c:923-939):
 // coarse argmin (optional) -> residual LUT rows -> first minimum per position
+__global__ void any_coarse_far_kernel(const uint32_t* __restrict__ qflags, int n, int32_t* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (qflags[i] & kWhyCoarseFar)) atomicExch(flag, 1);
+}
+
+// on_device: vectors / out_coarse_ids / out_codes are DEVICE pointers (index build: the rows are already in HBM)
 static int encode_impl(fb_engine* e, const Codebook& cb, bool with_coarse, const float* vectors, int64_t n,
-                       int32_t* out_coarse_ids, int16_t* out_codes) {
+                       int32_t* out_coarse_ids, int16_t* out_codes, bool on_device = false) {
   if (!cb.loaded) return fail(e, FB_ERR_INVALID, "codebook not loaded");
   if (with_coarse && !e->coarse_loaded) return fail(e, FB_ERR_INVALID, "coarse table not loaded");
   const int d = cb.m * cb.sub, m = cb.m, K = cb.K;
@@ -2224,31 +2230,43 @@ static int encode_impl(fb_engine* e, const Codebook& cb, bool with_coarse, const
   if (n == 0) return FB_OK;
   if (!vectors || !out_codes || (with_coarse && !out_coarse_ids)) return fail(e, FB_ERR_INVALID, "null buffer");
   FB_CUDA(e, cudaSetDevice(e->device));
-  const int64_t chunk = std::min<int64_t>(n, 4096);
+  const int64_t chunk = std::min<int64_t>(n, on_device ? 16384 : 4096);
   DevBuf<int16_t> d_codes;
-  FB_CUDA(e, e->q_stage.ensure((size_t)chunk * d));
+  if (!on_device) FB_CUDA(e, e->q_stage.ensure((size_t)chunk * d));
   FB_CUDA(e, e->lut.ensure((size_t)chunk * m * K));
-  FB_CUDA(e, d_codes.ensure((size_t)chunk * m));
+  if (!on_device) FB_CUDA(e, d_codes.ensure((size_t)chunk * m));
   FB_CUDA(e, e->probes.ensure((size_t)chunk));
   FB_CUDA(e, e->qflags.ensure((size_t)chunk));
+  FB_CUDA(e, cudaMemsetAsync(e->small.p + 3, 0, sizeof(int32_t), e->stream));
   std::vector<uint32_t> h_flags;
   int rc = FB_OK;
   for (int64_t r0 = 0; r0 < n && rc == FB_OK; r0 += chunk) {
     const int c = (int)std::min<int64_t>(chunk, n - r0);
-    FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, vectors + (size_t)r0 * d, (size_t)c * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    const float* dq = on_device ? vectors + (size_t)r0 * d : e->q_stage.p;
+    int16_t* dc = on_device ? out_codes + (size_t)r0 * m : d_codes.p;
+    if (!on_device)
+      FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, vectors + (size_t)r0 * d, (size_t)c * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     if (with_coarse) {
       // the w = 1 selection of the coarse kernel is the reference's argmin: smallest (distance, id) key
-      rc = launch_coarse(e, e->q_stage.p, c, 1, 1);   // (list lengths only feed the search flags; may be absent)
+      rc = launch_coarse(e, dq, c, 1, 1);   // (list lengths only feed the search flags; may be absent)
       if (rc) break;
-      rc = launch_lut(e, cb, e->q_stage.p, e->coarse.p, e->probes.p, 1, c, e->lut.p);
+      rc = launch_lut(e, cb, dq, e->coarse.p, e->probes.p, 1, c, e->lut.p);
     } else {
-      rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, c, e->lut.p);
+      rc = launch_lut(e, cb, dq, nullptr, nullptr, 1, c, e->lut.p);
     }
     if (rc) break;
     const int64_t warps = (int64_t)c * m;
-    lut_argmin_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, e->stream>>>(e->lut.p, c, m, K, d_codes.p, e->small.p + 2);
+    lut_argmin_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, e->stream>>>(e->lut.p, c, m, K, dc, e->small.p + 2);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
+    if (on_device) {
+      if (with_coarse) {
+        FB_CUDA(e, cudaMemcpyAsync(out_coarse_ids + r0, e->probes.p, (size_t)c * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+        any_coarse_far_kernel<<<(c + 255) / 256, 256, 0, e->stream>>>(e->qflags.p, c, e->small.p + 3);
+        e->launches++;
+      }
+      continue;
+    }
     FB_CUDA(e, cudaMemcpyAsync(out_codes + (size_t)r0 * m, d_codes.p, (size_t)c * m * sizeof(int16_t), cudaMemcpyDeviceToHost, e->stream));
     if (with_coarse) {
       FB_CUDA(e, cudaMemcpyAsync(out_coarse_ids + r0, e->probes.p, (size_t)c * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -2258,21 +2276,30 @@ static int encode_impl(fb_engine* e, const Codebook& cb, bool with_coarse, const
     FB_CUDA(e, cudaStreamSynchronize(e->stream));
     if (with_coarse)
       for (int i = 0; i < c; i++)
-        if (h_flags[i] & kWhyCoarseFar) {
-          d_codes.release();
+        if (h_flags[i] & kWhyCoarseFar)
           return fail(e, FB_ERR_REFERENCE_UB, "row %lld: every coarse distance >= 100, the reference's assignment is uninitialised (freddy.c:1570-1577)",
                       (long long)(r0 + i));
-        }
   }
-  d_codes.release();
   if (rc) return rc;
-  int32_t flag = 0;
-  FB_CUDA(e, cudaMemcpy(&flag, e->small.p + 2, sizeof flag, cudaMemcpyDeviceToHost));
-  if (flag) {
-    cudaMemset(e->small.p + 2, 0, sizeof(int32_t));
+  int32_t flag[2] = {0, 0};
+  FB_CUDA(e, cudaMemcpyAsync(flag, e->small.p + 2, sizeof flag, cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (flag[0] || flag[1]) {
+    cudaMemset(e->small.p + 2, 0, 2 * sizeof(int32_t));
+    if (flag[1]) return fail(e, FB_ERR_REFERENCE_UB, "a row is >= 100 away from every coarse centroid: the reference's assignment is uninitialised (freddy.c:1570-1577)");
     return fail(e, FB_ERR_REFERENCE_UB, "a sub-vector is >= 100 away from every codeword: the reference's assignment is uninitialised (index_utils.c:926-938)");
   }
   return FB_OK;
+}
+
+int fb_encode_ivfadc_dev(fb_engine* e, const float* d_vectors, int64_t n, int32_t* d_out_coarse_ids, int16_t* d_out_codes) {
+  if (!e || n < 0) return fail(e, FB_ERR_INVALID, "fb_encode_ivfadc_dev: bad arguments");
+  return encode_impl(e, e->cb[FB_CB_RESIDUAL], true, d_vectors, n, d_out_coarse_ids, d_out_codes, true);
+}
+
+int fb_encode_pq_dev(fb_engine* e, int kind, const float* d_vectors, int64_t n, int16_t* d_out_codes) {
+  if (!e || n < 0 || kind < 0 || kind >= FB_CB_KINDS) return fail(e, FB_ERR_INVALID, "fb_encode_pq_dev: bad arguments");
+  return encode_impl(e, e->cb[kind], false, d_vectors, n, nullptr, d_out_codes, true);
 }
 
 int fb_encode_ivfadc(fb_engine* e, const float* vectors, int64_t n, int32_t* out_coarse_ids, int16_t* out_codes) {

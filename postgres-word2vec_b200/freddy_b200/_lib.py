@@ -55,6 +55,8 @@ SIGNATURES = {
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "fb_encode_ivfadc": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "fb_encode_pq": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
+    "fb_encode_ivfadc_dev": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "fb_encode_pq_dev": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
     "fb_append_fine": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "fb_append_pq": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int64]),
     "fb_append_vectors": (C.c_int, [_P, _P, _P, C.c_int64]),

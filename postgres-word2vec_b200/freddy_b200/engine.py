@@ -220,6 +220,14 @@ class Engine:
         self._check(self._lib.fb_encode_ivfadc(self._h, _ptr(v), n, _ptr(cids), _ptr(codes)))
         return cids, codes
 
+    def encode_ivfadc_dev(self, d_vectors_ptr, n, d_coarse_ids_ptr, d_codes_ptr):
+        """device pointers (e.g. torch tensors' data_ptr()): [n][d] fp32 in, [n] int32 and [n][m] int16 out"""
+        self._check(self._lib.fb_encode_ivfadc_dev(self._h, C.c_void_p(d_vectors_ptr), n, C.c_void_p(d_coarse_ids_ptr), C.c_void_p(d_codes_ptr)))
+
+    def encode_pq_dev(self, d_vectors_ptr, n, d_codes_ptr, kind=None):
+        kind = _lib.FB_CB_PQ if kind is None else kind
+        self._check(self._lib.fb_encode_pq_dev(self._h, kind, C.c_void_p(d_vectors_ptr), n, C.c_void_p(d_codes_ptr)))
+
     def encode_pq(self, vectors, kind=None):
         """codes of raw rows against the pq (default) / ivpq codebook"""
         kind = _lib.FB_CB_PQ if kind is None else kind

@@ -48,10 +48,13 @@ def _nearest(x, cent, chunk=65536):
 
 def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clusters=1000,
                          sigma=0.3, kmeans_iters=10, seed=1234, device=None, with_pq=False,
-                         keep_vectors=False, zipf=0.7, coarse_from_centres=False):
+                         keep_vectors=False, zipf=0.7, coarse_from_centres=False, encoder=None):
     """Returns a dict of numpy arrays (plus 'vectors_t': the torch tensor, if keep_vectors).
     coarse_from_centres: start the coarse k-means from the (normalised) generating centres (needs C == n_clusters):
-    one centroid per true cluster, i.e. inverted lists of the nominal N / C rows."""
+    one centroid per true cluster, i.e. inverted lists of the nominal N / C rows.
+    encoder: a freddy_b200.Engine on the same CUDA device: coarse assignment and residual / pq codes of ALL rows then come from
+    fb_encode_ivfadc_dev / fb_encode_pq_dev, i.e. from the reference's own rule (strict `<`, first minimum in table order,
+    sequential fp32 distances; freddy.c:1567-1582, index_utils.c:923-939) instead of the ||c||^2 - 2 x.c shortcut below."""
     assert d % m == 0, "d must be divisible by m"
     sub = d // m
     dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
@@ -85,10 +88,27 @@ def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clus
     for p in range(m):
         res_cb[p] = _kmeans(res_train[:, p * sub:(p + 1) * sub].contiguous(), K, kmeans_iters, gen)
     codes = torch.empty(N, m, dtype=torch.int16, device=dev)
-    for s in range(0, N, step):
-        r = vecs[s:s + step] - coarse[coarse_ids[s:s + step]]
-        for p in range(m):
-            codes[s:s + step, p] = _nearest(r[:, p * sub:(p + 1) * sub].contiguous(), res_cb[p]).to(torch.int16)
+    encode_report = None
+    if encoder is not None and dev.type == "cuda":
+        from . import _lib
+        encoder.load_coarse(coarse.cpu().numpy())
+        encoder.load_codebook(_lib.FB_CB_RESIDUAL, res_cb.cpu().numpy())
+        cids32 = torch.empty(N, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        encoder.encode_ivfadc_dev(vecs.data_ptr(), N, cids32.data_ptr(), codes.data_ptr())
+        encoder.synchronize()
+        # how far the float shortcut (argmin of ||c||^2 - 2 x.c) is from the reference's rule: rows it would assign / encode differently
+        ns = min(N, 100_000)
+        r = vecs[:ns] - coarse[cids32[:ns].to(torch.long)]
+        short = torch.stack([_nearest(r[:, p * sub:(p + 1) * sub].contiguous(), res_cb[p]) for p in range(m)], 1).to(torch.int16)
+        encode_report = {"rows": N, "coarse_ids_differing_from_the_float_shortcut": int((cids32.to(torch.long) != coarse_ids).sum().item()),
+                         "sample_rows": ns, "sample_rows_with_other_codes": int((short != codes[:ns]).any(1).sum().item())}
+        coarse_ids = cids32.to(torch.long)
+    else:
+        for s in range(0, N, step):
+            r = vecs[s:s + step] - coarse[coarse_ids[s:s + step]]
+            for p in range(m):
+                codes[s:s + step, p] = _nearest(r[:, p * sub:(p + 1) * sub].contiguous(), res_cb[p]).to(torch.int16)
 
     out = {
         "d": d, "m": m, "K": K, "C": C, "N": N,
@@ -103,12 +123,21 @@ def make_synthetic_index(N, d=300, m=12, K=1024, C=1000, n_train=100_000, n_clus
         for p in range(m):
             pq_cb[p] = _kmeans(train[:, p * sub:(p + 1) * sub].contiguous(), K, kmeans_iters, gen)
         pq_codes = torch.empty(N, m, dtype=torch.int16, device=dev)
-        for s in range(0, N, step):
-            v = vecs[s:s + step]
-            for p in range(m):
-                pq_codes[s:s + step, p] = _nearest(v[:, p * sub:(p + 1) * sub].contiguous(), pq_cb[p]).to(torch.int16)
+        if encoder is not None and dev.type == "cuda":
+            from . import _lib
+            encoder.load_codebook(_lib.FB_CB_PQ, pq_cb.cpu().numpy())
+            torch.cuda.synchronize()
+            encoder.encode_pq_dev(vecs.data_ptr(), N, pq_codes.data_ptr())
+            encoder.synchronize()
+        else:
+            for s in range(0, N, step):
+                v = vecs[s:s + step]
+                for p in range(m):
+                    pq_codes[s:s + step, p] = _nearest(v[:, p * sub:(p + 1) * sub].contiguous(), pq_cb[p]).to(torch.int16)
         out["pq_codebook"] = pq_cb.cpu().numpy()
         out["pq_codes"] = pq_codes.cpu().numpy()
+    if encode_report is not None:
+        out["encode_report"] = encode_report
     if keep_vectors:
         out["vectors_t"] = vecs
     else:

@@ -1,5 +1,13 @@
-timeout 60 scripts/umma_probe 200 5000 300 5 | tail -3
-timeout 60 scripts/umma_probe 300 70000 300 10 | tail -3
-timeout 60 scripts/umma_probe 1000 3000000 300 1 perf | grep -E "rep 4|PROBE|candidates"
-timeout 300 python scripts/bench_prefilter.py 2>&1 | tail -12
-timeout 300 python -m pytest tests/test_prefilter_gpu.py tests/test_rerank_gpu.py tests/test_vector_udfs.py tests/test_append_gpu.py -q --timeout 280 2>&1 | tail -3
+set -x
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_r2_n2.json 2> gpurun_out/bench_r2_n2.err; tail -c 600 gpurun_out/bench_r2_n2.err
+python - <<'PY'
+import json
+try:
+    j=json.loads(open('gpurun_out/bench_r2_n2.json').read().strip().splitlines()[-1])
+    print("N=2 value", round(j["value"]), "e2e", round(j["e2e"]["value"]))
+    for r in j["config"]["per_rank"]: print("  rank", r)
+    for s in j["config"]["secondary"]:
+        print("   ", s.get("name","")[:40], s.get("seconds"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
+except Exception as ex:
+    print("no N=2 result", ex)
+PY

@@ -63,3 +63,41 @@ def test_encode_ties_and_far_rows(eng, oracle_mod):
         eng.encode_ivfadc(far)
     assert ei.value.code == _lib.FB_ERR_REFERENCE_UB
     assert oracle_mod.encode(far, cb, coarse)[2] != 0
+
+
+def test_encode_device_pointers_and_index_builder(eng, oracle_mod):
+    """the device-pointer form (index build: rows already in HBM) gives the host form's codes; the synthetic index
+    builder with encoder= produces an index whose every row is quantised by the reference's rule"""
+    import torch
+    from freddy_b200 import FreddyError, _lib
+    from freddy_b200.index_build import make_synthetic_index
+    ix = small_index(N=20000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100, with_pq=True)
+    eng.load_coarse(ix["coarse"])
+    eng.load_codebook(_lib.FB_CB_RESIDUAL, ix["residual_codebook"])
+    eng.load_codebook(_lib.FB_CB_PQ, ix["pq_codebook"])
+    v = np.ascontiguousarray(ix["vectors"][:18001])                 # two device chunks, the second ragged
+    cids, codes = eng.encode_ivfadc(v)
+    tv = torch.from_numpy(v).cuda()
+    tc = torch.empty(len(v), dtype=torch.int32, device="cuda")
+    tk = torch.empty(len(v), 12, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    eng.encode_ivfadc_dev(tv.data_ptr(), len(v), tc.data_ptr(), tk.data_ptr())
+    eng.synchronize()
+    np.testing.assert_array_equal(tc.cpu().numpy(), cids)
+    np.testing.assert_array_equal(tk.cpu().numpy(), codes)
+    eng.encode_pq_dev(tv.data_ptr(), len(v), tk.data_ptr())
+    eng.synchronize()
+    np.testing.assert_array_equal(tk.cpu().numpy(), eng.encode_pq(v))
+    far = torch.full((5, 300), 50.0, device="cuda")
+    with pytest.raises(FreddyError) as ei:
+        eng.encode_ivfadc_dev(far.data_ptr(), 5, tc.data_ptr(), tk.data_ptr())
+    assert ei.value.code == _lib.FB_ERR_REFERENCE_UB
+    ix2 = make_synthetic_index(30000, d=48, m=12, K=64, C=40, n_train=20000, n_clusters=50, kmeans_iters=3, seed=5, device="cuda",
+                               with_pq=True, keep_vectors=True, encoder=eng)
+    vec = ix2.pop("vectors_t").cpu().numpy()
+    ecids, ecodes, rc = oracle_mod.encode(vec, ix2["residual_codebook"], ix2["coarse"])
+    assert rc == 0
+    np.testing.assert_array_equal(ix2["coarse_ids"], ecids)
+    np.testing.assert_array_equal(ix2["codes"], ecodes)
+    _, epq, rc = oracle_mod.encode(vec, ix2["pq_codebook"])
+    np.testing.assert_array_equal(ix2["pq_codes"], epq)
