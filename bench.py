@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--secondary", default=None,
                     help="comma list of secondary workloads reported in config.secondary: 3,4,5 (BASELINE configs), sigma03, nominal; "
                          "'none' skips them.  Default: all five on one GPU, 4 and 5 (the sharded ones) on several")
+    ap.add_argument("--gpu-rotate", type=int, default=int(os.environ.get("FB_GPU_ROTATE", "0")),
+                    help="rank r runs on GPU (r + ROTATE) %% n_gpus: separates a slow GPU from a slow rank (VERDICT r1 item 5)")
     ap.add_argument("--secondary-sample", type=int, default=256, help="queries of each secondary workload checked against the reference")
     return ap.parse_args()
 
@@ -308,6 +310,8 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    if a.gpu_rotate:
+        local_rank = (local_rank + a.gpu_rotate) % max(1, torch.cuda.device_count())
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None

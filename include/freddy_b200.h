@@ -244,7 +244,7 @@ enum {
                                   slab for another query tile (default 0 = free running; >= 8 throttles): keeps shared tiles in L2 */
   FB_OPT_BYTE_CODES = 18,      /* 1 (default): tables with K <= 256 and m <= 16 also keep a true uint8 image of their codes
                                   (16 bytes per row, one 16-byte load per row in the scan kernels: the layout the
-                                  reference's index_creation/config/*.json, k = 256, call for); 0: 16-bit units only      */
+                                  reference's index_creation/config JSON files, k = 256, call for); 0: 16-bit units only      */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

@@ -459,24 +459,6 @@ __global__ void count_rows_kernel(const int32_t* __restrict__ probes, int n, con
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
 }
 
-// gather selected rows of the flat pq table (blocked in table order) into a
-// temporary blocked table (freddy.c:544-562 `WHERE id IN (...)`)
-__global__ void gather_rows_kernel(const uint2* __restrict__ src_units, int U, const int32_t* __restrict__ rows, int n,
-                                   uint2* __restrict__ dst_units, int32_t* __restrict__ dst_rowno, int n_dst_slots) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_dst_slots) return;
-  int db = s >> 5, dl = s & 31;
-  if (s < n) {
-    int r = rows[s];
-    int sb = r >> 5, sl = r & 31;
-    for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = src_units[((size_t)sb * U + u) * 32 + sl];
-    dst_rowno[s] = r;
-  } else {
-    for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = make_uint2(0, 0);
-    dst_rowno[s] = -1;
-  }
-}
-
 // ---- kernel launch helpers -------------------------------------------------
 template <int QT>
 int launch_coarse_t(fb_engine* e, const float* d_q, int nq, int w, int k, int64_t q0) {
@@ -2237,7 +2219,7 @@ static int encode_impl(fb_engine* e, const Codebook& cb, bool with_coarse, const
   if (!on_device) FB_CUDA(e, d_codes.ensure((size_t)chunk * m));
   FB_CUDA(e, e->probes.ensure((size_t)chunk));
   FB_CUDA(e, e->qflags.ensure((size_t)chunk));
-  FB_CUDA(e, cudaMemsetAsync(e->small.p + 3, 0, sizeof(int32_t), e->stream));
+  FB_CUDA(e, cudaMemsetAsync(e->small.p + 2, 0, 2 * sizeof(int32_t), e->stream));   // [2] sub-vector far, [3] coarse far
   std::vector<uint32_t> h_flags;
   int rc = FB_OK;
   for (int64_t r0 = 0; r0 < n && rc == FB_OK; r0 += chunk) {
