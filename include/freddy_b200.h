@@ -245,6 +245,10 @@ enum {
   FB_OPT_BYTE_CODES = 18,      /* 1 (default): tables with K <= 256 and m <= 16 also keep a true uint8 image of their codes
                                   (16 bytes per row, one 16-byte load per row in the scan kernels: the layout the
                                   reference's index_creation/config JSON files, k = 256, call for); 0: 16-bit units only      */
+  FB_OPT_DEVICE_BUILD = 20,    /* 1 (default): fb_load_fine / fb_load_pq / fb_load_ivpq / fb_load_vectors group the rows by list,
+                                  place them (FB_OPT_PLACEMENT_WINDOW <= 1024) and pack them with kernels, and sort the id
+                                  columns on the device; the host sends the raw columns once.  0: the host-side builder
+                                  (same layout; kept as the cross-check of tests/test_build_gpu.py)                      */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */
@@ -269,6 +273,24 @@ typedef struct {
 } fb_counters;
 int fb_get_counters(fb_engine* e, fb_counters* out);  /* synchronizes the stream */
 int fb_reset_counters(fb_engine* e);
+
+/* create_statistics (freddy--0.0.1.sql:150-171) over the pinned IVPQ table, on the device: stats[c] = (rows of cell c
+ * whose id is listed)::float8 / (all listed rows found) cast to float4, stats[Kc*Kc] = that total; a table row counts
+ * once per occurrence of its id in `ids` (the reference counts rows of the JOIN with the user's column).  ids = NULL:
+ * every row of the table.  out_stats (host, [Kc*Kc + 1]) may be NULL; install != 0 makes them the statistics
+ * fb_ivpq_search_in uses.  fb_load_ivpq(stats = NULL) calls this over all rows. */
+int fb_ivpq_statistics(fb_engine* e, const int32_t* ids, int64_t n_ids, float* out_stats, int install);
+
+/* Sidecar (include/freddy_sidecar.h): a thread of this process serves the single-query requests that backends post
+ * into the shared-memory segment `name`, batching whatever is pending into one fb_ivfadc_search call.  The engine must
+ * not be used by its owner between start and stop.  counters3 (may be NULL) = batches, queries, largest batch. */
+typedef struct fb_sidecar fb_sidecar;
+int fb_sidecar_start(fb_engine* e, const char* name, int max_k, int slots, int max_batch, int linger_us, fb_sidecar** out);
+int fb_sidecar_stop(fb_sidecar* sc, int64_t* counters3);
+
+/* Diagnostics: order-sensitive checksums of the layout of a pinned table (0 fine, 1 pq, 2 ivpq): out[0] over (slot,
+ * row number), out[1] over the packed code units.  Equal layouts give equal sums (device build vs host build). */
+int fb_table_checksum(fb_engine* e, int table, uint64_t* out);
 
 /* Host-only helper (no device needed): the slot order fb_load_fine gives the rows of ONE inverted list
  * under FB_OPT_PLACEMENT_WINDOW = window.  codes = [n][m] int16 of that list in arrival order;

@@ -584,3 +584,23 @@ def reference_update_codebook_assignments(vectors, codebook):
     R.updateCodebook.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     R.updateCodebook(rows, n, sub, entries, m, K, nearest, incs)
     return np.array([[nearest[i][p] for p in range(m)] for i in range(n)], np.int16)
+
+
+def create_statistics(table_ids, table_cells, listed_ids, n_cells):
+    """create_statistics (freddy--0.0.1.sql:150-171) restated: the statistics table of the kNN-join.
+    total = count(*) of `table JOIN vecs ON column = word` (:164) — a listed id counts once per occurrence and per
+    index row carrying it; coarse_freq(c) = (count of those rows with coarse_id = c)::float / total stored as float4
+    (:162, :166: float8 division, then the float4 column); the extra row n_cells holds the total (:168).
+    listed_ids None = every row of the index once."""
+    table_ids = np.asarray(table_ids, np.int64)
+    table_cells = np.asarray(table_cells, np.int64)
+    if listed_ids is None:
+        counts = np.bincount(table_cells, minlength=n_cells).astype(np.float64)
+    else:
+        vals, mult = np.unique(np.asarray(listed_ids, np.int64), return_counts=True)
+        pos = np.searchsorted(vals, table_ids)
+        pos[pos >= len(vals)] = 0
+        weight = np.where(vals[pos] == table_ids, mult[pos], 0) if len(vals) else np.zeros(len(table_ids), np.int64)
+        counts = np.bincount(table_cells, weights=weight.astype(np.float64), minlength=n_cells)
+    total = counts.sum()
+    return np.concatenate([(counts / total).astype(np.float32), np.asarray([total], np.float32)])

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/freddy_b200.h"
+#include "../../include/freddy_sidecar.h"
 #include "exact_kernels.cuh"
 #include "ivfadc_kernels.cuh"
 #include "vector_kernels.cuh"
@@ -27,6 +28,7 @@
 #include "grouping_kernels.cuh"
 #include "subset_kernels.cuh"
 #include "prefilter_kernels.cuh"
+#include "build_kernels.cuh"
 
 using namespace fb;
 
@@ -217,6 +219,7 @@ struct fb_engine {
   size_t pin_q_floats = 0;
   int pipe_shape = 0;
   int pipe_ramp = 0;
+  bool device_build = true;   // FB_OPT_DEVICE_BUILD: CSR, placement and packing of a pinned table run as kernels
   int placement_window = 256; // rows considered per slot by the conflict-aware placement of the fine table (<= 1: off)
   volatile float one = 1.0f;
 
@@ -346,9 +349,127 @@ void place_rows_of_list(const int16_t* codes, int m, int K, const std::vector<in
   }
 }
 
+int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
+                       int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K, int placement_window);
+int build_table_host(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
+                     int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K, int placement_window);
+
 int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
                 int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K,
                 int placement_window = 0) {
+  if (N < 0 || m <= 0) return fail(e, FB_ERR_INVALID, "bad table shape N=%lld m=%d", (long long)N, m);
+  if (N >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
+  if (e->device_build && N > 0 && placement_window <= 1024)
+    return build_table_device(e, tab, ids, list_of_row, n_lists, rows_per_pseudo_list, codes, N, m, K, placement_window);
+  return build_table_host(e, tab, ids, list_of_row, n_lists, rows_per_pseudo_list, codes, N, m, K, placement_window);
+}
+
+// CSR + placement + packing on the device (build_kernels.cuh); same layout as build_table_host
+int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
+                       int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K, int placement_window) {
+  const int U = (m + 3) / 4;
+  const bool pseudo = list_of_row == nullptr;
+  if (pseudo) n_lists = (int)std::max<int64_t>(1, (N + rows_per_pseudo_list - 1) / rows_per_pseudo_list);
+  cudaStream_t st = e->stream;
+  DevBuf<int32_t> d_list, d_len, d_diag, d_arrival, d_order, d_keys, d_iota, d_row_start;
+  DevBuf<int16_t> d_codes;
+  FB_CUDA(e, d_codes.ensure((size_t)N * m));
+  FB_CUDA(e, d_len.ensure((size_t)n_lists));
+  FB_CUDA(e, d_diag.ensure(4));
+  FB_CUDA(e, tab.ids.ensure((size_t)N));
+  FB_CUDA(e, cudaMemcpyAsync(d_codes.p, codes, (size_t)N * m * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  FB_CUDA(e, cudaMemcpyAsync(tab.ids.p, ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (!pseudo) {
+    FB_CUDA(e, d_list.ensure((size_t)N));
+    FB_CUDA(e, cudaMemcpyAsync(d_list.p, list_of_row, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  const int32_t diag0[4] = {0x7fffffff, 0x7fffffff, 0, 0};
+  FB_CUDA(e, cudaMemcpyAsync(d_diag.p, diag0, sizeof diag0, cudaMemcpyHostToDevice, st));
+  FB_CUDA(e, cudaMemsetAsync(d_len.p, 0, (size_t)n_lists * sizeof(int32_t), st));
+  const int grid_rows = (int)std::min<int64_t>((N + 255) / 256, (int64_t)e->num_sms * 16);
+  table_count_kernel<<<grid_rows, 256, 0, st>>>(pseudo ? nullptr : d_list.p, N, n_lists, d_codes.p, m, K, tab.ids.p, d_len.p, d_diag.p);
+  e->launches++;
+  std::vector<int32_t> len(n_lists, 0), blk(n_lists, 0), row_start(n_lists, 0);
+  int32_t diag[4];
+  FB_CUDA(e, cudaMemcpyAsync(diag, d_diag.p, sizeof diag, cudaMemcpyDeviceToHost, st));
+  if (!pseudo) FB_CUDA(e, cudaMemcpyAsync(len.data(), d_len.p, (size_t)n_lists * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FB_CUDA(e, cudaStreamSynchronize(st));
+  if (diag[0] != 0x7fffffff)
+    return fail(e, FB_ERR_INVALID, "row %lld: coarse_id %d out of range [0,%d)", (long long)diag[0], list_of_row[diag[0]], n_lists);
+  if (diag[1] != 0x7fffffff) {
+    const int64_t r = diag[1];
+    for (int p = 0; p < m; p++) {
+      const int code = codes[(size_t)r * m + p];
+      if (code < 0 || code >= K) return fail(e, FB_ERR_INVALID, "row %lld pos %d: code %d out of range [0,%d)", (long long)r, p, code, K);
+    }
+  }
+  if (pseudo)
+    for (int c = 0; c < n_lists; c++) len[c] = (int32_t)std::min<int64_t>(rows_per_pseudo_list, N - (int64_t)c * rows_per_pseudo_list);
+  int64_t n_blocks = 0, rows_before = 0;
+  for (int c = 0; c < n_lists; c++) {
+    blk[c] = (int32_t)n_blocks; row_start[c] = (int32_t)rows_before;
+    n_blocks += (len[c] + 31) / 32; rows_before += len[c];
+  }
+  const bool want8 = K <= 256 && m <= 16;
+  const size_t n_slots = (size_t)std::max<int64_t>(1, n_blocks) * 32;
+  FB_CUDA(e, tab.units.ensure(n_slots * U));
+  FB_CUDA(e, tab.rowno.ensure(n_slots));
+  FB_CUDA(e, tab.list_blk.ensure(n_lists));
+  FB_CUDA(e, tab.list_len.ensure(n_lists));
+  FB_CUDA(e, d_row_start.ensure(n_lists));
+  if (want8) FB_CUDA(e, tab.units8.ensure(n_slots));
+  FB_CUDA(e, cudaMemsetAsync(tab.units.p, 0, n_slots * U * sizeof(uint2), st));
+  FB_CUDA(e, cudaMemsetAsync(tab.rowno.p, 0xff, n_slots * sizeof(int32_t), st));
+  if (want8) FB_CUDA(e, cudaMemsetAsync(tab.units8.p, 0, n_slots * sizeof(uint4), st));
+  FB_CUDA(e, cudaMemcpyAsync(tab.list_blk.p, blk.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FB_CUDA(e, cudaMemcpyAsync(tab.list_len.p, len.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FB_CUDA(e, cudaMemcpyAsync(d_row_start.p, row_start.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int32_t* d_seq = nullptr;          // rows in list order (nullptr: table order is list order)
+  if (!pseudo) {
+    // stable sort of the rows by list = arrival order inside every list
+    int bits = 1;
+    while ((1ll << bits) < n_lists) bits++;
+    FB_CUDA(e, d_iota.ensure((size_t)N));
+    FB_CUDA(e, d_keys.ensure((size_t)N));
+    FB_CUDA(e, d_arrival.ensure((size_t)N));
+    iota_i32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_iota.p, N);
+    size_t tmp_bytes = 0;
+    FB_CUDA(e, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_list.p, d_keys.p, d_iota.p, d_arrival.p, (int)N, 0, bits, st));
+    DevBuf<unsigned char> d_tmp;
+    FB_CUDA(e, d_tmp.ensure(tmp_bytes));
+    FB_CUDA(e, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_list.p, d_keys.p, d_iota.p, d_arrival.p, (int)N, 0, bits, st));
+    e->launches += 2;
+    d_seq = d_arrival.p;
+    const size_t smem = place_rows_smem(m, K, std::max(32, placement_window));
+    if (placement_window > 1 && K <= 65536 && smem <= std::min<size_t>(e->smem_optin, 160 * 1024)) {
+      const int threads = std::min(1024, (std::max(32, std::max(placement_window, m)) + 31) / 32 * 32);
+      FB_CUDA(e, d_order.ensure((size_t)N));
+      FB_CUDA(e, cudaFuncSetAttribute(place_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      place_rows_kernel<<<n_lists, threads, smem, st>>>(d_codes.p, m, K, d_arrival.p, d_row_start.p, tab.list_len.p, placement_window, d_order.p);
+      e->launches++;
+      d_seq = d_order.p;
+    }
+    FB_CUDA(e, cudaStreamSynchronize(st));   // d_tmp goes out of scope
+  }
+  pack_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_codes.p, m, U, d_seq, pseudo ? nullptr : d_list.p, rows_per_pseudo_list,
+                                                               d_row_start.p, tab.list_blk.p, N, tab.units.p, want8 ? tab.units8.p : nullptr,
+                                                               tab.rowno.p);
+  e->launches++;
+  FB_CUDA(e, cudaGetLastError());
+  FB_CUDA(e, cudaStreamSynchronize(st));     // the staging buffers are freed on return
+  tab.has8 = want8;
+  tab.m = m; tab.U = U; tab.n_lists = n_lists; tab.N = N; tab.n_blocks = n_blocks;
+  tab.h_list_len = len;
+  tab.h_list_blk = blk;
+  tab.K = K;
+  tab.max_id = diag[2];
+  tab.loaded = true;
+  return FB_OK;
+}
+
+int build_table_host(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
+                     int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K,
+                     int placement_window) {
   if (N < 0 || m <= 0) return fail(e, FB_ERR_INVALID, "bad table shape N=%lld m=%d", (long long)N, m);
   if (N >= (1ll << 31) - 64) return fail(e, FB_ERR_UNSUPPORTED, "table too large");
   const int U = (m + 3) / 4;
@@ -1164,18 +1285,33 @@ int check_pq_ready(fb_engine* e) {
 int pq_dim(const fb_engine* e) { return e->cb[FB_CB_PQ].m * e->cb[FB_CB_PQ].sub; }
 
 // sorted (id, row) image of a table's id column on the device: the `WHERE id IN (...)` index
+// (id, row) pairs ordered by id, rows ascending inside an id: stable radix sort of an id column that is already on the device
+int device_id_index(fb_engine* e, const int32_t* d_ids, int64_t N, int32_t* d_sorted_ids, int32_t* d_sorted_rows) {
+  DevBuf<int32_t> d_iota;
+  DevBuf<unsigned char> d_tmp;
+  FB_CUDA(e, d_iota.ensure((size_t)N));
+  iota_i32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(d_iota.p, N);
+  size_t tmp_bytes = 0;
+  FB_CUDA(e, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ids, d_sorted_ids, d_iota.p, d_sorted_rows, (int)N, 0, 32, e->stream));
+  FB_CUDA(e, d_tmp.ensure(tmp_bytes));
+  FB_CUDA(e, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_ids, d_sorted_ids, d_iota.p, d_sorted_rows, (int)N, 0, 32, e->stream));
+  e->launches += 2;
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return FB_OK;
+}
+
 int build_id_index(fb_engine* e, CodeTable& tab, const int32_t* ids, int64_t N) {
+  FB_CUDA(e, tab.sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
+  FB_CUDA(e, tab.sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
+  if (N == 0) return FB_OK;
+  if (e->device_build) return device_id_index(e, tab.ids.p, N, tab.sorted_ids.p, tab.sorted_rows.p);   // tab.ids = table order
   std::vector<int32_t> order((size_t)N), sid((size_t)N);
   for (int64_t r = 0; r < N; r++) order[r] = (int32_t)r;
   if (!std::is_sorted(ids, ids + N))
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ids[a] < ids[b]; });
   for (int64_t r = 0; r < N; r++) sid[r] = ids[order[r]];
-  FB_CUDA(e, tab.sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
-  FB_CUDA(e, tab.sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
-  if (N > 0) {
-    FB_CUDA(e, cudaMemcpy(tab.sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-    FB_CUDA(e, cudaMemcpy(tab.sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-  }
+  FB_CUDA(e, cudaMemcpy(tab.sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+  FB_CUDA(e, cudaMemcpy(tab.sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
   return FB_OK;
 }
 
@@ -1603,6 +1739,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_PREFILTER: e->prefilter = value != 0; return FB_OK;
     case FB_OPT_BYTE_CODES: e->byte_codes = value != 0; return FB_OK;
     case FB_OPT_PREFILTER_LOCKSTEP: e->pf_lockstep = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
+    case FB_OPT_DEVICE_BUILD: e->device_build = value != 0; return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");
@@ -1802,17 +1939,18 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   e->vec_id_to_row.clear();
   if (!e->vec_ids_sorted)
     for (int64_t r = 0; r < N; r++) e->vec_id_to_row.emplace(ids[r], (int32_t)r);
-  {
+  FB_CUDA(e, e->vec_sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
+  FB_CUDA(e, e->vec_sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
+  if (N > 0 && e->device_build) {
+    int rc = device_id_index(e, e->vec_ids.p, N, e->vec_sorted_ids.p, e->vec_sorted_rows.p);
+    if (rc) return rc;
+  } else if (N > 0) {
     std::vector<int32_t> order((size_t)N), sid((size_t)N);
     for (int64_t r = 0; r < N; r++) order[r] = (int32_t)r;
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ids[a] < ids[b]; });
     for (int64_t r = 0; r < N; r++) sid[r] = ids[order[r]];
-    FB_CUDA(e, e->vec_sorted_ids.ensure((size_t)std::max<int64_t>(1, N)));
-    FB_CUDA(e, e->vec_sorted_rows.ensure((size_t)std::max<int64_t>(1, N)));
-    if (N > 0) {
-      FB_CUDA(e, cudaMemcpy(e->vec_sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-      FB_CUDA(e, cudaMemcpy(e->vec_sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-    }
+    FB_CUDA(e, cudaMemcpy(e->vec_sorted_ids.p, sid.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    FB_CUDA(e, cudaMemcpy(e->vec_sorted_rows.p, order.data(), (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   e->vec_N = N; e->vec_d = d; e->vec_loaded = true;
   return FB_OK;
@@ -2296,8 +2434,9 @@ int fb_encode_pq(fb_engine* e, int kind, const float* vectors, int64_t n, int16_
 
 int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const int32_t* ids, const int32_t* coarse_ids,
                  const int16_t* codes, int64_t N, int m, const float* stats) {
-  if (!e || !coarse_multi || !stats || Kc < 1 || d < 2 || (N > 0 && (!ids || !coarse_ids || !codes)))
+  if (!e || !coarse_multi || Kc < 1 || d < 2 || (N > 0 && (!ids || !coarse_ids || !codes)))
     return fail(e, FB_ERR_INVALID, "fb_load_ivpq: bad arguments");
+  if (!stats && N == 0) return fail(e, FB_ERR_INVALID, "fb_load_ivpq: statistics of an empty table are undefined (division by zero in create_statistics)");
   if (Kc > 32) return fail(e, FB_ERR_UNSUPPORTED, "Kc=%d: the cell-selection kernel handles up to 32 x 32 cells", Kc);
   if (d % 2) return fail(e, FB_ERR_INVALID, "d must be even for the 2-way multi-index");
   if (!e->cb[FB_CB_IVPQ].loaded) return fail(e, FB_ERR_INVALID, "fb_load_ivpq: load the ivpq codebook first");
@@ -2312,10 +2451,121 @@ int fb_load_ivpq(fb_engine* e, const float* coarse_multi, int Kc, int d, const i
   FB_CUDA(e, e->ivpq_stats.ensure((size_t)cells + 1));
   FB_CUDA(e, e->ivpq_cells.ensure((size_t)std::max<int64_t>(1, N)));
   FB_CUDA(e, cudaMemcpy(e->coarse_multi.p, coarse_multi, (size_t)2 * Kc * (d / 2) * sizeof(float), cudaMemcpyHostToDevice));
-  FB_CUDA(e, cudaMemcpy(e->ivpq_stats.p, stats, ((size_t)cells + 1) * sizeof(float), cudaMemcpyHostToDevice));
   if (N > 0) FB_CUDA(e, cudaMemcpy(e->ivpq_cells.p, coarse_ids, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice));
-  e->ivpq_stats_host.assign(stats, stats + cells + 1);
   e->ivpq_Kc = Kc; e->ivpq_d = d; e->ivpq_loaded = true;
+  if (stats == nullptr) return fb_ivpq_statistics(e, nullptr, 0, nullptr, 1);   // over every row of the table
+  FB_CUDA(e, cudaMemcpy(e->ivpq_stats.p, stats, ((size_t)cells + 1) * sizeof(float), cudaMemcpyHostToDevice));
+  e->ivpq_stats_host.assign(stats, stats + cells + 1);
+  return FB_OK;
+}
+
+// create_statistics (freddy--0.0.1.sql:150-171) on the device: cell frequencies of the table rows whose id is listed
+// (ids = NULL: all rows), coarse_freq = (count::float8 / total)::float4, last entry = total
+int fb_ivpq_statistics(fb_engine* e, const int32_t* ids, int64_t n_ids, float* out_stats, int install) {
+  if (!e || n_ids < 0 || n_ids > 0x7fffffff) return fail(e, FB_ERR_INVALID, "fb_ivpq_statistics: bad arguments");
+  if (!e->ivpq_loaded) return fail(e, FB_ERR_INVALID, "IVPQ index not loaded (fb_load_ivpq)");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  const int cells = e->ivpq_Kc * e->ivpq_Kc;
+  const int64_t N = e->ivpq.N;
+  DevBuf<unsigned long long> d_counts;
+  DevBuf<float> d_stats;
+  DevBuf<int32_t> d_wanted;
+  FB_CUDA(e, d_counts.ensure((size_t)cells + 1));
+  FB_CUDA(e, d_stats.ensure((size_t)cells + 1));
+  FB_CUDA(e, cudaMemsetAsync(d_counts.p, 0, ((size_t)cells + 1) * sizeof(unsigned long long), e->stream));
+  if (ids == nullptr) {
+    if (N > 0) cell_count_all_kernel<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->ivpq_cells.p, N, d_counts.p, cells);
+  } else if (n_ids > 0) {
+    FB_CUDA(e, d_wanted.ensure((size_t)n_ids));
+    FB_CUDA(e, cudaMemcpyAsync(d_wanted.p, ids, (size_t)n_ids * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    cell_count_listed_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, e->stream>>>(e->ivpq.sorted_ids.p, e->ivpq.sorted_rows.p, (int)N, d_wanted.p,
+                                                                                     (int)n_ids, e->ivpq_cells.p, d_counts.p, cells);
+  }
+  cell_freq_kernel<<<(cells + 256) / 256, 256, 0, e->stream>>>(d_counts.p, cells, d_stats.p);
+  e->launches += 2;
+  FB_CUDA(e, cudaGetLastError());
+  std::vector<float> h((size_t)cells + 1);
+  FB_CUDA(e, cudaMemcpyAsync(h.data(), d_stats.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (!(h[cells] > 0.0f)) return fail(e, FB_ERR_INVALID, "fb_ivpq_statistics: no table row matches (create_statistics divides by the match count)");
+  if (out_stats) memcpy(out_stats, h.data(), h.size() * sizeof(float));
+  if (install) {
+    FB_CUDA(e, e->ivpq_stats.ensure((size_t)cells + 1));
+    FB_CUDA(e, cudaMemcpy(e->ivpq_stats.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    e->ivpq_stats_host = h;
+    e->graph_epoch++;
+  }
+  return FB_OK;
+}
+
+// ---- sidecar: one engine answering the single-query calls of many backends (include/freddy_sidecar.h) ----
+struct fb_sidecar {
+  fb_engine* e = nullptr;
+  fbsc_server* srv = nullptr;
+  std::thread worker;
+  void* pinned[3] = {nullptr, nullptr, nullptr};
+  int run_rc = 0;
+};
+
+static int sidecar_batch(void* ctx, const float* queries, int nq, int k, int w, int32_t* out_ids, float* out_dists) {
+  return fb_ivfadc_search((fb_engine*)ctx, queries, nq, k, w, out_ids, out_dists);
+}
+
+int fb_sidecar_start(fb_engine* e, const char* name, int max_k, int slots, int max_batch, int linger_us, fb_sidecar** out) {
+  if (!e || !name || !out || max_k < 1 || slots < 1 || max_batch < 1) return fail(e, FB_ERR_INVALID, "fb_sidecar_start: bad arguments");
+  if (!e->fine.loaded) return fail(e, FB_ERR_INVALID, "fb_sidecar_start: IVFADC index not loaded");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  fb_sidecar* sc = new (std::nothrow) fb_sidecar;
+  if (!sc) return fail(e, FB_ERR_INVALID, "out of memory");
+  sc->e = e;
+  int rc = fbsc_server_create(name, e->d, max_k, slots, &sc->srv);
+  if (rc) { delete sc; return fail(e, FB_ERR_INVALID, "fbsc_server_create(%s) failed: %d", name, rc); }
+  float* bq; int32_t* bi; float* bd;
+  max_batch = std::min(max_batch, slots);
+  if ((rc = fbsc_server_buffers(sc->srv, max_batch, &bq, &bi, &bd))) { fbsc_server_destroy(sc->srv); delete sc; return fail(e, FB_ERR_INVALID, "sidecar buffers: %d", rc); }
+  // page-locked batch buffers: the engine's small-batch path copies from / to them without a staging pass
+  const size_t al = 4096;
+  const size_t sz[3] = {((size_t)max_batch * e->d * 4 + al - 1) / al * al, ((size_t)max_batch * max_k * 4 + al - 1) / al * al,
+                        ((size_t)max_batch * max_k * 4 + al - 1) / al * al};
+  void* ptr[3] = {bq, bi, bd};
+  for (int i = 0; i < 3; i++)
+    if (cudaHostRegister(ptr[i], sz[i], cudaHostRegisterDefault) == cudaSuccess) sc->pinned[i] = ptr[i]; else cudaGetLastError();
+  sc->worker = std::thread([sc, max_batch, linger_us]() { sc->run_rc = fbsc_server_run(sc->srv, sidecar_batch, sc->e, max_batch, linger_us); });
+  *out = sc;
+  return FB_OK;
+}
+
+int fb_sidecar_stop(fb_sidecar* sc, int64_t* counters3) {
+  if (!sc) return FB_ERR_INVALID;
+  fbsc_server_stop(sc->srv);
+  if (sc->worker.joinable()) sc->worker.join();
+  if (counters3) fbsc_server_counters(sc->srv, counters3 + 0, counters3 + 1, counters3 + 2);
+  cudaSetDevice(sc->e->device);
+  for (int i = 0; i < 3; i++)
+    if (sc->pinned[i]) cudaHostUnregister(sc->pinned[i]);
+  fbsc_server_destroy(sc->srv);
+  const int rc = sc->run_rc;
+  delete sc;
+  return rc;
+}
+
+// order-sensitive checksums of a pinned table's layout: out[0] over (slot, row), out[1] over the packed codes
+int fb_table_checksum(fb_engine* e, int table, uint64_t* out) {
+  if (!e || !out || table < 0 || table > 2) return fail(e, FB_ERR_INVALID, "fb_table_checksum: bad arguments");
+  CodeTable& tab = table == 0 ? e->fine : table == 1 ? e->pq : e->ivpq;
+  if (!tab.loaded) return fail(e, FB_ERR_INVALID, "fb_table_checksum: table not loaded");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  DevBuf<unsigned long long> d_out;
+  FB_CUDA(e, d_out.ensure(2));
+  FB_CUDA(e, cudaMemsetAsync(d_out.p, 0, 2 * sizeof(unsigned long long), e->stream));
+  const int64_t n_slots = tab.n_blocks * 32;
+  if (n_slots > 0)
+    table_checksum_kernel<<<(unsigned)std::min<int64_t>((n_slots + 255) / 256, 4096), 256, 0, e->stream>>>(
+        tab.rowno.p, tab.units.p, tab.has8 ? tab.units8.p : nullptr, n_slots, tab.U, d_out.p);
+  unsigned long long h[2];
+  FB_CUDA(e, cudaMemcpyAsync(h, d_out.p, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  out[0] = h[0]; out[1] = h[1];
   return FB_OK;
 }
 

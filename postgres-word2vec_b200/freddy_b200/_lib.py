@@ -17,7 +17,7 @@ FB_OPT_LUT_TILE = 6
 FB_OPT_LUT_CTAS_PER_SM, FB_OPT_OVERLAP = 7, 8
 FB_OPT_PIPELINE, FB_OPT_PIPE_CHUNK, FB_OPT_PIPE_DEBUG, FB_OPT_PLACEMENT_WINDOW = 9, 10, 11, 12
 FB_OPT_PIPE_SHAPE, FB_OPT_PIPE_RAMP, FB_OPT_CUDA_GRAPHS, FB_OPT_ZERO_COPY_UPLOAD = 13, 14, 15, 16
-FB_OPT_PREFILTER, FB_OPT_BYTE_CODES, FB_OPT_PREFILTER_LOCKSTEP = 17, 18, 19
+FB_OPT_PREFILTER, FB_OPT_BYTE_CODES, FB_OPT_PREFILTER_LOCKSTEP, FB_OPT_DEVICE_BUILD = 17, 18, 19, 20
 
 
 class Counters(C.Structure):
@@ -52,6 +52,10 @@ SIGNATURES = {
     "fb_load_ivpq": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "fb_ivpq_search_in": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_int, _P, _P]),
+    "fb_ivpq_statistics": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int]),
+    "fb_table_checksum": (C.c_int, [_P, C.c_int, _P]),
+    "fb_sidecar_start": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fb_sidecar_stop": (C.c_int, [_P, _P]),
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "fb_encode_ivfadc": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "fb_encode_pq": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),

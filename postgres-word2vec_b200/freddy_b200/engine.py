@@ -15,6 +15,10 @@ class FreddyError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"freddy_b200 error {code}: {msg}")
         self.code = code
+        self.msg = msg
+
+    def __reduce__(self):                       # crosses multiprocessing pipes
+        return (FreddyError, (self.code, self.msg))
 
 
 def _ptr(a):
@@ -145,10 +149,45 @@ class Engine:
         cm = _f32(ivpq["coarse_multi"])
         ids, cids = _i32(ivpq["ids"]), _i32(ivpq["ivpq_coarse_ids"])
         codes = np.ascontiguousarray(ivpq["ivpq_codes"], dtype=np.int16)
-        st = _f32(ivpq["stats"])
+        st = _f32(ivpq["stats"]) if ivpq.get("stats") is not None else None     # None: create_statistics over all rows, on the device
         self.d = int(ivpq["d"])
         self._check(self._lib.fb_load_ivpq(self._h, _ptr(cm), int(ivpq["Kc"]), self.d, _ptr(ids), _ptr(cids),
-                                           _ptr(codes), codes.shape[0], codes.shape[1], _ptr(st)))
+                                           _ptr(codes), codes.shape[0], codes.shape[1], _ptr(st) if st is not None else None))
+        self._ivpq_cells = int(ivpq["Kc"]) ** 2
+
+    def ivpq_statistics(self, ids=None, install=False):
+        """create_statistics (freddy--0.0.1.sql:150-171) over the pinned IVPQ table; ids = the ids of the user's column
+        (repeats count), None = every row.  Returns float32[Kc*Kc + 1]."""
+        out = np.empty(self._ivpq_cells + 1, np.float32)
+        if ids is None:
+            self._check(self._lib.fb_ivpq_statistics(self._h, None, 0, _ptr(out), 1 if install else 0))
+        else:
+            t = _i32(ids)
+            self._check(self._lib.fb_ivpq_statistics(self._h, _ptr(t), t.shape[0], _ptr(out), 1 if install else 0))
+        return out
+
+    # ---- sidecar (include/freddy_sidecar.h) ------------------------------
+    def sidecar_start(self, name, max_k=32, slots=256, max_batch=256, linger_us=0):
+        """serve the single-query requests backends post into the shared-memory segment `name` ("/..."); the engine
+        must not be used until sidecar_stop()"""
+        h = C.c_void_p()
+        self._check(self._lib.fb_sidecar_start(self._h, name.encode(), max_k, slots, max_batch, linger_us, C.byref(h)))
+        self._sidecar = h
+
+    def sidecar_stop(self):
+        """-> dict(batches, queries, largest_batch)"""
+        c = (C.c_int64 * 3)()
+        rc = self._lib.fb_sidecar_stop(self._sidecar, c)
+        self._sidecar = None
+        if rc != 0:
+            raise FreddyError(rc, "sidecar loop failed")
+        return {"batches": int(c[0]), "queries": int(c[1]), "largest_batch": int(c[2])}
+
+    def table_checksum(self, table):
+        """(layout checksum, code checksum) of a pinned table: 0 fine, 1 pq, 2 ivpq"""
+        out = np.zeros(2, np.uint64)
+        self._check(self._lib.fb_table_checksum(self._h, table, _ptr(out)))
+        return int(out[0]), int(out[1])
 
     def ivpq_search_in(self, queries, k, targets, alpha, pvf, method, use_target_lists, confidence,
                        double_threshold=10_000_000):

@@ -228,3 +228,23 @@ def test_oracle_against_committed_extended_golden():
     _, codes, rc = oracle.encode(g["encode_rows"], g["pq_codebook"])
     assert rc == 0
     np.testing.assert_array_equal(codes, g["encode_pq_codes"])
+
+
+def test_create_statistics_restatement(oracle_mod):
+    """create_statistics is plpgsql (freddy--0.0.1.sql:150-171): no compiled reference to run, so the restatement is
+    pinned to a hand-worked case of the SQL and to the rule the index builder already used (float8 division, float4 column)"""
+    ids = np.arange(1, 11)
+    cells = np.array([0, 1, 1, 2, 0, 3, 3, 3, 1, 0])
+    st = oracle_mod.create_statistics(ids, cells, None, 4)
+    np.testing.assert_array_equal(st, np.asarray([0.3, 0.3, 0.1, 0.3, 10.0], np.float32))
+    # user column holds word 1 twice, word 2 once, word 10 once and two words the index does not know: JOIN has 4 rows
+    st = oracle_mod.create_statistics(ids, cells, [1, 1, 2, 99, -4, 10], 4)
+    np.testing.assert_array_equal(st, np.asarray([0.75, 0.25, 0.0, 0.0, 4.0], np.float32))
+    # an index with a repeated id: both of its rows join
+    st = oracle_mod.create_statistics([5, 5, 6], [2, 0, 1], [5], 3)
+    np.testing.assert_array_equal(st, np.asarray([0.5, 0.0, 0.5, 2.0], np.float32))
+    rng = np.random.default_rng(1)
+    cells = rng.integers(0, 49, 5000)
+    st = oracle_mod.create_statistics(np.arange(5000), cells, None, 49)
+    exp = (np.bincount(cells, minlength=49).astype(np.float64) / 5000.0).astype(np.float32)
+    np.testing.assert_array_equal(st[:49].view(np.uint32), exp.view(np.uint32))
