@@ -286,6 +286,7 @@ int fb_ivpq_statistics(fb_engine* e, const int32_t* ids, int64_t n_ids, float* o
  * not be used by its owner between start and stop.  counters3 (may be NULL) = batches, queries, largest batch. */
 typedef struct fb_sidecar fb_sidecar;
 int fb_sidecar_start(fb_engine* e, const char* name, int max_k, int slots, int max_batch, int linger_us, fb_sidecar** out);
+int fb_sidecar_running(fb_sidecar* sc);     /* 0 once a client asked the loop to stop (fbsc_client_request_stop) */
 int fb_sidecar_stop(fb_sidecar* sc, int64_t* counters3);
 
 /* Diagnostics: order-sensitive checksums of the layout of a pinned table (0 fine, 1 pq, 2 ivpq): out[0] over (slot,

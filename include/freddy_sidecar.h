@@ -48,6 +48,7 @@ int fbsc_client_dim(const fbsc_client* c);
 /* Blocks until the sidecar answered; FBSC_ERR_GONE if the sidecar died, FBSC_ERR_BUSY if no slot came free within
  * timeout_ms (<= 0: wait for ever), else the engine's return code for the batch. */
 int fbsc_client_search(fbsc_client* c, const float* query, int k, int w, int32_t* out_ids, float* out_dists, int timeout_ms);
+int fbsc_client_request_stop(fbsc_client* c);               /* asks the sidecar to leave fbsc_server_run */
 void fbsc_client_close(fbsc_client* c);
 
 #ifdef __cplusplus

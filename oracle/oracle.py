@@ -367,6 +367,13 @@ class ReferenceSession:
     def repin(self):
         return self.R.ref_freddy_repin()
 
+    def sidecar_serve(self, d, max_k, seconds):
+        """shim only, blocking: freddy_sidecar_serve(dims, max_k, seconds) -> queries answered"""
+        return self.R.ref_freddy_sidecar_serve(int(d), int(max_k), int(seconds))
+
+    def sidecar_stop(self):
+        return self.R.ref_freddy_sidecar_stop()
+
     def ivfadc_search(self, queries, k):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.d)
         ids = np.empty((len(q), k), np.int32)

@@ -752,6 +752,8 @@ extern Datum ivfadc_search_pv(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum analogy_3cosadd_batch(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum cosine_similarity_batch(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum freddy_repin(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum freddy_sidecar_serve(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum freddy_sidecar_stop(PG_FUNCTION_ARGS) __attribute__((weak));
 
 static int collect_single_f32(int n, int k, const char* text, int32* ids, float* vals) {
   for (int i = 0; i < n && i < k; i++) {
@@ -822,6 +824,20 @@ int ref_cosine_similarity_batch(const float* a, const float* b, int n, int d, in
   }
   fb_emul_error_jmp = NULL;
   return rows;
+}
+/* the shim's sidecar entry points (blocking: call the first from a thread of its own) */
+int ref_freddy_sidecar_serve(int d, int max_k, int seconds) {
+  if (!freddy_sidecar_serve) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = Int32GetDatum(d);
+  fc.args[1] = Int32GetDatum(max_k);
+  fc.args[2] = Int32GetDatum(seconds);
+  return DatumGetInt32(call_plain(freddy_sidecar_serve, &fc));
+}
+int ref_freddy_sidecar_stop(void) {
+  if (!freddy_sidecar_stop) return -3;
+  FunctionCallInfoData fc = {0};
+  return DatumGetInt32(call_plain(freddy_sidecar_stop, &fc));
 }
 int ref_freddy_repin(void) {
   if (!freddy_repin) return -3;

@@ -364,6 +364,14 @@ int build_table(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t*
   return build_table_host(e, tab, ids, list_of_row, n_lists, rows_per_pseudo_list, codes, N, m, K, placement_window);
 }
 
+// FB_TRACE_BUILD=1: phase times of the device builder on stderr (diagnostics)
+struct BuildTrace {
+  bool on; cudaStream_t st; double t0; const char* what;
+  static double now() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+  BuildTrace(cudaStream_t s, const char* w) : on(getenv("FB_TRACE_BUILD") != nullptr), st(s), t0(0), what(w) { if (on) { cudaStreamSynchronize(st); t0 = now(); } }
+  void lap(const char* phase) { if (on) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[fb build] %s: %s %.2f ms\n", what, phase, (t - t0) * 1e3); t0 = t; } }
+};
+
 // CSR + placement + packing on the device (build_kernels.cuh); same layout as build_table_host
 int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const int32_t* list_of_row,
                        int n_lists, int rows_per_pseudo_list, const int16_t* codes, int64_t N, int m, int K, int placement_window) {
@@ -371,6 +379,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
   const bool pseudo = list_of_row == nullptr;
   if (pseudo) n_lists = (int)std::max<int64_t>(1, (N + rows_per_pseudo_list - 1) / rows_per_pseudo_list);
   cudaStream_t st = e->stream;
+  BuildTrace tr(st, "table");
   DevBuf<int32_t> d_list, d_len, d_diag, d_arrival, d_order, d_keys, d_iota, d_row_start;
   DevBuf<int16_t> d_codes;
   FB_CUDA(e, d_codes.ensure((size_t)N * m));
@@ -383,6 +392,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
     FB_CUDA(e, d_list.ensure((size_t)N));
     FB_CUDA(e, cudaMemcpyAsync(d_list.p, list_of_row, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   }
+  tr.lap("alloc + H2D of the raw columns");
   const int32_t diag0[4] = {0x7fffffff, 0x7fffffff, 0, 0};
   FB_CUDA(e, cudaMemcpyAsync(d_diag.p, diag0, sizeof diag0, cudaMemcpyHostToDevice, st));
   FB_CUDA(e, cudaMemsetAsync(d_len.p, 0, (size_t)n_lists * sizeof(int32_t), st));
@@ -394,6 +404,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
   FB_CUDA(e, cudaMemcpyAsync(diag, d_diag.p, sizeof diag, cudaMemcpyDeviceToHost, st));
   if (!pseudo) FB_CUDA(e, cudaMemcpyAsync(len.data(), d_len.p, (size_t)n_lists * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FB_CUDA(e, cudaStreamSynchronize(st));
+  tr.lap("count + validate");
   if (diag[0] != 0x7fffffff)
     return fail(e, FB_ERR_INVALID, "row %lld: coarse_id %d out of range [0,%d)", (long long)diag[0], list_of_row[diag[0]], n_lists);
   if (diag[1] != 0x7fffffff) {
@@ -424,6 +435,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
   FB_CUDA(e, cudaMemcpyAsync(tab.list_blk.p, blk.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   FB_CUDA(e, cudaMemcpyAsync(tab.list_len.p, len.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   FB_CUDA(e, cudaMemcpyAsync(d_row_start.p, row_start.data(), (size_t)n_lists * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  tr.lap("table alloc + clear");
   const int32_t* d_seq = nullptr;          // rows in list order (nullptr: table order is list order)
   if (!pseudo) {
     // stable sort of the rows by list = arrival order inside every list
@@ -440,6 +452,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
     FB_CUDA(e, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_list.p, d_keys.p, d_iota.p, d_arrival.p, (int)N, 0, bits, st));
     e->launches += 2;
     d_seq = d_arrival.p;
+    tr.lap("stable sort by list");
     const size_t smem = place_rows_smem(m, K, std::max(32, placement_window));
     if (placement_window > 1 && K <= 65536 && smem <= std::min<size_t>(e->smem_optin, 160 * 1024)) {
       const int threads = std::min(1024, (std::max(32, std::max(placement_window, m)) + 31) / 32 * 32);
@@ -450,6 +463,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
       d_seq = d_order.p;
     }
     FB_CUDA(e, cudaStreamSynchronize(st));   // d_tmp goes out of scope
+    tr.lap("placement");
   }
   pack_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_codes.p, m, U, d_seq, pseudo ? nullptr : d_list.p, rows_per_pseudo_list,
                                                                d_row_start.p, tab.list_blk.p, N, tab.units.p, want8 ? tab.units8.p : nullptr,
@@ -457,6 +471,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   FB_CUDA(e, cudaStreamSynchronize(st));     // the staging buffers are freed on return
+  tr.lap("pack");
   tab.has8 = want8;
   tab.m = m; tab.U = U; tab.n_lists = n_lists; tab.N = N; tab.n_blocks = n_blocks;
   tab.h_list_len = len;
@@ -2505,6 +2520,7 @@ struct fb_sidecar {
   std::thread worker;
   void* pinned[3] = {nullptr, nullptr, nullptr};
   int run_rc = 0;
+  std::atomic<int> running{1};
 };
 
 static int sidecar_batch(void* ctx, const float* queries, int nq, int k, int w, int32_t* out_ids, float* out_dists) {
@@ -2530,10 +2546,12 @@ int fb_sidecar_start(fb_engine* e, const char* name, int max_k, int slots, int m
   void* ptr[3] = {bq, bi, bd};
   for (int i = 0; i < 3; i++)
     if (cudaHostRegister(ptr[i], sz[i], cudaHostRegisterDefault) == cudaSuccess) sc->pinned[i] = ptr[i]; else cudaGetLastError();
-  sc->worker = std::thread([sc, max_batch, linger_us]() { sc->run_rc = fbsc_server_run(sc->srv, sidecar_batch, sc->e, max_batch, linger_us); });
+  sc->worker = std::thread([sc, max_batch, linger_us]() { sc->run_rc = fbsc_server_run(sc->srv, sidecar_batch, sc->e, max_batch, linger_us); sc->running = 0; });
   *out = sc;
   return FB_OK;
 }
+
+int fb_sidecar_running(fb_sidecar* sc) { return sc ? sc->running.load() : 0; }
 
 int fb_sidecar_stop(fb_sidecar* sc, int64_t* counters3) {
   if (!sc) return FB_ERR_INVALID;

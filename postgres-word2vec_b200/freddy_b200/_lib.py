@@ -55,6 +55,7 @@ SIGNATURES = {
     "fb_ivpq_statistics": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int]),
     "fb_table_checksum": (C.c_int, [_P, C.c_int, _P]),
     "fb_sidecar_start": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fb_sidecar_running": (C.c_int, [_P]),
     "fb_sidecar_stop": (C.c_int, [_P, _P]),
     "fb_load_vectors": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "fb_encode_ivfadc": (C.c_int, [_P, _P, C.c_int64, _P, _P]),

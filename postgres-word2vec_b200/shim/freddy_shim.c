@@ -28,6 +28,7 @@
 #include "output_utils.h"
 
 #include "freddy_b200.h"
+#include "freddy_sidecar.h"
 
 static fb_engine* engine = NULL;
 static int pinned_d = 0, vecs_d = 0;
@@ -291,6 +292,69 @@ static int* int_array(ArrayType* arr, int* n) {
   return out;
 }
 
+/* ---- sidecar: one backend owns the engine, the others post their single queries to it (freddy_sidecar.h) ----------
+ * FREDDY_SIDECAR (environment here; a GUC in a packaged extension) names the shared-memory segment.  A backend whose
+ * sidecar is absent, gone or too busy answers the query with its own engine, so the setting is safe to leave on. */
+static fbsc_client* sidecar = NULL;
+static char sidecar_name[128] = "";
+
+static bool sidecar_search(const float* q, int d, int k, int w, int32* ids, float* dist) {
+  const char* name = getenv("FREDDY_SIDECAR");
+  int rc;
+  if (name == NULL || name[0] == 0 || strlen(name) >= sizeof sidecar_name) return false;
+  if (sidecar != NULL && strcmp(name, sidecar_name) != 0) { fbsc_client_close(sidecar); sidecar = NULL; }
+  if (sidecar == NULL) {
+    if (fbsc_client_open(name, &sidecar) != FBSC_OK) { sidecar = NULL; return false; }
+    strcpy(sidecar_name, name);
+  }
+  if (fbsc_client_dim(sidecar) != d) elog(ERROR, "freddy_b200: query has %d dimensions, the sidecar's index %d", d, fbsc_client_dim(sidecar));
+  rc = fbsc_client_search(sidecar, q, k, w, ids, dist, 2000);
+  if (rc == FBSC_OK) return true;
+  if (rc == FBSC_ERR_GONE || rc == FBSC_ERR_BUSY) { fbsc_client_close(sidecar); sidecar = NULL; return false; }
+  if (rc == FBSC_ERR_ARG) return false;                      /* k beyond what the sidecar's slots hold */
+  elog(ERROR, "freddy_b200 sidecar: the engine refused the batch (%d)", rc);
+  return false;
+}
+
+/* freddy_sidecar_serve(dims int, max_k int, seconds int) -> queries answered.  Run it in a connection (or background
+ * worker) of its own: pins the IVFADC index like ivfadc_search does, then serves the segment FREDDY_SIDECAR until the
+ * time is up or another backend calls freddy_sidecar_stop().
+ * CREATE FUNCTION freddy_sidecar_serve(integer, integer, integer) RETURNS integer AS '$libdir/freddy' LANGUAGE C; */
+PG_FUNCTION_INFO_V1(freddy_sidecar_serve);
+Datum freddy_sidecar_serve(PG_FUNCTION_ARGS) {
+  const int d = PG_GETARG_INT32(0), max_k = PG_GETARG_INT32(1), seconds = PG_GETARG_INT32(2);
+  const char* name = getenv("FREDDY_SIDECAR");
+  fb_sidecar* sc = NULL;
+  int64_t counters[3] = {0, 0, 0};
+  struct timespec nap = {0, 5000000};
+  time_t until;
+  if (name == NULL || name[0] != '/') elog(ERROR, "freddy_sidecar_serve: set FREDDY_SIDECAR to a segment name like /freddy");
+  pin_ivfadc(d);
+  fb_check(fb_sidecar_start(engine, name, max_k, 256, 256, 0, &sc));
+  until = time(NULL) + seconds;
+  while (fb_sidecar_running(sc) && time(NULL) < until) {
+#ifdef CHECK_FOR_INTERRUPTS
+    CHECK_FOR_INTERRUPTS();
+#endif
+    nanosleep(&nap, NULL);
+  }
+  fb_sidecar_stop(sc, counters);
+  PG_RETURN_INT32((int32)counters[1]);
+}
+
+/* freddy_sidecar_stop() -> 1 if a sidecar was told to stop */
+PG_FUNCTION_INFO_V1(freddy_sidecar_stop);
+Datum freddy_sidecar_stop(PG_FUNCTION_ARGS) {
+  const char* name = getenv("FREDDY_SIDECAR");
+  fbsc_client* c = NULL;
+  int ok = 0;
+  if (name != NULL && fbsc_client_open(name, &c) == FBSC_OK) {
+    ok = fbsc_client_request_stop(c) == FBSC_OK;
+    fbsc_client_close(c);
+  }
+  PG_RETURN_INT32(ok);
+}
+
 /* ---- the SRFs --------------------------------------------------------------------------- */
 PG_FUNCTION_INFO_V1(ivfadc_search);
 Datum ivfadc_search(PG_FUNCTION_ARGS) {
@@ -303,8 +367,10 @@ Datum ivfadc_search(PG_FUNCTION_ARGS) {
     float* dist = palloc(sizeof(float) * k);
     getParameter(PARAM_W, &w);                                       /* freddy.c:229 */
     convert_bytea_float4(PG_GETARG_BYTEA_P(0), &q, &n);               /* freddy.c:249 */
-    pin_ivfadc(n);
-    fb_check(fb_ivfadc_search(engine, q, 1, k, w, ids, dist));        /* replaces freddy.c:251-378 */
+    if (!sidecar_search(q, n, k, w, ids, dist)) {                     /* FREDDY_SIDECAR: batched with other backends' calls */
+      pin_ivfadc(n);
+      fb_check(fb_ivfadc_search(engine, q, 1, k, w, ids, dist));      /* replaces freddy.c:251-378 */
+    }
     finish_single(funcctx, ids, dist, k);
     MemoryContextSwitchTo(old);
   }

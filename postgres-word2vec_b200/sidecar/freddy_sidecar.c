@@ -290,6 +290,14 @@ int fbsc_client_search(fbsc_client* c, const float* query, int k, int w, int32_t
   return rc;
 }
 
+int fbsc_client_request_stop(fbsc_client* c) {
+  if (!c) return FBSC_ERR_ARG;
+  atomic_store(&c->h->stop, 1);
+  atomic_fetch_add(&c->h->doorbell, 1);
+  futex(&c->h->doorbell, FUTEX_WAKE, 1, NULL);
+  return FBSC_OK;
+}
+
 void fbsc_client_close(fbsc_client* c) {
   if (!c) return;
   munmap(c->h, c->h->total_bytes);
