@@ -117,12 +117,19 @@ class ClockSampler:
                                           "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(lambda: self.proc and self.proc.poll() is None and self.proc.kill())
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """samples before this moment are dropped (nvidia-smi is started early: with 8 instances on an 8-GPU box its
+        start-up alone outlasts a short timed region)"""
+        self.t_from = time.time()
 
     def stop(self):
         if not self.proc:
@@ -132,11 +139,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        t_from = getattr(self, "t_from", 0.0)
+        rows = [r for (t, r) in self.rows if t >= t_from]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -321,6 +330,8 @@ def main():
 
     from freddy_b200 import Engine, _lib
 
+    clocks = ClockSampler(local_rank)   # started now, windowed by clocks.mark() below
+    clocks.start()
     # index: built once on rank 0, replicated to every rank (broadcast over NCCL)
     names = ["coarse", "residual_codebook", "coarse_ids", "codes"]
     if rank == 0:
@@ -428,8 +439,7 @@ def main():
             ms = float(t.item())
         return ms, ms_local
 
-    clocks = ClockSampler(local_rank)   # samples through warm-up + timed region (same load in both)
-    clocks.start()
+    clocks.mark()                       # samples through warm-up + timed region (same load in both)
     for _ in range(max(3, a.warmup)):
         step_dev()
     eng.synchronize()
@@ -521,7 +531,8 @@ def main():
     mine = {"rank": rank, "gpu": local_rank, "ms_per_step_device": ms_rank / a.steps, "ms_per_step_e2e": ms_e2e_rank / a.steps,
             "rows_scanned_per_query": c["rows_scanned"] / max(1, c["queries"]), "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons"),
             "stage_ms_per_step": {s_: c["ms_" + s_] / a.steps for s_ in ("coarse", "pipe", "lut", "scan", "exact")},
-            "exact_path_queries_per_step": exact_q / a.steps}
+            "exact_path_queries_per_step": exact_q / a.steps,
+            "exact_path_reasons_per_step": {r: c["exact_" + r] / a.steps for r in ("coarse_tie", "coarse_far", "few_rows", "scan_tie", "forced")}}
     per_rank = [mine]
     if world > 1:
         per_rank = [None] * world

@@ -46,14 +46,52 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / kWarp;
 constexpr int kLutMaxJobs = 16;
 
-// The w nearest lists of one query from its C coarse distances (one warp): top-(w+1) by (distance, centroid
-// id); lanes 0..w-1 hold the selection, lane w the runner-up; flags the rare cases for the general kernel.
+// Rare path of coarse_select_warp, kept out of line so that it costs the selection loop no registers: replays the
+// reference's loop over S (see below); true = S may be incomplete, the general kernel has to decide.
+__device__ __noinline__ bool coarse_tie_replay(u64& mine, u64 kw1, int w, int lane) {
+  const bool in_s = mine != kKeyInf && key_dbits(mine) <= key_dbits(kw1);
+  const unsigned smask = __ballot_sync(0xffffffffu, in_s);
+  if (((smask >> 31) & 1u) || key_dist(kw1) >= 100.0f) return true;    // (or the sentinel quirk applies)
+  const uint32_t my_id = key_t(mine);
+  int rank = 0;                                             // arrival position of my entry inside S
+  for (int j = 0; j < 32; j++) {
+    const uint32_t oid = __shfl_sync(0xffffffffu, my_id, j);
+    rank += (int)(((smask >> j) & 1u) && oid < my_id);
+  }
+  const int n_s = __popc(smask);
+  float td = 100.0f;                                        // cqSelection[lane] (freddy.c:266-269)
+  int tid = -1;
+  for (int r = 0; r < n_s; r++) {
+    const int src = __ffs(__ballot_sync(0xffffffffu, in_s && rank == r)) - 1;
+    const float dd = key_dist(shfl_u64(mine, src));
+    const int id = (int)__shfl_sync(0xffffffffu, my_id, src);
+    const float worst = __shfl_sync(0xffffffffu, td, w - 1);
+    if (dd < worst) {                                       // gate of freddy.c:278 (minDist = the w-th entry)
+      const int slot = __popc(__ballot_sync(0xffffffffu, lane < w && td < dd));   // updateTopK, index_utils.c:19-33
+      const float ud = __shfl_up_sync(0xffffffffu, td, 1);
+      const int ui = __shfl_up_sync(0xffffffffu, tid, 1);
+      if (lane > slot) { td = ud; tid = ui; }
+      else if (lane == slot) { td = dd; tid = id; }
+    }
+  }
+  if (lane < w) mine = make_key(td, (uint32_t)tid);
+  return false;
+}
+
+// The w nearest lists of one query from its C coarse distances (one warp): an ascending list of (distance, centroid id)
+// keys holding the w+1 smallest and everything tied with them; lanes 0..w-1 hold the selection, lane w the runner-up;
+// flags the rare cases for the general kernel.
+// A distance tie across the w-th place makes the kept SET depend on arrival order (updateTopK inserts before equal
+// entries, so the earliest of the tied entries sits last and is evicted first, freddy.c:272-283): the literal loop is
+// then replayed over S = {d <= v}, v = the w-th smallest distance, in centroid order — entries beyond v can neither
+// stay nor rearrange the entries up to v — with lane i holding entry i of cqSelection.  S is complete whenever the
+// 32nd key lies beyond v; only otherwise (more than 31 - w tied centroids) the query goes to the general kernel.
 __device__ __forceinline__ void coarse_select_warp(const float* __restrict__ dist_row, int C, int Cs,
                                                    const int32_t* __restrict__ list_len, int w, int k, int q,
                                                    int32_t* __restrict__ probes, uint32_t* __restrict__ qflags,
                                                    int force_exact, int lane) {
   u64 mine = kKeyInf;
-  u64 thr = kKeyInf;
+  uint32_t thr = 0xffffffffu;                        // distance bits of the (w+1)-th smallest key so far
   for (int c0 = 0; c0 < Cs; c0 += 128) {            // four independent loads in flight per lane
     float dv[4];
 #pragma unroll
@@ -65,21 +103,25 @@ __device__ __forceinline__ void coarse_select_warp(const float* __restrict__ dis
     for (int u = 0; u < 4; u++) {
       const int c = c0 + 32 * u + lane;
       u64 key = (c < C) ? make_key(dv[u], (uint32_t)c) : kKeyInf;
-      unsigned mask = __ballot_sync(0xffffffffu, key < thr);
+      // `<=` on the distance alone: every centroid tied with the runner-up stays in the list (the replay below needs
+      // all entries up to the w-th distance; ties are rare, so this admits what `key < (w+1)-th key` would)
+      unsigned mask = __ballot_sync(0xffffffffu, c < C && key_dbits(key) <= thr);
       while (mask) {
         int src = __ffs(mask) - 1;
         u64 nk = shfl_u64(key, src);
         warp_list_insert(mine, nk, lane);
-        thr = shfl_u64(mine, w);
+        thr = key_dbits(shfl_u64(mine, w));
         mask &= mask - 1;
-        mask &= __ballot_sync(0xffffffffu, key < thr);
+        mask &= __ballot_sync(0xffffffffu, c < C && key_dbits(key) <= thr);
       }
     }
   }
   uint32_t flags = force_exact ? (kFlagExact | kWhyForced) : 0u;
   u64 kw = shfl_u64(mine, w), kw1 = shfl_u64(mine, w - 1);
   // a tie across the w-th place makes the kept set order dependent
-  if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) flags |= kFlagExact | kWhyCoarseTie;
+  if (kw != kKeyInf && key_dbits(kw) == key_dbits(kw1)) {
+    if (coarse_tie_replay(mine, kw1, w, lane)) flags |= kFlagExact | kWhyCoarseTie;   // S may be incomplete
+  }
   // sentinel quirk of the reference: a selected distance >= 100 is undefined
   if (key_dist(kw1) >= 100.0f) flags |= kFlagExact | kWhyCoarseFar;
   int len = 0;

@@ -88,6 +88,35 @@ def test_ties_everywhere(eng, oracle_mod):
     assert general > 0
 
 
+def test_coarse_ties_replayed_in_the_selection_warp(eng, oracle_mod):
+    """equal centroids: the reference keeps the LATEST of the tied entries when a nearer centroid with a higher id
+    arrives afterwards (insert-before-equal, freddy.c:272-283) — not the lowest ids.  The coarse kernel replays that
+    in the warp (no general kernel) unless more than 31 - w centroids tie."""
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7)
+    coarse = ix["coarse"].copy()
+    coarse[[0, 1, 2]] = coarse[20]                  # a four-way tie whose members mostly precede the nearer centroids
+    coarse[[5, 30]] = coarse[11]                    # and a three-way one
+    ix = dict(ix, coarse=coarse)
+    q = queries_from(ix, 600, seed=5, noise=0.01)
+    straddled = 0
+    for k, w in ((5, 1), (5, 2), (5, 3), (3, 5), (8, 9)):
+        for qscan_min in (0, 1 << 30):
+            ids, d_, eids, ed, _ = _run_both(eng, oracle_mod, ix, q, k, w, qscan_min=qscan_min)
+            assert_same_topk(ids, d_, eids, ed, f"coarse ties k={k} w={w}")
+            assert eng.counters()["exact_coarse_tie"] == 0
+        dist = ((q[:, None, :] - coarse[None]) ** 2).sum(-1)
+        srt = np.sort(dist, axis=1)
+        straddled += int((srt[:, w - 1] == srt[:, w]).sum())
+    assert straddled > 100, "the fixture must put ties across the w-th place"
+    # 36 equal centroids: more than the warp's 32 keys can settle, the general kernel takes over — same answer
+    coarse = ix["coarse"].copy()
+    coarse[:36] = coarse[37]
+    ix2 = dict(ix, coarse=coarse)
+    ids, d_, eids, ed, _ = _run_both(eng, oracle_mod, ix2, q[:100], 5, 3)
+    assert_same_topk(ids, d_, eids, ed, "coarse ties beyond the warp list")
+    assert eng.counters()["exact_coarse_tie"] > 0
+
+
 def test_reprobe_loop(eng, oracle_mod):
     """lists much shorter than k: the reference re-probes with a blacklist (freddy.c:262)"""
     ix = small_index(N=150, d=24, m=12, K=8, C=64, seed=5, n_clusters=20)
