@@ -1,8 +1,13 @@
 set -x
-timeout 300 python bench.py --secondary none --no-cpu-baseline --batch 262144 --steps 3 --warmup 3 > gpurun_out/bench_8shards.json 2> gpurun_out/bench_8shards.err; tail -c 300 gpurun_out/bench_8shards.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --gpu-rotate 3 > gpurun_out/bench_r2_n8_rot3.json 2> gpurun_out/bench_r2_n8_rot3.err; tail -c 600 gpurun_out/bench_r2_n8_rot3.err
 python - <<'PY'
 import json
-j=json.loads(open('gpurun_out/bench_8shards.json').read().strip().splitlines()[-1])
-print("8 shards on one GPU: value", round(j["value"]), j["config"]["exact_path_queries_per_step"], j["config"]["exact_path_reasons_per_step"], j["config"]["per_rank"][0]["stage_ms_per_step"])
+try:
+    j=json.loads(open('gpurun_out/bench_r2_n8_rot3.json').read().strip().splitlines()[-1])
+    print("N=8 value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "clocks", j.get("clocks"))
+    for r in j["config"]["per_rank"]: print("  rank", r["rank"], "gpu", r["gpu"], round(r["ms_per_step_device"],3), round(r["ms_per_step_e2e"],3), r["sm_mhz"], r["stage_ms_per_step"], r["exact_path_queries_per_step"])
+    for s in j["config"]["secondary"]:
+        print("   ", s.get("name","")[:40], s.get("seconds"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
+except Exception as ex:
+    print("no N=8 result", ex)
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:'ivfadc|coarse_|count_rows|adc_scan|finalize|lut_|prefilter|pf_|subset_|join_|ivpq_|batch_unfilled|analogy|knn_|exact|rerank|cosine|table_|place_rows|pack_rows' --log-file gpurun_out/r2_launch_list.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -c 200 gpurun_out/ncu_bench.log; wc -l gpurun_out/r2_launch_list.csv

@@ -235,3 +235,37 @@ def test_shim_insert_batch_matches_the_reference(shim, oracle_mod):
         hits += int(ix["N"]) + 1 + i in set(ids[0].tolist())
         assert set(ids[0].tolist()) & new_ids or True
     assert hits >= 7, f"only {hits} of 9 inserted vectors find their own new row"
+
+
+def test_shim_ivfadc_search_through_the_sidecar(shim, oracle_mod):
+    """FREDDY_SIDECAR set: ivfadc_search posts its query to the backend that runs freddy_sidecar_serve() instead of
+    using an engine of its own; same rows, same bits; without a sidecar the backend answers itself."""
+    import threading
+    import time
+    ix = small_index()
+    q = queries_from(ix, 30, seed=21, noise=0.02)
+    k, w = 5, 4
+    s = shim()
+    s.load_ivfadc(ix, w)
+    direct = s.ivfadc_search(q, k)
+    name = f"/fbsc_shim_{os.getpid()}"
+    served = []
+    os.environ["FREDDY_SIDECAR"] = name
+    try:
+        t = threading.Thread(target=lambda: served.append(s.sidecar_serve(ix["d"], 16, 60)))
+        t.start()
+        deadline = time.time() + 30
+        while not os.path.exists("/dev/shm" + name) and time.time() < deadline:
+            time.sleep(0.01)
+        assert os.path.exists("/dev/shm" + name), "the sidecar did not come up"
+        via = s.ivfadc_search(q, k)
+        assert s.sidecar_stop() == 1
+        t.join(60)
+        assert not t.is_alive()
+        assert served == [len(q)]                    # every query was answered by the sidecar's engine
+        for a, b in zip(direct, via):
+            _same(a, b) if a.dtype == np.float32 else np.testing.assert_array_equal(a, b)
+        again = s.ivfadc_search(q[:3], k)            # segment gone: the backend's own engine
+        np.testing.assert_array_equal(again[0], direct[0][:3])
+    finally:
+        os.environ.pop("FREDDY_SIDECAR", None)
