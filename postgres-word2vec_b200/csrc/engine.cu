@@ -2524,6 +2524,7 @@ struct fb_sidecar {
 };
 
 static int sidecar_batch(void* ctx, const float* queries, int nq, int k, int w, int32_t* out_ids, float* out_dists) {
+  cudaSetDevice(((fb_engine*)ctx)->device);     // the server loop runs on a thread of its own
   return fb_ivfadc_search((fb_engine*)ctx, queries, nq, k, w, out_ids, out_dists);
 }
 

@@ -1,15 +1,4 @@
 set -x
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/gputests.log 2>&1; tail -5 gpurun_out/gputests.log
-timeout 600 python bench.py > gpurun_out/bench_r2_default.json 2> gpurun_out/bench_r2_default.err; tail -c 400 gpurun_out/bench_r2_default.err
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r2_reference.json 2> gpurun_out/bench_r2_reference.err; tail -c 300 gpurun_out/bench_r2_reference.err; cut -c1-600 gpurun_out/bench_r2_reference.json
-python - <<'PY'
-import json
-try:
-    j=json.loads(open('gpurun_out/bench_r2_default.json').read().strip().splitlines()[-1])
-    print("value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "frac", j["roofline"]["frac"], "cpu", j["cpu_baseline"]["value"], j["clocks"], "launches", j["gpu_launches"])
-    for s in j["config"]["secondary"]:
-        print("   ", s.get("name","")[:60], s.get("seconds"), s.get("queries_per_s"), s.get("roofline",{}).get("frac"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
-except Exception as ex:
-    print("no result", ex)
-PY
+timeout 300 python -m pytest tests/test_sidecar_gpu.py tests/test_shim_gpu.py -m gpu -q --timeout 300 2>&1 | tail -3
+timeout 300 python scripts/bench_concurrent.py --direct 0 --procs 4,16,64 --seconds 3 > gpurun_out/r2_sidecar_callers_l0.json 2> gpurun_out/sidecar.err; grep sidecar gpurun_out/r2_sidecar_callers_l0.json | cut -c1-400 | head -4; tail -c 400 gpurun_out/sidecar.err
+timeout 300 python scripts/bench_concurrent.py --direct 0 --procs 16,64 --seconds 3 --linger-us 40 > gpurun_out/r2_sidecar_callers_l40.json 2> gpurun_out/sidecar40.err; grep sidecar gpurun_out/r2_sidecar_callers_l40.json | cut -c1-400 | head -3; tail -c 400 gpurun_out/sidecar40.err
