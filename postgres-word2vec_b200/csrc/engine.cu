@@ -146,7 +146,8 @@ struct fb_engine {
   DevBuf<u64> j_keys;
   int64_t join_rounds = 0, join_pairs = 0;
   // word-vector table (analogy / exact rerank)
-  DevBuf<float> vecT;
+  DevBuf<float> vecT;                        // dimension-major 32-row blocks: the whole-table fp32 scans
+  DevBuf<float> vecR;                        // row-major [N][d]: everything that gathers rows (post-verification, re-score, re-rank)
   DevBuf<int32_t> vec_ids, vec_sorted_ids, vec_sorted_rows;   // sorted (id, row) pairs: id -> row on the device
   DevBuf<float> sub_vT;                                        // gathered subset (knn_in_exact)
   DevBuf<int32_t> sub_rows, pv_cand;
@@ -1436,7 +1437,7 @@ void fb_destroy(fb_engine* e) {
   e->ivpq.release(); e->jtmp.release(); e->coarse_multi.release(); e->ivpq_stats.release(); e->ivpq_cells.release();
   e->j_cell.release(); e->j_vrow.release(); e->j_id.release(); e->j_active.release(); e->j_ncells.release();
   e->j_filled.release(); e->j_tcounts.release(); e->j_bitmaps.release(); e->j_keys.release();
-  e->vecT.release(); e->vec_ids.release(); e->va.release(); e->vb.release(); e->vo.release(); e->vdo.release();
+  e->vecT.release(); e->vecR.release(); e->vec_ids.release(); e->va.release(); e->vb.release(); e->vo.release(); e->vdo.release();
   e->ana_rows.release(); e->ana_partial.release();
   e->lut.release(); e->exact_lut.release(); e->q_stage.release(); e->dist_stage.release();
   e->probes.release(); e->exact_list.release(); e->id_stage.release(); e->sel_rows.release();
@@ -1911,10 +1912,10 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   const int64_t n_blocks = std::max<int64_t>(1, (N + 31) / 32);
   FB_CUDA(e, e->vecT.ensure((size_t)n_blocks * d * 32));
   FB_CUDA(e, e->vec_ids.ensure((size_t)std::max<int64_t>(1, N)));
-  // stage row-major through a temporary device buffer in slices, transpose on the device
+  // the rows land in the row-major image (what the gathers read); the dimension-major blocks of the whole-table scans
+  // and the bf16 image of the pre-filter are made from it on the device, slice by slice
   const int64_t slice_rows = 32 * 8192;
-  DevBuf<float> stage;
-  FB_CUDA(e, stage.ensure((size_t)std::min<int64_t>(std::max<int64_t>(N, 1), slice_rows) * d));
+  FB_CUDA(e, e->vecR.ensure((size_t)std::max<int64_t>(N, 1) * d));
   // bf16 image for the tensor-core pre-filter of the exact scans (d <= 320): [N_pad][kpa], zero padded
   e->pf_ready = false;
   const int kch = (d + kPfBK - 1) / kPfBK;
@@ -1929,15 +1930,15 @@ int fb_load_vectors(fb_engine* e, const int32_t* ids, const float* vectors, int6
   }
   for (int64_t r0 = 0; r0 < N; r0 += slice_rows) {
     const int64_t n = std::min(slice_rows, N - r0);
-    FB_CUDA(e, cudaMemcpyAsync(stage.p, vectors + (size_t)r0 * d, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    transpose_rows_kernel<<<(unsigned)((n + 31) / 32), 256, 0, e->stream>>>(stage.p, n, d, e->vecT.p + (size_t)(r0 / 32) * d * 32);
+    float* slice = e->vecR.p + (size_t)r0 * d;
+    FB_CUDA(e, cudaMemcpyAsync(slice, vectors + (size_t)r0 * d, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    transpose_rows_kernel<<<(unsigned)((n + 31) / 32), 256, 0, e->stream>>>(slice, n, d, e->vecT.p + (size_t)(r0 / 32) * d * 32);
     if (want_pf)
-      pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(stage.p, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)r0 * e->pf_kpa,
+      pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(slice, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)r0 * e->pf_kpa,
                                                                             e->pf_norm.p);
     FB_CUDA(e, cudaGetLastError());
-    FB_CUDA(e, cudaStreamSynchronize(e->stream));
   }
-  stage.release();
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
   if (want_pf) {
     uint32_t nb = 0;
     FB_CUDA(e, cudaMemcpy(&nb, e->pf_norm.p, sizeof nb, cudaMemcpyDeviceToHost));
@@ -1992,10 +1993,10 @@ int fb_append_vectors(fb_engine* e, const int32_t* ids, const float* vectors, in
   FB_CUDA(e, cudaStreamSynchronize(e->stream));
   FB_CUDA(e, e->vecT.grow((size_t)b1 * d * 32, (size_t)b0 * d * 32));
   if (b1 > b0) FB_CUDA(e, cudaMemset(e->vecT.p + (size_t)b0 * d * 32, 0, (size_t)(b1 - b0) * d * 32 * sizeof(float)));
-  DevBuf<float> stage;
-  FB_CUDA(e, stage.ensure((size_t)n * d));
-  FB_CUDA(e, cudaMemcpy(stage.p, vectors, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice));
-  append_vec_rows_kernel<<<(unsigned)n, 128, 0, e->stream>>>(stage.p, n, d, N0, e->vecT.p);
+  FB_CUDA(e, e->vecR.grow((size_t)N1 * d, (size_t)N0 * d));
+  float* fresh = e->vecR.p + (size_t)N0 * d;                 // the new rows, row-major, behind the old ones
+  FB_CUDA(e, cudaMemcpy(fresh, vectors, (size_t)n * d * sizeof(float), cudaMemcpyHostToDevice));
+  append_vec_rows_kernel<<<(unsigned)n, 128, 0, e->stream>>>(fresh, n, d, N0, e->vecT.p);
   e->launches++;
   FB_CUDA(e, e->vec_ids.grow((size_t)N1, (size_t)N0));
   FB_CUDA(e, cudaMemcpy(e->vec_ids.p + N0, ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -2003,7 +2004,7 @@ int fb_append_vectors(fb_engine* e, const int32_t* ids, const float* vectors, in
     const int64_t pad0 = e->pf_N_pad, pad1 = (N1 + kPfBN - 1) / kPfBN * kPfBN;
     FB_CUDA(e, e->vec_bf16.grow((size_t)pad1 * e->pf_kpa, (size_t)pad0 * e->pf_kpa));
     if (pad1 > pad0) FB_CUDA(e, cudaMemset(e->vec_bf16.p + (size_t)pad0 * e->pf_kpa, 0, (size_t)(pad1 - pad0) * e->pf_kpa * sizeof(__nv_bfloat16)));
-    pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(stage.p, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)N0 * e->pf_kpa, e->pf_norm.p);
+    pf_rows_to_bf16_kernel<<<(unsigned)((n + 7) / 8), 256, 0, e->stream>>>(fresh, n, d, e->pf_kpa, e->vec_bf16.p + (size_t)N0 * e->pf_kpa, e->pf_norm.p);
     e->launches++;
     FB_CUDA(e, cudaGetLastError());
     uint32_t nb = 0;
@@ -2220,7 +2221,7 @@ static int knn_prefilter_dev(fb_engine* e, const float* d_q, int nq, int k, int 
       StageTimer t(e, ST_FINALIZE);
       const size_t smem = (size_t)kPfCandCap * sizeof(u64) + (size_t)d * sizeof(float);
       pf_rescore_kernel<<<n, kPfRescoreThreads, smem, e->stream>>>(
-          d_q + (size_t)q0 * d, d, e->vecT.p, e->pf_cnt.p, e->pf_cand.p, kPfCandCap, kk, e->pf_eps2.p,
+          d_q + (size_t)q0 * d, d, e->vecR.p, e->pf_cnt.p, e->pf_cand.p, kPfCandCap, kk, e->pf_eps2.p,
           d_exclude ? d_exclude + (size_t)q0 * 3 : nullptr, k, e->vec_ids.p, d_out_ids + (size_t)q0 * k, d_out_sims + (size_t)q0 * k,
           d_out_rows ? d_out_rows + (size_t)q0 * k : nullptr, e->pf_ovf.p + 1, e->pf_ovf.p, nullptr);
       e->launches++;
@@ -2295,7 +2296,7 @@ int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_
     FB_CUDA(e, e->sub_vT.ensure((size_t)nb * d * 32));
     if (n > 0) {
       FB_CUDA(e, cudaMemcpyAsync(e->sub_rows.p, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-      gather_vec_blocks_kernel<<<nb, 256, 0, e->stream>>>(e->vecT.p, d, e->sub_rows.p, n, e->sub_vT.p);
+      gather_vec_blocks_kernel<<<nb, 256, 0, e->stream>>>(e->vecR.p, d, e->sub_rows.p, n, e->sub_vT.p);
       e->launches++;
       FB_CUDA(e, cudaGetLastError());
       FB_CUDA(e, cudaStreamSynchronize(e->stream));   // rows is a local
@@ -2336,7 +2337,7 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
   const size_t smem = (size_t)((d + 3) & ~3) * sizeof(float) + (size_t)n_pad * sizeof(u64);
   {
     StageTimer t(e, ST_FINALIZE);
-    pv_rerank_kernel<<<nq, kPvThreads, smem, e->stream>>>(e->q_stage.p, d, e->pv_cand.p, kp, k, e->vecT.p, e->vec_ids.p,
+    pv_rerank_kernel<<<nq, kPvThreads, smem, e->stream>>>(e->q_stage.p, d, e->pv_cand.p, kp, k, e->vecR.p, e->vec_ids.p,
                                                           e->vec_sorted_ids.p, e->vec_sorted_rows.p, (int)e->vec_N,
                                                           e->id_stage.p, e->dist_stage.p);
     e->launches++;
@@ -2698,7 +2699,7 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
     {
       StageTimer t(e, ST_SCAN);
       ivpq_scan_cells_kernel<<<std::min(scan_ctas, n_active), kJoinThreads, smem, e->stream>>>(
-          e->q_stage.p, act, n_active, prm, ctab, e->j_cell_start.p, e->j_perm.p, e->j_vrow.p, e->j_id.p, e->vecT.p, e->lut.p,
+          e->q_stage.p, act, n_active, prm, ctab, e->j_cell_start.p, e->j_perm.p, e->j_vrow.p, e->j_id.p, e->vecR.p, e->lut.p,
           e->j_sel_cells.p, e->j_ncells.p, e->j_state.p, e->j_tcounts.p, e->j_keys.p, (size_t)nt_up, e->id_stage.p, e->dist_stage.p,
           e->j_filled.p, e->j_state.p + 2, e->counters64.p + 7);
       e->launches++;
@@ -2727,12 +2728,12 @@ int fb_ivpq_search_in(fb_engine* e, const float* queries, int nq, int k, const i
 
 extern "C" {
 
-__global__ void gather_vec_rows_kernel(const float* __restrict__ vT, int d, const int32_t* __restrict__ rows, int n,
+__global__ void gather_vec_rows_kernel(const float* __restrict__ vR, int d, const int32_t* __restrict__ rows, int n,
                                        float* __restrict__ out) {
   const int q = blockIdx.x;
   if (q >= n) return;
   const int r = rows[q];
-  for (int i = threadIdx.x; i < d; i += blockDim.x) out[(size_t)q * d + i] = vT[((size_t)(r >> 5) * d + i) * 32 + (r & 31)];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) out[(size_t)q * d + i] = vR[(size_t)r * d + i];
 }
 
 int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, int k, int32_t* out_query_ids,
@@ -2760,7 +2761,7 @@ int fb_ivfadc_batch_search(fb_engine* e, const int32_t* query_ids, int n_ids, in
   FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
   FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
   FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, rows.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  gather_vec_rows_kernel<<<nq, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, nq, e->q_stage.p);
+  gather_vec_rows_kernel<<<nq, 128, 0, e->stream>>>(e->vecR.p, d, e->ana_rows.p, nq, e->q_stage.p);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   FB_CUDA(e, cudaStreamSynchronize(e->stream));   // rows is a local
@@ -2821,7 +2822,7 @@ int fb_grouping_pq(fb_engine* e, const int32_t* ids, int n_ids, const int32_t* g
   FB_CUDA(e, e->lut.ensure((size_t)n_groups * m * K));
   FB_CUDA(e, e->id_stage.ensure((size_t)n_slots));
   FB_CUDA(e, cudaMemcpyAsync(e->ana_rows.p, grows.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  gather_vec_rows_kernel<<<n_groups, 128, 0, e->stream>>>(e->vecT.p, d, e->ana_rows.p, n_groups, e->q_stage.p);
+  gather_vec_rows_kernel<<<n_groups, 128, 0, e->stream>>>(e->vecR.p, d, e->ana_rows.p, n_groups, e->q_stage.p);
   e->launches++;
   FB_CUDA(e, cudaGetLastError());
   if ((rc = launch_lut(e, cb, e->q_stage.p, nullptr, nullptr, 1, n_groups, e->lut.p))) return rc;   // freddy.c:1291-1299

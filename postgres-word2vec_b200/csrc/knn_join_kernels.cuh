@@ -460,7 +460,7 @@ ivpq_scan_cells_kernel(const float* __restrict__ queries, const int32_t* __restr
                        CodeTableDev ctab,                     // compact cell-major code table (slot = position in perm)
                        const int32_t* __restrict__ cell_start, const int32_t* __restrict__ perm,
                        const int32_t* __restrict__ t_vrow, const int32_t* __restrict__ t_id,
-                       const float* __restrict__ vT, const float* __restrict__ luts,
+                       const float* __restrict__ vR, const float* __restrict__ luts,
                        const uint16_t* __restrict__ sel_cells, const int32_t* __restrict__ n_cells,
                        const int32_t* __restrict__ round_state,   // [0] = last iteration (set by the select kernel of this round)
                        int32_t* __restrict__ target_counts,
@@ -524,10 +524,10 @@ ivpq_scan_cells_kernel(const float* __restrict__ queries, const int32_t* __restr
         if (cand) {
           if (prm.method == 1) {
             const int vr = t_vrow[t];
-            const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
+            const float* vp = vR + (size_t)vr * d;               // row-major image: one row = d contiguous floats
             float acc = 0.0f;
             for (int i = 0; i < d; i++) {
-              const float tt = xsub(qv[i], vp[(size_t)i * 32]);
+              const float tt = xsub(qv[i], __ldg(vp + i));
               acc = xadd(acc, xmul(tt, tt));
             }
             dist = acc;
@@ -596,10 +596,10 @@ ivpq_scan_cells_kernel(const float* __restrict__ queries, const int32_t* __restr
         for (int j = tid; j < n_s; j += kJoinThreads) {
           if (!(key_dist(sbuf[j]) < MAX_DIST)) { pv_d[j] = MAX_DIST; continue; }   // never entered the PV buffer (:505)
           const int vr = t_vrow[key_t(sbuf[j])];
-          const float* vp = vT + ((size_t)(vr >> 5) * d) * 32 + (vr & 31);
+          const float* vp = vR + (size_t)vr * d;
           float acc = 0.0f;
           for (int i = 0; i < d; i++) {
-            const float tt = xsub(qv[i], vp[(size_t)i * 32]);
+            const float tt = xsub(qv[i], __ldg(vp + i));
             acc = xadd(acc, xmul(tt, tt));
           }
           pv_d[j] = acc;

@@ -510,7 +510,7 @@ __device__ __forceinline__ void pf_block_sort_desc(u64* s, int n_pad) {
 }
 
 __global__ void __launch_bounds__(kPfRescoreThreads)
-pf_rescore_kernel(const float* __restrict__ queries, int d, const float* __restrict__ vT,
+pf_rescore_kernel(const float* __restrict__ queries, int d, const float* __restrict__ vR,
                   const int32_t* __restrict__ cand_cnt, const int2* __restrict__ cand, int cap, int kk,
                   const float* __restrict__ eps2, const int32_t* __restrict__ exclude_rows, int k,
                   const int32_t* __restrict__ ids, int32_t* __restrict__ out_ids, float* __restrict__ out_sims,
@@ -561,9 +561,9 @@ pf_rescore_kernel(const float* __restrict__ queries, int d, const float* __restr
     if (i < ns) {
       const int row = (int)(0xFFFFFFFFu - (uint32_t)keys[i]);
       if (row != ex0 && row != ex1 && row != ex2) {
-        const float* vp = vT + ((size_t)(row >> 5) * d) * 32 + (row & 31);
+        const float* vp = vR + (size_t)row * d;                  // row-major fp32 image
         float acc = 0.0f;
-        for (int j = 0; j < d; j++) acc = xadd(acc, xmul(qs[j], __ldg(vp + (size_t)j * 32)));
+        for (int j = 0; j < d; j++) acc = xadd(acc, xmul(qs[j], __ldg(vp + j)));
         key = score_key(acc, (uint32_t)row);
       }
     }

@@ -135,15 +135,15 @@ __global__ void exact_knn_reduce_kernel(const u64* __restrict__ partial, int n_s
   }
 }
 
-// gather rows of the dimension-major blocked table into a compact blocked table (knn_in_exact subset)
-__global__ void gather_vec_blocks_kernel(const float* __restrict__ vT, int d, const int32_t* __restrict__ rows, int n,
+// gather rows of the row-major image into a compact dimension-major blocked table (knn_in_exact subset)
+__global__ void gather_vec_blocks_kernel(const float* __restrict__ vR, int d, const int32_t* __restrict__ rows, int n,
                                          float* __restrict__ out) {
   const int s = blockIdx.x * 32 + (threadIdx.x & 31);      // destination slot
   const int i0 = threadIdx.x >> 5, step = blockDim.x >> 5;
   const bool ok = s < n;
   const int r = ok ? rows[s] : 0;
   for (int i = i0; i < d; i += step)
-    out[((size_t)blockIdx.x * d + i) * 32 + (s & 31)] = ok ? vT[((size_t)(r >> 5) * d + i) * 32 + (r & 31)] : 0.0f;
+    out[((size_t)blockIdx.x * d + i) * 32 + (s & 31)] = ok ? vR[(size_t)r * d + i] : 0.0f;
 }
 
 // Post-verification: one CTA per query.  cand_ids[q][kp] are the ids ivfadc_search / pq_search returned (rank
@@ -165,7 +165,7 @@ __device__ __forceinline__ int find_row_sorted(const int32_t* __restrict__ sorte
 
 __global__ void __launch_bounds__(kPvThreads)
 pv_rerank_kernel(const float* __restrict__ queries, int d, const int32_t* __restrict__ cand_ids, int kp, int k,
-                 const float* __restrict__ vT, const int32_t* __restrict__ vec_ids,
+                 const float* __restrict__ vR, const int32_t* __restrict__ vec_ids,
                  const int32_t* __restrict__ sorted_ids, const int32_t* __restrict__ sorted_rows, int n_vec,
                  int32_t* __restrict__ out_ids, float* __restrict__ out_sims) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -182,9 +182,9 @@ pv_rerank_kernel(const float* __restrict__ queries, int d, const int32_t* __rest
       const int id = cand_ids[(size_t)q * kp + c];
       const int row = (id >= 0) ? find_row_sorted(sorted_ids, sorted_rows, n_vec, id) : -1;
       if (row >= 0) {
-        const float* vp = vT + ((size_t)(row >> 5) * d) * 32 + (row & 31);
+        const float* vp = vR + (size_t)row * d;                  // row-major fp32 image
         float acc = 0.0f;
-        for (int i = 0; i < d; i++) acc = xadd(acc, xmul(qs[i], __ldg(vp + (size_t)i * 32)));
+        for (int i = 0; i < d; i++) acc = xadd(acc, xmul(qs[i], __ldg(vp + i)));
         key = score_key(acc, (uint32_t)row);
       }
     }

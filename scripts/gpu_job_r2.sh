@@ -1,4 +1,11 @@
 set -x
-timeout 300 python -m pytest tests/test_sidecar_gpu.py tests/test_shim_gpu.py -m gpu -q --timeout 300 2>&1 | tail -3
-timeout 300 python scripts/bench_concurrent.py --direct 0 --procs 4,16,64 --seconds 3 > gpurun_out/r2_sidecar_callers_l0.json 2> gpurun_out/sidecar.err; grep sidecar gpurun_out/r2_sidecar_callers_l0.json | cut -c1-400 | head -4; tail -c 400 gpurun_out/sidecar.err
-timeout 300 python scripts/bench_concurrent.py --direct 0 --procs 16,64 --seconds 3 --linger-us 40 > gpurun_out/r2_sidecar_callers_l40.json 2> gpurun_out/sidecar40.err; grep sidecar gpurun_out/r2_sidecar_callers_l40.json | cut -c1-400 | head -3; tail -c 400 gpurun_out/sidecar40.err
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 -x > gpurun_out/gputests.log 2>&1; tail -4 gpurun_out/gputests.log
+timeout 600 python bench.py --secondary 4,5 --no-cpu-baseline --steps 5 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; tail -c 300 gpurun_out/bench_tmp.err
+python - <<'PY'
+import json
+j=json.loads(open('gpurun_out/bench_tmp.json').read().strip().splitlines()[-1])
+print("value", round(j["value"]))
+for s in j["config"]["secondary"]:
+    print("   ", s.get("name","")[:40], s.get("seconds"), s.get("stage_ms_rank0"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
+PY
+timeout 120 python scripts/bench_prefilter.py 2>&1 | tail -8 | cut -c1-300
