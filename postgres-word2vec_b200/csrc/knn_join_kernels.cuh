@@ -79,9 +79,7 @@ ivpq_select_kernel(const float* __restrict__ queries, const int32_t* __restrict_
                    int32_t* __restrict__ round_state) {       // [0]: AND over the active queries of "all cells selected"
   __shared__ float sd[64];
   __shared__ u64 keys[1024];
-  __shared__ float prob[1025];
-  __shared__ int first_ok;
-  const int x = blockIdx.x, q = active[x], tid = threadIdx.x;
+  const int x = blockIdx.x, q = active[x], tid = threadIdx.x, lane = tid & 31;
   const int cells = Kc * Kc, half = d / 2;
   const float* qv = queries + (size_t)q * d;
   if (tid < 2 * Kc) {                                                             // index_utils.c:296-305
@@ -94,37 +92,57 @@ ivpq_select_kernel(const float* __restrict__ queries, const int32_t* __restrict_
     }
     sd[tid] = acc;
   }
-  if (tid == 0) first_ok = cells;
   __syncthreads();
   u64 key = kKeyInf;
   if (tid < cells) key = make_key(xadd(xadd(0.0f, sd[tid % Kc]), sd[Kc + tid / Kc]), (uint32_t)tid);   // :306-313
-  keys[tid] = key;
-  __syncthreads();
-  for (int size = 2; size <= 1024; size <<= 1) {                                  // ascending bitonic sort
+  // every warp sorts its 32 keys in registers (ascending over the lanes); the 32 sorted runs go to shared memory
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (tid < 512) {
-        const int lo = 2 * tid - (tid & (stride - 1)), hi = lo + stride;
-        const bool asc = (lo & size) == 0;
-        const u64 a = keys[lo], b = keys[hi];
-        if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
-      }
-      __syncthreads();
+      const u64 other = shfl_xor_u64(key, stride);
+      const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+      key = keep_min ? (key < other ? key : other) : (key > other ? key : other);
     }
   }
-  if (tid == 0) {                                                                 // prob += statistics[next.id], in visit order
-    float p = 0.0f;
-    prob[0] = 0.0f;
-    for (int n = 0; n < cells; n++) { p = xadd(p, stats[key_t(keys[n])]); prob[n + 1] = p; }
+  keys[tid] = key;
+  __syncthreads();
+  if (tid >= 32) return;
+  // Warp 0 merges the runs lazily: cells are visited in ascending sum order only as far as the confidence test needs
+  // (typically a handful of the 1024).  Lane l owns run l.  Per batch of 32 visited cells: prob[n] — the sequential
+  // fp32 sum of the statistics of the cells visited before n, in visit order — then one confidence test per lane.
+  // The loop `while (conf(prob) < confidence && visited < cells)` stops at the first n with conf(prob[n]) >= confidence.
+  int head = 0;
+  u64 cur = keys[32 * lane];
+  int n_done = 0, n_sel = cells;
+  float p = 0.0f;
+  bool found = false;
+  while (n_done < cells && !found) {
+    const int batch = min(32, cells - n_done);
+    u64 mine = kKeyInf;                                   // lane j: the j-th cell of this batch
+    for (int j = 0; j < batch; j++) {
+      u64 m = cur;
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) { const u64 o = shfl_xor_u64(m, sft); m = o < m ? o : m; }
+      if (cur == m) { head++; cur = head < 32 ? keys[32 * lane + head] : kKeyInf; }   // keys are unique (cell id in the low word)
+      if (lane == j) mine = m;
+    }
+    const float sj = lane < batch ? stats[key_t(mine)] : 0.0f;
+    float pj = p;                                         // prob[n_done + lane]
+    for (int i = 0; i < batch; i++) {
+      const float si = __shfl_sync(0xffffffffu, sj, i);
+      if (lane > i) pj = xadd(pj, si);
+    }
+    const float p_end = xadd(__shfl_sync(0xffffffffu, pj, batch - 1), __shfl_sync(0xffffffffu, sj, batch - 1));
+    const bool ok = lane < batch && !(confidence_hyp(prm.min_target, prm.n_targets_sql, pj, prm.stat_total) < prm.confidence);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int upto = bal ? __ffs(bal) - 1 : batch;        // cells of this batch that are visited
+    if (lane < upto) sel_cells[(size_t)x * 1024 + n_done + lane] = (uint16_t)key_t(mine);
+    if (bal) { n_sel = n_done + upto; found = true; }
+    n_done += batch;
+    p = p_end;
   }
-  __syncthreads();
-  // the loop `while (conf(prob) < confidence && visited < cells)` stops at the first n with conf(prob_n) >= confidence
-  for (int n = tid; n <= cells; n += 1024)
-    if (n < cells && !(confidence_hyp(prm.min_target, prm.n_targets_sql, prob[n], prm.stat_total) < prm.confidence))
-      atomicMin(&first_ok, n);
-  __syncthreads();
-  const int n_sel = first_ok;
-  if (tid < n_sel) sel_cells[(size_t)x * 1024 + tid] = (uint16_t)key_t(keys[tid]);
-  if (tid == 0) {
+  if (lane == 0) {
     n_cells[x] = n_sel;
     if (n_sel < cells) atomicAnd(round_state, 0);                                 // index_utils.c:404-406 (lastIteration)
   }
