@@ -380,6 +380,7 @@ int build_table_device(fb_engine* e, CodeTable& tab, const int32_t* ids, const i
   const bool pseudo = list_of_row == nullptr;
   if (pseudo) n_lists = (int)std::max<int64_t>(1, (N + rows_per_pseudo_list - 1) / rows_per_pseudo_list);
   cudaStream_t st = e->stream;
+  tab.loaded = false;          // the id column is overwritten before the rows are validated: a failed load leaves no table
   BuildTrace tr(st, "table");
   DevBuf<int32_t> d_list, d_len, d_diag, d_arrival, d_order, d_keys, d_iota, d_row_start;
   DevBuf<int16_t> d_codes;

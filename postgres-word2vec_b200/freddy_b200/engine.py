@@ -48,6 +48,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_sidecar", None):          # the server thread uses the engine: stop it first
+                self._lib.fb_sidecar_stop(self._sidecar, None)
+                self._sidecar = None
             self._lib.fb_destroy(self._h)
             self._h = None
 
