@@ -156,11 +156,15 @@ int fb_analogy_scan(fb_engine* e, const float* qvecs, const int32_t* exclude_ids
  * TMA-staged table, error bound proven in csrc/prefilter_kernels.cuh) followed by the fp32 chain on the
  * candidates: same ids, same similarity bits as the plain fp32 scan (FB_OPT_PREFILTER = 0).
  * fb_ivfadc_search_pv: k_nearest_neighbour_ivfadc_pv(bytea, k) (:574-591) with pvf = get_pvf(), w = get_w():
- * ivfadc_search(v, pvf*k) INNER JOIN vectors ON idx = id, re-ranked by cosine_similarity_bytea.          */
+ * ivfadc_search(v, pvf*k) INNER JOIN vectors ON idx = id, re-ranked by cosine_similarity_bytea.
+ * fb_pq_search_pv: k_nearest_neighbour_pq_pv(bytea, k) (:624-662): the same with pq_search(v, pvf*k) as the
+ * candidate source (the reference's SQL passes the candidate's word to cosine_similarity_bytea and cannot run
+ * as written; this is the query its ivfadc twin spells out).                                              */
 int fb_knn_exact(fb_engine* e, const float* queries, int nq, int k, const int32_t* targets, int n_targets,
                  int32_t* out_ids, float* out_sims);
 int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int w,
                         int32_t* out_ids, float* out_sims);
+int fb_pq_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int32_t* out_ids, float* out_sims);
 
 /* ---- quantisation of new rows (the encode step of index build / insert_batch) ------
  * As insert_batch assigns them: nearest coarse centroid with strict `<` from 100, first minimum wins

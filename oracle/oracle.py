@@ -346,6 +346,15 @@ class ReferenceSession:
             self._err("ivfadc_search_pv", n)
         return ids[:n], sims[:n]
 
+    def pq_search_pv(self, query, k):
+        q = np.ascontiguousarray(query, np.float32).ravel()
+        ids, sims = np.full(k, -1, np.int32), np.zeros(k, np.float32)
+        self.R.ref_pq_search_pv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        n = self.R.ref_pq_search_pv(_p(q), len(q), k, _p(ids), _p(sims))
+        if n < 0:
+            self._err("pq_search_pv", n)
+        return ids[:n], sims[:n]
+
     def analogy_3cosadd_batch(self, ids_abc):
         t = np.ascontiguousarray(ids_abc, np.int32).reshape(-1, 3)
         ids, sc = np.empty(len(t), np.int32), np.empty(len(t), np.float32)
@@ -528,14 +537,26 @@ def knn_exact(vectors, vec_ids, queries, k, targets=None):
     return out_ids, out_s
 
 
+def pq_search_pv(oracle_index, vectors, vec_ids, queries, k, pvf):
+    """k_nearest_neighbour_pq_pv(bytea, k)   freddy--0.0.1.sql:624-662: candidates = pq_search(v, pvf*k) (flat PQ oracle
+    index), INNER JOIN vectors ON idx = id, ORDER BY cosine_similarity_bytea DESC FETCH FIRST k.  (The reference's SQL
+    names the candidate's word where its ivfadc twin, :574-591, names the vector; the twin's form is restated.)"""
+    cand, _ = oracle_index.pq_search(queries, k * pvf)
+    return _rerank(vectors, vec_ids, queries, cand, k)
+
+
 def ivfadc_search_pv(oracle_index, vectors, vec_ids, queries, k, pvf, w, threads=4):
     """k_nearest_neighbour_ivfadc_pv(bytea, k)   freddy--0.0.1.sql:574-591: candidates = ivfadc_search(v, pvf*k),
     INNER JOIN vectors ON idx = id, ORDER BY cosine_similarity_bytea DESC FETCH FIRST k"""
+    cand, _, rc, _ = oracle_index.ivfadc_search(queries, k * pvf, w, threads=threads)
+    assert rc == 0
+    return _rerank(vectors, vec_ids, queries, cand, k)
+
+
+def _rerank(vectors, vec_ids, queries, cand, k):
     v = np.ascontiguousarray(vectors, np.float32)
     ids = np.asarray(vec_ids, np.int32)
     row_of = {int(i): r for r, i in enumerate(ids)}
-    cand, _, rc, _ = oracle_index.ivfadc_search(queries, k * pvf, w, threads=threads)
-    assert rc == 0
     out_ids = np.full((len(queries), k), -1, np.int32)
     out_s = np.zeros((len(queries), k), np.float32)
     for qi, q in enumerate(np.ascontiguousarray(queries, np.float32)):

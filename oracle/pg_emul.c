@@ -749,6 +749,7 @@ int ref_insert_batch(int n, const char** terms) {
 extern Datum knn_exact_search(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum knn_in_exact_search(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum ivfadc_search_pv(PG_FUNCTION_ARGS) __attribute__((weak));
+extern Datum pq_search_pv(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum analogy_3cosadd_batch(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum cosine_similarity_batch(PG_FUNCTION_ARGS) __attribute__((weak));
 extern Datum freddy_repin(PG_FUNCTION_ARGS) __attribute__((weak));
@@ -782,6 +783,17 @@ int ref_ivfadc_search_pv(const float* q, int d, int k, int32* ids, float* sims) 
   fc.args[1] = Int32GetDatum(k);
   char* text = malloc((size_t)k * 2 * 16 + 16);
   int n = run_srf(ivfadc_search_pv, &fc, 2, k, text, NULL);
+  if (n > 0) collect_single_f32(n, k, text, ids, sims);
+  free(text);
+  return n;
+}
+int ref_pq_search_pv(const float* q, int d, int k, int32* ids, float* sims) {
+  if (!pq_search_pv) return -3;
+  FunctionCallInfoData fc = {0};
+  fc.args[0] = PointerGetDatum(make_bytea(q, sizeof(float) * (size_t)d));
+  fc.args[1] = Int32GetDatum(k);
+  char* text = malloc((size_t)k * 2 * 16 + 16);
+  int n = run_srf(pq_search_pv, &fc, 2, k, text, NULL);
   if (n > 0) collect_single_f32(n, k, text, ids, sims);
   free(text);
   return n;

@@ -2350,6 +2350,48 @@ int fb_ivfadc_search_pv(fb_engine* e, const float* queries, int nq, int k, int p
   return check_error_flag(e);
 }
 
+// k_nearest_neighbour_pq_pv (freddy--0.0.1.sql:624-662): candidates = pq_search(v, pvf * k), joined with the word
+// vectors by id, ordered by the exact cosine_similarity_bytea, first k.  (As written, the reference's SQL hands the
+// candidate's WORD to cosine_similarity_bytea and cannot run; this is the query its ivfadc twin at :574-591 spells out.)
+int fb_pq_search_pv(fb_engine* e, const float* queries, int nq, int k, int pvf, int32_t* out_ids, float* out_sims) {
+  if (!e || nq < 0) return fail(e, FB_ERR_INVALID, "fb_pq_search_pv: bad arguments");
+  if (k < 1 || pvf < 1) return fail(e, FB_ERR_INVALID, "fb_pq_search_pv: k=%d pvf=%d", k, pvf);
+  const int64_t kp64 = (int64_t)k * pvf;
+  if (kp64 > kExactMaxK || kp64 > kPvMaxCand) return fail(e, FB_ERR_UNSUPPORTED, "pvf*k=%lld outside [1,%d]", (long long)kp64, kExactMaxK);
+  const int kp = (int)kp64;
+  int rc = check_pq_ready(e);
+  if (rc) return rc;
+  const int d = pq_dim(e);
+  if (!e->vec_loaded) return fail(e, FB_ERR_INVALID, "post-verification joins the word-vector table: fb_load_vectors first");
+  if (e->vec_d != d) return fail(e, FB_ERR_INVALID, "word vectors have d=%d, PQ index d=%d", e->vec_d, d);
+  if (nq == 0) return FB_OK;
+  if (!queries || !out_ids || !out_sims) return fail(e, FB_ERR_INVALID, "null buffer");
+  FB_CUDA(e, cudaSetDevice(e->device));
+  FB_CUDA(e, e->q_stage.ensure((size_t)nq * d));
+  FB_CUDA(e, e->pv_cand.ensure((size_t)nq * kp));
+  FB_CUDA(e, e->vo.ensure((size_t)nq * kp));
+  FB_CUDA(e, e->id_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, e->dist_stage.ensure((size_t)nq * k));
+  FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if ((rc = pq_dev(e, e->pq.dev(), e->pq.N, e->q_stage.p, nq, kp, 100.0f, e->pv_cand.p, e->vo.p))) return rc;   // pq_search: sentinel 100.0 (freddy.c:90-92)
+  e->host_rows += (int64_t)nq * e->pq.N;
+  int n_pad = 32;
+  while (n_pad < kp) n_pad <<= 1;
+  const size_t smem = (size_t)((d + 3) & ~3) * sizeof(float) + (size_t)n_pad * sizeof(u64);
+  {
+    StageTimer t(e, ST_FINALIZE);
+    pv_rerank_kernel<<<nq, kPvThreads, smem, e->stream>>>(e->q_stage.p, d, e->pv_cand.p, kp, k, e->vecR.p, e->vec_ids.p,
+                                                          e->vec_sorted_ids.p, e->vec_sorted_rows.p, (int)e->vec_N,
+                                                          e->id_stage.p, e->dist_stage.p);
+    e->launches++;
+    FB_CUDA(e, cudaGetLastError());
+  }
+  FB_CUDA(e, cudaMemcpyAsync(out_ids, e->id_stage.p, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaMemcpyAsync(out_sims, e->dist_stage.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  FB_CUDA(e, cudaStreamSynchronize(e->stream));
+  return check_error_flag(e);
+}
+
 // quantisation of new rows as insert_batch assigns them (freddy.c:1567-1582, index_utils.c:923-939):
 // coarse argmin (optional) -> residual LUT rows -> first minimum per position
 __global__ void any_coarse_far_kernel(const uint32_t* __restrict__ qflags, int n, int32_t* __restrict__ flag) {

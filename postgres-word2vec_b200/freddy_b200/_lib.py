@@ -68,6 +68,7 @@ SIGNATURES = {
     "fb_grouping_pq": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "fb_knn_exact": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "fb_ivfadc_search_pv": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "fb_pq_search_pv": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "fb_cosine_similarity": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "fb_vec_op": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P]),
     "fb_analogy_3cosadd": (C.c_int, [_P, _P, C.c_int, _P, _P]),

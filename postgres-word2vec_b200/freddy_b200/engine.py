@@ -246,6 +246,13 @@ class Engine:
                                            _ptr(ids), _ptr(sims)))
         return ids, sims
 
+    def pq_search_pv(self, queries, k, pvf):
+        """k_nearest_neighbour_pq_pv(bytea, k) for a batch: pq_search(v, pvf*k) re-ranked exactly"""
+        q = _f32(queries).reshape(-1, self._cb_d[_lib.FB_CB_PQ])
+        ids, sims = np.empty((len(q), k), np.int32), np.empty((len(q), k), np.float32)
+        self._check(self._lib.fb_pq_search_pv(self._h, _ptr(q), len(q), k, pvf, _ptr(ids), _ptr(sims)))
+        return ids, sims
+
     def ivfadc_search_pv(self, queries, k, pvf, w):
         """k_nearest_neighbour_ivfadc_pv(bytea, k) for a batch: ivfadc_search(v, pvf*k) re-ranked exactly"""
         q = _f32(queries).reshape(-1, self.d)

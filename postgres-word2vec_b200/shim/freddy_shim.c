@@ -628,6 +628,28 @@ Datum ivfadc_search_pv(PG_FUNCTION_ARGS) {
   return emit_single_exact(fcinfo);
 }
 
+/* pq_search_pv(bytea, int) -> SETOF (id int4, similarity float4): the body of k_nearest_neighbour_pq_pv
+ * (freddy--0.0.1.sql:624-662): pq_search(v, pvf * k), joined with the word vectors, exact re-rank */
+PG_FUNCTION_INFO_V1(pq_search_pv);
+Datum pq_search_pv(PG_FUNCTION_ARGS) {
+  if (SRF_IS_FIRSTCALL()) {
+    FuncCallContext* funcctx = SRF_FIRSTCALL_INIT();
+    MemoryContext old = MemoryContextSwitchTo(funcctx->multi_call_memory_ctx);
+    int k = PG_GETARG_INT32(1), n = 0, pvf;
+    float4* q;
+    int32* ids = palloc(sizeof(int32) * (k > 0 ? k : 1));
+    float* sims = palloc(sizeof(float) * (k > 0 ? k : 1));
+    getParameter(PARAM_PVF, &pvf);
+    convert_bytea_float4(PG_GETARG_BYTEA_P(0), &q, &n);
+    pin_pq(n);
+    pin_vectors();
+    fb_check(fb_pq_search_pv(engine, q, 1, k, pvf, ids, sims));
+    finish_single(funcctx, ids, sims, drop_unfilled(ids, sims, k));
+    MemoryContextSwitchTo(old);
+  }
+  return emit_single_exact(fcinfo);
+}
+
 /* analogy_3cosadd_batch(int[] ids) -> SETOF (query int4, id int4, score float4): ids = flattened (a, b, c) word-id
  * triples; per triple the row analogy_3cosadd returns (freddy--0.0.1.sql:1270-1288).  One call answers a batch. */
 PG_FUNCTION_INFO_V1(analogy_3cosadd_batch);

@@ -1,15 +1,2 @@
 set -x
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/gputests.log 2>&1; tail -4 gpurun_out/gputests.log
-timeout 600 python bench.py > gpurun_out/bench_r2_default.json 2> gpurun_out/bench_r2_default.err; tail -c 300 gpurun_out/bench_r2_default.err
-python - <<'PY'
-import json
-try:
-    j=json.loads(open('gpurun_out/bench_r2_default.json').read().strip().splitlines()[-1])
-    print("value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "frac", j["roofline"]["frac"], "cpu", j["cpu_baseline"]["value"], j["clocks"], "launches", j["gpu_launches"])
-    for s in j["config"]["secondary"]:
-        print("   ", s.get("name","")[:60], s.get("seconds"), s.get("queries_per_s"), s.get("roofline",{}).get("frac"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
-except Exception as ex:
-    print("no result", ex)
-PY
-timeout 400 python scripts/bench_configs.py --which 6,7 > gpurun_out/r2_configs_pv_exact.jsonl 2> gpurun_out/configs67.err; cut -c1-400 gpurun_out/r2_configs_pv_exact.jsonl; tail -c 300 gpurun_out/configs67.err
+timeout 600 python -m pytest tests/test_rerank_gpu.py tests/test_shim_gpu.py tests/test_sidecar_gpu.py -m gpu -q --timeout 300 2>&1 | tail -4

@@ -114,6 +114,6 @@ def test_shim_defines_every_symbol_the_sql_script_binds(oracle_mod):
     defined = {line.split()[-1] for line in out.splitlines() if line.strip()}
     missing = [s for s in want if s not in defined]
     assert not missing, f"symbols the SQL script binds but the shim library lacks: {missing}"
-    for extra in ("knn_exact_search", "knn_in_exact_search", "ivfadc_search_pv", "analogy_3cosadd_batch",
-                  "cosine_similarity_batch", "freddy_repin"):
+    for extra in ("knn_exact_search", "knn_in_exact_search", "ivfadc_search_pv", "pq_search_pv", "analogy_3cosadd_batch",
+                  "cosine_similarity_batch", "freddy_repin", "freddy_sidecar_serve", "freddy_sidecar_stop"):
         assert extra in defined, extra

@@ -77,6 +77,19 @@ def test_ivfadc_search_pv(eng, oracle_mod, k, pvf, w):
     _same(ids, s, eids, es, f"ivfadc_pv k={k} pvf={pvf} w={w}")
 
 
+@pytest.mark.parametrize("k,pvf", [(5, 20), (3, 4)])
+def test_pq_search_pv(eng, oracle_mod, k, pvf):
+    """k_nearest_neighbour_pq_pv: flat-PQ candidates (pq_search, sentinel 100.0) re-ranked by the exact cosine"""
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    eng.load_pq_index(ix)
+    eng.load_vectors(vec_ids, ix["vectors"])
+    q = queries_from(ix, 40, seed=6, noise=0.03)
+    ids, s = eng.pq_search_pv(q, k, pvf)
+    eids, es = oracle_mod.pq_search_pv(oracle_mod.OracleIndex(ix, flat_pq=True), ix["vectors"], vec_ids, q, k, pvf)
+    _same(ids, s, eids, es, f"pq_pv k={k} pvf={pvf}")
+
+
 def test_pv_readme_shape_and_udf_mirror(eng, oracle_mod):
     from freddy_b200.udf import Session, vec_to_bytea
     ix = small_index(N=60000, d=300, m=12, K=1024, C=100, seed=1, n_clusters=100)

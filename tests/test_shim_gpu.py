@@ -237,6 +237,24 @@ def test_shim_insert_batch_matches_the_reference(shim, oracle_mod):
     assert hits >= 7, f"only {hits} of 9 inserted vectors find their own new row"
 
 
+def test_shim_pq_search_pv(shim, oracle_mod):
+    """k_nearest_neighbour_pq_pv's body as one SRF: pq_search(v, pvf * k) + exact re-rank, pvf = get_pvf()"""
+    ix = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    vec_ids = np.asarray(ix["ids"], np.int32)
+    s = shim()
+    s.load_pq(ix)
+    s.load_vectors_table(ix["vectors"], vec_ids)
+    s.set_config("get_pvf()", 10)
+    q = queries_from(ix, 5, seed=17, noise=0.03)
+    oi = oracle_mod.OracleIndex(ix, flat_pq=True)
+    for i in range(len(q)):
+        ids, sims = s.pq_search_pv(q[i], 5)
+        eids, es = oracle_mod.pq_search_pv(oi, ix["vectors"], vec_ids, q[i:i + 1], 5, 10)
+        keep = eids[0] >= 0
+        np.testing.assert_array_equal(ids, eids[0][keep])
+        _same(sims, es[0][keep])
+
+
 def test_shim_ivfadc_search_through_the_sidecar(shim, oracle_mod):
     """FREDDY_SIDECAR set: ivfadc_search posts its query to the backend that runs freddy_sidecar_serve() instead of
     using an engine of its own; same rows, same bits; without a sidecar the backend answers itself."""
