@@ -253,6 +253,8 @@ enum {
                                   place them (FB_OPT_PLACEMENT_WINDOW <= 1024) and pack them with kernels, and sort the id
                                   columns on the device; the host sends the raw columns once.  0: the host-side builder
                                   (same layout; kept as the cross-check of tests/test_build_gpu.py)                      */
+  FB_OPT_SUBSET_PLACEMENT = 21, /* 1 (default): the per-call target subset of pq_search_in_batch gets the conflict-aware row placement
+                                  (groups of 512 rows, one CTA each) when queries x targets >= 2^26; 0: table order; 2: always */
   FB_OPT_QSCAN_MIN_QUERIES = 4 /* chunks with at least this many queries use the
                                   one-CTA-per-query scan (default 64); smaller
                                   ones use one CTA per (query, list)          */

@@ -39,27 +39,17 @@ __global__ void iota_i32_kernel(int32_t* __restrict__ out, int64_t n) {
   if (i < n) out[i] = (int32_t)i;
 }
 
-// Conflict-aware placement of the rows of one list (one CTA per list; thread j owns one candidate of the window).
-// arrival[row_start[c] ..] = the list's rows in arrival order; order[row_start[c] + s] = the row placed in slot s.
+// Conflict-aware placement of n rows into 32-row blocks by one CTA (thread j owns one candidate of the window).
+// code_of(a, p) = code of the row with arrival index a at position p; emit(slot, a) records the row placed in `slot`.
 // The window is the `window` earliest-arrived unplaced rows; per slot the candidate with the lowest
 // (cost, arrival index) wins, cost = 4096 x (positions whose per-bank maximum of distinct codes it raises) + (codes
 // already in its banks) — the same choice the host loop makes (first candidate with the smallest cost; all costs are
 // equal in an empty block, so slot 0 takes the earliest row).
-__global__ void __launch_bounds__(1024)
-place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t* __restrict__ arrival, const int32_t* __restrict__ row_start,
-                  const int32_t* __restrict__ len, int window, int32_t* __restrict__ order) {
-  extern __shared__ __align__(16) unsigned char place_smem[];
-  const int c = blockIdx.x;
-  const int n = len[c];
-  const int32_t* rows = arrival + row_start[c];
-  int32_t* out = order + row_start[c];
+template <typename CodeOf, typename Emit>
+__device__ __forceinline__ void place_rows_cta(int n, int m, int K, int window, unsigned char* smem, CodeOf code_of, Emit emit) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  if (n <= 32 || m > 64) {
-    for (int i = tid; i < n; i += nthr) out[i] = rows[i];
-    return;
-  }
   const int kw = (K + 31) >> 5;
-  uint32_t* seen = reinterpret_cast<uint32_t*>(place_smem);                 // [m][kw] bit per code present in the open block
+  uint32_t* seen = reinterpret_cast<uint32_t*>(smem);                        // [m][kw] bit per code present in the open block
   unsigned long long* red = reinterpret_cast<unsigned long long*>(seen + (size_t)m * kw + ((m * kw) & 1));   // [32]
   int16_t* wcode = reinterpret_cast<int16_t*>(red + 32);                     // [window][m]
   uint8_t* cnt = reinterpret_cast<uint8_t*>(wcode + (size_t)window * m);     // [m][32] distinct codes per bank
@@ -68,10 +58,12 @@ place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t
 
   int mine = (tid < window && tid < n) ? tid : -1;     // arrival index of my candidate
   int next = min(window, n);                           // next arrival index to enter the window (uniform)
-  if (mine >= 0) {
-    const int16_t* cr = codes + (size_t)rows[mine] * m;
-    for (int p = 0; p < m; p++) wcode[(size_t)tid * m + p] = cr[p];
-  }
+  if (mine >= 0)
+    for (int p = 0; p < m; p++) wcode[(size_t)tid * m + p] = (int16_t)code_of(mine, p);
+  // rows enter the window in arrival order, so the entrant of the NEXT step is known: thread p < m keeps its code of
+  // position p in a register, fetched one step ahead (the loop is a chain of n dependent steps; nothing in it may wait
+  // for global memory)
+  int pre = (tid < m && next < n) ? code_of(next, tid) : 0;
   for (int placed = 0; placed < n; placed++) {
     if ((placed & 31) == 0) {
       for (int i = tid; i < m * kw; i += nthr) seen[i] = 0u;
@@ -81,12 +73,14 @@ place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t
     unsigned long long key = ~0ull;
     if (mine >= 0) {
       int raises = 0, load = 0;
-      for (int p = 0; p < m; p++) {
-        const int code = wcode[(size_t)tid * m + p];
-        if ((seen[p * kw + (code >> 5)] >> (code & 31)) & 1u) continue;     // same address as a placed row: merged
+      const int16_t* wc = wcode + (size_t)tid * m;
+#pragma unroll 4
+      for (int p = 0; p < m; p++) {                       // branch-free: the loads of all positions overlap
+        const int code = wc[p];
+        const int fresh = 1 - (int)((seen[p * kw + (code >> 5)] >> (code & 31)) & 1u);   // 0: same address as a placed row, merged
         const int l = cnt[p * 32 + (code & 31)];
-        raises += (l + 1 > mx[p]);
-        load += l;
+        raises += fresh & (int)(l + 1 > mx[p]);
+        load += fresh * l;
       }
       key = ((unsigned long long)(raises * 4096 + load) << 42) | ((unsigned long long)(uint32_t)mine << 10) | (unsigned long long)tid;
     }
@@ -100,7 +94,7 @@ place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t
     for (int wv = 1; wv < nwarps; wv++) { const unsigned long long o = red[wv]; best = o < best ? o : best; }
     const int win_thread = (int)(best & 1023u);
     const int win_arrival = (int)((best >> 10) & 0xffffffffu);
-    // threads p < m record the winner's code of position p
+    // threads p < m record the winner's code of position p and hand its window slot to the entrant
     if (tid < m) {
       const int code = wcode[(size_t)win_thread * m + tid];
       uint32_t& wd = seen[tid * kw + (code >> 5)];
@@ -109,18 +103,64 @@ place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t
         const uint8_t l = ++cnt[tid * 32 + (code & 31)];
         if (l > mx[tid]) mx[tid] = l;
       }
+      if (next < n) wcode[(size_t)win_thread * m + tid] = (int16_t)pre;
     }
-    if (tid == 0) out[placed] = rows[win_arrival];
-    __syncthreads();
-    if (tid == win_thread) {
-      mine = next < n ? next : -1;
-      if (mine >= 0) {
-        const int16_t* cr = codes + (size_t)rows[mine] * m;
-        for (int p = 0; p < m; p++) wcode[(size_t)tid * m + p] = cr[p];
-      }
-    }
+    if (tid == 0) emit(placed, win_arrival);
+    if (tid == win_thread) mine = next < n ? next : -1;
     if (next < n) next++;
+    if (tid < m && next < n) pre = code_of(next, tid);     // in flight during the next step
+    __syncthreads();
   }
+}
+
+// one CTA per list: arrival[row_start[c] ..] = the list's rows in arrival order; order[row_start[c] + s] = the row in slot s
+__global__ void __launch_bounds__(1024)
+place_rows_kernel(const int16_t* __restrict__ codes, int m, int K, const int32_t* __restrict__ arrival, const int32_t* __restrict__ row_start,
+                  const int32_t* __restrict__ len, int window, int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char place_smem[];
+  const int c = blockIdx.x;
+  const int n = len[c];
+  const int32_t* rows = arrival + row_start[c];
+  int32_t* out = order + row_start[c];
+  if (n <= 32 || m > 64) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = rows[i];
+    return;
+  }
+  place_rows_cta(n, m, K, window, place_smem,
+                 [&](int a, int p) { return (int)codes[(size_t)rows[a] * m + p]; },
+                 [&](int slot, int a) { out[slot] = rows[a]; });
+}
+
+// The same placement for a per-call target subset (`WHERE id IN (...)`): the selected rows, in table order, are cut into
+// groups of `group` rows (a multiple of 32), one CTA places each group.  order[s] = index into sel_rows of the row that
+// goes to slot s of the compact table (slots beyond the selection keep the identity).
+__global__ void __launch_bounds__(1024)
+subset_place_kernel(const uint2* __restrict__ src_units, int U, int m, int K, const int32_t* __restrict__ sel_rows,
+                    const int32_t* __restrict__ n_sel, int window, int group, size_t place_bytes, int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char place_smem[];
+  const int g0 = blockIdx.x * group;
+  const int n = min(group, *n_sel - g0);
+  if (n <= 0) return;
+  if (n <= 32) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) order[g0 + i] = g0 + i;
+    return;
+  }
+  // the group's codes first go to shared memory (one scattered 8-byte load per row and unit, all threads): the
+  // placement loop is a chain of n dependent steps and must not wait for global memory in any of them
+  int16_t* gcode = reinterpret_cast<int16_t*>(place_smem + place_bytes);     // [group][4 * U]
+  const int mp = 4 * U;
+  for (int i = threadIdx.x; i < n * U; i += blockDim.x) {
+    const int a = i / U, u = i - a * U;
+    const int row = sel_rows[g0 + a];
+    const uint2 v = src_units[((size_t)(row >> 5) * U + u) * 32 + (row & 31)];
+    int16_t* dst = gcode + (size_t)a * mp + 4 * u;
+    dst[0] = (int16_t)((v.x & 0xFFFFu) >> 2); dst[1] = (int16_t)(v.x >> 18);
+    dst[2] = (int16_t)((v.y & 0xFFFFu) >> 2); dst[3] = (int16_t)(v.y >> 18);
+  }
+  __syncthreads();
+  place_rows_cta(n, m, K, window, place_smem,
+                 [&](int a, int p) { return (int)gcode[(size_t)a * mp + p]; },
+                 [&](int slot, int a) { order[g0 + slot] = g0 + a; });
 }
 
 inline size_t place_rows_smem(int m, int K, int window) {

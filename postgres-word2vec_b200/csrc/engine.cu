@@ -185,7 +185,7 @@ struct fb_engine {
 
   // scratch
   DevBuf<float> lut, exact_lut, q_stage, dist_stage, coarse_dist;
-  DevBuf<int32_t> probes, exact_list, id_stage, sel_rows;
+  DevBuf<int32_t> probes, exact_list, id_stage, sel_rows, sel_order;
   DevBuf<uint32_t> qflags;
   DevBuf<u64> partial, kth;
   DevBuf<int32_t> small;   // [0]=exact_count [1]=work_counter [2]=error_flag
@@ -220,6 +220,7 @@ struct fb_engine {
   size_t pin_q_floats = 0;
   int pipe_shape = 0;
   int pipe_ramp = 0;
+  int subset_placement = 1;       // FB_OPT_SUBSET_PLACEMENT: 0 off, 1 when it pays, 2 always
   bool device_build = true;   // FB_OPT_DEVICE_BUILD: CSR, placement and packing of a pinned table run as kernels
   int placement_window = 256; // rows considered per slot by the conflict-aware placement of the fine table (<= 1: off)
   volatile float one = 1.0f;
@@ -1336,7 +1337,8 @@ int build_id_index(fb_engine* e, CodeTable& tab, const int32_t* ids, int64_t N) 
 // :1286-1300), gathered on the device into the compact one-list table e->tmp.  Nothing comes back to the host:
 // the row count stays in e->sel_total[0] (= the list length the scan kernels read).  `view` describes the
 // subset for the kernels; rows_upper bounds its row count.
-int build_subset(fb_engine* e, const CodeTable& src, const int32_t* wanted, int n_wanted, CodeTableDev& view, int64_t& rows_upper) {
+int build_subset(fb_engine* e, const CodeTable& src, const int32_t* wanted, int n_wanted, CodeTableDev& view, int64_t& rows_upper,
+                 int64_t n_queries = 0) {
   const int64_t N = src.N;
   const int n_words = (int)std::max<int64_t>(1, (N + 31) / 32);
   rows_upper = std::min<int64_t>(N, n_wanted);
@@ -1360,8 +1362,24 @@ int build_subset(fb_engine* e, const CodeTable& src, const int32_t* wanted, int 
   }
   subset_scan_kernel<<<1, 1024, 0, e->stream>>>(e->sel_bitmap.p, n_words, e->sel_word_base.p, e->sel_total.p, nullptr);
   subset_compact_kernel<<<(n_words + 255) / 256, 256, 0, e->stream>>>(e->sel_bitmap.p, n_words, e->sel_word_base.p, e->sel_rows.p);
-  subset_gather_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(src.units.p, src.U, e->sel_rows.p, e->sel_total.p, tmp.units.p,
-                                                                     tmp.rowno.p, n_slots);
+  // Many queries over the subset: its rows get the conflict-aware placement of the pinned fine table, in groups of 512
+  // rows (one CTA each, ~0.1 ms) — the shared-memory gather of the scan then replays far fewer bank conflicts
+  // (profiles/r2_config3_config4_ncu.txt: two thirds of the wavefronts were replays).  Few queries: not worth the kernel.
+  const int32_t* d_order = nullptr;
+  constexpr int kGroup = 512, kWindow = 128;
+  const size_t place_bytes = (place_rows_smem(src.m, src.K, kWindow) + 15) / 16 * 16;
+  const size_t place_smem = place_bytes + (size_t)kGroup * 4 * src.U * sizeof(int16_t);
+  if ((e->subset_placement == 2 || (e->subset_placement == 1 && n_queries * rows_upper >= ((int64_t)1 << 26))) && src.m <= 64 && src.K > 0 &&
+      place_smem <= std::min<size_t>(e->smem_optin, 96 * 1024)) {
+    FB_CUDA(e, e->sel_order.ensure((size_t)n_slots));
+    FB_CUDA(e, cudaFuncSetAttribute(subset_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
+    subset_place_kernel<<<(unsigned)((rows_upper + kGroup - 1) / kGroup), std::max(kWindow, (src.m + 31) / 32 * 32), place_smem, e->stream>>>(
+        src.units.p, src.U, src.m, src.K, e->sel_rows.p, e->sel_total.p, kWindow, kGroup, place_bytes, e->sel_order.p);
+    e->launches++;
+    d_order = e->sel_order.p;
+  }
+  subset_gather_kernel<<<(n_slots + 255) / 256, 256, 0, e->stream>>>(src.units.p, src.U, e->sel_rows.p, e->sel_total.p, d_order,
+                                                                     tmp.units.p, tmp.rowno.p, n_slots);
   e->launches += 3;
   FB_CUDA(e, cudaGetLastError());
   view.units8 = nullptr;
@@ -1585,7 +1603,7 @@ int fb_pq_search_in_batch(fb_engine* e, const float* queries, int nq, int k, con
   FB_CUDA(e, cudaMemcpyAsync(e->q_stage.p, queries, (size_t)nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   CodeTableDev view;
   int64_t rows_upper = 0;
-  if ((rc = build_subset(e, e->pq, targets, n_targets, view, rows_upper))) return rc;
+  if ((rc = build_subset(e, e->pq, targets, n_targets, view, rows_upper, nq))) return rc;
   rc = pq_dev(e, view, rows_upper, e->q_stage.p, nq, k, 1000.0f, e->id_stage.p, e->dist_stage.p);  // freddy.c:415
   if (rc) return rc;
   int32_t n_sel = 0;
@@ -1757,6 +1775,7 @@ int fb_set_option(fb_engine* e, int option, int64_t value) {
     case FB_OPT_BYTE_CODES: e->byte_codes = value != 0; return FB_OK;
     case FB_OPT_PREFILTER_LOCKSTEP: e->pf_lockstep = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_DEVICE_BUILD: e->device_build = value != 0; return FB_OK;
+    case FB_OPT_SUBSET_PLACEMENT: e->subset_placement = (int)std::max<int64_t>(0, std::min<int64_t>(2, value)); return FB_OK;
     case FB_OPT_PLACEMENT_WINDOW: e->placement_window = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20)); return FB_OK;
     case FB_OPT_PIPE_CHUNK:
       if (value < 1) return fail(e, FB_ERR_INVALID, "pipeline chunk must be >= 1");

@@ -73,15 +73,17 @@ __global__ void subset_compact_kernel(const uint32_t* __restrict__ bitmap, int n
 
 // gather the selected rows of a blocked code table (blocks in table order) into a compact blocked table;
 // *n_sel rows are live, the remaining slots of the last block are padding (rowno -1)
+// `order` (may be null): slot s takes the order[s]-th selected row (conflict-aware placement inside groups of rows,
+// subset_place_kernel); the rows' table order travels in dst_rowno
 __global__ void subset_gather_kernel(const uint2* __restrict__ src_units, int U, const int32_t* __restrict__ sel_rows,
-                                     const int32_t* __restrict__ n_sel, uint2* __restrict__ dst_units,
-                                     int32_t* __restrict__ dst_rowno, int n_dst_slots) {
+                                     const int32_t* __restrict__ n_sel, const int32_t* __restrict__ order,
+                                     uint2* __restrict__ dst_units, int32_t* __restrict__ dst_rowno, int n_dst_slots) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = *n_sel;
   if (s >= n_dst_slots || s >= ((n + 31) & ~31)) return;     // slots beyond the last live block are never read
   const int db = s >> 5, dl = s & 31;
   if (s < n) {
-    const int r = sel_rows[s];
+    const int r = sel_rows[order != nullptr ? order[s] : s];
     const int sb = r >> 5, sl = r & 31;
     for (int u = 0; u < U; u++) dst_units[((size_t)db * U + u) * 32 + dl] = src_units[((size_t)sb * U + u) * 32 + sl];
     dst_rowno[s] = r;

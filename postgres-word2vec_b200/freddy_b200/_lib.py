@@ -17,7 +17,7 @@ FB_OPT_LUT_TILE = 6
 FB_OPT_LUT_CTAS_PER_SM, FB_OPT_OVERLAP = 7, 8
 FB_OPT_PIPELINE, FB_OPT_PIPE_CHUNK, FB_OPT_PIPE_DEBUG, FB_OPT_PLACEMENT_WINDOW = 9, 10, 11, 12
 FB_OPT_PIPE_SHAPE, FB_OPT_PIPE_RAMP, FB_OPT_CUDA_GRAPHS, FB_OPT_ZERO_COPY_UPLOAD = 13, 14, 15, 16
-FB_OPT_PREFILTER, FB_OPT_BYTE_CODES, FB_OPT_PREFILTER_LOCKSTEP, FB_OPT_DEVICE_BUILD = 17, 18, 19, 20
+FB_OPT_PREFILTER, FB_OPT_BYTE_CODES, FB_OPT_PREFILTER_LOCKSTEP, FB_OPT_DEVICE_BUILD, FB_OPT_SUBSET_PLACEMENT = 17, 18, 19, 20, 21
 
 
 class Counters(C.Structure):

@@ -204,11 +204,15 @@ def test_flat_pq_in_batch_shapes(eng, oracle_mod):
     eng.load_pq_index(ix)
     oi = oracle_mod.OracleIndex(ix, flat_pq=True)
     targets = np.concatenate([ids[90:150], ids[4990:5050], rng.choice(ids, 4000), [10 ** 8, -5]]).astype(np.int32)
+    from freddy_b200 import _lib
     for nq in (1, 7, 400):
         q = queries_from(ix, nq, seed=nq)
-        got = eng.pq_search_in_batch(q, 5, targets)
         exp = oi.pq_search_in_batch(q, 5, targets)
-        assert_same_topk(got[0], got[1], exp[0], exp[1], f"pq_search_in_batch nq={nq}")
+        for placement in (1, 2, 0):                     # 2: the subset's rows are placed bank-aware (what large batches get)
+            eng.set_option(_lib.FB_OPT_SUBSET_PLACEMENT, placement)
+            got = eng.pq_search_in_batch(q, 5, targets)
+            assert_same_topk(got[0], got[1], exp[0], exp[1], f"pq_search_in_batch nq={nq} placement={placement}")
+    eng.set_option(_lib.FB_OPT_SUBSET_PLACEMENT, 1)
     q = queries_from(ix, 9, seed=2)
     for t in (np.zeros(0, np.int32), np.asarray([10 ** 8], np.int32)):
         got = eng.pq_search_in_batch(q, 4, t)
