@@ -1,11 +1,12 @@
 set -x
-timeout 600 python -m pytest tests/test_build_gpu.py tests/test_ivfadc_gpu.py tests/test_append_gpu.py -m gpu -q --timeout 300 2>&1 | tail -4
-timeout 600 python bench.py --secondary 3 --no-cpu-baseline --steps 3 > gpurun_out/bench_tmp.json 2> gpurun_out/bench_tmp.err; tail -c 300 gpurun_out/bench_tmp.err
+timeout 600 python bench.py > gpurun_out/bench_r2_default.json 2> gpurun_out/bench_r2_default.err; tail -c 300 gpurun_out/bench_r2_default.err
 python - <<'PY'
 import json
-j=json.loads(open('gpurun_out/bench_tmp.json').read().strip().splitlines()[-1])
-print("headline", round(j["value"]))
-for s in j["config"]["secondary"]:
-    print("   ", s.get("name","")[:40], s.get("seconds"), s.get("stage_ms"), s.get("roofline",{}).get("frac"), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
+try:
+    j=json.loads(open('gpurun_out/bench_r2_default.json').read().strip().splitlines()[-1])
+    print("value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "frac", j["roofline"]["frac"], "cpu", j["cpu_baseline"]["value"], j["clocks"], "launches", j["gpu_launches"])
+    for s in j["config"]["secondary"]:
+        print("   ", s.get("name","")[:60], s.get("seconds"), s.get("queries_per_s"), s.get("roofline",{}).get("frac"), s.get("stage_ms", s.get("stage_ms_rank0")), s.get("equals_reference_on_sample",{}).get("ok"), s.get("error"))
+except Exception as ex:
+    print("no result", ex)
 PY
-FB_TRACE_BUILD=1 timeout 300 python scripts/bench_upload.py > gpurun_out/r2_upload.json 2> gpurun_out/upload.err; cat gpurun_out/r2_upload.json; grep "fb build" gpurun_out/upload.err | sed -n 1,6p
