@@ -29,6 +29,22 @@ def test_header_symbols_all_exported(lib):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
 
 
+def test_sidecar_header_symbols_exported_by_both_libraries(lib):
+    """include/freddy_sidecar.h: the CUDA-free library a backend links (libfreddy_sidecar.so) and the engine library
+    (which runs the server loop) both export every declared entry point"""
+    hdr = open(os.path.join(ROOT, "include", "freddy_sidecar.h")).read()
+    declared = set(re.findall(r"\b(fbsc_[a-z0-9_]+)\s*\(", hdr)) - {"fbsc_batch_fn"}
+    assert len(declared) >= 11, declared
+    side = C.CDLL(os.path.join(ROOT, "postgres-word2vec_b200", "libfreddy_sidecar.so"))
+    for name in declared:
+        assert hasattr(side, name), f"{name} missing from libfreddy_sidecar.so"
+        assert hasattr(lib, name), f"{name} missing from libfreddy_b200.so"
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", os.path.join(ROOT, "postgres-word2vec_b200", "libfreddy_sidecar.so")],
+                            capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower(), "the backend-side library must not depend on CUDA"
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
