@@ -111,3 +111,39 @@ def test_sidecar_batches_concurrent_single_query_callers():
     lib.fbsc_client_close(h)
     h2 = C.c_void_p()
     assert lib.fbsc_client_open(name, C.byref(h2)) == -3
+
+
+@pytest.mark.timeout(60)
+def test_sidecar_busy_slots_remote_stop():
+    """one slot, no server yet: a second caller gets FBSC_ERR_BUSY after its timeout; a client can ask the server to stop"""
+    lib = _lib()
+    lib.fbsc_client_request_stop = lib.fbsc_client_request_stop
+    lib.fbsc_client_request_stop.argtypes = [C.c_void_p]
+    name = f"/fbsc_busy_{os.getpid()}".encode()
+    srv = C.c_void_p()
+    assert lib.fbsc_server_create(name, D, 4, 1, C.byref(srv)) == 0
+    ha, hb = C.c_void_p(), C.c_void_p()
+    assert lib.fbsc_client_open(name, C.byref(ha)) == 0 and lib.fbsc_client_open(name, C.byref(hb)) == 0
+    q = np.zeros(D, np.float32)
+    q[0], q[1] = 3.0, 0.5
+    ids_a, d_a = np.empty(2, np.int32), np.empty(2, np.float32)
+    rc_a = []
+    ta = threading.Thread(target=lambda: rc_a.append(lib.fbsc_client_search(
+        ha, q.ctypes.data_as(C.c_void_p), 2, 1, ids_a.ctypes.data_as(C.c_void_p), d_a.ctypes.data_as(C.c_void_p), 0)))
+    ta.start()
+    time.sleep(0.2)                                   # A holds the only slot, nobody serves yet
+    ids_b, d_b = np.empty(2, np.int32), np.empty(2, np.float32)
+    t0 = time.time()
+    assert lib.fbsc_client_search(hb, q.ctypes.data_as(C.c_void_p), 2, 1, ids_b.ctypes.data_as(C.c_void_p),
+                                  d_b.ctypes.data_as(C.c_void_p), 100) == -4
+    assert 0.05 < time.time() - t0 < 5.0
+    cb = BATCH_FN(_stub)
+    ts = threading.Thread(target=lambda: lib.fbsc_server_run(srv, cb, None, 8, 0))
+    ts.start()
+    ta.join(20)
+    assert rc_a == [0] and ids_a.tolist() == [301, 302] and np.allclose(d_a, [0.5, 1.5])
+    assert lib.fbsc_client_request_stop(hb) == 0      # what freddy_sidecar_stop() does from another backend
+    ts.join(20)
+    assert not ts.is_alive()
+    lib.fbsc_client_close(ha); lib.fbsc_client_close(hb)
+    lib.fbsc_server_destroy(srv)
