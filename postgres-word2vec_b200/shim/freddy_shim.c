@@ -5,8 +5,9 @@
  *   libfreddy_b200.so (include/freddy_b200.h);
  *   insert_batch (quantisation on the GPU, table mutation through the reference's own helpers);
  *   the converters read_bytea / read_bytea_int16 / read_bytea_float / vec_to_bytea;
- * plus SRFs for the GPU paths SQL reaches through plpgsql today (exact k-NN, post verification, analogy, batched
- * cosine) and freddy_repin().  Built with PGXS next to the reference's index_utils.c / output_utils.c /
+ * plus SRFs for the GPU paths SQL reaches through plpgsql today (exact k-NN, post verification over IVFADC and flat-PQ
+ * candidates, analogy, batched cosine), freddy_repin(), and freddy_sidecar_serve() / freddy_sidecar_stop(): one backend
+ * owns the engine and answers the ivfadc_search calls of all others in batches (include/freddy_sidecar.h).  Built with PGXS next to the reference's index_utils.c / output_utils.c /
  * core_functions.c / cosine_similarity.c (table-name and parameter lookup, bytea converters, the scalar UDFs stay
  * the reference's own code).
  *
