@@ -203,6 +203,18 @@ def test_sql_level_oracles_are_built_from_pinned_pieces():
         assert [int(vec_ids[r]) for _, r in scored] == [int(i) for i in got_ids[qi] if i >= 0]
         np.testing.assert_array_equal(np.array([-s for s, _ in scored], np.float32).view(np.uint32),
                                       got_s[qi][:len(scored)].view(np.uint32))
+    # (2b) the flat-PQ twin (k_nearest_neighbour_pq_pv): real pq_search SRF candidates + real similarities
+    ixp = small_index(N=20000, d=48, m=12, K=64, C=40, seed=7, with_pq=True)
+    rs2 = oracle.ReferenceSession()
+    rs2.load_pq(ixp)
+    cand, _ = rs2.pq_search(q[:6], k * pvf)
+    got_ids, got_s = oracle.pq_search_pv(oracle.OracleIndex(ixp, flat_pq=True), ixp["vectors"], vec_ids, q[:6], k, pvf)
+    for qi in range(6):
+        rows = [row_of[int(c)] for c in cand[qi] if int(c) in row_of]
+        scored = sorted(((-float(ref_sim(q[qi], ixp["vectors"][r])), r) for r in rows))[:k]
+        assert [int(vec_ids[r]) for _, r in scored] == [int(i) for i in got_ids[qi] if i >= 0]
+        np.testing.assert_array_equal(np.array([-s for s, _ in scored], np.float32).view(np.uint32),
+                                      got_s[qi][:len(scored)].view(np.uint32))
     # (3) exact k-NN over a slice of the table
     sub_ids = vec_ids[:600]
     e_ids, e_s = oracle.knn_exact(vectors[:600], sub_ids, q[:3], 5)
