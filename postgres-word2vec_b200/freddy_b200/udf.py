@@ -107,6 +107,12 @@ class Session:
         ids, s = self.engine.ivfadc_search_pv(bytea_to_vec(query_bytea)[None, :], int(k), self._pvf, self._w)
         return [(int(i), float(x)) for i, x in zip(ids[0], s[0]) if i >= 0]
 
+    def k_nearest_neighbour_pq_pv(self, query_bytea, k):
+        """k_nearest_neighbour_pq_pv(bytea, int) -> TABLE (id, similarity float4)   freddy--0.0.1.sql:624-641,
+        post-verification factor get_pvf()"""
+        ids, s = self.engine.pq_search_pv(bytea_to_vec(query_bytea)[None, :], int(k), self._pvf)
+        return [(int(i), float(x)) for i, x in zip(ids[0], s[0]) if i >= 0]
+
     def pq_search(self, query_bytea, k):
         """pq_search(bytea, int) -> SETOF (id, distance)   freddy.c:28-170"""
         q = bytea_to_vec(query_bytea)
